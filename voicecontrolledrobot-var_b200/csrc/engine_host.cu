@@ -1,0 +1,321 @@
+// Host launchers for the tcgen05 engine (see tc_engine.cuh).
+#include "engine_host.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+static thread_local char g_last_error[512] = "";
+void var_set_last_error(const char* msg, const char* file, int line) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s (%s:%d)", msg, file, line);
+}
+extern "C" const char* var_last_error(void) { return g_last_error; }
+
+namespace var {
+
+MnCfg& mn_cfg() {
+  static MnCfg c;
+  return c;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int rows, cols, box_rows, swz;
+  long long pitch;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows &&
+           swz == o.swz && pitch == o.pitch;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1315423911u + (size_t)k.rows;
+    h = h * 1315423911u + (size_t)k.cols;
+    h = h * 1315423911u + (size_t)k.box_rows;
+    h = h * 1315423911u + (size_t)k.swz;
+    h = h * 1315423911u + (size_t)k.pitch;
+    return h;
+  }
+};
+
+int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_rows, int swizzle,
+                CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, rows, cols, box_rows, swizzle, pitch};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return VAR_OK;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    var_set_last_error("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((pitch * 4) & 15)) {
+    var_set_last_error("tensor map needs 16-byte aligned base and pitch", __FILE__, __LINE__);
+    return VAR_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: %d (rows=%d cols=%d box_rows=%d)",
+             (int)r, rows, cols, box_rows);
+    var_set_last_error(buf, __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = m;
+  }
+  *out = m;
+  return VAR_OK;
+}
+
+// ---------------------------------------------------------------------------
+template <int GMODE, int EPI>
+static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const GemmParams& p,
+                         dim3 grid, cudaStream_t st) {
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<GMODE, EPI>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, p);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+int launch_gemm(int gmode, int epi, const CUtensorMap& t0, const CUtensorMap& t1,
+                const GemmParams& p, dim3 grid, cudaStream_t st) {
+  if (epi == EPI_GRU_FWD) {
+    if (gmode != G_VEC_FWD) return VAR_ERR_UNSUPPORTED;
+    return launch_gemm_t<G_VEC_FWD, EPI_GRU_FWD>(t0, t1, p, grid, st);
+  }
+  switch (gmode) {
+    case G_VEC_FWD: return launch_gemm_t<G_VEC_FWD, EPI_STD>(t0, t1, p, grid, st);
+    case G_VEC_DGRAD: return launch_gemm_t<G_VEC_DGRAD, EPI_STD>(t0, t1, p, grid, st);
+    case G_SCALAR_F32: return launch_gemm_t<G_SCALAR_F32, EPI_STD>(t0, t1, p, grid, st);
+    case G_SCALAR_U8: return launch_gemm_t<G_SCALAR_U8, EPI_STD>(t0, t1, p, grid, st);
+  }
+  return VAR_ERR_UNSUPPORTED;
+}
+
+template <int GMODE>
+static int launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t st) {
+  const size_t smem = wgrad_smem_bytes(p.cout, p.stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<GMODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  tc_wgrad_kernel<GMODE><<<grid, 160, smem, st>>>(p);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+static void pick_pipeline(int bn, int* stages, int* la) {
+  if (bn <= 64) { *stages = 4; *la = 2; }
+  else if (bn <= 128) { *stages = 3; *la = 1; }
+  else { *stages = 4; *la = 2; }
+}
+
+static int pick_bn(int n) {
+  if (n <= 256) return n;
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (n % bn == 0) return bn;
+  return 0;
+}
+
+static int fill_fwd_geom(GatherGeom* g, const ConvShape& cs, const void* x, int src_kind,
+                         const SrcLayout* sl) {
+  g->src = x;
+  g->M = cs.N * cs.P * cs.Q;
+  g->P = cs.P; g->Q = cs.Q;
+  g->H = cs.H; g->W = cs.W; g->C = cs.Cin;
+  g->R = cs.R; g->S = cs.S;
+  g->sh = cs.sh; g->sw = cs.sw; g->ph = cs.ph; g->pw = cs.pw;
+  g->K = cs.R * cs.S * cs.Cin;
+  if (src_kind == SRC_NHWC_F32) {
+    if (cs.Cin % 32) return VAR_ERR_UNSUPPORTED;
+    g->sC = 1; g->sW = cs.Cin; g->sH = (long long)cs.W * cs.Cin;
+    g->sN = (long long)cs.H * cs.W * cs.Cin;
+    g->scale = 1.f;
+  } else {
+    if (!sl || g->K > 256) return VAR_ERR_UNSUPPORTED;
+    g->sN = sl->sN; g->sH = sl->sH; g->sW = sl->sW; g->sC = sl->sC;
+    g->scale = sl->scale;
+  }
+  return VAR_OK;
+}
+
+static int gmode_of(int src_kind) {
+  return src_kind == SRC_NHWC_F32 ? G_VEC_FWD
+                                  : (src_kind == SRC_STRIDED_F32 ? G_SCALAR_F32 : G_SCALAR_U8);
+}
+
+int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
+             const float* bias, float* y, int relu, int round_out, cudaStream_t st) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_fwd_geom(&p.g[0], cs, x, src_kind, sl);
+  if (rc) return rc;
+  const int K = p.g[0].K, kpad = round_up32(K);
+  const int bn = pick_bn(cs.Cout);
+  if (bn == 0 || bn % 16) return VAR_ERR_UNSUPPORTED;
+  p.bn = bn;
+  p.nbox = 1; p.box_rows = bn; p.boxbase[0] = 0;
+  p.num_kb = kpad / 32;
+  pick_pipeline(bn, &p.stages, &p.lookahead);
+  EpiParams& e = p.e[0];
+  e.out = y; e.ldo = cs.Cout; e.bias = bias; e.ncols = cs.Cout; e.relu = relu;
+  e.round_out = round_out;
+  CUtensorMap tm;
+  rc = get_tmap_2d(w, cs.Cout, kpad, kpad, bn, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm);
+  if (rc) return rc;
+  dim3 grid((p.g[0].M + 127) / 128, cs.Cout / bn, 1);
+  return launch_gemm(gmode_of(src_kind), EPI_STD, tm, tm, p, grid, st);
+}
+
+int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
+               int round_out, cudaStream_t st) {
+  if (cs.Cout % 32 || cs.Cin % 32) return VAR_ERR_UNSUPPORTED;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  GatherGeom& g = p.g[0];
+  g.src = dy;
+  g.M = cs.N * cs.H * cs.W;         // rows are input pixels
+  g.P = cs.H; g.Q = cs.W;
+  g.H = cs.P; g.W = cs.Q; g.C = cs.Cout;  // source = dY
+  g.R = cs.R; g.S = cs.S;
+  g.sh = cs.sh; g.sw = cs.sw; g.ph = cs.ph; g.pw = cs.pw;
+  g.sC = 1; g.sW = cs.Cout; g.sH = (long long)cs.Q * cs.Cout;
+  g.sN = (long long)cs.P * cs.Q * cs.Cout;
+  g.K = cs.R * cs.S * cs.Cout;
+  g.scale = 1.f;
+  const int bn = pick_bn(cs.Cin);
+  if (bn == 0) return VAR_ERR_UNSUPPORTED;
+  p.bn = bn;
+  p.b_mn_major = 1;
+  p.num_kb = g.K / 32;
+  p.kb_per_rs = cs.Cout / 32;
+  p.cin_total = cs.Cin;
+  p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
+  pick_pipeline(bn, &p.stages, &p.lookahead);
+  EpiParams& e = p.e[0];
+  e.out = dx; e.ldo = cs.Cin; e.ncols = cs.Cin; e.mask = mask; e.ldm = cs.Cin;
+  e.round_out = round_out;
+  const int kfwd = cs.R * cs.S * cs.Cin, kpad = round_up32(kfwd);
+  CUtensorMap tm;
+  int rc = get_tmap_2d(w, cs.Cout, kpad, kpad, 32, mn_cfg().tma_swizzle, &tm);
+  if (rc) return rc;
+  dim3 grid((g.M + 127) / 128, cs.Cin / bn, 1);
+  return launch_gemm(G_VEC_DGRAD, EPI_STD, tm, tm, p, grid, st);
+}
+
+// ---- bias gradient: column sums of dY [M, ld] over a slab of C <= 256 columns
+__global__ void colsum_kernel(const float* __restrict__ dy, long long M, long long ld, int C,
+                              float* __restrict__ db, int rows_per_cta) {
+  extern __shared__ float red[];
+  const int lanes = blockDim.x / C;
+  const int col = threadIdx.x % C, rl = threadIdx.x / C;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(r0 + (long long)rows_per_cta, M);
+  float acc = 0.f;
+  for (long long r = r0 + rl; r < r1; r += lanes) acc += dy[r * ld + col];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int l = 1; l < lanes; ++l) acc += red[l * C + col];
+    atomicAdd(db + col, acc);
+  }
+}
+
+int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st) {
+  for (int c0 = 0; c0 < C; c0 += 256) {
+    const int cs = C - c0 < 256 ? C - c0 : 256;
+    const int threads = (256 / cs) * cs;
+    long long rp = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);
+    if (rp < 64) rp = 64;
+    const int grid = (int)((M + rp - 1) / rp);
+    colsum_kernel<<<grid, threads, threads * sizeof(float), st>>>(dy + c0, M, ld, cs, db + c0,
+                                                                  (int)rp);
+    VAR_CUDA_CHECK(cudaGetLastError());
+  }
+  return VAR_OK;
+}
+
+int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
+               const float* dy, float* dw, float* db, cudaStream_t st) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_fwd_geom(&p.g, cs, x, src_kind, sl);
+  if (rc) return rc;
+  if (cs.Cout % 16) return VAR_ERR_UNSUPPORTED;
+  const int K = p.g.K;
+  p.kpad = round_up32(K);
+  p.ldy = cs.Cout;
+  p.stages = 4; p.lookahead = 2;
+  p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
+  p.mn_swz32 = mn_cfg().swz32;
+  const int ktiles = (K + 127) / 128;
+  const int M = p.g.M;
+  const int slab = pick_bn(cs.Cout);
+  if (slab == 0) return VAR_ERR_UNSUPPORTED;
+  const int nslab = cs.Cout / slab;
+  int splits = (4 * kNumSMs + ktiles * nslab - 1) / (ktiles * nslab);
+  int ppc = (M + splits - 1) / splits;
+  ppc = ((ppc + 31) / 32) * 32;
+  if (ppc < 256) ppc = 256;
+  splits = (M + ppc - 1) / ppc;
+  p.pix_per_cta = ppc;
+  dim3 grid(ktiles, splits, 1);
+  const int gm = gmode_of(src_kind);
+  for (int c0 = 0; c0 < cs.Cout; c0 += slab) {
+    p.dy = dy + c0; p.cout = slab; p.dw = dw + (long long)c0 * p.kpad;
+    if (gm == G_VEC_FWD) rc = launch_wgrad_t<G_VEC_FWD>(p, grid, st);
+    else if (gm == G_SCALAR_F32) rc = launch_wgrad_t<G_SCALAR_F32>(p, grid, st);
+    else rc = launch_wgrad_t<G_SCALAR_U8>(p, grid, st);
+    if (rc) return rc;
+  }
+  if (db) return colsum(dy, M, cs.Cout, cs.Cout, db, st);
+  return VAR_OK;
+}
+
+}  // namespace var

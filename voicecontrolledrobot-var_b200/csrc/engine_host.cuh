@@ -1,0 +1,48 @@
+// Host side of the tcgen05 engine: TMA descriptor cache and kernel launchers.
+#pragma once
+#include "tc_engine.cuh"
+
+namespace var {
+
+// MN-major (transposed) tf32 operands use the 32-byte-granule 128B swizzle.
+struct MnCfg {
+  int lbo = 4096, sbo = 512, type = 1, swz32 = 1;
+  int tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+};
+MnCfg& mn_cfg();  // process-wide (selftest may override to probe the hardware)
+
+// 2-D fp32 tensor map over a row-major [rows, cols] matrix with row pitch
+// `pitch` elements; box = {32 cols, box_rows}.  Cached by value of all args.
+int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_rows, int swizzle,
+                CUtensorMap* out);
+
+struct ConvShape {
+  int N, H, W, Cin;       // input  (H, W spatial)
+  int Cout, R, S;
+  int sh, sw, ph, pw;
+  int P, Q;               // output spatial
+};
+
+enum SrcKind : int { SRC_NHWC_F32 = 0, SRC_STRIDED_F32 = 1, SRC_STRIDED_U8 = 2 };
+
+struct SrcLayout {       // element strides for strided sources
+  long long sN, sH, sW, sC;
+  float scale;
+};
+
+inline int round_up32(int k) { return (k + 31) & ~31; }
+
+// y[N,P,Q,Cout] = act(conv(x, w) + b).  w packed [Cout, Kpad], k = (r*S+s)*Cin + c.
+int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
+             const float* bias, float* y, int relu, int round_out, cudaStream_t st);
+
+// dx[N,H,W,Cin] = conv_transpose(dy, w) [* (mask > 0)] ; mask = forward output of the
+// previous layer (ReLU backward fused), may be null.
+int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
+               int round_out, cudaStream_t st);
+
+// dw[Cout, Kpad] += im2col(x)^T dy ; db[Cout] += colsum(dy) (db may be null).
+int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
+               const float* dy, float* dw, float* db, cudaStream_t st);
+
+}  // namespace var

@@ -1,0 +1,612 @@
+// tcgen05 implicit-GEMM engine for the VAR encoders (sm_100a).
+//
+// Two kernels cover every dense contraction on the hot path:
+//
+//  tc_gemm_kernel  : D[m, n] = sum_k A(m, k) * B(n, k)
+//      A (K-major) is *gathered* by 4 producer warps straight from the NHWC
+//      activation tensor (implicit im2col; cp.async 16 B with zero fill for
+//      padding) into 128B-swizzled shared tiles.  B (the weights) arrives by
+//      TMA, either K-major (forward / linear / GRU step) or MN-major (all
+//      dgrads: the forward-packed weight matrix is read transposed, no second
+//      copy).  One thread issues tcgen05.mma kind::tf32 (M=128, N<=256, K=8),
+//      accumulators live in TMEM, the producer warps double as the epilogue
+//      warps (tcgen05.ld -> bias / ReLU / mask / GRU cell -> HBM).
+//
+//  tc_wgrad_kernel : dW[k, o] = sum_pixels A'(pix, k) * dY(pix, o)
+//      both operands MN-major (reduction runs over pixels, the slow dimension
+//      of both NHWC tensors), split over pixel ranges, red.global.add to dW.
+//
+// Replaces cuDNN convolution / cuBLAS calls made by torch for
+// models/pretext/arm_pretext_model.py:9-34 and ai2thor_pretext_model.py:5-38.
+#pragma once
+#include "common.cuh"
+
+namespace var {
+
+enum GatherMode : int {
+  G_VEC_FWD = 0,    // NHWC source, C % 32 == 0, forward im2col
+  G_VEC_DGRAD = 1,  // NHWC dY source, rows are input pixels (transposed conv)
+  G_SCALAR_F32 = 2, // generic strides, float source (C in {1,3}), forward im2col
+  G_SCALAR_U8 = 3   // generic strides, uint8 source scaled by `scale`
+};
+
+struct GatherGeom {
+  const void* src;
+  int M;              // number of rows (pixels)
+  int P, Q;           // row m -> (n, p, q): m = (n*P + p)*Q + q
+  int H, W, C;        // source spatial extent / channels
+  int R, S;           // filter taps
+  int sh, sw, ph, pw; // stride / padding
+  long long sN, sH, sW, sC;  // element strides of src
+  int K;              // R*S*C
+  float scale;        // scalar path multiplier (1/255 for u8 images)
+};
+
+enum EpiKind : int { EPI_STD = 0, EPI_GRU_FWD = 1 };
+
+struct EpiParams {
+  float* out;            // [M, ldo]
+  long long ldo;
+  const float* bias;     // per output column or nullptr
+  const float* mask;     // ReLU-backward mask source ([M, ldm], >0 keeps) or nullptr
+  long long ldm;
+  const float* addsrc;   // out = acc*... + addsrc[m, n] (nullptr = none)
+  long long lda;
+  int ncols;             // total valid output columns
+  int relu;
+  int round_out;         // store tf32-rounded values
+};
+
+// GRU cell epilogue (forward): columns of the tile are [r | z | n] blocks of
+// `jb` hidden units.  Follows torch.nn.GRU gate order (r, z, n).
+struct GruEpiParams {
+  const float* xproj;   // [B, T, 3H] (includes b_ih), row pitch ldx, offset for step t pre-applied
+  long long ldx;
+  const float* bhh;     // [3H]
+  const float* hprev;   // [B, H]
+  float* hnew;          // [B, H]
+  float* gates;         // [B, 3H] saved r, z, n for backward (nullptr = inference)
+  float* hn_save;       // [B, H] saved (W_hn h + b_hn) for backward (nullptr = inference)
+  int Hdim;
+};
+
+struct GemmParams {
+  GatherGeom g[2];
+  EpiParams e[2];
+  GruEpiParams gru[2];
+  int bn;          // UMMA N / tile columns
+  int b_mn_major;  // 0: B K-major boxes {32k, box_rows}; 1: MN-major boxes {32n, 32k}
+  int nbox;        // K-major: number of row boxes (1 or 3)
+  int box_rows;    // K-major: rows per box
+  int boxbase[3];  // K-major: first global row of each box (tile n adds n*box_rows)
+  int num_kb;      // K blocks of 32
+  int kb_per_rs;   // dgrad MN-major: C_out/32 (k-blocks per filter tap)
+  int cin_total;   // dgrad MN-major: C_in (columns per tap in packed weight)
+  int stages;
+  int lookahead;
+  int mn_lbo, mn_sbo, mn_type;  // MN-major descriptor fields (bytes, bytes, layout type)
+};
+
+constexpr int kTileM = 128;
+constexpr int kTileABytes = kTileM * 128;  // 128 rows x 32 tf32
+
+__host__ __device__ inline int tmem_cols_for(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+__host__ __device__ inline size_t gemm_smem_bytes(int bn, int stages) {
+  return (size_t)stages * (kTileABytes + (size_t)bn * 128) + 1024 /*align*/ + 256 /*barriers*/;
+}
+
+// ---------------------------------------------------------------------------
+// A-row gather for one K block.  Thread `row` owns one 128-byte row.
+// ---------------------------------------------------------------------------
+struct RowCtx {
+  bool valid;
+  int n, p, q;
+  long long base;  // n*sN
+};
+
+template <int GMODE>
+__device__ __forceinline__ void gather_row(const GatherGeom& g, const RowCtx& rc, int kb,
+                                           uint32_t tile, int row, const int* lut_off,
+                                           const int* lut_rs) {
+  if constexpr (GMODE == G_VEC_FWD || GMODE == G_VEC_DGRAD) {
+    const int cpb = g.C >> 5;
+    const int rs = kb / cpb;
+    const int c0 = (kb - rs * cpb) << 5;
+    const int r = rs / g.S, s = rs - r * g.S;
+    bool ok = rc.valid;
+    int h, w;
+    if constexpr (GMODE == G_VEC_FWD) {
+      h = rc.p * g.sh - g.ph + r;
+      w = rc.q * g.sw - g.pw + s;
+    } else {
+      int th = rc.p + g.ph - r, tw = rc.q + g.pw - s;
+      ok = ok && th >= 0 && tw >= 0;
+      h = th / g.sh;
+      w = tw / g.sw;
+      ok = ok && (h * g.sh == th) && (w * g.sw == tw);
+    }
+    ok = ok && h >= 0 && h < g.H && w >= 0 && w < g.W;
+    const float* src = reinterpret_cast<const float*>(g.src);
+    if (ok) src += rc.base + (long long)h * g.sH + (long long)w * g.sW + c0;
+    const uint32_t nb = ok ? 16u : 0u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cp_async_16(tile + swz128(row, c), src + (ok ? c * 4 : 0), nb);
+  } else {
+    // scalar im2col: k = (r*S + s)*C + c ; lut_off[k] = r*sH + s*sW + c*sC, lut_rs[k] = r<<16|s
+    const int h0 = rc.p * g.sh - g.ph, w0 = rc.q * g.sw - g.pw;
+    const long long b0 = rc.base + (long long)h0 * g.sH + (long long)w0 * g.sW;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb * 32 + c * 4 + j;
+        float x = 0.f;
+        if (rc.valid && k < g.K) {
+          const int rs = lut_rs[k];
+          const int h = h0 + (rs >> 16), w = w0 + (rs & 0xFFFF);
+          if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+            if constexpr (GMODE == G_SCALAR_U8)
+              x = (float)reinterpret_cast<const uint8_t*>(g.src)[b0 + lut_off[k]] * g.scale;
+            else
+              x = reinterpret_cast<const float*>(g.src)[b0 + lut_off[k]] * g.scale;
+          }
+        }
+        v[j] = round_tf32(x);
+      }
+      st_shared_v4(tile + swz128(row, c), v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    default: cp_async_wait<3>(); break;
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------
+// Main GEMM kernel.  grid = (M tiles, N tiles, instances<=2), block = 160.
+// ---------------------------------------------------------------------------
+template <int GMODE, int EPI>
+__global__ void __launch_bounds__(160)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int z = blockIdx.z;
+  const CUtensorMap* tmB = z == 0 ? &tmB0 : &tmB1;
+  const GatherGeom& g = p.g[z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages, bn = p.bn, num_kb = p.num_kb;
+  const uint32_t tileB_bytes = (uint32_t)bn * 128u;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + (uint32_t)stages * kTileABytes;
+  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;  // full[s], empty[s], tmem_full, slot
+  auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
+  const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
+  const uint32_t tslot = tfull_bar + 8u;
+
+  __shared__ int lut_off[(GMODE >= G_SCALAR_F32) ? 256 : 1];
+  __shared__ int lut_rs[(GMODE >= G_SCALAR_F32) ? 256 : 1];
+  if constexpr (GMODE >= G_SCALAR_F32) {
+    for (int k = tid; k < g.K && k < 256; k += blockDim.x) {
+      const int c = k % g.C, rs = k / g.C, s = rs % g.S, r = rs / g.S;
+      lut_off[k] = (int)(r * g.sH + s * g.sW + c * g.sC);
+      lut_rs[k] = (r << 16) | s;
+    }
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tmB);
+  }
+  const uint32_t ncols = (uint32_t)tmem_cols_for(bn);
+  if (warp == 4) tmem_alloc(tslot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int m0 = blockIdx.x * kTileM;
+  const int ntile = blockIdx.y;
+
+  if (warp < 4) {
+    // ===================== producers (then epilogue) =====================
+    const int row = tid;
+    RowCtx rc;
+    {
+      const int m = m0 + row;
+      rc.valid = m < g.M;
+      const int pq = g.P * g.Q;
+      const int mm = rc.valid ? m : 0;
+      rc.n = mm / pq;
+      const int rem = mm - rc.n * pq;
+      rc.p = rem / g.Q;
+      rc.q = rem - rc.p * g.Q;
+      rc.base = (long long)rc.n * g.sN;
+    }
+    const int la = p.lookahead;
+    int st_issue = 0, ph_issue = 0, st_arr = 0;
+    for (int it = 0; it < num_kb + la; ++it) {
+      if (it < num_kb) {
+        mbar_wait(empty_bar(st_issue), (uint32_t)(ph_issue ^ 1));
+        if (tid == 0) {
+          mbar_arrive_expect_tx(full_bar(st_issue), tileB_bytes);
+          const uint32_t dstB = sB + (uint32_t)st_issue * tileB_bytes;
+          if (!p.b_mn_major) {
+            for (int b = 0; b < p.nbox; ++b)
+              tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st_issue),
+                          it * 32, p.boxbase[b] + ntile * p.box_rows);
+          } else {
+            // MN-major: k-block `it` -> tap rs and k0; box = {32 n, 32 k}
+            const int rs = it / p.kb_per_rs;
+            const int k0 = (it - rs * p.kb_per_rs) << 5;
+            for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+              tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st_issue),
+                          rs * p.cin_total + ntile * bn + gidx * 32, k0);
+          }
+        }
+        gather_row<GMODE>(g, rc, it, sA + (uint32_t)st_issue * kTileABytes, row, lut_off, lut_rs);
+        if (++st_issue == stages) { st_issue = 0; ph_issue ^= 1; }
+      }
+      cp_async_commit();
+      if (it >= la) {
+        cp_async_wait_dyn(la);
+        fence_proxy_async_smem();
+        mbar_arrive(full_bar(st_arr));
+        if (++st_arr == stages) st_arr = 0;
+      }
+    }
+
+    // ===================== epilogue =====================
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if constexpr (EPI == EPI_STD) {
+      const EpiParams& e = p.e[z];
+      for (int c = 0; c < bn; c += 32) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int col0 = ntile * bn + c;
+        if (m < g.M && col0 < e.ncols) {
+          float* o = e.out + (long long)m * e.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (e.bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(e.bias + col0 + j);
+              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+            }
+            if (e.addsrc) {
+              const float4 a4 =
+                  *reinterpret_cast<const float4*>(e.addsrc + (long long)m * e.lda + col0 + j);
+              r4.x += a4.x; r4.y += a4.y; r4.z += a4.z; r4.w += a4.w;
+            }
+            if (e.relu) {
+              r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
+              r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+            }
+            if (e.mask) {
+              const float4 k4 =
+                  *reinterpret_cast<const float4*>(e.mask + (long long)m * e.ldm + col0 + j);
+              r4.x = k4.x > 0.f ? r4.x : 0.f; r4.y = k4.y > 0.f ? r4.y : 0.f;
+              r4.z = k4.z > 0.f ? r4.z : 0.f; r4.w = k4.w > 0.f ? r4.w : 0.f;
+            }
+            if (e.round_out) {
+              r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+              r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+            }
+            *reinterpret_cast<float4*>(o + j) = r4;
+          }
+        }
+      }
+    } else {
+      // GRU forward cell: tile columns = [r(jb) | z(jb) | n(jb)], jb = bn/3
+      const GruEpiParams& q = p.gru[z];
+      const int jb = bn / 3;
+      const int Hd = q.Hdim;
+      for (int c = 0; c < jb; c += 32) {
+        float vr[32], vz[32], vn[32];
+        tmem_ld32(trow + (uint32_t)c, vr);
+        tmem_ld32(trow + (uint32_t)(jb + c), vz);
+        tmem_ld32(trow + (uint32_t)(2 * jb + c), vn);
+        tmem_ld_wait();
+        if (m < g.M) {
+          const int j0 = ntile * jb + c;
+          const float* xp = q.xproj + (long long)m * q.ldx;
+          const float* hp = q.hprev + (long long)m * Hd + j0;
+          float* hn = q.hnew + (long long)m * Hd + j0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 xr = *reinterpret_cast<const float4*>(xp + j0 + j);
+            const float4 xz = *reinterpret_cast<const float4*>(xp + Hd + j0 + j);
+            const float4 xn = *reinterpret_cast<const float4*>(xp + 2 * Hd + j0 + j);
+            const float4 br = *reinterpret_cast<const float4*>(q.bhh + j0 + j);
+            const float4 bz = *reinterpret_cast<const float4*>(q.bhh + Hd + j0 + j);
+            const float4 bq = *reinterpret_cast<const float4*>(q.bhh + 2 * Hd + j0 + j);
+            const float4 h4 = *reinterpret_cast<const float4*>(hp + j);
+            float rr[4], zz[4], nn[4], hh[4], hnv[4];
+            const float xr_[4] = {xr.x, xr.y, xr.z, xr.w}, xz_[4] = {xz.x, xz.y, xz.z, xz.w},
+                        xn_[4] = {xn.x, xn.y, xn.z, xn.w}, br_[4] = {br.x, br.y, br.z, br.w},
+                        bz_[4] = {bz.x, bz.y, bz.z, bz.w}, bn_[4] = {bq.x, bq.y, bq.z, bq.w},
+                        hp_[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              rr[u] = sigmoidf_(xr_[u] + vr[j + u] + br_[u]);
+              zz[u] = sigmoidf_(xz_[u] + vz[j + u] + bz_[u]);
+              hnv[u] = vn[j + u] + bn_[u];
+              nn[u] = tanhf(xn_[u] + rr[u] * hnv[u]);
+              hh[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp_[u];
+            }
+            *reinterpret_cast<float4*>(hn + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            if (q.gates) {
+              float* gs = q.gates + (long long)m * 3 * Hd + j0 + j;
+              *reinterpret_cast<float4*>(gs) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+              *reinterpret_cast<float4*>(gs + Hd) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+              *reinterpret_cast<float4*>(gs + 2 * Hd) = make_float4(nn[0], nn[1], nn[2], nn[3]);
+              *reinterpret_cast<float4*>(q.hn_save + (long long)m * Hd + j0 + j) =
+                  make_float4(hnv[0], hnv[1], hnv[2], hnv[3]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== MMA issuer (warp 4) =====================
+    const uint32_t idesc = make_idesc_tf32(bn, 0, p.b_mn_major);
+    int st = 0, ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full_bar(st), (uint32_t)ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a0 = sA + (uint32_t)st * kTileABytes;
+        const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
+          const uint64_t bd = p.b_mn_major ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
+                                                            (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                           : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
+          umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+        }
+        umma_commit(empty_bar(st));
+        if (kb == num_kb - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++st == stages) { st = 0; ph ^= 1; }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Weight-gradient kernel: dW[o, k] += sum_{pix} dY[pix, o] * im2col(X)[pix, k]
+// D tile = [128 k-rows x Cout columns]; both operands MN-major.
+// grid = (ceil(Kfwd/128), splits), block = 160.
+// ---------------------------------------------------------------------------
+struct WgradParams {
+  GatherGeom g;       // forward im2col geometry of X (rows = output pixels)
+  const float* dy;    // [M, ldy] (a slab of `cout` columns)
+  long long ldy;
+  int cout;           // multiple of 16, <= 256
+  float* dw;          // [cout, kpad]
+  int kpad;
+  int pix_per_cta;    // multiple of 32
+  int stages;
+  int lookahead;
+  int mn_lbo, mn_sbo, mn_type;  // MN-major descriptor fields
+  int mn_swz32;       // 1: 32-byte-granule swizzle (BASE32B), 0: 16-byte (plain 128B)
+};
+
+__host__ __device__ inline size_t wgrad_smem_bytes(int cout, int stages) {
+  const int bgroups = (cout + 31) / 32;
+  return (size_t)stages * (4 * 4096 + (size_t)bgroups * 4096) + 1024 + 256;
+}
+
+template <int GMODE>
+__global__ void __launch_bounds__(160)
+tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const GatherGeom& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages;
+  const int bgroups = (p.cout + 31) >> 5;
+  const uint32_t tileA_bytes = 4u * 4096u;
+  const uint32_t tileB_bytes = (uint32_t)bgroups * 4096u;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + (uint32_t)stages * tileA_bytes;
+  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
+  const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
+  const uint32_t tslot = tfull_bar + 8u;
+
+  __shared__ int lut_off[(GMODE >= G_SCALAR_F32) ? 256 : 1];
+  __shared__ int lut_rs[(GMODE >= G_SCALAR_F32) ? 256 : 1];
+  if constexpr (GMODE >= G_SCALAR_F32) {
+    for (int k = tid; k < g.K && k < 256; k += blockDim.x) {
+      const int c = k % g.C, rs = k / g.C, s = rs % g.S, r = rs / g.S;
+      lut_off[k] = (int)(r * g.sH + s * g.sW + c * g.sC);
+      lut_rs[k] = (r << 16) | s;
+    }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  const uint32_t ncols = (uint32_t)tmem_cols_for(p.cout);
+  if (warp == 4) tmem_alloc(tslot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int ktile = blockIdx.x;  // 128 k-rows
+  const int pix0 = blockIdx.y * p.pix_per_cta;
+  const int pix1 = min(pix0 + p.pix_per_cta, g.M);
+  const int num_kb = (pix1 - pix0 + 31) / 32;  // may be <= 0 for trailing CTAs
+
+  if (num_kb > 0) {
+    if (warp < 4) {
+      const int grp = tid >> 5, row = tid & 31;
+      const int la = p.lookahead;
+      auto swz = [&](uint32_t r, uint32_t c) { return p.mn_swz32 ? swz128_32(r, c) : swz128(r, c); };
+      const int pq = g.P * g.Q;
+      int st_issue = 0, ph_issue = 0, st_arr = 0;
+      for (int it = 0; it < num_kb + la; ++it) {
+        if (it < num_kb) {
+          mbar_wait(empty_bar(st_issue), (uint32_t)(ph_issue ^ 1));
+          const int m = pix0 + it * 32 + row;
+          const bool mv = m < pix1;
+          const uint32_t tA = sA + (uint32_t)st_issue * tileA_bytes + (uint32_t)grp * 4096u;
+          // ---- A' group `grp`: k index range [k0, k0+32)
+          const int k0 = ktile * 128 + grp * 32;
+          const int mm = mv ? m : 0;
+          const int n = mm / pq;
+          const int rem = mm - n * pq;
+          const int pp = rem / g.Q, qq = rem - pp * g.Q;
+          if constexpr (GMODE == G_VEC_FWD) {
+            bool ok = mv && k0 < g.K;
+            const float* src = reinterpret_cast<const float*>(g.src);
+            if (ok) {
+              const int cpb = g.C >> 5;
+              const int kb = k0 >> 5;
+              const int rs = kb / cpb;
+              const int c0 = (kb - rs * cpb) << 5;
+              const int r = rs / g.S, s = rs - r * g.S;
+              const int h = pp * g.sh - g.ph + r, w = qq * g.sw - g.pw + s;
+              ok = h >= 0 && h < g.H && w >= 0 && w < g.W;
+              if (ok) src += (long long)n * g.sN + (long long)h * g.sH + (long long)w * g.sW + c0;
+            }
+            const uint32_t nb = ok ? 16u : 0u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cp_async_16(tA + swz(row, c), src + (ok ? c * 4 : 0), nb);
+          } else {
+            const int h0 = pp * g.sh - g.ph, w0 = qq * g.sw - g.pw;
+            const long long b0 = (long long)n * g.sN + (long long)h0 * g.sH + (long long)w0 * g.sW;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = k0 + c * 4 + j;
+                float x = 0.f;
+                if (mv && k < g.K) {
+                  const int rs = lut_rs[k];
+                  const int h = h0 + (rs >> 16), w = w0 + (rs & 0xFFFF);
+                  if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+                    if constexpr (GMODE == G_SCALAR_U8)
+                      x = (float)reinterpret_cast<const uint8_t*>(g.src)[b0 + lut_off[k]] * g.scale;
+                    else
+                      x = reinterpret_cast<const float*>(g.src)[b0 + lut_off[k]] * g.scale;
+                  }
+                }
+                v[j] = round_tf32(x);
+              }
+              st_shared_v4(tA + swz(row, c), v[0], v[1], v[2], v[3]);
+            }
+          }
+          // ---- B' (dY) groups
+          if (grp < bgroups) {
+            const uint32_t tB = sB + (uint32_t)st_issue * tileB_bytes + (uint32_t)grp * 4096u;
+            const float* src = p.dy;
+            const int cvalid = p.cout - grp * 32;  // may be < 32 (cout = 16 mult)
+            if (mv) src += (long long)m * p.ldy + grp * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const bool ok = mv && (c * 4 < cvalid);
+              cp_async_16(tB + swz(row, c), ok ? src + c * 4 : p.dy, ok ? 16u : 0u);
+            }
+          }
+          if (++st_issue == stages) { st_issue = 0; ph_issue ^= 1; }
+        }
+        cp_async_commit();
+        if (it >= la) {
+          cp_async_wait_dyn(la);
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar(st_arr));
+          if (++st_arr == stages) st_arr = 0;
+        }
+      }
+      // ---- epilogue: row = k index, columns = output channel
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const int k = ktile * 128 + warp * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int c = 0; c < p.cout; c += 32) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (k < g.K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c + j < p.cout) atomicAdd(p.dw + (long long)(c + j) * p.kpad + k, v[j]);
+        }
+      }
+      tc_fence_before();
+    } else {
+      const uint32_t idesc = make_idesc_tf32(p.cout, 1, 1);
+      const uint32_t lbo = (uint32_t)p.mn_lbo, sbo = (uint32_t)p.mn_sbo, lt = (uint32_t)p.mn_type;
+      int st = 0, ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(st), (uint32_t)ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = sA + (uint32_t)st * tileA_bytes;
+          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 1024u, lbo, sbo, lt);
+            const uint64_t bd = make_smem_desc(b0 + (uint32_t)j * 1024u, lbo, sbo, lt);
+            umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+          }
+          umma_commit(empty_bar(st));
+          if (kb == num_kb - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+}  // namespace var
