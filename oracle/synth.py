@@ -1,0 +1,44 @@
+"""ORACLE-side deterministic synthetic inputs.  Shared by the
+golden generator, the tests and bench.py so that every party sees identical data."""
+import numpy as np
+
+
+def make_clip(rng, n_samples, fs=16000):
+    """int16 mono clip: band-limited noise burst + 2-4 sinusoids with leading/trailing
+    silence so the log(.+1e-6) floor is exercised."""
+    t = np.arange(n_samples) / fs
+    amp = rng.uniform(0.05, 0.9)
+    x = np.zeros(n_samples)
+    for _ in range(int(rng.integers(2, 5))):
+        f = rng.uniform(80.0, 6000.0)
+        x += rng.uniform(0.2, 1.0) * np.sin(2 * np.pi * f * t + rng.uniform(0, 2 * np.pi))
+    noise = rng.standard_normal(n_samples)
+    k = int(rng.integers(2, 16))
+    noise = np.convolve(noise, np.ones(k) / k, mode="same")
+    x += 0.5 * noise / (np.abs(noise).max() + 1e-9)
+    x /= np.abs(x).max() + 1e-9
+    lead = int(rng.integers(0, n_samples // 5))
+    trail = int(rng.integers(0, n_samples // 5))
+    x[:lead] = 0.0
+    if trail:
+        x[-trail:] = 0.0
+    return np.round(x * amp * 32767.0).astype(np.int16)
+
+
+def make_clips(seed, count, n_samples):
+    rng = np.random.default_rng(seed)
+    if np.isscalar(n_samples):
+        return [make_clip(rng, int(n_samples)) for _ in range(count)]
+    lo, hi = n_samples
+    return [make_clip(rng, int(rng.integers(lo, hi + 1))) for _ in range(count)]
+
+
+def make_images(seed, count):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(count, 3, 96, 96), dtype=np.uint8)
+
+
+def make_labels(seed, count, task_num=4, mix=(50, 50, 50, 50, 100)):
+    rng = np.random.default_rng(seed)
+    p = np.asarray(mix, dtype=np.float64)
+    return rng.choice(task_num + 1, size=count, p=p / p.sum()).astype(np.int64)
