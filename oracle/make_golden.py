@@ -82,19 +82,6 @@ def gold_mfcc():
     print("mfcc:", {k: v.shape for k, v in out.items()})
 
 
-def _model_case(net, B, seed):
-    rng = np.random.default_rng(seed)
-    images = synth.make_images(seed, B).astype(np.float32) / np.float32(255.0)
-    F = 100 if net == omodel.KUKA else 600
-    # MFCC-like dynamic range; tail frames zero-padded like processSoundFeat
-    def snd():
-        s = (rng.standard_normal((B, 1, F, 40)) * np.array([20.0] + [4.0] * 39)).astype(np.float32)
-        if net == omodel.ITHOR:
-            s[:, :, 101:, :] = 0.0
-        return s
-    return images, snd(), snd()
-
-
 def gold_model(net, B, seed):
     if net == omodel.KUKA:
         from models.pretext.arm_pretext_model import VARPretextNet
@@ -108,7 +95,7 @@ def gold_model(net, B, seed):
     assert list(m.state_dict().keys()) == list(sd.keys()), (list(m.state_dict().keys()), list(sd.keys()))
     m.load_state_dict(sd)
     m.train()
-    images, sp, sn = _model_case(net, B, seed)
+    images, sp, sn = synth.model_case(net, B, seed)
     d = m(torch.from_numpy(images), torch.from_numpy(sp), torch.from_numpy(sn))
     crit = torch.nn.TripletMarginLoss(margin=1.0, p=2)
     loss = crit(d["image_feat"], d["sound_feat_positive"], d["sound_feat_negative"])

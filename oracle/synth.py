@@ -42,3 +42,22 @@ def make_labels(seed, count, task_num=4, mix=(50, 50, 50, 50, 100)):
     rng = np.random.default_rng(seed)
     p = np.asarray(mix, dtype=np.float64)
     return rng.choice(task_num + 1, size=count, p=p / p.sum()).astype(np.int64)
+
+
+def model_case(net, B, seed):
+    """Seeded inputs of the model golden vectors (oracle/make_golden.py::gold_model):
+    images f32 in [0,1] from uint8, two MFCC-like sound batches [B,1,F,40] (iTHOR: frames
+    >= 101 zero like processSoundFeat's padding)."""
+    rng = np.random.default_rng(seed)
+    images_u8 = make_images(seed, B)
+    images = images_u8.astype(np.float32) / np.float32(255.0)
+    F = 100 if net == "kuka" else 600
+
+    def snd():
+        s = (rng.standard_normal((B, 1, F, 40)) * np.array([20.0] + [4.0] * 39)).astype(np.float32)
+        if net == "ithor":
+            s[:, :, 101:, :] = 0.0
+        return s
+    sp = snd()
+    sn = snd()
+    return images, sp, sn

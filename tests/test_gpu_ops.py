@@ -1,0 +1,202 @@
+"""GPU operator tests through the C ABI: each stand-alone entry point of include/var_b200.h
+against plain fp32 PyTorch on the CPU.  Operands are pre-rounded to tf32 (10-bit mantissa), so
+every product is exact in fp32 and the only difference left is the summation order: the
+comparison is tight and any layout / indexing / masking mistake is a gross mismatch."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_to_max
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def tf32(x):
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _pack(lib, w):
+    O, I, R, S = w.shape
+    kpad = (R * S * I + 31) // 32 * 32
+    wd = w.to(DEV).contiguous()
+    packed = torch.empty(O, kpad, device=DEV)
+    mma = torch.empty(O, kpad, device=DEV)
+    assert lib.var_pack_weight(wd.data_ptr(), packed.data_ptr(), mma.data_ptr(), O, I, R, S, kpad, None) == 0
+    back = torch.empty_like(wd)
+    assert lib.var_unpack_weight(packed.data_ptr(), back.data_ptr(), O, I, R, S, kpad, None) == 0
+    assert torch.equal(back, wd)
+    return mma, kpad
+
+
+CONV_CASES = [  # N, H, W, Cin, Cout, R, S, sh, sw, ph, pw
+    (3, 24, 24, 32, 32, 3, 3, 2, 2, 1, 1),     # kuka.img.conv2-like
+    (5, 12, 12, 64, 64, 3, 3, 2, 2, 1, 1),
+    (2, 48, 1, 32, 32, 3, 1, 2, 1, 0, 0),      # kuka.snd.conv2
+    (7, 5, 1, 32, 32, 3, 1, 2, 1, 0, 0),       # M = 14 rows only
+    (2, 20, 20, 32, 64, 3, 3, 1, 1, 1, 1),     # thor.img.conv3-like
+    (1, 12, 12, 64, 128, 3, 3, 1, 1, 1, 1),
+    (3, 6, 6, 128, 128, 3, 3, 2, 2, 1, 1),
+    (1, 60, 20, 64, 64, 11, 5, 2, 2, 5, 5),    # thor.snd.conv2-like (K = 3520)
+    (2, 31, 13, 64, 64, 7, 3, 2, 2, 1, 1),     # thor.snd.conv3-like, odd extents
+    (300, 1, 1, 576, 128, 1, 1, 1, 1, 0, 0),   # Linear 576 -> 128
+    (41, 1, 1, 1024, 128, 1, 1, 1, 1, 0, 0),
+    (130, 1, 1, 128, 64, 1, 1, 1, 1, 0, 0),
+    (146, 1, 1, 448, 1536, 1, 1, 1, 1, 0, 0),  # GRU input projection
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad_vs_torch(vb, case):
+    lib = vb._lib.lib
+    N, H, W, Cin, Cout, R, S, sh, sw, ph, pw = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = tf32(torch.randn(N, Cin, H, W, generator=g)).requires_grad_(True)
+    w = tf32(torch.randn(Cout, Cin, R, S, generator=g) / (R * S * Cin) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, generator=g)
+    y_ref = F.relu(F.conv2d(x, w, b, stride=(sh, sw), padding=(ph, pw)))
+    dy = tf32(torch.randn(y_ref.shape, generator=g)) * (y_ref > 0)
+    y_ref.backward(dy)
+    P, Q = y_ref.shape[2], y_ref.shape[3]
+    x_nhwc = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV)
+    wp, kpad = _pack(lib, w.detach())
+    bd = b.to(DEV)
+    y = torch.empty(N, P, Q, Cout, device=DEV)
+    rc = lib.var_conv2d_fwd(x_nhwc.data_ptr(), 0, None, 1.0, N, H, W, Cin, Cout, R, S, sh, sw, ph, pw,
+                            wp.data_ptr(), bd.data_ptr(), y.data_ptr(), 1, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    assert rel_to_max(y.cpu().permute(0, 3, 1, 2).numpy(), y_ref.detach().numpy()) < 1e-5
+    dy_nhwc = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    # dgrad with the ReLU mask of a (synthetic) previous layer folded in
+    mask = (torch.rand(N, H, W, Cin, generator=g) > 0.3).float().to(DEV)
+    dx = torch.full((N, H, W, Cin), float("nan"), device=DEV)
+    rc = lib.var_conv2d_dgrad(dy_nhwc.data_ptr(), wp.data_ptr(), dx.data_ptr(), mask.data_ptr(), N, H, W, Cin, Cout,
+                              R, S, sh, sw, ph, pw, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    dx_ref = x.grad.permute(0, 2, 3, 1) * mask.cpu()
+    assert rel_to_max(dx.cpu().numpy(), dx_ref.numpy()) < 1e-5
+    dw = torch.zeros(Cout, kpad, device=DEV)
+    db = torch.zeros(Cout, device=DEV)
+    rc = lib.var_conv2d_wgrad(x_nhwc.data_ptr(), 0, None, 1.0, dy_nhwc.data_ptr(), dw.data_ptr(), db.data_ptr(), N, H,
+                              W, Cin, Cout, R, S, sh, sw, ph, pw, None)
+    assert rc == 0, vb._lib.last_error()
+    dw_ref = torch.empty(Cout, Cin, R, S, device=DEV)
+    assert lib.var_unpack_weight(dw.data_ptr(), dw_ref.data_ptr(), Cout, Cin, R, S, kpad, None) == 0
+    assert rel_to_max(dw_ref.cpu().numpy(), w.grad.numpy()) < 2e-5
+    assert float(dw[:, R * S * Cin:].abs().max() if kpad > R * S * Cin else 0.0) == 0.0  # K padding stays zero
+    assert rel_to_max(db.cpu().numpy(), dy.sum(dim=(0, 2, 3)).numpy()) < 2e-5
+
+
+FIRST_LAYER_CASES = [  # strided (NCHW / single channel) sources
+    ("u8", 3, 96, 96, 3, 32, 3, 3, 2, 2, 1, 1),
+    ("u8", 2, 96, 96, 3, 32, 3, 3, 1, 1, 1, 1),
+    ("f32", 4, 40, 40, 3, 32, 3, 3, 2, 2, 1, 1),
+    ("f32", 5, 100, 40, 1, 32, 5, 40, 2, 1, 0, 0),
+    ("f32", 2, 120, 40, 1, 64, 11, 11, 2, 2, 5, 5),
+]
+
+
+@pytest.mark.parametrize("case", FIRST_LAYER_CASES)
+def test_first_layer_conv_vs_torch(vb, case):
+    lib = vb._lib.lib
+    kind, N, H, W, Cin, Cout, R, S, sh, sw, ph, pw = case
+    g = torch.Generator().manual_seed(7)
+    if kind == "u8":
+        xu = torch.randint(0, 256, (N, Cin, H, W), generator=g, dtype=torch.uint8)
+        x = tf32(xu.float() * np.float32(1.0 / 255.0))  # the kernel rounds the scaled value to tf32
+        src, src_kind, scale = xu.to(DEV), 2, 1.0 / 255.0
+    else:
+        x = tf32(torch.randn(N, Cin, H, W, generator=g))
+        src, src_kind, scale = x.to(DEV), 1, 1.0
+    w = tf32(torch.randn(Cout, Cin, R, S, generator=g) / (R * S * Cin) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, generator=g)
+    y_ref = F.relu(F.conv2d(x, w, b, stride=(sh, sw), padding=(ph, pw)))
+    dy = tf32(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    P, Q = y_ref.shape[2], y_ref.shape[3]
+    import ctypes as C
+    strides = (C.c_int64 * 4)(Cin * H * W, W, 1, H * W)  # N, H, W, C element strides of NCHW
+    wp, kpad = _pack(lib, w.detach())
+    y = torch.empty(N, P, Q, Cout, device=DEV)
+    bd = b.to(DEV)
+    rc = lib.var_conv2d_fwd(src.data_ptr(), src_kind, strides, scale, N, H, W, Cin, Cout, R, S, sh, sw, ph, pw,
+                            wp.data_ptr(), bd.data_ptr(), y.data_ptr(), 1, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    assert rel_to_max(y.cpu().permute(0, 3, 1, 2).numpy(), y_ref.detach().numpy()) < 1e-5
+    dy_nhwc = (dy * (y_ref > 0)).permute(0, 2, 3, 1).contiguous().to(DEV)
+    dw = torch.zeros(Cout, kpad, device=DEV)
+    db = torch.zeros(Cout, device=DEV)
+    rc = lib.var_conv2d_wgrad(src.data_ptr(), src_kind, strides, scale, dy_nhwc.data_ptr(), dw.data_ptr(),
+                              db.data_ptr(), N, H, W, Cin, Cout, R, S, sh, sw, ph, pw, None)
+    assert rc == 0, vb._lib.last_error()
+    dw_ref = torch.empty(Cout, Cin, R, S, device=DEV)
+    assert lib.var_unpack_weight(dw.data_ptr(), dw_ref.data_ptr(), Cout, Cin, R, S, kpad, None) == 0
+    assert rel_to_max(dw_ref.cpu().numpy(), w.grad.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(3, 96, 96, 32), (2, 12, 12, 128), (5, 6, 10, 64)])
+def test_maxpool_fwd_bwd_vs_torch(vb, shape):
+    lib = vb._lib.lib
+    N, H, W, Cc = shape
+    g = torch.Generator().manual_seed(3)
+    x = F.relu(torch.randn(N, Cc, H, W, generator=g)).requires_grad_(True)  # post-ReLU: many exact zeros
+    y_ref = F.max_pool2d(x, 2, 2)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    xd = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV)
+    y = torch.empty(N, H // 2, W // 2, Cc, device=DEV)
+    assert lib.var_maxpool2x2_fwd(xd.data_ptr(), y.data_ptr(), N, H, W, Cc, None) == 0
+    assert torch.equal(y.cpu().permute(0, 3, 1, 2), y_ref.detach())
+    dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dx = torch.full((N, H, W, Cc), float("nan"), device=DEV)
+    assert lib.var_maxpool2x2_bwd(xd.data_ptr(), dyd.data_ptr(), dx.data_ptr(), N, H, W, Cc, None) == 0
+    # reference: pool backward followed by the ReLU backward of the layer that produced x
+    ref = (x.grad * (x.detach() > 0)).permute(0, 2, 3, 1)
+    assert torch.equal(dx.cpu(), ref)
+
+
+@pytest.mark.parametrize("B,Ki,Ks", [(1, 128, 128), (37, 128, 64), (1000, 128, 128)])
+def test_fused_triplet_kernel_vs_torch(vb, B, Ki, Ks):
+    lib = vb._lib.lib
+    g = torch.Generator().manual_seed(B)
+    D = 3
+    mk = lambda *s: torch.randn(*s, generator=g)
+    h_img, h_pos, h_neg = F.relu(mk(B, Ki)), F.relu(mk(B, Ks)), F.relu(mk(B, Ks))
+    W_i, b_i, W_s, b_s = mk(D, Ki) * 0.1, mk(D) * 0.1, mk(D, Ks) * 0.1, mk(D) * 0.1
+    leaves = [t.clone().requires_grad_(True) for t in (h_img, h_pos, h_neg, W_i, b_i, W_s, b_s)]
+    hi, hp, hn, Wi, bi, Ws, bs = leaves
+    fa = F.normalize(F.linear(hi, Wi, bi), p=2, dim=1)
+    fp = F.normalize(F.linear(hp, Ws, bs), p=2, dim=1)
+    fn = F.normalize(F.linear(hn, Ws, bs), p=2, dim=1)
+    crit = torch.nn.TripletMarginLoss(margin=1.0, p=2, reduction="none")
+    rows = crit(fa, fp, fn)
+    loss = rows.mean()
+    loss.backward()
+    d = lambda t: t.to(DEV).contiguous()
+    dv = [d(t) for t in (h_img, h_pos, h_neg, W_i, b_i, W_s, b_s)]
+    feats = torch.empty(3, B, D, device=DEV)
+    out_loss = torch.zeros((), device=DEV)
+    loss_rows = torch.empty(B, device=DEV)
+    dh = [torch.empty(B, Ki, device=DEV), torch.empty(B, Ks, device=DEV), torch.empty(B, Ks, device=DEV)]
+    dW_i, db_i = torch.zeros(D, Ki, device=DEV), torch.zeros(4, device=DEV)
+    dW_s, db_s = torch.zeros(D, Ks, device=DEV), torch.zeros(4, device=DEV)
+    rc = lib.var_triplet_fwd_bwd(dv[0].data_ptr(), dv[1].data_ptr(), dv[2].data_ptr(), B, D, Ki, Ks, dv[3].data_ptr(),
+                                 dv[4].data_ptr(), dv[5].data_ptr(), dv[6].data_ptr(), 1.0, float(B), feats.data_ptr(),
+                                 out_loss.data_ptr(), loss_rows.data_ptr(), dh[0].data_ptr(), dh[1].data_ptr(),
+                                 dh[2].data_ptr(), dW_i.data_ptr(), db_i.data_ptr(), dW_s.data_ptr(), db_s.data_ptr(),
+                                 None)
+    assert rc == 0, vb._lib.last_error()
+    assert abs(float(out_loss) - float(loss)) < 2e-6 * max(1.0, float(loss))
+    assert np.abs(loss_rows.cpu().numpy() - rows.detach().numpy()).max() < 1e-5
+    for i, f in enumerate((fa, fp, fn)):
+        assert np.abs(feats[i].cpu().numpy() - f.detach().numpy()).max() < 1e-5
+    # grads of the head inputs are stored ReLU-masked and tf32-rounded (they feed the next MMAs)
+    for got, leaf, hsrc in zip(dh, (hi, hp, hn), (h_img, h_pos, h_neg)):
+        ref = leaf.grad * (hsrc > 0)
+        assert rel_to_max(got.cpu().numpy(), ref.numpy()) < 1e-3
+    assert rel_to_max(dW_i.cpu().numpy(), Wi.grad.numpy()) < 1e-4
+    assert rel_to_max(dW_s.cpu().numpy(), Ws.grad.numpy()) < 1e-4
+    assert rel_to_max(db_i[:D].cpu().numpy(), bi.grad.numpy()) < 1e-4
+    assert rel_to_max(db_s[:D].cpu().numpy(), bs.grad.numpy()) < 1e-4

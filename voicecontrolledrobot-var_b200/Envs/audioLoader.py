@@ -1,0 +1,269 @@
+"""Host mirror of Envs/audioLoader.py::audioLoader with the MFCC arithmetic on the GPU.
+
+Same constructor, attributes (`fs`, `words`, `param_dict`, ...) and methods as the reference
+class (Envs/audioLoader.py:12-252): wav loading stays host IO (scipy), clip selection keeps
+the reference's draw order, and `get_mfcc` / `genSoundFeat*` return the same numpy arrays --
+computed by the fused sm_100a kernel (`var_mfcc_fwd`) instead of torchaudio /
+python_speech_features on the CPU.  `mfcc_batch` and `build_arena` are the batched, device
+resident entry points the triplet trainer uses.
+"""
+import ctypes as C
+import glob
+import os
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from .._lib import check, lib, ptr, stream_ptr
+
+_PLANS = {}
+
+
+def _plan(flavour, fs, n_fft, win_length, hop):
+    key = (flavour, fs, n_fft, win_length, hop, torch.cuda.current_device())
+    if key not in _PLANS:
+        h = C.c_void_p()
+        check(lib.var_mfcc_plan_create(flavour, fs, n_fft, win_length, hop, C.byref(h)), "var_mfcc_plan_create")
+        _PLANS[key] = h
+    return _PLANS[key]
+
+
+def mfcc_device(wav, offsets, lengths, fs, n_fft, win_length, hop, F, flavour=0, out=None):
+    """Device-resident batch: int16 arena `wav`, int64 `offsets` (<0 = empty class -> zero rows),
+    int32 `lengths` -> float32 [B, F, 40]."""
+    B = offsets.shape[0]
+    if out is None:
+        out = torch.empty(B, F, 40, dtype=torch.float32, device=offsets.device)
+    check(lib.var_mfcc_fwd(_plan(flavour, fs, n_fft, win_length, hop), ptr(wav), ptr(offsets), ptr(lengths), B, F,
+                           ptr(out), stream_ptr()), "var_mfcc_fwd")
+    return out
+
+
+def mfcc_batch(clips, fs, n_fft, win_length, hop, F, flavour=0, device=None):
+    """Host clips (list of int16 arrays; None = empty class) -> device float32 [B, F, 40]."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("the MFCC front-end runs on CUDA only; there is no CPU fallback")
+    device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+    offs, lens, parts, cur = [], [], [], 0
+    for c in clips:
+        if c is None:
+            offs.append(-1); lens.append(0)
+            continue
+        c = np.ascontiguousarray(c)
+        if c.dtype != np.int16:
+            raise TypeError("clips must be int16 PCM (as returned by scipy.io.wavfile.read)")
+        offs.append(cur); lens.append(len(c)); parts.append(c)
+        cur += len(c) + (len(c) & 1)  # keep every clip 4-byte aligned
+        if len(c) & 1:
+            parts.append(np.zeros(1, np.int16))
+    arena = np.concatenate(parts) if parts else np.zeros(2, np.int16)
+    wav = torch.from_numpy(arena).to(device)
+    return mfcc_device(wav, torch.tensor(offs, dtype=torch.int64, device=device),
+                       torch.tensor(lens, dtype=torch.int32, device=device), fs, n_fft, win_length, hop, F, flavour)
+
+
+class ClipArena:
+    """All loaded clips in one int16 device buffer + the tables the device sampler indexes."""
+
+    def __init__(self, words, task_num, device):
+        self.task_num = task_num
+        self.dataset_names = [list(words[i].keys()) for i in range(task_num)]
+        self.dataset_sizes = [[len(words[i][k]) for k in words[i]] for i in range(task_num)]
+        offs, lens, parts, cur = [], [], [], 0
+        for i in range(task_num):
+            for k in words[i]:
+                for c in words[i][k]:
+                    c = np.ascontiguousarray(c, dtype=np.int16)
+                    offs.append(cur); lens.append(len(c)); parts.append(c)
+                    if len(c) & 1:
+                        parts.append(np.zeros(1, np.int16))
+                    cur += len(c) + (len(c) & 1)
+        self.wav = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(2, np.int16)).to(device)
+        self.clip_off = torch.tensor(offs, dtype=torch.int64, device=device)
+        self.clip_len = torch.tensor(lens, dtype=torch.int32, device=device)
+
+
+class audioLoader(object):
+    def __init__(self, config):
+        self.config = config
+        self.soundSource = self.config.soundSource
+        self.param_func = namedtuple('sound_param', ['nFFT', 'windowLenTime', 'windowStepTime'])
+        short = self.param_func(nFFT=512, windowLenTime=0.025, windowStepTime=0.01)
+        long_ = self.param_func(nFFT=1024, windowLenTime=0.05, windowStepTime=0.04)
+        # Envs/audioLoader.py:23-31
+        self.param_dict = {'GoogleCommand': short, 'NSynth': long_, 'UrbanSound': long_, 'ESC50': short,
+                           'FSC': short, 'Spatial': short, 'Synthetic': short}
+        self.fs = None
+        self.words = {}
+        self.env_type = os.path.split(self.config.envFolder)[0]
+        if len(self.env_type) == 0:
+            self.env_type = self.config.envFolder
+        self.counter = 0
+
+    # ------------------------------------------------------------------ loading (host IO)
+    def loadData(self):
+        if self.env_type == 'pybullet':
+            for i in range(self.config.taskNum):
+                self.words[i] = {}
+            for dataset in self.config.soundSource['dataset']:
+                if dataset == 'FSC':
+                    self.loadFSCData_pybullet()
+                else:
+                    self.loadSoundData_pybullet(datasetName=dataset)
+        elif self.env_type == 'ai2thor':
+            self.audioDataFrame = {}
+            self.transcription = {}
+            self.loadFSCData_ai2thor(loadSize=self.config.soundSource['size'])
+        else:
+            raise NotImplementedError
+        print("Sound Loaded")
+
+    def _read(self, path):
+        from scipy.io import wavfile
+        self.fs, x = wavfile.read(path)
+        return x
+
+    def load2Words(self, path_list, idx, datasetName, max_sound_dur, loadSize):
+        bucket = self.words[idx][datasetName]
+        for path in path_list:
+            x = self._read(path)
+            if x.size / self.fs > max_sound_dur:
+                continue
+            bucket.append(x)
+            if len(bucket) >= loadSize:
+                break
+
+    def loadSoundData_pybullet(self, datasetName):
+        src = self.config.soundSource
+        word_dir = os.path.join(self.config.commonMediaPath, datasetName, self.soundSource['train_test'])
+        assert os.path.isdir(word_dir)
+        for i, item in enumerate(src['items'][datasetName]):
+            if item is None:
+                continue
+            assert datasetName not in self.words[i]
+            self.words[i][datasetName] = []
+            paths = glob.glob(os.path.join(word_dir, item, '*.wav'))
+            self.load2Words(paths, i, datasetName, src['max_sound_dur'][datasetName], src['size'][datasetName][i])
+
+    def _fsc_frame(self):
+        import pandas as pd
+        return pd.read_csv(os.path.join(self.config.commonMediaPath, 'FSC', 'data', self.config.soundSource['FSC_csv']))
+
+    def loadFSCData_pybullet(self):
+        src = self.config.soundSource
+        df = self._fsc_frame()
+        for i, item in enumerate(src['items']['FSC']):
+            if item is None:
+                continue
+            loc, obj, act = item.split('_')
+            assert 'FSC' not in self.words[i]
+            self.words[i]['FSC'] = []
+            sub = df[(df.object == obj) & (df.action == act) & (df.location == loc)]
+            paths = (os.path.join(self.config.commonMediaPath, 'FSC') + os.sep + sub['path']).tolist()
+            self.load2Words(paths, i, 'FSC', src['max_sound_dur']['FSC'], src['size']['FSC'][i])
+
+    def loadFSCData_ai2thor(self, loadSize=-1):
+        src = self.config.soundSource
+        df = self._fsc_frame()
+        objs = src['FSC_obj_act'].keys()
+        df = df[df.object.isin(objs)]
+        for loc in src['FSC_locations']:
+            loc_df = df[df.location.isin([loc])]
+            self.audioDataFrame[loc], self.transcription[loc], self.words[loc] = {}, {}, {}
+            for obj in objs:
+                obj_df = loc_df[loc_df.object == obj]
+                if obj_df.empty:
+                    continue
+                self.audioDataFrame[loc][obj], self.transcription[loc][obj], self.words[loc][obj] = {}, {}, {}
+                for act in src['FSC_obj_act'][obj]:
+                    frame = obj_df[obj_df.action == act]
+                    self.audioDataFrame[loc][obj][act] = frame
+                    clips, trans = [], []
+                    for path, tr in zip(frame['path'].tolist(), frame['transcription'].tolist()):
+                        x = self._read(os.path.join(self.config.commonMediaPath, 'FSC', path))
+                        if x.size / self.fs > src['FSC_max_sound_dur']:
+                            continue
+                        clips.append(x); trans.append(tr)
+                        if len(clips) >= loadSize:
+                            break
+                    self.words[loc][obj][act] = clips
+                    self.transcription[loc][obj][act] = trans
+
+    # ------------------------------------------------------------------ features (GPU)
+    def stft_params(self, param):
+        """(n_fft, win_length, hop) in samples, Envs/audioLoader.py:151-152."""
+        return param.nFFT, int(param.windowLenTime * self.fs), int(param.windowStepTime * self.fs)
+
+    def get_mfcc(self, audioSamples, param, mfcc_from):
+        """One clip -> numpy [1, F, 40] exactly as Envs/audioLoader.py:147-164 returns it (float32
+        when cropped, float64 when zero-padded), computed on the GPU."""
+        n_fft, win, hop = self.stft_params(param)
+        flavour = 0 if mfcc_from == 'torchaudio' else 1
+        x = np.asarray(audioSamples)
+        if x.dtype != np.int16:
+            if flavour == 0 and np.issubdtype(x.dtype, np.floating):
+                # the reference feeds float clips (trans_fn output, already / 32768) straight in
+                x = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+            else:
+                x = x.astype(np.int16)
+        F = self.config.sound_dim[1]
+        plan = _plan(flavour, self.fs, n_fft, win, hop)
+        nf = lib.var_mfcc_num_frames(plan, len(x))
+        feat = mfcc_batch([x], self.fs, n_fft, win, hop, F, flavour=flavour).cpu().numpy()
+        if F < nf:  # cropped: reference keeps the MFCC dtype
+            return feat.astype(np.float32 if flavour == 0 else np.float64)
+        return feat.astype(np.float64)  # np.concatenate with float64 zeros (audioLoader.py:248-250)
+
+    def getAudioSamples(self, intentIdx, rand_fn, trans_fn=None):
+        if intentIdx > self.config.taskNum - 1:
+            intentIdx = self.config.taskNum - 1
+        names = list(self.words[intentIdx].keys())
+        chosen = names[rand_fn(0, len(names), size=())]
+        idx = rand_fn(0, len(self.words[intentIdx][chosen]), size=())
+        audioSamples = self.words[intentIdx][chosen][idx]
+        if trans_fn is not None:
+            audioSamples = trans_fn((audioSamples / 32768.).astype(np.float32), self.fs)
+        return audioSamples, self.param_dict[chosen]
+
+    def genSoundFeat(self, intentIdx, featType, rand_fn, mfcc_from='torchaudio', trans_fn=None):
+        audioSamples, param = self.getAudioSamples(intentIdx, rand_fn, trans_fn)
+        if featType != 'MFCC':
+            raise NotImplementedError
+        return self.get_mfcc(audioSamples, param, mfcc_from), audioSamples
+
+    def genSoundFeatFromTask(self, task, featType, mfcc_from=None, rand_fn=None):
+        soundList = self.words[task.loc][task.obj][task.act]
+        idx = rand_fn(0, len(soundList), size=())
+        audioSamples = soundList[idx]
+        transcription = self.transcription[task.loc][task.obj][task.act][idx]
+        if featType != 'MFCC':
+            raise NotImplementedError
+        param = self.param_dict[self.config.soundSource['dataset']]
+        return self.get_mfcc(audioSamples, param, mfcc_from), audioSamples, transcription
+
+    def getAudioFromTask(self, random_func, tsk, Task, trans_fn=None):
+        idx = random_func.randint(low=0, high=len(self.config.synonym[tsk.loc]), size=())
+        loc = self.config.synonym[tsk.loc][idx]
+        idx = random_func.randint(low=0, high=len(self.config.synonym[tsk.obj]), size=())
+        obj = self.config.synonym[tsk.obj][idx]
+        obj_act = self.config.soundSource['FSC_obj_act'][obj]
+        act = list(set(obj_act).intersection(self.config.synonym[tsk.act]))[0]
+        return self.genSoundFeatFromTask(task=Task(loc, obj, act), featType='MFCC', rand_fn=random_func.randint)
+
+    def processSoundFeat(self, sound_feat):
+        """Crop / zero-pad a host feature matrix (kept for callers that hold their own features;
+        the GPU kernel applies the same rule while writing its output)."""
+        sound_feat = np.expand_dims(sound_feat, axis=0)
+        nf, F = sound_feat.shape[1], self.config.sound_dim[1]
+        if F < nf:
+            return sound_feat[:, :F, :]
+        pad = list(self.config.sound_dim)
+        pad[1] = F - nf
+        return np.concatenate((sound_feat, np.zeros(pad)), axis=1)
+
+    # ------------------------------------------------------------------ device residency
+    def build_arena(self, device=None):
+        """Upload every clip of the pybullet-style `words[intent][dataset]` table once."""
+        device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        return ClipArena(self.words, self.config.taskNum, device)

@@ -1,0 +1,144 @@
+// extern "C" surface of libvar_b200.so that is not tied to a net object
+// (include/var_b200.h).  Thin argument marshalling only.
+#include <cstring>
+
+#include "../../include/var_b200.h"
+#include "aux_kernels.cuh"
+#include "engine_host.cuh"
+#include "mfcc.cuh"
+#include "triplet.cuh"
+
+#define ST(s) (reinterpret_cast<cudaStream_t>(s))
+
+using namespace var;
+
+static ConvShape make_shape(int N, int H, int W, int Cin, int Cout, int R, int S, int sh, int sw,
+                            int ph, int pw) {
+  ConvShape c{N, H, W, Cin, Cout, R, S, sh, sw, ph, pw, 0, 0};
+  c.P = (H + 2 * ph - R) / sh + 1;
+  c.Q = (W + 2 * pw - S) / sw + 1;
+  return c;
+}
+static SrcLayout make_layout(const int64_t* strides, float scale) {
+  SrcLayout sl{0, 0, 0, 0, scale};
+  if (strides) { sl.sN = strides[0]; sl.sH = strides[1]; sl.sW = strides[2]; sl.sC = strides[3]; }
+  return sl;
+}
+
+extern "C" {
+
+int var_version(void) { return VAR_B200_VERSION; }
+
+int var_mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, void** plan) {
+  if (!plan) return VAR_ERR_ARG;
+  MfccPlan* p = nullptr;
+  const int rc = mfcc_plan_create(flavour, fs, n_fft, win_length, hop, &p);
+  if (rc) return rc;
+  *plan = p;
+  return VAR_OK;
+}
+int var_mfcc_plan_destroy(void* plan) {
+  mfcc_plan_destroy(reinterpret_cast<MfccPlan*>(plan));
+  return VAR_OK;
+}
+int var_mfcc_num_frames(void* plan, int n_samples) {
+  return mfcc_num_frames(reinterpret_cast<MfccPlan*>(plan), n_samples);
+}
+int var_mfcc_fwd(void* plan, const int16_t* wav, const int64_t* offsets, const int32_t* lengths, int B,
+                 int F, float* out, void* stream) {
+  if (!plan || !offsets || !lengths || !out) return VAR_ERR_ARG;
+  return mfcc_fwd(reinterpret_cast<MfccPlan*>(plan), wav,
+                  reinterpret_cast<const long long*>(offsets), lengths, B, F, out, ST(stream));
+}
+
+int var_sampler_seed(uint32_t* state, uint64_t seed, void* stream) {
+  if (!state) return VAR_ERR_ARG;
+  return sampler_seed(state, seed, ST(stream));
+}
+int var_sampler_epoch(uint32_t* state, int n_items, int32_t* perm, void* stream) {
+  if (!state || !perm) return VAR_ERR_ARG;
+  return sampler_epoch(state, n_items, perm, ST(stream));
+}
+int var_sampler_batch(uint32_t* state, int B, int task_num, const int32_t* items, const int32_t* gt,
+                      const int32_t* stored_sn, const int32_t* nds, const int32_t* nclips,
+                      const int32_t* clip_base, int max_ds, const int64_t* clip_off,
+                      const int32_t* clip_len, int32_t* scratch, int32_t* out_item, int32_t* out_gt,
+                      int32_t* out_sn, int32_t* out_rec, int64_t* out_off, int32_t* out_len,
+                      void* stream) {
+  if (!state || !gt || !nds || !nclips || !clip_base || !clip_off || !clip_len || !scratch ||
+      !out_item || !out_gt || !out_sn || !out_rec || !out_off || !out_len)
+    return VAR_ERR_ARG;
+  SamplerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.state = state; a.B = B; a.task_num = task_num; a.items = items; a.gt = gt;
+  a.stored_sn = stored_sn; a.nds = nds; a.nclips = nclips; a.clip_base = clip_base;
+  a.max_ds = max_ds; a.clip_off = reinterpret_cast<const long long*>(clip_off); a.clip_len = clip_len;
+  a.scratch_off = scratch; a.out_item = out_item; a.out_gt = out_gt; a.out_sn = out_sn;
+  a.out_rec = out_rec; a.out_off = reinterpret_cast<long long*>(out_off); a.out_len = out_len;
+  return sampler_batch(a, ST(stream));
+}
+
+int var_adam_step(float* p, const float* g, float* m, float* v, float* p_mma, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float wd, int64_t step, float grad_scale,
+                  void* stream) {
+  if (!p || !g || !m || !v || step < 1) return VAR_ERR_ARG;
+  return adam_step(p, g, m, v, p_mma, n, lr, beta1, beta2, eps, wd, step, grad_scale, ST(stream));
+}
+
+int var_pack_weight(const float* ref, float* packed, float* packed_mma, int Cout, int Cin, int R,
+                    int S, int kpad, void* stream) {
+  return pack_weight(ref, packed, packed_mma, Cout, Cin, R, S, kpad, ST(stream));
+}
+int var_unpack_weight(const float* packed, float* ref, int Cout, int Cin, int R, int S, int kpad,
+                      void* stream) {
+  return unpack_weight(packed, ref, Cout, Cin, R, S, kpad, ST(stream));
+}
+
+int var_conv2d_fwd(const void* x, int src_kind, const int64_t* strides, float scale, int N, int H,
+                   int W, int Cin, int Cout, int R, int S, int sh, int sw, int ph, int pw,
+                   const float* w, const float* bias, float* y, int relu, int round_out, void* stream) {
+  const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
+  const SrcLayout sl = make_layout(strides, scale);
+  return conv_fwd(cs, x, src_kind, &sl, w, bias, y, relu, round_out, ST(stream));
+}
+int var_conv2d_dgrad(const float* dy, const float* w, float* dx, const float* mask, int N, int H, int W,
+                     int Cin, int Cout, int R, int S, int sh, int sw, int ph, int pw, int round_out,
+                     void* stream) {
+  const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
+  return conv_dgrad(cs, dy, w, dx, mask, nullptr, round_out, ST(stream));
+}
+int var_conv2d_wgrad(const void* x, int src_kind, const int64_t* strides, float scale, const float* dy,
+                     float* dw, float* db, int N, int H, int W, int Cin, int Cout, int R, int S, int sh,
+                     int sw, int ph, int pw, void* stream) {
+  const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
+  const SrcLayout sl = make_layout(strides, scale);
+  return conv_wgrad(cs, x, src_kind, &sl, dy, dw, db, ST(stream));
+}
+int var_maxpool2x2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  return maxpool_fwd(x, y, N, H, W, C, ST(stream));
+}
+int var_maxpool2x2_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C,
+                       void* stream) {
+  return maxpool_bwd(x, dy, dx, N, H, W, C, ST(stream));
+}
+
+int var_triplet_fwd_bwd(const float* h_img, const float* h_pos, const float* h_neg, int B, int D,
+                        int Kh_img, int Kh_snd, const float* W_img, const float* b_img,
+                        const float* W_snd, const float* b_snd, float margin, float loss_denominator,
+                        float* feats, float* loss, float* loss_rows, float* dh_img, float* dh_pos,
+                        float* dh_neg, float* dW_img, float* db_img, float* dW_snd, float* db_snd,
+                        void* stream) {
+  TailArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TAIL_TRIPLET; a.B = B; a.D = D; a.Kh_img = Kh_img; a.Kh_snd = Kh_snd;
+  a.h_img = h_img; a.h_pos = h_pos; a.h_neg = h_neg;
+  a.W_img = W_img; a.b_img = b_img; a.W_snd = W_snd; a.b_snd = b_snd;
+  a.margin = margin; a.grad_scale = 1.f / loss_denominator; a.loss_scale = 1.f / loss_denominator;
+  a.loss = loss; a.loss_rows = loss_rows;
+  if (feats) { a.feat_img = feats; a.feat_pos = feats + (long long)B * D; a.feat_neg = feats + 2LL * B * D; }
+  a.dh_img = dh_img; a.dh_pos = dh_pos; a.dh_neg = dh_neg;
+  a.dW_img = dW_img; a.db_img = db_img; a.dW_snd = dW_snd; a.db_snd = db_snd;
+  return tail_launch(a, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// HBM-bound helper kernels around the tcgen05 engine: weight (un)packing between
+// the reference state_dict layout and the engine's K-major packed layout, NHWC
+// 2x2 max pooling (forward / backward with the ReLU mask folded in), the GRU
+// cell backward, fused Adam(+L2) that also refreshes the tf32 operand copy, and
+// small utilities.  All kernels are grid-stride, 128-bit vectorised where the
+// layout allows, and stream ordered.
+#include "aux_kernels.cuh"
+
+namespace var {
+
+static inline int grid_for(long long work, int threads, int max_waves = 8) {
+  long long g = (work + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// Weight packing.  Reference tensor [O][I][R][S] (OIHW; a Linear that follows a
+// NCHW flatten is [O][C][H][W]; a plain Linear is R=S=1) <-> packed
+// [O][kpad], k = (r*S + s)*I + c.  Columns k >= K are zero.
+// ---------------------------------------------------------------------------
+__global__ void pack_w_kernel(const float* __restrict__ ref, float* __restrict__ master,
+                              float* __restrict__ mma, int O, int I, int R, int S, int kpad) {
+  const long long total = (long long)O * kpad;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % kpad);
+    const int o = (int)(idx / kpad);
+    float v = 0.f;
+    if (k < R * S * I) {
+      const int c = k % I, rs = k / I, s = rs % S, r = rs / S;
+      v = ref[(((long long)o * I + c) * R + r) * S + s];
+    }
+    master[idx] = v;
+    if (mma) mma[idx] = round_tf32(v);
+  }
+}
+
+__global__ void unpack_w_kernel(const float* __restrict__ packed, float* __restrict__ ref, int O,
+                                int I, int R, int S, int kpad) {
+  const long long total = (long long)O * I * R * S;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % S);
+    long long t = idx / S;
+    const int r = (int)(t % R); t /= R;
+    const int c = (int)(t % I);
+    const int o = (int)(t / I);
+    ref[idx] = packed[(long long)o * kpad + (r * S + s) * I + c];
+  }
+}
+
+int pack_weight(const float* ref, float* master, float* mma, int O, int I, int R, int S, int kpad,
+                cudaStream_t st) {
+  const long long total = (long long)O * kpad;
+  pack_w_kernel<<<grid_for(total, 256), 256, 0, st>>>(ref, master, mma, O, I, R, S, kpad);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+int unpack_weight(const float* packed, float* ref, int O, int I, int R, int S, int kpad,
+                  cudaStream_t st) {
+  const long long total = (long long)O * I * R * S;
+  unpack_w_kernel<<<grid_for(total, 256), 256, 0, st>>>(packed, ref, O, I, R, S, kpad);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+__global__ void round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                  long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = round_tf32(src[i]);
+}
+int round_copy(const float* src, float* dst, long long n, cudaStream_t st) {
+  round_copy_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 2x2/2 max pooling, NHWC, C % 4 == 0 (nn.MaxPool2d(2, 2) of
+// models/pretext/ai2thor_pretext_model.py:9-11).
+// ---------------------------------------------------------------------------
+__global__ void pool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H,
+                                int W, int C4) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * C4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4);
+    long long t = idx / C4;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const long long base = (((long long)n * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const float4 a = x[base], b = x[base + C4], d = x[base + (long long)W * C4],
+                 e = x[base + (long long)W * C4 + C4];
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x));
+    m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y));
+    m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z));
+    m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w));
+    y[idx] = m;
+  }
+}
+
+// dx = dy routed to the first arg-max of each window, and zero where x <= 0
+// (x is a post-ReLU activation, so this also applies the ReLU backward).
+__device__ __forceinline__ void route(float a, float b, float d, float e, float g, float& oa,
+                                      float& ob, float& od, float& oe) {
+  const float m = fmaxf(fmaxf(a, b), fmaxf(d, e));
+  oa = ob = od = oe = 0.f;
+  if (!(m > 0.f)) return;
+  if (a == m) oa = g;
+  else if (b == m) ob = g;
+  else if (d == m) od = g;
+  else oe = g;
+}
+__global__ void pool_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                float4* __restrict__ dx, int N, int H, int W, int C4) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * C4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4);
+    long long t = idx / C4;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const long long base = (((long long)n * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const long long o1 = base + C4, o2 = base + (long long)W * C4, o3 = o2 + C4;
+    const float4 a = x[base], b = x[o1], d = x[o2], e = x[o3], g = dy[idx];
+    float4 ra, rb, rd, re;
+    route(a.x, b.x, d.x, e.x, g.x, ra.x, rb.x, rd.x, re.x);
+    route(a.y, b.y, d.y, e.y, g.y, ra.y, rb.y, rd.y, re.y);
+    route(a.z, b.z, d.z, e.z, g.z, ra.z, rb.z, rd.z, re.z);
+    route(a.w, b.w, d.w, e.w, g.w, ra.w, rb.w, rd.w, re.w);
+    dx[base] = ra; dx[o1] = rb; dx[o2] = rd; dx[o3] = re;
+  }
+}
+
+int maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st) {
+  if ((C & 3) || (H & 1) || (W & 1)) return VAR_ERR_UNSUPPORTED;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+  pool_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), N, H, W, C / 4);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+int maxpool_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C,
+                cudaStream_t st) {
+  if ((C & 3) || (H & 1) || (W & 1)) return VAR_ERR_UNSUPPORTED;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+  pool_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),
+      reinterpret_cast<float4*>(dx), N, H, W, C / 4);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// GRU cell backward (torch.nn.GRU semantics, gate order r, z, n):
+//   h' = (1-z) n + z h ;  n = tanh(x_n + r * hn) ; hn = W_hn h + b_hn
+// Given dh' it emits, per direction (blockIdx.y),
+//   dgi = [d r_pre, d z_pre, d n_pre]      (grad wrt W_ih x + b_ih)   -> [B, ldgi] slot
+//   dgh = [d r_pre, d z_pre, d n_pre * r]  (grad wrt W_hh h + b_hh)   -> [B, 3H]
+//   dhd = dh' * z                          (direct path to h)
+// Both gate gradients are stored tf32-rounded: they are MMA operands next.
+// ---------------------------------------------------------------------------
+__global__ void gru_cell_bwd_kernel(GruBwdArgs a0, GruBwdArgs a1, int B, int Hd) {
+  const GruBwdArgs& a = blockIdx.y == 0 ? a0 : a1;
+  const int H4 = Hd >> 2;
+  const long long total = (long long)B * H4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % H4) * 4;
+    const long long b = idx / H4;
+    const float4 dh = *reinterpret_cast<const float4*>(a.dh + b * Hd + j);
+    const float* gt = a.gates + b * 3 * Hd + j;
+    const float4 r = *reinterpret_cast<const float4*>(gt);
+    const float4 z = *reinterpret_cast<const float4*>(gt + Hd);
+    const float4 n = *reinterpret_cast<const float4*>(gt + 2 * Hd);
+    const float4 hn = *reinterpret_cast<const float4*>(a.hn_save + b * Hd + j);
+    const float4 hp = *reinterpret_cast<const float4*>(a.hprev + b * Hd + j);
+    float dr[4], dz[4], dn[4], dnr[4], dd[4];
+    const float dh_[4] = {dh.x, dh.y, dh.z, dh.w}, r_[4] = {r.x, r.y, r.z, r.w},
+                z_[4] = {z.x, z.y, z.z, z.w}, n_[4] = {n.x, n.y, n.z, n.w},
+                hn_[4] = {hn.x, hn.y, hn.z, hn.w}, hp_[4] = {hp.x, hp.y, hp.z, hp.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float dnn = dh_[u] * (1.f - z_[u]);
+      const float dzz = dh_[u] * (hp_[u] - n_[u]);
+      const float dnp = dnn * (1.f - n_[u] * n_[u]);
+      const float dzp = dzz * z_[u] * (1.f - z_[u]);
+      const float drp = dnp * hn_[u] * r_[u] * (1.f - r_[u]);
+      dr[u] = round_tf32(drp);
+      dz[u] = round_tf32(dzp);
+      dn[u] = round_tf32(dnp);
+      dnr[u] = round_tf32(dnp * r_[u]);
+      dd[u] = dh_[u] * z_[u];
+    }
+    float* gi = a.dgi + b * a.ldgi + j;
+    *reinterpret_cast<float4*>(gi) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+    *reinterpret_cast<float4*>(gi + Hd) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    *reinterpret_cast<float4*>(gi + 2 * Hd) = make_float4(dn[0], dn[1], dn[2], dn[3]);
+    float* gh = a.dgh + b * 3 * Hd + j;
+    *reinterpret_cast<float4*>(gh) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+    *reinterpret_cast<float4*>(gh + Hd) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    *reinterpret_cast<float4*>(gh + 2 * Hd) = make_float4(dnr[0], dnr[1], dnr[2], dnr[3]);
+    *reinterpret_cast<float4*>(a.dhd + b * Hd + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+  }
+}
+
+int gru_cell_bwd(const GruBwdArgs& a0, const GruBwdArgs& a1, int ndir, int B, int Hd,
+                 cudaStream_t st) {
+  if (Hd & 3) return VAR_ERR_UNSUPPORTED;
+  dim3 grid(grid_for((long long)B * (Hd / 4), 256), ndir);
+  gru_cell_bwd_kernel<<<grid, 256, 0, st>>>(a0, a1, B, Hd);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Adam with L2 folded into the gradient (torch.optim.Adam(weight_decay) as used
+// at VAR/pretext_VAR.py:33-35), on the flat packed parameter buffer.  Operation
+// order follows torch's single-tensor path: lerp, mul+addcmul, sqrt/bc2_sqrt+eps,
+// addcdiv.  Also writes the tf32-rounded operand copy consumed by the MMAs.
+// ---------------------------------------------------------------------------
+__global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                            float4* __restrict__ m, float4* __restrict__ v,
+                            float4* __restrict__ pr, long long n4, float beta1, float beta2,
+                            float eps, float wd, float step_size, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 P = p[i], G = g[i], M = m[i], V = v[i], R;
+    float* pp = &P.x; const float* gg = &G.x; float* mm = &M.x; float* vv = &V.x; float* rr = &R.x;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float grad = gg[u] * gscale + wd * pp[u];
+      mm[u] = mm[u] + (grad - mm[u]) * (1.f - beta1);
+      vv[u] = vv[u] * beta2 + (1.f - beta2) * grad * grad;
+      const float denom = sqrtf(vv[u]) / bc2_sqrt + eps;
+      pp[u] = pp[u] - step_size * (mm[u] / denom);
+      rr[u] = round_tf32(pp[u]);
+    }
+    p[i] = P; m[i] = M; v[i] = V;
+    if (pr) pr[i] = R;
+  }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, float* p_mma, long long n, float lr,
+              float beta1, float beta2, float eps, float wd, long long step, float gscale,
+              cudaStream_t st) {
+  if (n & 3) return VAR_ERR_ARG;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(p_mma), n / 4, beta1, beta2, eps, wd,
+      step_size, bc2_sqrt, gscale);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// NHWC [B, HW, C] -> reference NCHW-flatten order [B, C*HW] (image_feat_raw of
+// models/pretext/pretext_base.py:40); tiny, one thread per element.
+// ---------------------------------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                    int HW, int C) {
+  const long long total = (long long)B * HW * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(idx % HW);
+    long long t = idx / HW;
+    const int c = (int)(t % C);
+    const long long b = t / C;
+    y[idx] = x[(b * HW + hw) * C + c];
+  }
+}
+int nhwc_to_nchw(const float* x, float* y, int B, int HW, int C, cudaStream_t st) {
+  nhwc_to_nchw_kernel<<<grid_for((long long)B * HW * C, 256), 256, 0, st>>>(x, y, B, HW, C);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// out[b, :] = cat(a[b, :H], c[b, :H])  (GRU final hidden states of both directions)
+__global__ void concat2_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                               float* __restrict__ out, float* __restrict__ out_r, int B, int Hd) {
+  const long long total = (long long)B * 2 * Hd;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % (2 * Hd));
+    const long long b = idx / (2 * Hd);
+    const float v = j < Hd ? a[b * Hd + j] : c[b * Hd + j - Hd];
+    out[idx] = v;
+    if (out_r) out_r[idx] = round_tf32(v);
+  }
+}
+int concat2(const float* a, const float* c, float* out, float* out_r, int B, int Hd,
+            cudaStream_t st) {
+  concat2_kernel<<<grid_for((long long)B * 2 * Hd, 256), 256, 0, st>>>(a, c, out, out_r, B, Hd);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// a[b, :] = x[b, :H] ; c[b, :] = x[b, H:]
+__global__ void split2_kernel(const float* __restrict__ x, float* __restrict__ a,
+                              float* __restrict__ c, int B, int Hd) {
+  const long long total = (long long)B * 2 * Hd;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % (2 * Hd));
+    const long long b = idx / (2 * Hd);
+    if (j < Hd) a[b * Hd + j] = x[idx];
+    else c[b * Hd + j - Hd] = x[idx];
+  }
+}
+int split2(const float* x, float* a, float* c, int B, int Hd, cudaStream_t st) {
+  split2_kernel<<<grid_for((long long)B * 2 * Hd, 256), 256, 0, st>>>(x, a, c, B, Hd);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+}  // namespace var

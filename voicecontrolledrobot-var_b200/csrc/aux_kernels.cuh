@@ -1,0 +1,39 @@
+// Launchers of the HBM-bound helper kernels (aux_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace var {
+
+int pack_weight(const float* ref, float* master, float* mma, int O, int I, int R, int S, int kpad,
+                cudaStream_t st);
+int unpack_weight(const float* packed, float* ref, int O, int I, int R, int S, int kpad,
+                  cudaStream_t st);
+int round_copy(const float* src, float* dst, long long n, cudaStream_t st);
+
+int maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st);
+int maxpool_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C,
+                cudaStream_t st);
+
+struct GruBwdArgs {
+  const float* dh;       // [B, H] grad wrt h_t
+  const float* gates;    // [B, 3H] saved r, z, n
+  const float* hn_save;  // [B, H] saved W_hn h + b_hn
+  const float* hprev;    // [B, H] h_{t-1}
+  float* dgi;            // [B, ldgi] slot for this step (batch-major [B, T, 3H])
+  long long ldgi;
+  float* dgh;            // [B, 3H]
+  float* dhd;            // [B, H] dh * z
+};
+int gru_cell_bwd(const GruBwdArgs& a0, const GruBwdArgs& a1, int ndir, int B, int Hd,
+                 cudaStream_t st);
+
+int adam_step(float* p, const float* g, float* m, float* v, float* p_mma, long long n, float lr,
+              float beta1, float beta2, float eps, float wd, long long step, float gscale,
+              cudaStream_t st);
+
+int nhwc_to_nchw(const float* x, float* y, int B, int HW, int C, cudaStream_t st);
+int concat2(const float* a, const float* c, float* out, float* out_r, int B, int Hd,
+            cudaStream_t st);
+int split2(const float* x, float* a, float* c, int B, int Hd, cudaStream_t st);
+
+}  // namespace var

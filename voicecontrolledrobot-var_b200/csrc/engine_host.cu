@@ -213,12 +213,10 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
   return launch_gemm(gmode_of(src_kind), EPI_STD, tm, tm, p, grid, st);
 }
 
-int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
-               int round_out, cudaStream_t st) {
+static int fill_dgrad(GemmParams& p, int z, const ConvShape& cs, const float* dy, float* dx,
+                      const float* mask, const float* addsrc, int round_out) {
   if (cs.Cout % 32 || cs.Cin % 32) return VAR_ERR_UNSUPPORTED;
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  GatherGeom& g = p.g[0];
+  GatherGeom& g = p.g[z];
   g.src = dy;
   g.M = cs.N * cs.H * cs.W;         // rows are input pixels
   g.P = cs.H; g.Q = cs.W;
@@ -238,15 +236,76 @@ int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, 
   p.cin_total = cs.Cin;
   p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
   pick_pipeline(bn, &p.stages, &p.lookahead);
-  EpiParams& e = p.e[0];
+  EpiParams& e = p.e[z];
   e.out = dx; e.ldo = cs.Cin; e.ncols = cs.Cin; e.mask = mask; e.ldm = cs.Cin;
+  e.addsrc = addsrc; e.lda = cs.Cin;
   e.round_out = round_out;
+  return VAR_OK;
+}
+
+int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
+               const float* addsrc, int round_out, cudaStream_t st) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_dgrad(p, 0, cs, dy, dx, mask, addsrc, round_out);
+  if (rc) return rc;
   const int kfwd = cs.R * cs.S * cs.Cin, kpad = round_up32(kfwd);
   CUtensorMap tm;
-  int rc = get_tmap_2d(w, cs.Cout, kpad, kpad, 32, mn_cfg().tma_swizzle, &tm);
+  rc = get_tmap_2d(w, cs.Cout, kpad, kpad, 32, mn_cfg().tma_swizzle, &tm);
   if (rc) return rc;
-  dim3 grid((g.M + 127) / 128, cs.Cin / bn, 1);
+  dim3 grid((p.g[0].M + 127) / 128, cs.Cin / p.bn, 1);
   return launch_gemm(G_VEC_DGRAD, EPI_STD, tm, tm, p, grid, st);
+}
+
+// Two independent linear dgrads of identical shape in one launch (grid.z = 2):
+// dx[z] = dy[z] @ W[z] + addsrc[z]   (GRU backward recurrence, both directions)
+int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
+                  const float* const w[2], float* const dx[2], const float* const addsrc[2],
+                  int round_out, cudaStream_t st) {
+  ConvShape cs{M, 1, 1, Cin, Cout, 1, 1, 1, 1, 0, 0, 1, 1};
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap tm[2];
+  const int kpad = round_up32(Cin);
+  for (int z = 0; z < ndir; ++z) {
+    int rc = fill_dgrad(p, z, cs, dy[z], dx[z], nullptr, addsrc[z], round_out);
+    if (rc) return rc;
+    rc = get_tmap_2d(w[z], Cout, kpad, kpad, 32, mn_cfg().tma_swizzle, &tm[z]);
+    if (rc) return rc;
+  }
+  if (ndir == 1) tm[1] = tm[0];
+  dim3 grid((M + 127) / 128, Cin / p.bn, ndir);
+  return launch_gemm(G_VEC_DGRAD, EPI_STD, tm[0], tm[1], p, grid, st);
+}
+
+// One GRU time step for up to two directions: gates = hprev @ W_hh^T fused with the
+// cell update in the epilogue (EPI_GRU_FWD).  W_hh is [3H, H] K-major, rows r|z|n.
+int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const float* const whh[2],
+                 const GruEpiParams q[2], cudaStream_t st) {
+  if (Hd % 64) return VAR_ERR_UNSUPPORTED;
+  const int jb = 64;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap tm[2];
+  for (int z = 0; z < ndir; ++z) {
+    GatherGeom& g = p.g[z];
+    g.src = hprev_r[z];
+    g.M = B; g.P = 1; g.Q = 1; g.H = 1; g.W = 1; g.C = Hd; g.R = 1; g.S = 1;
+    g.sh = g.sw = 1; g.ph = g.pw = 0;
+    g.sC = 1; g.sW = Hd; g.sH = Hd; g.sN = Hd; g.K = Hd; g.scale = 1.f;
+    p.gru[z] = q[z];
+    p.gru[z].Hdim = Hd;
+    int rc = get_tmap_2d(whh[z], 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[z]);
+    if (rc) return rc;
+  }
+  if (ndir == 1) tm[1] = tm[0];
+  p.bn = 3 * jb;
+  p.nbox = 3; p.box_rows = jb;
+  p.boxbase[0] = 0; p.boxbase[1] = Hd; p.boxbase[2] = 2 * Hd;
+  p.num_kb = Hd / 32;
+  p.stages = 4; p.lookahead = 2;
+  dim3 grid((B + 127) / 128, Hd / jb, ndir);
+  return launch_gemm(G_VEC_FWD, EPI_GRU_FWD, tm[0], tm[1], p, grid, st);
 }
 
 // ---- bias gradient: column sums of dY [M, ld] over a slab of C <= 256 columns

@@ -38,8 +38,15 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
 
 // dx[N,H,W,Cin] = conv_transpose(dy, w) [* (mask > 0)] ; mask = forward output of the
 // previous layer (ReLU backward fused), may be null.
+// `addsrc` ([rows, Cin], nullable) is added before the mask.
 int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
-               int round_out, cudaStream_t st);
+               const float* addsrc, int round_out, cudaStream_t st);
+int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
+                  const float* const w[2], float* const dx[2], const float* const addsrc[2],
+                  int round_out, cudaStream_t st);
+int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const float* const whh[2],
+                 const GruEpiParams q[2], cudaStream_t st);
+int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st);
 
 // dw[Cout, Kpad] += im2col(x)^T dy ; db[Cout] += colsum(dy) (db may be null).
 int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,

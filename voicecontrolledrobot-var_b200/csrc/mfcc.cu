@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <vector>
 
-#include "common.cuh"
+#include <cstring>
+
+#include "mfcc.cuh"
 
 namespace var {
 
@@ -321,7 +323,10 @@ static void linspace_f32(float start, float end, int steps, std::vector<float>& 
     out[i] = i < half ? start + step * (float)i : end - step * (float)(steps - 1 - i);
 }
 
-int mfcc_plan_create(int fs, int n_fft, int win_length, int hop, MfccPlan** out) {
+int mfcc_num_frames(const MfccPlan* p, int n_samples) { return 1 + n_samples / p->hop; }
+
+int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, MfccPlan** out) {
+  if (flavour != 0) return VAR_ERR_UNSUPPORTED;
   if ((n_fft != 512 && n_fft != 1024) || win_length > n_fft || hop <= 0) return VAR_ERR_UNSUPPORTED;
   const int nfreq = n_fft / 2 + 1;
   std::vector<float> window(n_fft, 0.f);

@@ -1,0 +1,723 @@
+// Layer plans and the forward / backward executors of the two VAR encoders:
+//   kind 0  Kuka   models/pretext/arm_pretext_model.py:9-59
+//   kind 1  iTHOR  models/pretext/ai2thor_pretext_model.py:5-64
+// orchestrated like PretextNetBase.VAR_forward (models/pretext/pretext_base.py:10-42).
+// Activations are NHWC fp32 (tf32-representable values) in a caller-provided
+// workspace; parameters live in one flat packed buffer (see include/var_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/var_b200.h"
+#include "aux_kernels.cuh"
+#include "engine_host.cuh"
+#include "triplet.cuh"
+
+namespace var {
+
+namespace {
+
+struct TensorDesc {
+  std::string name;
+  int ndim;
+  int shape[4];
+  int O, I, R, S, kpad;  // packed [O][kpad], k = (r*S+s)*I + c
+  long long off, packed;
+};
+
+enum LayerType : int { LT_CONV = 0, LT_POOL = 1 };
+
+struct Layer {
+  int type;
+  int H, W, Cin, Cout, R, S, sh, sw, ph, pw, P, Q;
+  int relu, round_out, mask_in;
+  int tw, tb;  // tensor indices of weight / bias
+  // run state
+  const void* in;
+  int in_kind;
+  SrcLayout in_sl;
+  float* out;
+  int N;
+};
+
+struct Arena {
+  uint8_t* base;
+  long long cap, used;
+  bool overflow;
+  Arena(void* b, long long c) : base(reinterpret_cast<uint8_t*>(b)), cap(c), used(0), overflow(false) {}
+  float* alloc(long long floats) {
+    const long long bytes = ((floats * 4 + 255) / 256) * 256;
+    const long long o = used;
+    used += bytes;
+    if (!base) return nullptr;
+    if (used > cap) { overflow = true; return nullptr; }
+    return reinterpret_cast<float*>(base + o);
+  }
+};
+
+constexpr int kGruT = 73, kGruH = 512, kGruI = 448;
+
+struct GruState {
+  int B;
+  const float* x;       // [B*T, 448]
+  float* xproj[2];      // [B*T, 1536]
+  float* gates[2];      // [T][B, 1536]
+  float* hn_save[2];    // [T][B, 512]
+  float* h_r[2];        // [T+1][B, 512] tf32-rounded hidden states (slot 0 = zeros)
+  float* h32[2][2];     // ping-pong fp32 hidden state
+  float* out;           // [B, 1024]
+  float* out_r;
+};
+
+}  // namespace
+
+struct Net {
+  int kind, F, D;
+  std::vector<TensorDesc> tensors;
+  std::vector<Layer> img_trunk, img_head, snd_trunk, snd_head;
+  bool has_gru = false;
+  int t_gru[2][4];  // [dir][wih, whh, bih, bhh]
+  int t_tail_img_w, t_tail_img_b, t_tail_snd_w, t_tail_snd_b;
+  int Kh_img, Kh_snd;
+  int img_raw_dim, snd_raw_dim;
+  long long nparams = 0;
+  float *P = nullptr, *PR = nullptr, *G = nullptr;
+  // run state of the last forward
+  int n_img = 0, n_snd = 0;
+  long long fwd_used = 0;
+  GruState gru;
+  float *h_img = nullptr, *h_snd = nullptr;  // inputs of the tail
+  float *img_raw_nhwc = nullptr, *snd_raw = nullptr;
+
+  int add_tensor(const std::string& name, int ndim, const int* shape, int O, int I, int R, int S,
+                 int kpad) {
+    TensorDesc t;
+    t.name = name; t.ndim = ndim;
+    for (int i = 0; i < 4; ++i) t.shape[i] = i < ndim ? shape[i] : 1;
+    t.O = O; t.I = I; t.R = R; t.S = S; t.kpad = kpad;
+    t.off = nparams;
+    t.packed = (((long long)O * kpad) + 3) / 4 * 4;
+    nparams += t.packed;
+    tensors.push_back(t);
+    return (int)tensors.size() - 1;
+  }
+  // conv weight + bias named `<name>.weight/.bias`
+  void add_conv(std::vector<Layer>& v, const std::string& name, int H, int W, int Cin, int Cout,
+                int R, int S, int sh, int sw, int ph, int pw, int relu, int round_out, int mask_in) {
+    Layer l;
+    memset(&l, 0, sizeof(l));
+    l.type = LT_CONV;
+    l.H = H; l.W = W; l.Cin = Cin; l.Cout = Cout; l.R = R; l.S = S;
+    l.sh = sh; l.sw = sw; l.ph = ph; l.pw = pw;
+    l.P = (H + 2 * ph - R) / sh + 1;
+    l.Q = (W + 2 * pw - S) / sw + 1;
+    l.relu = relu; l.round_out = round_out; l.mask_in = mask_in;
+    const int shp[4] = {Cout, Cin, R, S};
+    l.tw = add_tensor(name + ".weight", 4, shp, Cout, Cin, R, S, round_up32(R * S * Cin));
+    const int bs[1] = {Cout};
+    l.tb = add_tensor(name + ".bias", 1, bs, 1, Cout, 1, 1, Cout);
+    v.push_back(l);
+  }
+  // Linear whose input is the NHWC tensor [C, Hh, Ww] flattened (reference flattens NCHW)
+  void add_linear(std::vector<Layer>& v, const std::string& name, int C, int Hh, int Ww, int Cout,
+                  int relu, int round_out, int mask_in) {
+    Layer l;
+    memset(&l, 0, sizeof(l));
+    l.type = LT_CONV;
+    const int In = C * Hh * Ww;
+    l.H = 1; l.W = 1; l.Cin = In; l.Cout = Cout; l.R = 1; l.S = 1;
+    l.sh = l.sw = 1; l.P = l.Q = 1;
+    l.relu = relu; l.round_out = round_out; l.mask_in = mask_in;
+    const int shp[2] = {Cout, In};
+    l.tw = add_tensor(name + ".weight", 2, shp, Cout, C, Hh, Ww, round_up32(In));
+    const int bs[1] = {Cout};
+    l.tb = add_tensor(name + ".bias", 1, bs, 1, Cout, 1, 1, Cout);
+    v.push_back(l);
+  }
+  void add_pool(std::vector<Layer>& v, int H, int W, int C) {
+    Layer l;
+    memset(&l, 0, sizeof(l));
+    l.type = LT_POOL;
+    l.H = H; l.W = W; l.Cin = C; l.Cout = C; l.P = H / 2; l.Q = W / 2;
+    v.push_back(l);
+  }
+  void add_tail(const std::string& name, int Kh, int* tw, int* tb) {
+    const int shp[2] = {D, Kh};
+    *tw = add_tensor(name + ".weight", 2, shp, D, Kh, 1, 1, Kh);
+    const int bs[1] = {D};
+    *tb = add_tensor(name + ".bias", 1, bs, 1, D, 1, 1, (D + 3) / 4 * 4);
+  }
+
+  int build() {
+    if (kind == 0) {
+      // registration order of arm_pretext_model.py:37-56: imgBranch, soundCNN, imgTriplet, soundTriplet
+      if (F != 100) return VAR_ERR_UNSUPPORTED;
+      const int ch[6] = {3, 32, 32, 64, 64, 64};
+      int hw = 96;
+      for (int i = 0; i < 5; ++i) {
+        add_conv(img_trunk, "imgBranch." + std::to_string(2 * i), hw, hw, ch[i], ch[i + 1], 3, 3, 2,
+                 2, 1, 1, 1, 1, i > 0);
+        hw = (hw + 2 - 3) / 2 + 1;
+      }
+      img_raw_dim = 64 * hw * hw;  // 576
+      add_conv(snd_trunk, "soundCNN.0", F, 40, 1, 32, 5, 40, 2, 1, 0, 0, 1, 1, 0);
+      int h = snd_trunk.back().P;
+      for (int i = 1; i < 4; ++i) {
+        add_conv(snd_trunk, "soundCNN." + std::to_string(2 * i), h, 1, 32, 32, 3, 1, 2, 1, 0, 0, 1, 1, 1);
+        h = snd_trunk.back().P;
+      }
+      snd_raw_dim = 32 * h;  // 160
+      add_linear(img_head, "imgTriplet.0", 64, hw, hw, 128, 1, 0, 1);
+      add_tail("imgTriplet.2", 128, &t_tail_img_w, &t_tail_img_b);
+      add_linear(snd_head, "soundTriplet.0", 32, h, 1, 128, 1, 0, 1);
+      add_tail("soundTriplet.2", 128, &t_tail_snd_w, &t_tail_snd_b);
+      Kh_img = 128; Kh_snd = 128;
+    } else if (kind == 1) {
+      // registration order of ai2thor_pretext_model.py:41-61: imgBranch, rnn, cnn, imgTriplet, soundTriplet
+      if (F != 600) return VAR_ERR_UNSUPPORTED;
+      add_conv(img_trunk, "imgBranch.0", 96, 96, 3, 32, 3, 3, 1, 1, 1, 1, 1, 1, 0);
+      add_conv(img_trunk, "imgBranch.2", 96, 96, 32, 32, 3, 3, 1, 1, 1, 1, 1, 1, 1);
+      add_pool(img_trunk, 96, 96, 32);
+      add_conv(img_trunk, "imgBranch.5", 48, 48, 32, 64, 3, 3, 1, 1, 1, 1, 1, 1, 1);
+      add_pool(img_trunk, 48, 48, 64);
+      add_conv(img_trunk, "imgBranch.8", 24, 24, 64, 64, 3, 3, 1, 1, 1, 1, 1, 1, 1);
+      add_pool(img_trunk, 24, 24, 64);
+      add_conv(img_trunk, "imgBranch.11", 12, 12, 64, 128, 3, 3, 1, 1, 1, 1, 1, 1, 1);
+      add_pool(img_trunk, 12, 12, 128);
+      add_conv(img_trunk, "imgBranch.14", 6, 6, 128, 128, 3, 3, 2, 2, 1, 1, 1, 1, 1);
+      img_raw_dim = 128 * 3 * 3;
+      has_gru = true;
+      for (int d = 0; d < 2; ++d) {
+        const std::string sfx = d ? "_reverse" : "";
+        // torch order: weight_ih, weight_hh, bias_ih, bias_hh (per direction)
+        const int s_ih[2] = {3 * kGruH, kGruI};
+        // W_ih columns follow x = transpose(conv_out, 1, 2).reshape(B, 73, 64*7): col = c*7 + w
+        t_gru[d][0] = add_tensor("rnn.weight_ih_l0" + sfx, 2, s_ih, 3 * kGruH, 64, 1, 7, kGruI);
+        const int s_hh[2] = {3 * kGruH, kGruH};
+        t_gru[d][1] = add_tensor("rnn.weight_hh_l0" + sfx, 2, s_hh, 3 * kGruH, kGruH, 1, 1, kGruH);
+        const int s_b[1] = {3 * kGruH};
+        t_gru[d][2] = add_tensor("rnn.bias_ih_l0" + sfx, 1, s_b, 1, 3 * kGruH, 1, 1, 3 * kGruH);
+        t_gru[d][3] = add_tensor("rnn.bias_hh_l0" + sfx, 1, s_b, 1, 3 * kGruH, 1, 1, 3 * kGruH);
+      }
+      add_conv(snd_trunk, "cnn.0", F, 40, 1, 64, 11, 11, 2, 2, 5, 5, 1, 1, 0);
+      add_conv(snd_trunk, "cnn.2", 300, 20, 64, 64, 11, 5, 2, 2, 5, 5, 1, 1, 1);
+      add_conv(snd_trunk, "cnn.4", 150, 13, 64, 64, 7, 3, 2, 2, 1, 1, 1, 1, 1);
+      if (snd_trunk.back().P != kGruT || snd_trunk.back().Q != 7) return VAR_ERR_UNSUPPORTED;
+      snd_raw_dim = 2 * kGruH;
+      add_linear(img_head, "imgTriplet.0", 128, 3, 3, 128, 1, 0, 1);
+      add_tail("imgTriplet.2", 128, &t_tail_img_w, &t_tail_img_b);
+      add_linear(snd_head, "soundTriplet.0", 2 * kGruH, 1, 1, 128, 1, 1, 0);
+      add_linear(snd_head, "soundTriplet.2", 128, 1, 1, 64, 1, 0, 1);
+      add_tail("soundTriplet.4", 64, &t_tail_snd_w, &t_tail_snd_b);
+      Kh_img = 128; Kh_snd = 64;
+    } else {
+      return VAR_ERR_UNSUPPORTED;
+    }
+    return VAR_OK;
+  }
+
+  const float* wr(int t) const { return PR + tensors[t].off; }  // tf32 operand copy
+  const float* wm(int t) const { return P + tensors[t].off; }   // fp32 master
+  float* gr(int t) const { return G + tensors[t].off; }
+
+  // ------------------------------------------------------------------ forward
+  int run_layers_fwd(std::vector<Layer>& L, const void* input, int in_kind, const SrcLayout& in_sl,
+                     int N, Arena& ar, cudaStream_t st, float** last_out) {
+    const void* cur = input;
+    int kind_ = in_kind;
+    SrcLayout sl = in_sl;
+    for (size_t i = 0; i < L.size(); ++i) {
+      Layer& l = L[i];
+      l.in = cur; l.in_kind = kind_; l.in_sl = sl; l.N = N;
+      l.out = ar.alloc((long long)N * l.P * l.Q * l.Cout);
+      if (ar.base) {
+        if (ar.overflow) return VAR_ERR_WORKSPACE;
+        int rc;
+        if (l.type == LT_CONV) {
+          ConvShape cs{N, l.H, l.W, l.Cin, l.Cout, l.R, l.S, l.sh, l.sw, l.ph, l.pw, l.P, l.Q};
+          rc = conv_fwd(cs, cur, kind_, &sl, wr(l.tw), wm(l.tb), l.out, l.relu, l.round_out, st);
+        } else {
+          rc = maxpool_fwd(reinterpret_cast<const float*>(cur), l.out, N, l.H, l.W, l.Cin, st);
+        }
+        if (rc) return rc;
+      }
+      cur = l.out;
+      kind_ = SRC_NHWC_F32;
+    }
+    *last_out = const_cast<float*>(reinterpret_cast<const float*>(cur));
+    return VAR_OK;
+  }
+
+  int gru_forward(const float* x, int B, bool train, Arena& ar, cudaStream_t st) {
+    GruState& g = gru;
+    g.B = B; g.x = x;
+    const long long BT = (long long)B * kGruT;
+    for (int d = 0; d < 2; ++d) {
+      g.xproj[d] = ar.alloc(BT * 3 * kGruH);
+      g.gates[d] = train ? ar.alloc(BT * 3 * kGruH) : nullptr;
+      g.hn_save[d] = train ? ar.alloc(BT * kGruH) : nullptr;
+      g.h_r[d] = ar.alloc((train ? (long long)(kGruT + 1) : 2) * B * kGruH);
+      g.h32[d][0] = ar.alloc((long long)B * kGruH);
+      g.h32[d][1] = ar.alloc((long long)B * kGruH);
+    }
+    g.out = ar.alloc((long long)B * 2 * kGruH);
+    g.out_r = ar.alloc((long long)B * 2 * kGruH);
+    if (!ar.base) return VAR_OK;
+    if (ar.overflow) return VAR_ERR_WORKSPACE;
+    for (int d = 0; d < 2; ++d) {
+      // x-projection for all steps: [B*T, 448] x W_ih^T + b_ih
+      ConvShape cs{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
+      int rc = conv_fwd(cs, x, SRC_NHWC_F32, nullptr, wr(t_gru[d][0]), wm(t_gru[d][2]), g.xproj[d], 0,
+                        0, st);
+      if (rc) return rc;
+      VAR_CUDA_CHECK(cudaMemsetAsync(g.h_r[d], 0, (size_t)B * kGruH * 4, st));
+      VAR_CUDA_CHECK(cudaMemsetAsync(g.h32[d][0], 0, (size_t)B * kGruH * 4, st));
+    }
+    const long long slot = (long long)B * kGruH;
+    for (int s = 0; s < kGruT; ++s) {
+      const float* hp[2];
+      const float* whh[2];
+      GruEpiParams q[2];
+      for (int d = 0; d < 2; ++d) {
+        const int t = d == 0 ? s : kGruT - 1 - s;
+        const int cur_slot = train ? s : (s & 1), nxt_slot = train ? s + 1 : ((s + 1) & 1);
+        hp[d] = g.h_r[d] + cur_slot * slot;
+        whh[d] = wr(t_gru[d][1]);
+        memset(&q[d], 0, sizeof(GruEpiParams));
+        q[d].xproj = g.xproj[d] + (long long)t * 3 * kGruH;
+        q[d].ldx = (long long)kGruT * 3 * kGruH;
+        q[d].bhh = wm(t_gru[d][3]);
+        q[d].hprev = g.h32[d][s & 1];
+        q[d].hnew = g.h32[d][(s + 1) & 1];
+        q[d].hnew_r = g.h_r[d] + nxt_slot * slot;
+        q[d].gates = train ? g.gates[d] + (long long)s * B * 3 * kGruH : nullptr;
+        q[d].hn_save = train ? g.hn_save[d] + (long long)s * B * kGruH : nullptr;
+        q[d].Hdim = kGruH;
+      }
+      int rc = gru_step_fwd(2, B, kGruH, hp, whh, q, st);
+      if (rc) return rc;
+    }
+    return concat2(g.h32[0][kGruT & 1], g.h32[1][kGruT & 1], g.out, g.out_r, B, kGruH, st);
+  }
+
+  int forward(const void* images, int image_kind, int n_images, const float* sounds, int n_sounds,
+              void* ws, long long ws_bytes, bool train, cudaStream_t st) {
+    Arena ar(ws, ws_bytes);
+    n_img = n_images; n_snd = n_sounds;
+    h_img = h_snd = img_raw_nhwc = snd_raw = nullptr;
+    if (n_images > 0) {
+      SrcLayout sl;
+      sl.sW = 1; sl.sH = 96; sl.sC = 96 * 96; sl.sN = 3 * 96 * 96;  // NCHW
+      sl.scale = image_kind == 0 ? 1.f / 255.f : 1.f;
+      float* t;
+      int rc = run_layers_fwd(img_trunk, images, image_kind == 0 ? SRC_STRIDED_U8 : SRC_STRIDED_F32,
+                              sl, n_images, ar, st, &t);
+      if (rc) return rc;
+      img_raw_nhwc = t;
+      rc = run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st, &h_img);
+      if (rc) return rc;
+    }
+    if (n_sounds > 0) {
+      SrcLayout sl;
+      sl.sC = 0; sl.sW = 1; sl.sH = 40; sl.sN = (long long)F * 40;
+      sl.scale = 1.f;
+      float* t;
+      int rc = run_layers_fwd(snd_trunk, sounds, SRC_STRIDED_F32, sl, n_sounds, ar, st, &t);
+      if (rc) return rc;
+      if (has_gru) {
+        rc = gru_forward(t, n_sounds, train, ar, st);
+        if (rc) return rc;
+        snd_raw = gru.out;
+        t = gru.out_r;
+      } else {
+        snd_raw = t;
+      }
+      rc = run_layers_fwd(snd_head, t, SRC_NHWC_F32, sl, n_sounds, ar, st, &h_snd);
+      if (rc) return rc;
+    }
+    fwd_used = ar.used;
+    return VAR_OK;
+  }
+
+  // ----------------------------------------------------------------- backward
+  // dY: grad wrt the output of the last layer of L (ReLU-masked, tf32-rounded).
+  // Returns in *dx_out the grad wrt the input of L[0] (nullptr when L[0] reads the
+  // branch input, which needs no gradient).
+  int run_layers_bwd(std::vector<Layer>& L, float* dY, Arena& ar, cudaStream_t st, float** dx_out) {
+    float* dy = dY;
+    for (int i = (int)L.size() - 1; i >= 0; --i) {
+      Layer& l = L[i];
+      const int N = l.N;
+      const bool need_dx = l.in_kind == SRC_NHWC_F32;
+      float* dx = need_dx ? ar.alloc((long long)N * l.H * l.W * l.Cin) : nullptr;
+      if (ar.base) {
+        if (ar.overflow) return VAR_ERR_WORKSPACE;
+        int rc = VAR_OK;
+        if (l.type == LT_CONV) {
+          ConvShape cs{N, l.H, l.W, l.Cin, l.Cout, l.R, l.S, l.sh, l.sw, l.ph, l.pw, l.P, l.Q};
+          rc = conv_wgrad(cs, l.in, l.in_kind, &l.in_sl, dy, gr(l.tw), gr(l.tb), st);
+          if (rc) return rc;
+          if (need_dx)
+            rc = conv_dgrad(cs, dy, wr(l.tw), dx,
+                            l.mask_in ? reinterpret_cast<const float*>(l.in) : nullptr, nullptr, 1, st);
+        } else {
+          rc = maxpool_bwd(reinterpret_cast<const float*>(l.in), dy, dx, N, l.H, l.W, l.Cin, st);
+        }
+        if (rc) return rc;
+      }
+      dy = dx;
+    }
+    *dx_out = dy;
+    return VAR_OK;
+  }
+
+  // d_out: [B, 1024] grad wrt cat(h_fwd_T, h_bwd_T).  Produces dX [B*T, 448] masked by X > 0.
+  int gru_backward(const float* d_out, Arena& ar, cudaStream_t st, float** dx_out) {
+    GruState& g = gru;
+    const int B = g.B;
+    const long long BT = (long long)B * kGruT, slot = (long long)B * kGruH;
+    float* dgi[2]; float* dgh[2]; float* dh[2][2]; float* dhd[2];
+    for (int d = 0; d < 2; ++d) {
+      dgi[d] = ar.alloc(BT * 3 * kGruH);   // batch-major [B, T, 3H]
+      dgh[d] = ar.alloc(BT * 3 * kGruH);   // step-major  [T][B, 3H]
+      dh[d][0] = ar.alloc(slot);
+      dh[d][1] = ar.alloc(slot);
+      dhd[d] = ar.alloc(slot);
+    }
+    float* dx0 = ar.alloc(BT * kGruI);
+    float* dx = ar.alloc(BT * kGruI);
+    if (!ar.base) { *dx_out = nullptr; return VAR_OK; }
+    if (ar.overflow) return VAR_ERR_WORKSPACE;
+    int rc = split2(d_out, dh[0][0], dh[1][0], B, kGruH, st);
+    if (rc) return rc;
+    for (int s = kGruT - 1; s >= 0; --s) {
+      const int cur = (kGruT - 1 - s) & 1;
+      GruBwdArgs a[2];
+      for (int d = 0; d < 2; ++d) {
+        const int t = d == 0 ? s : kGruT - 1 - s;
+        a[d].dh = dh[d][cur];
+        a[d].gates = g.gates[d] + (long long)s * B * 3 * kGruH;
+        a[d].hn_save = g.hn_save[d] + (long long)s * slot;
+        a[d].hprev = g.h_r[d] + (long long)s * slot;
+        a[d].dgi = dgi[d] + (long long)t * 3 * kGruH;
+        a[d].ldgi = (long long)kGruT * 3 * kGruH;
+        a[d].dgh = dgh[d] + (long long)s * B * 3 * kGruH;
+        a[d].dhd = dhd[d];
+      }
+      rc = gru_cell_bwd(a[0], a[1], 2, B, kGruH, st);
+      if (rc) return rc;
+      if (s > 0) {
+        const float* dy2[2] = {a[0].dgh, a[1].dgh};
+        const float* w2[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
+        float* dx2[2] = {dh[0][cur ^ 1], dh[1][cur ^ 1]};
+        const float* add2[2] = {dhd[0], dhd[1]};
+        rc = linear_dgrad2(2, B, kGruH, 3 * kGruH, dy2, w2, dx2, add2, 0, st);
+        if (rc) return rc;
+      }
+    }
+    for (int d = 0; d < 2; ++d) {
+      // dW_hh += dgh^T h_prev ; db_hh += colsum(dgh)      (rows: step-major)
+      ConvShape chh{(int)BT, 1, 1, kGruH, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
+      rc = conv_wgrad(chh, g.h_r[d], SRC_NHWC_F32, nullptr, dgh[d], gr(t_gru[d][1]), gr(t_gru[d][3]), st);
+      if (rc) return rc;
+      // dW_ih += dgi^T x ; db_ih += colsum(dgi)           (rows: batch-major)
+      ConvShape cih{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
+      rc = conv_wgrad(cih, g.x, SRC_NHWC_F32, nullptr, dgi[d], gr(t_gru[d][0]), gr(t_gru[d][2]), st);
+      if (rc) return rc;
+      // dX = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd, ReLU mask of the conv output
+      rc = conv_dgrad(cih, dgi[d], wr(t_gru[d][0]), d == 0 ? dx0 : dx, d == 0 ? nullptr : g.x,
+                      d == 0 ? nullptr : dx0, d == 0 ? 0 : 1, st);
+      if (rc) return rc;
+    }
+    *dx_out = dx;
+    return VAR_OK;
+  }
+
+  int backward_from_dh(float* dh_img, float* dh_snd, void* ws, long long ws_bytes, cudaStream_t st) {
+    Arena ar(ws, ws_bytes);
+    ar.used = fwd_used;
+    const long long mark = ar.used;
+    if (n_img > 0 && dh_img) {
+      float* d;
+      int rc = run_layers_bwd(img_head, dh_img, ar, st, &d);
+      if (rc) return rc;
+      rc = run_layers_bwd(img_trunk, d, ar, st, &d);
+      if (rc) return rc;
+    }
+    ar.used = mark;  // the two branches reuse the same gradient scratch
+    if (n_snd > 0 && dh_snd) {
+      float* d;
+      int rc = run_layers_bwd(snd_head, dh_snd, ar, st, &d);
+      if (rc) return rc;
+      if (has_gru) {
+        rc = gru_backward(d, ar, st, &d);
+        if (rc) return rc;
+      }
+      rc = run_layers_bwd(snd_trunk, d, ar, st, &d);
+      if (rc) return rc;
+    }
+    return VAR_OK;
+  }
+
+  long long bwd_scratch_bytes(int n_images, int n_sounds) {
+    // dry run with the per-layer shapes of a forward of the same sizes
+    Arena ar(nullptr, 0);
+    long long best = 0;
+    float* d = nullptr;
+    if (n_images > 0) {
+      for (auto& l : img_head) { l.N = n_images; l.in_kind = SRC_NHWC_F32; }
+      for (size_t i = 0; i < img_trunk.size(); ++i) {
+        img_trunk[i].N = n_images;
+        img_trunk[i].in_kind = i == 0 ? SRC_STRIDED_U8 : SRC_NHWC_F32;
+      }
+      run_layers_bwd(img_head, nullptr, ar, 0, &d);
+      run_layers_bwd(img_trunk, nullptr, ar, 0, &d);
+      best = ar.used;
+    }
+    ar.used = 0;
+    if (n_sounds > 0) {
+      for (auto& l : snd_head) { l.N = n_sounds; l.in_kind = SRC_NHWC_F32; }
+      for (size_t i = 0; i < snd_trunk.size(); ++i) {
+        snd_trunk[i].N = n_sounds;
+        snd_trunk[i].in_kind = i == 0 ? SRC_STRIDED_F32 : SRC_NHWC_F32;
+      }
+      run_layers_bwd(snd_head, nullptr, ar, 0, &d);
+      if (has_gru) { gru.B = n_sounds; gru_backward(nullptr, ar, 0, &d); }
+      run_layers_bwd(snd_trunk, nullptr, ar, 0, &d);
+      if (ar.used > best) best = ar.used;
+    }
+    return best;
+  }
+
+  void fill_tail_weights(TailArgs& a, bool grads) const {
+    a.D = D; a.Kh_img = Kh_img; a.Kh_snd = Kh_snd;
+    a.W_img = wm(t_tail_img_w); a.b_img = wm(t_tail_img_b);
+    a.W_snd = wm(t_tail_snd_w); a.b_snd = wm(t_tail_snd_b);
+    if (grads) {
+      a.dW_img = gr(t_tail_img_w); a.db_img = gr(t_tail_img_b);
+      a.dW_snd = gr(t_tail_snd_w); a.db_snd = gr(t_tail_snd_b);
+    }
+  }
+};
+
+}  // namespace var
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using var::Net;
+using var::TailArgs;
+
+#define NET(p) (reinterpret_cast<Net*>(p))
+#define ST(s) (reinterpret_cast<cudaStream_t>(s))
+
+extern "C" {
+
+int var_net_create(int kind, int sound_frames, int rep_dim, void** out) {
+  if (!out || rep_dim < 1 || rep_dim > 8) return VAR_ERR_ARG;
+  Net* n = new Net();
+  n->kind = kind; n->F = sound_frames; n->D = rep_dim;
+  const int rc = n->build();
+  if (rc) { delete n; return rc; }
+  *out = n;
+  return VAR_OK;
+}
+int var_net_destroy(void* net) { delete NET(net); return VAR_OK; }
+int64_t var_net_param_floats(void* net) { return NET(net)->nparams; }
+int var_net_num_tensors(void* net) { return (int)NET(net)->tensors.size(); }
+int var_net_tensor_info(void* net, int index, char* name, int name_cap, int* ndim, int* shape,
+                        int64_t* offset, int64_t* packed_floats) {
+  Net* n = NET(net);
+  if (index < 0 || index >= (int)n->tensors.size()) return VAR_ERR_ARG;
+  const auto& t = n->tensors[index];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", t.name.c_str());
+  if (ndim) *ndim = t.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = t.shape[i];
+  if (offset) *offset = t.off;
+  if (packed_floats) *packed_floats = t.packed;
+  return VAR_OK;
+}
+int var_net_bind(void* net, float* p, float* pr, float* g) {
+  Net* n = NET(net);
+  n->P = p; n->PR = pr; n->G = g;
+  return VAR_OK;
+}
+int var_net_load_tensor(void* net, int index, const float* src, void* stream) {
+  Net* n = NET(net);
+  if (index < 0 || index >= (int)n->tensors.size() || !n->P || !n->PR) return VAR_ERR_ARG;
+  const auto& t = n->tensors[index];
+  return var::pack_weight(src, n->P + t.off, n->PR + t.off, t.O, t.I, t.R, t.S, t.kpad, ST(stream));
+}
+int var_net_store_tensor(void* net, int index, int which, float* dst, void* stream) {
+  Net* n = NET(net);
+  if (index < 0 || index >= (int)n->tensors.size()) return VAR_ERR_ARG;
+  const float* src = which == 0 ? n->P : n->G;
+  if (!src) return VAR_ERR_ARG;
+  const auto& t = n->tensors[index];
+  return var::unpack_weight(src + t.off, dst, t.O, t.I, t.R, t.S, t.kpad, ST(stream));
+}
+int var_net_refresh_mma(void* net, void* stream) {
+  Net* n = NET(net);
+  if (!n->P || !n->PR) return VAR_ERR_ARG;
+  return var::round_copy(n->P, n->PR, n->nparams, ST(stream));
+}
+int var_net_raw_dims(void* net, int* img_raw, int* snd_raw) {
+  if (img_raw) *img_raw = NET(net)->img_raw_dim;
+  if (snd_raw) *snd_raw = NET(net)->snd_raw_dim;
+  return VAR_OK;
+}
+int64_t var_net_workspace_bytes(void* net, int n_images, int n_sounds, int train) {
+  Net* n = NET(net);
+  int rc = n->forward(nullptr, 0, n_images, nullptr, n_sounds, nullptr, 0, train != 0, 0);
+  if (rc) return rc;
+  long long total = n->fwd_used;
+  // tail scratch: feats / dh buffers
+  total += 4096 + (long long)(n_images + n_sounds) * (n->Kh_img + n->Kh_snd + 64) * 4;
+  if (train) total += n->bwd_scratch_bytes(n_images, n_sounds);
+  return total + 4096;
+}
+
+int var_net_forward(void* net, const void* images, int image_kind, int n_images, const float* sounds,
+                    int n_sounds, void* ws, int64_t ws_bytes, int train, float* img_feat,
+                    float* img_raw, float* snd_feat, float* snd_raw, void* stream) {
+  Net* n = NET(net);
+  if (!n->P || !n->PR || !ws) return VAR_ERR_ARG;
+  cudaStream_t st = ST(stream);
+  int rc = n->forward(images, image_kind, n_images, sounds, n_sounds, ws, ws_bytes, train != 0, st);
+  if (rc) return rc;
+  if (n_images > 0 && img_feat) {
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    n->fill_tail_weights(a, false);
+    a.mode = var::TAIL_FWD; a.B = n_images; a.h_img = n->h_img; a.feat_img = img_feat;
+    rc = var::tail_launch(a, st);
+    if (rc) return rc;
+  }
+  if (n_sounds > 0 && snd_feat) {
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    n->fill_tail_weights(a, false);
+    a.mode = var::TAIL_FWD; a.B = n_sounds; a.h_pos = n->h_snd; a.feat_pos = snd_feat;
+    rc = var::tail_launch(a, st);
+    if (rc) return rc;
+  }
+  if (n_images > 0 && img_raw) {
+    const var::Layer& l = n->img_trunk.back();
+    rc = var::nhwc_to_nchw(n->img_raw_nhwc, img_raw, n_images, l.P * l.Q, l.Cout, st);
+    if (rc) return rc;
+  }
+  if (n_sounds > 0 && snd_raw) {
+    if (n->has_gru) {
+      if (cudaMemcpyAsync(snd_raw, n->snd_raw, (size_t)n_sounds * n->snd_raw_dim * 4,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return VAR_ERR_CUDA;
+    } else {
+      const var::Layer& l = n->snd_trunk.back();
+      rc = var::nhwc_to_nchw(n->snd_raw, snd_raw, n_sounds, l.P * l.Q, l.Cout, st);
+      if (rc) return rc;
+    }
+  }
+  return VAR_OK;
+}
+
+int var_net_backward(void* net, const float* img_dfeat, const float* snd_dfeat, void* ws,
+                     int64_t ws_bytes, void* stream) {
+  Net* n = NET(net);
+  if (!n->G || !ws) return VAR_ERR_ARG;
+  cudaStream_t st = ST(stream);
+  var::Arena ar(ws, ws_bytes);
+  ar.used = n->fwd_used;
+  float* dh_img = (n->n_img > 0 && img_dfeat) ? ar.alloc((long long)n->n_img * n->Kh_img) : nullptr;
+  float* dh_snd = (n->n_snd > 0 && snd_dfeat) ? ar.alloc((long long)n->n_snd * n->Kh_snd) : nullptr;
+  if (ar.overflow) return VAR_ERR_WORKSPACE;
+  int rc;
+  if (dh_img) {
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    n->fill_tail_weights(a, true);
+    a.dW_snd = nullptr; a.db_snd = nullptr;
+    a.mode = var::TAIL_BWD; a.B = n->n_img; a.h_img = n->h_img; a.dfeat_img = img_dfeat;
+    a.dh_img = dh_img;
+    rc = var::tail_launch(a, st);
+    if (rc) return rc;
+  }
+  if (dh_snd) {
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    n->fill_tail_weights(a, true);
+    a.dW_img = nullptr; a.db_img = nullptr;
+    a.mode = var::TAIL_BWD; a.B = n->n_snd; a.h_pos = n->h_snd; a.dfeat_pos = snd_dfeat;
+    a.dh_pos = dh_snd;
+    rc = var::tail_launch(a, st);
+    if (rc) return rc;
+  }
+  const long long keep = n->fwd_used;
+  n->fwd_used = ar.used;
+  rc = n->backward_from_dh(dh_img, dh_snd, ws, ws_bytes, st);
+  n->fwd_used = keep;
+  return rc;
+}
+
+int var_net_triplet_step(void* net, const void* images, int image_kind, const float* sounds, int B,
+                         float margin, float loss_denominator, void* ws, int64_t ws_bytes,
+                         float* loss, float* feats, void* stream) {
+  Net* n = NET(net);
+  if (!n->P || !n->PR || !n->G || !ws || B <= 0 || !loss) return VAR_ERR_ARG;
+  cudaStream_t st = ST(stream);
+  int rc = n->forward(images, image_kind, B, sounds, 2 * B, ws, ws_bytes, true, st);
+  if (rc) return rc;
+  var::Arena ar(ws, ws_bytes);
+  ar.used = n->fwd_used;
+  float* dh_img = ar.alloc((long long)B * n->Kh_img);
+  float* dh_snd = ar.alloc((long long)2 * B * n->Kh_snd);
+  if (ar.overflow) return VAR_ERR_WORKSPACE;
+  TailArgs a;
+  memset(&a, 0, sizeof(a));
+  n->fill_tail_weights(a, true);
+  a.mode = var::TAIL_TRIPLET; a.B = B;
+  a.h_img = n->h_img; a.h_pos = n->h_snd; a.h_neg = n->h_snd + (long long)B * n->Kh_snd;
+  a.margin = margin; a.grad_scale = 1.f / loss_denominator; a.loss_scale = 1.f / loss_denominator;
+  a.loss = loss;
+  if (feats) {
+    a.feat_img = feats; a.feat_pos = feats + (long long)B * n->D;
+    a.feat_neg = feats + (long long)2 * B * n->D;
+  }
+  a.dh_img = dh_img; a.dh_pos = dh_snd; a.dh_neg = dh_snd + (long long)B * n->Kh_snd;
+  rc = var::tail_launch(a, st);
+  if (rc) return rc;
+  const long long keep = n->fwd_used;
+  n->fwd_used = ar.used;
+  rc = n->backward_from_dh(dh_img, dh_snd, ws, ws_bytes, st);
+  n->fwd_used = keep;
+  return rc;
+}
+
+int var_net_reward(void* net, const void* images, int image_kind, const float* goal_sounds,
+                   const float* goal_feat_cached, const float* env_reward, int N, void* ws,
+                   int64_t ws_bytes, float* img_feat, float* goal_feat, float* dot, float* reward,
+                   void* stream) {
+  Net* n = NET(net);
+  if (!n->P || !n->PR || !ws || N <= 0 || (!goal_sounds && !goal_feat_cached)) return VAR_ERR_ARG;
+  cudaStream_t st = ST(stream);
+  int rc = n->forward(images, image_kind, N, goal_sounds, goal_sounds ? N : 0, ws, ws_bytes, false, st);
+  if (rc) return rc;
+  TailArgs a;
+  memset(&a, 0, sizeof(a));
+  n->fill_tail_weights(a, false);
+  a.mode = var::TAIL_REWARD; a.B = N;
+  a.h_img = n->h_img; a.h_pos = goal_sounds ? n->h_snd : nullptr;
+  a.goal_feat_in = goal_feat_cached;
+  a.feat_img = img_feat; a.feat_pos = goal_sounds ? goal_feat : nullptr;
+  a.env_reward = env_reward; a.dot_out = dot; a.reward_out = reward;
+  rc = var::tail_launch(a, st);
+  if (rc) return rc;
+  if (!goal_sounds && goal_feat && goal_feat != goal_feat_cached) {
+    if (cudaMemcpyAsync(goal_feat, goal_feat_cached, (size_t)N * n->D * 4, cudaMemcpyDeviceToDevice,
+                        st) != cudaSuccess)
+      return VAR_ERR_CUDA;
+  }
+  return VAR_OK;
+}
+
+}  // extern "C"

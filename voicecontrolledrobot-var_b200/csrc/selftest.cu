@@ -195,7 +195,7 @@ static void run_case(const Case& c, bool do_fwd, bool do_dgrad, bool do_wgrad) {
     CK(cudaMemset(gx_out, 0xFF, nx * 4));
     const float* mask = reinterpret_cast<const float*>(dx_in);
     ref_dgrad<<<(unsigned)((nx + 255) / 256), 256>>>(cs, dgy, dw, kpad, gx_ref, mask);
-    int rc = conv_dgrad(cs, dgy, dw, gx_out, mask, 0, 0);
+    int rc = conv_dgrad(cs, dgy, dw, gx_out, mask, nullptr, 0, 0);
     if (rc) { printf("  conv_dgrad rc=%d %s\n", rc, var_last_error()); ++nfail; }
     CK(cudaDeviceSynchronize());
     double e = max_abs_diff(gx_out, gx_ref, nx, &ref);
@@ -291,7 +291,7 @@ int main(int argc, char** argv) {
         const char* nm = pass == 0 ? "fwd" : pass == 1 ? "dgrad" : "wgrad";
         for (int i = 0; i < 3; ++i) {
           if (pass == 0) conv_fwd(cs, x, SRC_NHWC_F32, nullptr, w, b, y, 1, 1, 0);
-          else if (pass == 1) conv_dgrad(cs, y, w, gx, x, 1, 0);
+          else if (pass == 1) conv_dgrad(cs, y, w, gx, x, nullptr, 1, 0);
           else conv_wgrad(cs, x, SRC_NHWC_F32, nullptr, y, gw, nullptr, 0);
         }
         CK(cudaDeviceSynchronize());
@@ -299,7 +299,7 @@ int main(int argc, char** argv) {
         const int iters = 10;
         for (int i = 0; i < iters; ++i) {
           if (pass == 0) conv_fwd(cs, x, SRC_NHWC_F32, nullptr, w, b, y, 1, 1, 0);
-          else if (pass == 1) conv_dgrad(cs, y, w, gx, x, 1, 0);
+          else if (pass == 1) conv_dgrad(cs, y, w, gx, x, nullptr, 1, 0);
           else conv_wgrad(cs, x, SRC_NHWC_F32, nullptr, y, gw, nullptr, 0);
         }
         cudaEventRecord(e1);

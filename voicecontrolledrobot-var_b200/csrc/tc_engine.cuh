@@ -65,6 +65,7 @@ struct GruEpiParams {
   const float* bhh;     // [3H]
   const float* hprev;   // [B, H]
   float* hnew;          // [B, H]
+  float* hnew_r;        // [B, H] tf32-rounded copy (next step's MMA operand; nullptr = skip)
   float* gates;         // [B, 3H] saved r, z, n for backward (nullptr = inference)
   float* hn_save;       // [B, H] saved (W_hn h + b_hn) for backward (nullptr = inference)
   int Hdim;
@@ -359,6 +360,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
               hh[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp_[u];
             }
             *reinterpret_cast<float4*>(hn + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            if (q.hnew_r)
+              *reinterpret_cast<float4*>(q.hnew_r + (long long)m * Hd + j0 + j) = make_float4(
+                  round_tf32(hh[0]), round_tf32(hh[1]), round_tf32(hh[2]), round_tf32(hh[3]));
             if (q.gates) {
               float* gs = q.gates + (long long)m * 3 * Hd + j0 + j;
               *reinterpret_cast<float4*>(gs) = make_float4(rr[0], rr[1], rr[2], rr[3]);
@@ -539,12 +543,12 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
               st_shared_v4(tA + swz(row, c), v[0], v[1], v[2], v[3]);
             }
           }
-          // ---- B' (dY) groups
-          if (grp < bgroups) {
-            const uint32_t tB = sB + (uint32_t)st_issue * tileB_bytes + (uint32_t)grp * 4096u;
+          // ---- B' (dY) groups: 32 output channels each, 4 producer warps share them
+          for (int bg = grp; bg < bgroups; bg += 4) {
+            const uint32_t tB = sB + (uint32_t)st_issue * tileB_bytes + (uint32_t)bg * 4096u;
             const float* src = p.dy;
-            const int cvalid = p.cout - grp * 32;  // may be < 32 (cout = 16 mult)
-            if (mv) src += (long long)m * p.ldy + grp * 32;
+            const int cvalid = p.cout - bg * 32;  // may be < 32 (cout = 16 mult)
+            if (mv) src += (long long)m * p.ldy + bg * 32;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const bool ok = mv && (c * 4 < cvalid);

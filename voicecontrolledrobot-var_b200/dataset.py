@@ -1,0 +1,245 @@
+"""Host mirror of dataset.py (VARDataset, VARFineTuneDataset, loadEnvData) with the triplet
+assembly on the GPU.
+
+The reference builds every triplet on the CPU inside `Dataset.__getitem__` (integer draws on
+torch's global generator, then a per-clip MFCC).  Here the pickled triplet records are
+uploaded once (uint8 images, labels), every clip lives in a device arena, and one batch is
+assembled by two launches: `var_sampler_batch` (bit-exact index draws) and `var_mfcc_fwd`
+(features of the 2B selected clips).  `loadEnvData` keeps the reference signature and returns
+`(generator, final_dataset)`; the generator yields the reference's
+`(image, sound_positive, sound_negative, gt)` tuples, already on the device.
+
+Pybullet/Kuka sampling (intent -> dataset -> clip, audioLoader.py:166-177) is covered by the
+device sampler; the iTHOR synonym-table draw (audioLoader.py:223-237) needs the simulator's
+task tables and is out of this path's scope.
+"""
+import glob
+import os
+import pickle
+
+import numpy as np
+import torch
+from torch.utils.data.dataset import ConcatDataset, Dataset
+
+from ._lib import check, lib, ptr, stream_ptr
+from .Envs.audioLoader import audioLoader, mfcc_device
+
+
+class DeviceTripletSampler:
+    """Device-resident mt19937 + the tables of one triplet dataset (see var_sampler_* in
+    include/var_b200.h).  Consumes the stream exactly like torch's global CPU generator does in
+    the reference's `for batch in DataLoader(shuffle=True, num_workers=0)` loop."""
+
+    def __init__(self, task_num, dataset_sizes, gt, stored_sn=None, seed=0, device=None, clip_off=None,
+                 clip_len=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceTripletSampler needs CUDA; there is no CPU fallback")
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        self.task_num = int(task_num)
+        i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=self.device)
+        self.max_ds = max(1, max(len(s) for s in dataset_sizes))
+        nds = [len(s) for s in dataset_sizes]
+        if min(nds) < 1 or any(c < 1 for s in dataset_sizes for c in s):
+            raise ValueError("every intent needs at least one dataset with at least one clip")
+        nclips = np.zeros((self.task_num, self.max_ds), np.int32)
+        base = np.zeros((self.task_num, self.max_ds), np.int32)
+        cur = 0
+        for i, s in enumerate(dataset_sizes):
+            for j, c in enumerate(s):
+                nclips[i, j] = c
+                base[i, j] = cur
+                cur += c
+        self.n_clips = cur
+        self.nds, self.nclips, self.clip_base = i32(nds), i32(nclips), i32(base)
+        self.clip_off = clip_off if clip_off is not None else torch.zeros(cur, dtype=torch.int64, device=self.device)
+        self.clip_len = clip_len if clip_len is not None else torch.zeros(cur, dtype=torch.int32, device=self.device)
+        self.gt = i32(gt)
+        self.n_items = int(self.gt.numel())
+        self.stored_sn = i32(stored_sn) if stored_sn is not None else None
+        self.state = torch.zeros(625, dtype=torch.int32, device=self.device)
+        self.seed(seed)
+        self.perm = torch.empty(self.n_items, dtype=torch.int32, device=self.device)
+
+    def seed(self, seed):
+        check(lib.var_sampler_seed(ptr(self.state), int(seed) & 0xFFFFFFFFFFFFFFFF, stream_ptr()), "var_sampler_seed")
+
+    def begin_epoch(self):
+        """DataLoader iterator creation + RandomSampler permutation -> int32 [n_items] on device."""
+        check(lib.var_sampler_epoch(ptr(self.state), self.n_items, ptr(self.perm), stream_ptr()), "var_sampler_epoch")
+        return self.perm
+
+    def sample(self, items):
+        """items: int32 device tensor of dataset indices (a slice of the epoch permutation)."""
+        B = int(items.numel())
+        dev = self.device
+        out = {"item": torch.empty(B, dtype=torch.int32, device=dev),
+               "gt": torch.empty(B, dtype=torch.int32, device=dev),
+               "sn": torch.empty(B, dtype=torch.int32, device=dev),
+               "rec": torch.empty(B, 6, dtype=torch.int32, device=dev),
+               "off": torch.empty(2 * B, dtype=torch.int64, device=dev),
+               "len": torch.empty(2 * B, dtype=torch.int32, device=dev)}
+        scratch = torch.empty(B, dtype=torch.int32, device=dev)
+        items = items.contiguous()
+        check(lib.var_sampler_batch(ptr(self.state), B, self.task_num, ptr(items), ptr(self.gt), ptr(self.stored_sn),
+                                    ptr(self.nds), ptr(self.nclips), ptr(self.clip_base), self.max_ds,
+                                    ptr(self.clip_off), ptr(self.clip_len), ptr(scratch), ptr(out["item"]),
+                                    ptr(out["gt"]), ptr(out["sn"]), ptr(out["rec"]), ptr(out["off"]), ptr(out["len"]),
+                                    stream_ptr()), "var_sampler_batch")
+        out["_keep"] = (scratch, items)
+        return out
+
+
+class VARDataset(Dataset):
+    """Same constructor / fields as dataset.py:10-32: `ground_truth_pair` is the pickled list of
+    {'image': u8[3,96,96], 'ground_truth': int[, 'sound_negative_id': int]} records."""
+
+    def __init__(self, picklePath, config, **kwargs):
+        self.filePath = picklePath
+        self.config = config
+        with open(self.filePath, 'rb') as f:
+            self.ground_truth_pair = pickle.load(f)
+        self.audio = kwargs['audio']
+        if config.name == 'AI2ThorConfig':
+            raise NotImplementedError("iTHOR task-table sampling needs the simulator package (out of scope)")
+
+    def __len__(self):
+        return len(self.ground_truth_pair)
+
+    def _draw_sn(self, item, gt):
+        if 'sound_negative_id' in item:
+            return int(item['sound_negative_id'])
+        sn_id = torch.randint(low=0, high=self.config.taskNum, size=()).item()  # dataset.py:76
+        return self.config.taskNum if gt == sn_id else sn_id
+
+    def getImgSoundPair(self, gt, sn_id):
+        """dataset.py:34-62 for the pybullet config; features come from the GPU MFCC kernel."""
+        T = self.config.taskNum
+        zeros = lambda: np.zeros(shape=self.config.sound_dim)
+        feat = lambda i: self.audio.genSoundFeat(intentIdx=i, featType='MFCC', rand_fn=torch.randint)[0]
+        if gt == T:
+            return zeros(), feat(sn_id)
+        pos = feat(gt)
+        return pos, (zeros() if sn_id == T else feat(sn_id))
+
+    def __getitem__(self, index):
+        item = self.ground_truth_pair[index]
+        image = (torch.from_numpy(item['image']) / 255.).float()
+        gt = int(item['ground_truth'])
+        if 'sound_negative' not in item:
+            sp, sn = self.getImgSoundPair(gt, self._draw_sn(item, gt))
+        else:
+            sp, sn = item['sound_positive'], item['sound_negative']
+        return image, sp, sn, gt
+
+
+class VARFineTuneDataset(VARDataset):
+    """dataset.py:94-133: the image-sound association is drawn once, at construction."""
+
+    def __init__(self, picklePath, config, **kwargs):
+        VARDataset.__init__(self, picklePath, config, **kwargs)
+        for item in self.ground_truth_pair:
+            if 'sound_negative' in item:
+                continue
+            gt = int(item['ground_truth'])
+            item['sound_positive'], item['sound_negative'] = self.getImgSoundPair(gt, self._draw_sn(item, gt))
+
+    def __getitem__(self, index):
+        item = self.ground_truth_pair[index]
+        image = (torch.from_numpy(item['image']) / 255.).float()
+        return image, item['sound_positive'], item['sound_negative'], int(item['ground_truth'])
+
+
+class DeviceTripletLoader:
+    """Iterable replacing `DataLoader(ConcatDataset, batch_size, shuffle=True, num_workers=0)` for
+    VARDataset records: device-resident images / labels / clips, batches assembled by
+    var_sampler_batch + var_mfcc_fwd.  Yields the reference tuples; `raw_batches()` yields the
+    uint8 / [2B, F, 40] form the fused trainer consumes (rank-sliced under data parallelism)."""
+
+    def __init__(self, images_u8, gt, stored_sn, audio, arena, config, batch_size, shuffle=True, drop_last=False,
+                 seed=None, device=None, rank=0, world_size=1):
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        self.config, self.audio, self.arena = config, audio, arena
+        self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
+        self.rank, self.world_size = rank, world_size
+        self.images = torch.as_tensor(images_u8, dtype=torch.uint8).to(self.device).contiguous()
+        self.n_items = self.images.shape[0]
+        # one STFT parameter set per loader: the reference picks it per drawn dataset
+        # (audioLoader.py:183); mixing NSynth/UrbanSound (1024-point) with the 512-point sets in
+        # ONE intent table would need two plans per batch and is rejected here.
+        names = sorted({n for row in arena.dataset_names for n in row})
+        params = {audio.param_dict[n] for n in names}
+        if len(params) != 1:
+            raise NotImplementedError(f"datasets {names} mix STFT parameter sets")
+        self.param = params.pop()
+        if seed is None:
+            seed = torch.initial_seed()
+        self.sampler = DeviceTripletSampler(config.taskNum, arena.dataset_sizes, gt, stored_sn, seed, self.device,
+                                            arena.clip_off, arena.clip_len)
+
+    def __len__(self):
+        n = self.n_items // self.batch_size
+        return n if (self.drop_last or self.n_items % self.batch_size == 0) else n + 1
+
+    def raw_batches(self):
+        n, bs = self.n_items, self.batch_size
+        if self.shuffle:
+            perm = self.sampler.begin_epoch()
+        else:
+            perm = torch.arange(n, dtype=torch.int32, device=self.device)
+        n_fft, win, hop = self.audio.stft_params(self.param)
+        F = self.config.sound_dim[1]
+        for s in range(0, n, bs):
+            items = perm[s:s + bs]
+            B = int(items.numel())
+            if B < bs and self.drop_last:
+                break
+            rec = self.sampler.sample(items)  # every rank draws the GLOBAL batch: identical streams
+            lo, hi = (B * self.rank) // self.world_size, (B * (self.rank + 1)) // self.world_size
+            idx = rec["item"][lo:hi].long()
+            off = torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]])
+            ln = torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]])
+            sounds = mfcc_device(self.arena.wav, off, ln, self.audio.fs, n_fft, win, hop, F)
+            yield self.images[idx], sounds, rec["gt"][lo:hi], B, rec
+
+    def __iter__(self):
+        for img_u8, sounds, gt, _, _ in self.raw_batches():
+            b = img_u8.shape[0]
+            F = sounds.shape[1]
+            yield ((img_u8.float() / 255.), sounds[:b].view(b, 1, F, 40), sounds[b:].view(b, 1, F, 40), gt.long())
+
+
+def loadEnvData(data_dir, config, batch_size, shuffle, num_workers, drop_last, loadNum=None,
+                dtype=VARDataset, train_test='train'):
+    """dataset.py:136-168.  `num_workers` is accepted and ignored: batches are assembled on the
+    device, in the draw order the reference has with num_workers=0."""
+    audio = audioLoader(config=config)
+    audio.loadData()
+    all_datasets = []
+    for i, dirs in enumerate(data_dir):
+        assert os.path.exists(dirs)
+        path = os.path.join(dirs, train_test)
+        fileList = glob.glob(os.path.join(path, '*.pickle'))
+        if not (loadNum is None or loadNum[i] == 'all') and len(fileList) > int(loadNum[i]):
+            fileList = np.random.choice(fileList, size=int(loadNum[i]))
+        for filePath in fileList:
+            all_datasets.append(dtype(picklePath=str(filePath), config=config, audio=audio))
+    final_dataset = ConcatDataset(all_datasets)
+    records = [p for d in final_dataset.datasets for p in d.ground_truth_pair]
+    num = [0] * (config.taskNum + 1)
+    for p in records:
+        num[int(p['ground_truth'])] += 1
+    if dtype is VARFineTuneDataset or any('sound_negative' in p for p in records):
+        # features are fixed per record (dataset.py:94-133): plain tensors, no sampling left
+        generator = torch.utils.data.DataLoader(final_dataset, batch_size=batch_size, shuffle=shuffle, num_workers=0,
+                                                pin_memory=True, drop_last=drop_last)
+    else:
+        images = np.stack([np.asarray(p['image'], dtype=np.uint8)[:3] for p in records])
+        gt = [int(p['ground_truth']) for p in records]
+        has_sn = ['sound_negative_id' in p for p in records]
+        if any(has_sn) and not all(has_sn):
+            raise ValueError("records mix stored and drawn sound_negative_id")
+        stored = [int(p['sound_negative_id']) for p in records] if all(has_sn) else None
+        generator = DeviceTripletLoader(images, gt, stored, audio, audio.build_arena(), config, batch_size,
+                                        shuffle=shuffle, drop_last=drop_last)
+    print("The number of pairs for each object in the dataset is:", num)
+    return generator, final_dataset

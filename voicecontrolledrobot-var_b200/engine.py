@@ -1,0 +1,192 @@
+"""Host-side owner of one VAR encoder pair on one GPU.
+
+`VarEngine` wraps a `var_net_*` object of libvar_b200.so: it owns the flat packed
+parameter / tf32-operand / gradient / Adam buffers and the activation workspace (torch
+tensors used purely as device memory), converts to and from the reference `state_dict`
+layout (models/pretext/*.py), and exposes the four calls the hot path needs:
+forward, backward, the fused triplet step (VAR/pretext_VAR.py:56-69) and the batched
+reward query (Envs/vec_env/vec_pretext_normalize.py:82-101).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+KUKA, ITHOR = 0, 1
+
+
+class VarEngine:
+    def __init__(self, kind, sound_frames, rep_dim=3, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("VarEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.kind, self.F, self.D = kind, sound_frames, rep_dim
+        h = C.c_void_p()
+        check(lib.var_net_create(kind, sound_frames, rep_dim, C.byref(h)), "var_net_create")
+        self._net = h
+        self.nparams = int(lib.var_net_param_floats(h))
+        z = lambda: torch.zeros(self.nparams, dtype=torch.float32, device=self.device)
+        self.params, self.params_mma, self.grads = z(), z(), z()
+        self.adam_m = self.adam_v = None
+        self.adam_steps = 0
+        check(lib.var_net_bind(h, ptr(self.params), ptr(self.params_mma), ptr(self.grads)), "var_net_bind")
+        self.tensors = []  # (name, shape, offset, packed)
+        name = C.create_string_buffer(128)
+        nd, shp, off, pk = C.c_int(), (C.c_int * 4)(), C.c_int64(), C.c_int64()
+        for i in range(lib.var_net_num_tensors(h)):
+            check(lib.var_net_tensor_info(h, i, name, 128, C.byref(nd), shp, C.byref(off), C.byref(pk)),
+                  "var_net_tensor_info")
+            self.tensors.append((name.value.decode(), tuple(shp[:nd.value]), off.value, pk.value))
+        self.index = {t[0]: i for i, t in enumerate(self.tensors)}
+        ir, sr = C.c_int(), C.c_int()
+        lib.var_net_raw_dims(h, C.byref(ir), C.byref(sr))
+        self.img_raw_dim, self.snd_raw_dim = ir.value, sr.value
+        self._ws = None
+        self._ws_need = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_net", None):
+                lib.var_net_destroy(self._net)
+                self._net = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd):
+        """reference-layout tensors (any device) -> packed master + tf32 copy."""
+        missing = [t[0] for t in self.tensors if t[0] not in sd]
+        if missing:
+            raise KeyError(f"state_dict is missing {missing}")
+        st = stream_ptr()
+        keep = []
+        for i, (name, shape, _, _) in enumerate(self.tensors):
+            src = sd[name].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(src.shape) != shape:
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(src.shape)}")
+            keep.append(src)
+            check(lib.var_net_load_tensor(self._net, i, ptr(src), st), f"var_net_load_tensor({name})")
+        torch.cuda.current_stream().synchronize()  # sources may be freed after return
+
+    def _store(self, which):
+        out = {}
+        st = stream_ptr()
+        for i, (name, shape, _, _) in enumerate(self.tensors):
+            dst = torch.empty(shape, dtype=torch.float32, device=self.device)
+            check(lib.var_net_store_tensor(self._net, i, which, ptr(dst), st), f"var_net_store_tensor({name})")
+            out[name] = dst
+        return out
+
+    def state_dict(self):
+        return self._store(0)
+
+    def grad_dict(self):
+        return self._store(1)
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    # ------------------------------------------------------------------- workspace
+    def _workspace(self, n_img, n_snd, train):
+        key = (n_img, n_snd, bool(train))
+        need = self._ws_need.get(key)
+        if need is None:
+            need = int(lib.var_net_workspace_bytes(self._net, n_img, n_snd, 1 if train else 0))
+            check(need, "var_net_workspace_bytes")
+            self._ws_need[key] = need
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _image_kind(images):
+        if images.dtype == torch.uint8:
+            return 0
+        if images.dtype == torch.float32:
+            return 1
+        raise TypeError(f"images must be uint8 or float32, got {images.dtype}")
+
+    def _check_inputs(self, images, sounds):
+        if images is not None:
+            if not images.is_cuda or not images.is_contiguous() or tuple(images.shape[1:]) != (3, 96, 96):
+                raise ValueError("images must be a contiguous CUDA tensor [N, 3, 96, 96]")
+        if sounds is not None:
+            if (not sounds.is_cuda or not sounds.is_contiguous() or sounds.dtype != torch.float32
+                    or tuple(sounds.shape[-2:]) != (self.F, 40)):
+                raise ValueError(f"sounds must be a contiguous CUDA float32 tensor [N, (1,) {self.F}, 40]")
+
+    # --------------------------------------------------------------------- compute
+    def forward(self, images, sounds, train=False, want_raw=True):
+        """-> (img_feat [Ni, D], img_raw [Ni, raw], snd_feat [Ns, D], snd_raw [Ns, raw]); None where absent."""
+        self._check_inputs(images, sounds)
+        ni = 0 if images is None else images.shape[0]
+        ns = 0 if sounds is None else sounds.shape[0]
+        ws = self._workspace(ni, ns, train)
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        img_feat = e(ni, self.D) if ni else None
+        snd_feat = e(ns, self.D) if ns else None
+        img_raw = e(ni, self.img_raw_dim) if (ni and want_raw) else None
+        snd_raw = e(ns, self.snd_raw_dim) if (ns and want_raw) else None
+        check(lib.var_net_forward(self._net, ptr(images), self._image_kind(images) if ni else 0, ni, ptr(sounds),
+                                  ns, ptr(ws), ws.numel(), 1 if train else 0, ptr(img_feat), ptr(img_raw),
+                                  ptr(snd_feat), ptr(snd_raw), stream_ptr()), "var_net_forward")
+        return img_feat, img_raw, snd_feat, snd_raw
+
+    def backward(self, d_img_feat, d_snd_feat):
+        """Backward of the last forward(train=True); accumulates into self.grads."""
+        ws = self._ws
+        if ws is None:
+            raise RuntimeError("backward() before forward(train=True)")
+        for d in (d_img_feat, d_snd_feat):
+            if d is not None and (not d.is_cuda or not d.is_contiguous() or d.dtype != torch.float32):
+                raise ValueError("gradients must be contiguous CUDA float32 tensors")
+        check(lib.var_net_backward(self._net, ptr(d_img_feat), ptr(d_snd_feat), ptr(ws), ws.numel(), stream_ptr()),
+              "var_net_backward")
+
+    def triplet_step(self, images, sounds, margin=1.0, loss_denominator=None, loss_out=None, feats_out=None):
+        """Forward + fused triplet loss + backward for B images and 2B sounds (positives, then
+        negatives).  Gradients accumulate into self.grads; returns the device scalar that received
+        sum(hinge) / loss_denominator."""
+        self._check_inputs(images, sounds)
+        B = images.shape[0]
+        if sounds.shape[0] != 2 * B:
+            raise ValueError("sounds must hold B positives followed by B negatives")
+        ws = self._workspace(B, 2 * B, True)
+        if loss_out is None:
+            loss_out = torch.zeros((), dtype=torch.float32, device=self.device)
+        denom = float(B if loss_denominator is None else loss_denominator)
+        check(lib.var_net_triplet_step(self._net, ptr(images), self._image_kind(images), ptr(sounds), B,
+                                       float(margin), denom, ptr(ws), ws.numel(), ptr(loss_out), ptr(feats_out),
+                                       stream_ptr()), "var_net_triplet_step")
+        return loss_out
+
+    def reward(self, images, goal_sounds=None, goal_feat_cached=None, env_reward=None):
+        """-> (img_feat [N, D], goal_feat [N, D], img_sound_dot [N], reward [N])."""
+        self._check_inputs(images, goal_sounds)
+        N = images.shape[0]
+        ws = self._workspace(N, N if goal_sounds is not None else 0, False)
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        img_feat, goal_feat, dot, rew = e(N, self.D), e(N, self.D), e(N), e(N)
+        check(lib.var_net_reward(self._net, ptr(images), self._image_kind(images), ptr(goal_sounds),
+                                 ptr(goal_feat_cached), ptr(env_reward), N, ptr(ws), ws.numel(), ptr(img_feat),
+                                 ptr(goal_feat), ptr(dot), ptr(rew), stream_ptr()), "var_net_reward")
+        return img_feat, goal_feat, dot, rew
+
+    def adam_step(self, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+        self.adam_steps += 1
+        check(lib.var_adam_step(ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v),
+                                ptr(self.params_mma), self.nparams, float(lr), float(betas[0]), float(betas[1]),
+                                float(eps), float(weight_decay), self.adam_steps, float(grad_scale), stream_ptr()),
+              "var_adam_step")
+
+
+def multistep_lr(base_lr, epoch, milestones, gamma):
+    """MultiStepLR as built by utils.get_scheduler (utils.py:42-46), stepped once per epoch
+    (VAR/pretext_VAR.py:72-73): LR in effect during `epoch`."""
+    return base_lr * math.pow(gamma, sum(1 for m in milestones if epoch >= m))
