@@ -163,6 +163,18 @@ int var_triplet_fwd_bwd(const float* d_h_img, const float* d_h_pos, const float*
                         float* d_dh_img, float* d_dh_pos, float* d_dh_neg, float* d_dW_img,
                         float* d_db_img, float* d_dW_snd, float* d_db_snd, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Launch accounting (bench.py): number of kernels this library has launched so far, and a
+ * per-kernel-family CUDA-event profiler (events recorded on the launching stream).
+ * var_prof_end fills arrays of var_prof_num_tags() entries: total ms, algorithmic FLOPs of
+ * the GEMM families, launch count.  Tag order: gemm_fwd, gemm_dgrad, gemm_scalar, gru_step,
+ * wgrad, colsum, mfcc, tail, pool, adam, gru_cell_bwd, sampler, misc.
+ * ---------------------------------------------------------------------------------- */
+long long var_launch_count(void);
+int var_prof_begin(void);
+int var_prof_end(double* ms, double* flops, long long* count, int ntags);
+int var_prof_num_tags(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,95 @@
+"""Host mirror of VAR/pretext_VAR.py::VAR_Pretext.
+
+`trainRepresentation(epoch, lr, start_ep=0, plot=False)` keeps the reference's side effects
+(`<ep>.pt` legacy-format checkpoints, `progress.csv`, per-epoch MultiStepLR) but each iteration
+is ONE fused device step instead of the reference's zero_grad / forward / TripletMarginLoss /
+backward / Adam sequence (VAR/pretext_VAR.py:55-70):
+
+    var_sampler_batch -> var_mfcc_fwd -> var_net_triplet_step -> [NCCL all-reduce] -> var_adam_step
+
+Under `torch.distributed` every rank draws the same global index stream, takes its slice of
+the batch, and the flat gradient buffer is summed over ranks before an identical Adam step
+(weights stay replicated).  The loss is read back once per epoch, not once per step."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..dataset import DeviceTripletLoader, loadEnvData
+from ..engine import multistep_lr
+from ..pretext import Pretext
+
+
+class VAR_Pretext(Pretext):
+    def __init__(self, config=None):
+        if config is None:
+            from cfg import main_config  # inside the reference tree, as VAR/pretext_VAR.py:14
+            config = main_config()
+        super().__init__(config)
+
+    def _lr(self, base_lr, ep):
+        if self.config.pretextLRStep == "step":
+            return multistep_lr(base_lr, ep, self.config.pretextLRDecayEpoch, self.config.pretextLRDecayGamma)
+        return base_lr
+
+    def train_epoch(self, eng, data_generator, lr, world=1, rank=0):
+        """One pass over the generator; returns the per-step device loss scalars."""
+        cfg = self.config
+        losses = []
+        if isinstance(data_generator, DeviceTripletLoader):
+            data_generator.rank, data_generator.world_size = rank, world
+            batches = ((img, snd, gB) for img, snd, _, gB, _ in data_generator.raw_batches())
+        else:
+            def host_batches():
+                for image, sp, sn, _ in data_generator:
+                    b = image.shape[0]
+                    lo, hi = (b * rank) // world, (b * (rank + 1)) // world
+                    F = cfg.sound_dim[1]
+                    snd = torch.cat([sp[lo:hi].reshape(-1, F, 40), sn[lo:hi].reshape(-1, F, 40)]).float()
+                    yield (image[lo:hi].to(self.device).contiguous(), snd.to(self.device).contiguous(), b)
+            batches = host_batches()
+        for img, snd, global_b in batches:
+            eng.zero_grad()
+            loss = eng.triplet_step(img, snd, margin=cfg.tripletMargin, loss_denominator=global_b)
+            if world > 1:
+                dist.all_reduce(eng.grads)
+                dist.all_reduce(loss)
+            eng.adam_step(lr, weight_decay=cfg.pretextAdamL2)
+            losses.append(loss)
+        return losses
+
+    def trainRepresentation(self, epoch, lr, start_ep=0, plot=False):
+        print('Begin representation training')
+        cfg = self.config
+        data_generator, ds = loadEnvData(data_dir=cfg.pretextDataDir, config=cfg,
+                                         batch_size=cfg.pretextTrainBatchSize, shuffle=True,
+                                         num_workers=cfg.pretextDataNumWorkers, drop_last=False,
+                                         loadNum=cfg.pretextDataFileLoadNum, dtype=cfg.pretextDataset)
+        os.makedirs(cfg.pretextModelSaveDir, exist_ok=True)
+        self.pretextModel.train()
+        eng = self.pretextModel._get_engine(self.device)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        loss_list = []
+        for ep in range(epoch):
+            losses = self.train_epoch(eng, data_generator, self._lr(lr, ep), world, rank)
+            if (ep + 1) % cfg.pretextModelSaveInterval == 0 or ep + 1 == epoch:
+                self.pretextModel.sync_from_engine()
+                if rank == 0:
+                    fname = os.path.join(cfg.pretextModelSaveDir, str(start_ep + ep) + '.pt')
+                    torch.save(self.pretextModel.state_dict(), fname, _use_new_zipfile_serialization=False)
+                    print('Model saved to ' + fname)
+            avg_loss = float(torch.stack(losses).mean()) if losses else float('nan')
+            loss_list.append(avg_loss)
+            print('average loss', avg_loss)
+        if epoch > 0:
+            self.pretextModel.sync_from_engine()
+        if cfg.pretextTrain and rank == 0:
+            import pandas as pd
+            save_path = os.path.join(cfg.pretextModelSaveDir, 'progress.csv')
+            pd.DataFrame({'avg_loss': loss_list}).to_csv(save_path, mode='w', header=True, index=False)
+            print('results saved to', save_path)
+        print('Pretext Training Complete')
+        self.pretextModel.eval()
+        return np.asarray(loss_list)

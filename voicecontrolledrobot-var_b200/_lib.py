@@ -62,6 +62,10 @@ PROTOTYPES = {
     "var_conv2d_wgrad": (_i, [_p, _i, _p, _f, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "var_maxpool2x2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "var_maxpool2x2_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "var_launch_count": (C.c_longlong, []),
+    "var_prof_begin": (_i, []),
+    "var_prof_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), _i]),
+    "var_prof_num_tags": (_i, []),
     "var_triplet_fwd_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _p]),
 }
@@ -70,6 +74,18 @@ for _name, (_res, _args) in PROTOTYPES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header / library mismatch
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+PROF_TAGS = ["gemm_fwd", "gemm_dgrad", "gemm_scalar", "gru_step", "wgrad", "colsum", "mfcc", "tail", "pool", "adam",
+             "gru_cell_bwd", "sampler", "misc"]
+
+
+def prof_end():
+    """-> {tag: (ms, flops, launches)} of the launches since var_prof_begin()."""
+    n = lib.var_prof_num_tags()
+    ms, fl, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+    check(lib.var_prof_end(ms, fl, cnt, n), "var_prof_end")
+    return {PROF_TAGS[i]: (ms[i], fl[i], cnt[i]) for i in range(n) if cnt[i]}
 
 
 def last_error():

@@ -55,6 +55,7 @@ __global__ void unpack_w_kernel(const float* __restrict__ packed, float* __restr
 int pack_weight(const float* ref, float* master, float* mma, int O, int I, int R, int S, int kpad,
                 cudaStream_t st) {
   const long long total = (long long)O * kpad;
+  LaunchScope sc(T_MISC, 0, st);
   pack_w_kernel<<<grid_for(total, 256), 256, 0, st>>>(ref, master, mma, O, I, R, S, kpad);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -62,6 +63,7 @@ int pack_weight(const float* ref, float* master, float* mma, int O, int I, int R
 int unpack_weight(const float* packed, float* ref, int O, int I, int R, int S, int kpad,
                   cudaStream_t st) {
   const long long total = (long long)O * I * R * S;
+  LaunchScope sc(T_MISC, 0, st);
   unpack_w_kernel<<<grid_for(total, 256), 256, 0, st>>>(packed, ref, O, I, R, S, kpad);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -74,6 +76,7 @@ __global__ void round_copy_kernel(const float* __restrict__ src, float* __restri
     dst[i] = round_tf32(src[i]);
 }
 int round_copy(const float* src, float* dst, long long n, cudaStream_t st) {
+  LaunchScope sc(T_MISC, 0, st);
   round_copy_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -144,6 +147,7 @@ __global__ void pool_bwd_kernel(const float4* __restrict__ x, const float4* __re
 int maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st) {
   if ((C & 3) || (H & 1) || (W & 1)) return VAR_ERR_UNSUPPORTED;
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+  LaunchScope sc(T_POOL, 0, st);
   pool_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(
       reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), N, H, W, C / 4);
   VAR_CUDA_CHECK(cudaGetLastError());
@@ -153,6 +157,7 @@ int maxpool_bwd(const float* x, const float* dy, float* dx, int N, int H, int W,
                 cudaStream_t st) {
   if ((C & 3) || (H & 1) || (W & 1)) return VAR_ERR_UNSUPPORTED;
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+  LaunchScope sc(T_POOL, 0, st);
   pool_bwd_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),
       reinterpret_cast<float4*>(dx), N, H, W, C / 4);
@@ -217,6 +222,7 @@ int gru_cell_bwd(const GruBwdArgs& a0, const GruBwdArgs& a1, int ndir, int B, in
                  cudaStream_t st) {
   if (Hd & 3) return VAR_ERR_UNSUPPORTED;
   dim3 grid(grid_for((long long)B * (Hd / 4), 256), ndir);
+  LaunchScope sc(T_GRU_CELL_BWD, 0, st);
   gru_cell_bwd_kernel<<<grid, 256, 0, st>>>(a0, a1, B, Hd);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -258,6 +264,7 @@ int adam_step(float* p, const float* g, float* m, float* v, float* p_mma, long l
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float bc2_sqrt = (float)sqrt(bc2);
+  LaunchScope sc(T_ADAM, 0, st);
   adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(p_mma), n / 4, beta1, beta2, eps, wd,
@@ -283,6 +290,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restri
   }
 }
 int nhwc_to_nchw(const float* x, float* y, int B, int HW, int C, cudaStream_t st) {
+  LaunchScope sc(T_MISC, 0, st);
   nhwc_to_nchw_kernel<<<grid_for((long long)B * HW * C, 256), 256, 0, st>>>(x, y, B, HW, C);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -303,6 +311,7 @@ __global__ void concat2_kernel(const float* __restrict__ a, const float* __restr
 }
 int concat2(const float* a, const float* c, float* out, float* out_r, int B, int Hd,
             cudaStream_t st) {
+  LaunchScope sc(T_MISC, 0, st);
   concat2_kernel<<<grid_for((long long)B * 2 * Hd, 256), 256, 0, st>>>(a, c, out, out_r, B, Hd);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -321,6 +330,7 @@ __global__ void split2_kernel(const float* __restrict__ x, float* __restrict__ a
   }
 }
 int split2(const float* x, float* a, float* c, int B, int Hd, cudaStream_t st) {
+  LaunchScope sc(T_MISC, 0, st);
   split2_kernel<<<grid_for((long long)B * 2 * Hd, 256), 256, 0, st>>>(x, a, c, B, Hd);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;

@@ -27,6 +27,20 @@ namespace var {
 
 constexpr int kNumSMs = 148;
 
+// Launch accounting: every kernel launch of the library goes through a LaunchScope.  It
+// counts launches (var_launch_count) and, while profiling is on (var_prof_begin/end),
+// brackets the launch with CUDA events on the launching stream.
+enum LaunchTag : int {
+  T_GEMM_FWD = 0, T_GEMM_DGRAD, T_GEMM_SCALAR, T_GRU_STEP, T_WGRAD, T_COLSUM, T_MFCC, T_TAIL,
+  T_POOL, T_ADAM, T_GRU_CELL_BWD, T_SAMPLER, T_MISC, T_NUM_TAGS
+};
+struct LaunchScope {
+  LaunchScope(int tag, double flops, cudaStream_t st);
+  ~LaunchScope();
+  int idx;
+  cudaStream_t st;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

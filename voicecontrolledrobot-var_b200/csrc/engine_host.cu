@@ -6,6 +6,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 static thread_local char g_last_error[512] = "";
 void var_set_last_error(const char* msg, const char* file, int line) {
@@ -14,6 +15,42 @@ void var_set_last_error(const char* msg, const char* file, int line) {
 extern "C" const char* var_last_error(void) { return g_last_error; }
 
 namespace var {
+
+// ---------------------------------------------------------------------------
+// launch accounting / per-kernel event profiler
+// ---------------------------------------------------------------------------
+namespace {
+struct ProfRec { int tag; double flops; cudaEvent_t e0, e1; };
+struct Prof {
+  std::mutex mu;
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  long long launches = 0;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+Prof& prof() { static Prof p; return p; }
+}  // namespace
+
+LaunchScope::LaunchScope(int tag, double flops, cudaStream_t s) : idx(-1), st(s) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  ++p.launches;
+  if (!p.on) return;
+  ProfRec r{tag, flops, p.get(), p.get()};
+  cudaEventRecord(r.e0, st);
+  idx = (int)p.recs.size();
+  p.recs.push_back(r);
+}
+LaunchScope::~LaunchScope() {
+  if (idx < 0) return;
+  Prof& p = prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  cudaEventRecord(p.recs[idx].e1, st);
+}
 
 MnCfg& mn_cfg() {
   static MnCfg c;
@@ -116,7 +153,15 @@ static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const Gem
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, p);
+  {
+    double flops = 0;
+    for (unsigned z = 0; z < grid.z; ++z)
+      flops += 2.0 * p.g[z].M * (double)(EPI == EPI_GRU_FWD ? p.bn * grid.y : p.e[z].ncols) * p.g[z].K;
+    const int tag = EPI == EPI_GRU_FWD ? T_GRU_STEP
+                    : (GMODE == G_VEC_FWD ? T_GEMM_FWD : (GMODE == G_VEC_DGRAD ? T_GEMM_DGRAD : T_GEMM_SCALAR));
+    LaunchScope sc(tag, flops, st);
+    tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, p);
+  }
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
@@ -145,7 +190,10 @@ static int launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t st) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  tc_wgrad_kernel<GMODE><<<grid, 160, smem, st>>>(p);
+  {
+    LaunchScope sc(T_WGRAD, 2.0 * p.g.M * (double)p.cout * p.g.K, st);
+    tc_wgrad_kernel<GMODE><<<grid, 160, smem, st>>>(p);
+  }
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
@@ -333,6 +381,7 @@ int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStr
     long long rp = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);
     if (rp < 64) rp = 64;
     const int grid = (int)((M + rp - 1) / rp);
+    LaunchScope sc(T_COLSUM, 0, st);
     colsum_kernel<<<grid, threads, threads * sizeof(float), st>>>(dy + c0, M, ld, cs, db + c0,
                                                                   (int)rp);
     VAR_CUDA_CHECK(cudaGetLastError());
@@ -378,3 +427,36 @@ int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout
 }
 
 }  // namespace var
+
+extern "C" {
+long long var_launch_count(void) {
+  auto& p = var::prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  return p.launches;
+}
+int var_prof_begin(void) {
+  auto& p = var::prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  for (auto& r : p.recs) { p.pool.push_back(r.e0); p.pool.push_back(r.e1); }
+  p.recs.clear();
+  p.on = true;
+  return VAR_OK;
+}
+// Stops profiling, waits for the device and accumulates per-tag totals (arrays of T_NUM_TAGS).
+int var_prof_end(double* ms, double* flops, long long* count, int ntags) {
+  auto& p = var::prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  p.on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return VAR_ERR_CUDA;
+  for (int i = 0; i < ntags; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
+  for (auto& r : p.recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (r.tag < ntags) { ms[r.tag] += t; flops[r.tag] += r.flops; ++count[r.tag]; }
+    p.pool.push_back(r.e0); p.pool.push_back(r.e1);
+  }
+  p.recs.clear();
+  return VAR_OK;
+}
+int var_prof_num_tags(void) { return var::T_NUM_TAGS; }
+}

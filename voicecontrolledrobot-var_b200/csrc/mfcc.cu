@@ -416,6 +416,7 @@ int mfcc_fwd(const MfccPlan* p, const int16_t* wav, const long long* offsets, co
   a.wav = wav; a.offsets = offsets; a.lengths = lengths; a.B = B; a.F = F; a.hop = p->hop;
   a.out = out; a.t = p->t;
   dim3 grid((F + kFramesPerCta - 1) / kFramesPerCta, B);
+  LaunchScope sc(T_MFCC, 0, st);
   if (p->n_fft == 512) {
     const size_t smem = mfcc_smem_bytes<512>(p->hop, p->t.nnz);
     static bool cfg = false;

@@ -244,12 +244,14 @@ __global__ void sampler_batch_kernel(SamplerArgs a) {
 }
 
 int sampler_seed(uint32_t* state, unsigned long long seed, cudaStream_t st) {
+  LaunchScope sc(T_SAMPLER, 0, st);
   sampler_seed_kernel<<<1, 256, 0, st>>>(state, (uint32_t)(seed & 0xFFFFFFFFull));
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
 int sampler_epoch(uint32_t* state, int n, int* perm, cudaStream_t st) {
   if (n <= 0) return VAR_ERR_ARG;
+  LaunchScope sc(T_SAMPLER, 0, st);
   sampler_epoch_kernel<<<1, 256, 0, st>>>(state, n, perm);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -265,6 +267,7 @@ int sampler_batch(const SamplerArgs& a_in, cudaStream_t st) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  LaunchScope sc(T_SAMPLER, 0, st);
   sampler_batch_kernel<<<1, 256, smem, st>>>(a);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -492,6 +495,7 @@ int tail_launch(const TailArgs& a, cudaStream_t st) {
   int grid = (a.B + warps_per_cta * 4 - 1) / (warps_per_cta * 4);  // >= 4 rows per warp
   if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
   if (grid < 1) grid = 1;
+  LaunchScope sc(T_TAIL, 0, st);
   tail_kernel<<<grid, warps_per_cta * 32, smem2, st>>>(a);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;

@@ -64,6 +64,14 @@ class PretextNetBase(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def sync_from_engine(self):
+        """Copy the engine's (trained) packed weights back into the nn.Parameters."""
+        sd = self._engine.state_dict()
+        with torch.no_grad():
+            for k, p in self._ordered_params():
+                p.copy_(sd[k].view_as(p))
+        self._engine_key = tuple((p.data_ptr(), p._version) for _, p in self._ordered_params())
+
     @staticmethod
     def _prep_image(image):
         if image.dim() != 4 or image.shape[1] < 3:
