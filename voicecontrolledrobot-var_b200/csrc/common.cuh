@@ -118,6 +118,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// 4-D im2col load (NHWC tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` base
+// pixels starting at (w, h, n), walked in W-then-H-then-N order inside the map's bounding
+// box with the map's traversal strides; each loads `channelsPerPixel` channels from c of the
+// pixel at base + (woff, hoff).  Out-of-tensor pixels are zero filled (= conv padding).
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                   int c, int w, int h, int n, uint16_t woff,
+                                                   uint16_t hoff) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(woff),
+      "h"(hoff)
+      : "memory");
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

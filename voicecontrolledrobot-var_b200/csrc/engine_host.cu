@@ -142,10 +142,66 @@ int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_r
   return VAR_OK;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  });
+  return fn;
+}
+
+// im2col-mode map over an NHWC fp32 tensor [N, H, W, C]: base pixels walk the box
+// [low, extent-1+up] with `stride`; each load covers `pixels` base pixels x 32 channels.
+int get_tmap_im2col(const float* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w,
+                    int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  if (!fn) {
+    var_set_last_error("cuTensorMapEncodeIm2col entry point unavailable", __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (C & 3)) return VAR_ERR_ARG;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  int lower[2] = {low_w, low_h};
+  int upper[2] = {up_w, up_h};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), gdim, gstr, lower,
+                  upper, 32u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeIm2col failed: %d (N=%d H=%d W=%d C=%d low=%d,%d up=%d,%d stride=%d,%d)",
+             (int)r, N, H, W, C, low_w, low_h, up_w, up_h, stride_w, stride_h);
+    var_set_last_error(buf, __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  return VAR_OK;
+}
+
+int gather_mode() {  // VAR_GATHER=cp_async keeps the LSU gather kernels (A/B testing)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VAR_GATHER");
+    mode = (e && !strcmp(e, "cp_async")) ? 0 : 1;
+  }
+  return mode;
+}
+
 // ---------------------------------------------------------------------------
 template <int GMODE, int EPI>
-static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const GemmParams& p,
-                         dim3 grid, cudaStream_t st) {
+static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& a0,
+                         const CUtensorMap& a1, const GemmParams& p, dim3 grid, cudaStream_t st) {
   const size_t smem = gemm_smem_bytes(p.bn, p.stages);
   static size_t configured = 0;
   if (smem > configured) {
@@ -157,26 +213,32 @@ static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const Gem
     double flops = 0;
     for (unsigned z = 0; z < grid.z; ++z)
       flops += 2.0 * p.g[z].M * (double)(EPI == EPI_GRU_FWD ? p.bn * grid.y : p.e[z].ncols) * p.g[z].K;
-    const int tag = EPI == EPI_GRU_FWD ? T_GRU_STEP
-                    : (GMODE == G_VEC_FWD ? T_GEMM_FWD : (GMODE == G_VEC_DGRAD ? T_GEMM_DGRAD : T_GEMM_SCALAR));
+    int tag = T_GEMM_SCALAR;
+    if (EPI == EPI_GRU_FWD) tag = T_GRU_STEP;
+    else if (p.b_mn_major) tag = T_GEMM_DGRAD;
+    else if (GMODE == G_VEC_FWD || GMODE == G_TMA_IM2COL || GMODE == G_TMA_TILED) tag = T_GEMM_FWD;
     LaunchScope sc(tag, flops, st);
-    tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, p);
+    tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, a0, a1, p);
   }
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
 
 int launch_gemm(int gmode, int epi, const CUtensorMap& t0, const CUtensorMap& t1,
-                const GemmParams& p, dim3 grid, cudaStream_t st) {
+                const CUtensorMap& a0, const CUtensorMap& a1, const GemmParams& p, dim3 grid,
+                cudaStream_t st) {
   if (epi == EPI_GRU_FWD) {
-    if (gmode != G_VEC_FWD) return VAR_ERR_UNSUPPORTED;
-    return launch_gemm_t<G_VEC_FWD, EPI_GRU_FWD>(t0, t1, p, grid, st);
+    if (gmode == G_VEC_FWD) return launch_gemm_t<G_VEC_FWD, EPI_GRU_FWD>(t0, t1, a0, a1, p, grid, st);
+    if (gmode == G_TMA_TILED) return launch_gemm_t<G_TMA_TILED, EPI_GRU_FWD>(t0, t1, a0, a1, p, grid, st);
+    return VAR_ERR_UNSUPPORTED;
   }
   switch (gmode) {
-    case G_VEC_FWD: return launch_gemm_t<G_VEC_FWD, EPI_STD>(t0, t1, p, grid, st);
-    case G_VEC_DGRAD: return launch_gemm_t<G_VEC_DGRAD, EPI_STD>(t0, t1, p, grid, st);
-    case G_SCALAR_F32: return launch_gemm_t<G_SCALAR_F32, EPI_STD>(t0, t1, p, grid, st);
-    case G_SCALAR_U8: return launch_gemm_t<G_SCALAR_U8, EPI_STD>(t0, t1, p, grid, st);
+    case G_VEC_FWD: return launch_gemm_t<G_VEC_FWD, EPI_STD>(t0, t1, a0, a1, p, grid, st);
+    case G_VEC_DGRAD: return launch_gemm_t<G_VEC_DGRAD, EPI_STD>(t0, t1, a0, a1, p, grid, st);
+    case G_SCALAR_F32: return launch_gemm_t<G_SCALAR_F32, EPI_STD>(t0, t1, a0, a1, p, grid, st);
+    case G_SCALAR_U8: return launch_gemm_t<G_SCALAR_U8, EPI_STD>(t0, t1, a0, a1, p, grid, st);
+    case G_TMA_IM2COL: return launch_gemm_t<G_TMA_IM2COL, EPI_STD>(t0, t1, a0, a1, p, grid, st);
+    case G_TMA_TILED: return launch_gemm_t<G_TMA_TILED, EPI_STD>(t0, t1, a0, a1, p, grid, st);
   }
   return VAR_ERR_UNSUPPORTED;
 }
@@ -254,13 +316,40 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
   EpiParams& e = p.e[0];
   e.out = y; e.ldo = cs.Cout; e.bias = bias; e.ncols = cs.Cout; e.relu = relu;
   e.round_out = round_out;
-  CUtensorMap tm;
+  CUtensorMap tm, ta;
   rc = get_tmap_2d(w, cs.Cout, kpad, kpad, bn, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm);
   if (rc) return rc;
-  dim3 grid((p.g[0].M + 127) / 128, cs.Cout / bn, 1);
-  return launch_gemm(gmode_of(src_kind), EPI_STD, tm, tm, p, grid, st);
+  ta = tm;
+  int gmode = gmode_of(src_kind);
+  const int M = p.g[0].M;
+  if (gmode == G_VEC_FWD && gather_mode() == 1) {
+    if (cs.R == 1 && cs.S == 1 && cs.sh == 1 && cs.sw == 1 && cs.ph == 0 && cs.pw == 0) {
+      // 1x1 / Linear: the activation is a plain [M, K] matrix
+      rc = get_tmap_2d(reinterpret_cast<const float*>(x), M, cs.Cin, cs.Cin, 128,
+                       (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+      if (rc) return rc;
+      gmode = G_TMA_TILED;
+    } else if (cs.R * cs.S <= kMaxTaps) {
+      rc = get_tmap_im2col(reinterpret_cast<const float*>(x), cs.N, cs.H, cs.W, cs.Cin, -cs.pw, -cs.ph,
+                           cs.pw - (cs.S - 1), cs.ph - (cs.R - 1), cs.sw, cs.sh, 128,
+                           (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+      if (rc) return rc;
+      gmode = G_TMA_IM2COL;
+      p.ntaps = cs.R * cs.S; p.cpb = cs.Cin / 32;
+      p.base_w = -cs.pw; p.base_h = -cs.ph; p.step_w = cs.sw; p.step_h = cs.sh;
+      for (int r = 0; r < cs.R; ++r)
+        for (int s_ = 0; s_ < cs.S; ++s_) {
+          const int t = r * cs.S + s_;
+          p.tap_w[t] = (uint8_t)s_; p.tap_h[t] = (uint8_t)r; p.tap_id[t] = (uint8_t)t;
+        }
+    }
+  }
+  dim3 grid((M + 127) / 128, cs.Cout / bn, 1);
+  return launch_gemm(gmode, EPI_STD, tm, tm, ta, ta, p, grid, st);
 }
 
+// dgrad geometry shared by all paths: rows of the GEMM are input pixels, K runs over
+// (tap, cout), the packed forward weights are read transposed (MN-major B operand).
 static int fill_dgrad(GemmParams& p, int z, const ConvShape& cs, const float* dy, float* dx,
                       const float* mask, const float* addsrc, int round_out) {
   if (cs.Cout % 32 || cs.Cin % 32) return VAR_ERR_UNSUPPORTED;
@@ -291,6 +380,10 @@ static int fill_dgrad(GemmParams& p, int z, const ConvShape& cs, const float* dy
   return VAR_OK;
 }
 
+static bool is_linear(const ConvShape& cs) {
+  return cs.R == 1 && cs.S == 1 && cs.sh == 1 && cs.sw == 1 && cs.ph == 0 && cs.pw == 0;
+}
+
 int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
                const float* addsrc, int round_out, cudaStream_t st) {
   GemmParams p;
@@ -298,11 +391,58 @@ int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, 
   int rc = fill_dgrad(p, 0, cs, dy, dx, mask, addsrc, round_out);
   if (rc) return rc;
   const int kfwd = cs.R * cs.S * cs.Cin, kpad = round_up32(kfwd);
-  CUtensorMap tm;
+  CUtensorMap tm, ta;
   rc = get_tmap_2d(w, cs.Cout, kpad, kpad, 32, mn_cfg().tma_swizzle, &tm);
   if (rc) return rc;
-  dim3 grid((p.g[0].M + 127) / 128, cs.Cin / p.bn, 1);
-  return launch_gemm(G_VEC_DGRAD, EPI_STD, tm, tm, p, grid, st);
+  if (gather_mode() == 0 || cs.R * cs.S > kMaxTaps) {
+    dim3 grid((p.g[0].M + 127) / 128, cs.Cin / p.bn, 1);
+    return launch_gemm(G_VEC_DGRAD, EPI_STD, tm, tm, tm, tm, p, grid, st);
+  }
+  if (is_linear(cs)) {
+    rc = get_tmap_2d(dy, p.g[0].M, cs.Cout, cs.Cout, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+    if (rc) return rc;
+    dim3 grid((p.g[0].M + 127) / 128, cs.Cin / p.bn, 1);
+    return launch_gemm(G_TMA_TILED, EPI_STD, tm, tm, ta, ta, p, grid, st);
+  }
+  // One sub-problem per output-pixel parity class (hp, wp): pixels h = h2*sh + hp only meet
+  // taps r = r0 + sh*j, so each class is a stride-1 correlation over dY with ~1/(sh*sw) of the
+  // taps -- no multiply-by-zero work for strided convolutions.
+  if (cs.R < cs.sh || cs.S < cs.sw) return VAR_ERR_UNSUPPORTED;
+  p.cpb = cs.Cout / 32;
+  p.step_w = 1; p.step_h = 1;
+  for (int hp = 0; hp < cs.sh; ++hp)
+    for (int wp = 0; wp < cs.sw; ++wp) {
+      const int H2 = (cs.H - hp + cs.sh - 1) / cs.sh, W2 = (cs.W - wp + cs.sw - 1) / cs.sw;
+      if (H2 <= 0 || W2 <= 0) continue;
+      const int r0 = (hp + cs.ph) % cs.sh, s0 = (wp + cs.pw) % cs.sw;
+      const int J = (cs.R - r0 + cs.sh - 1) / cs.sh, I = (cs.S - s0 + cs.sw - 1) / cs.sw;
+      const int a_h = (hp + cs.ph - r0) / cs.sh, a_w = (wp + cs.pw - s0) / cs.sw;
+      GemmParams q = p;
+      q.base_h = a_h - (J - 1); q.base_w = a_w - (I - 1);
+      q.ntaps = J * I;
+      for (int j = 0; j < J; ++j)
+        for (int i = 0; i < I; ++i) {
+          const int t = j * I + i;
+          q.tap_h[t] = (uint8_t)(J - 1 - j); q.tap_w[t] = (uint8_t)(I - 1 - i);
+          q.tap_id[t] = (uint8_t)((r0 + cs.sh * j) * cs.S + (s0 + cs.sw * i));
+        }
+      q.num_kb = q.ntaps * q.cpb;
+      GatherGeom& g = q.g[0];
+      g.M = cs.N * H2 * W2; g.P = H2; g.Q = W2;
+      g.K = q.num_kb * 32;
+      EpiParams& e = q.e[0];
+      if (cs.sh > 1 || cs.sw > 1) {
+        e.map.on = 1; e.map.P2 = H2; e.map.Q2 = W2; e.map.H = cs.H; e.map.W = cs.W;
+        e.map.sh = cs.sh; e.map.sw = cs.sw; e.map.oh = hp; e.map.ow = wp;
+      }
+      rc = get_tmap_im2col(dy, cs.N, cs.P, cs.Q, cs.Cout, q.base_w, q.base_h, W2 - cs.Q + q.base_w,
+                           H2 - cs.P + q.base_h, 1, 1, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+      if (rc) return rc;
+      dim3 grid((g.M + 127) / 128, cs.Cin / q.bn, 1);
+      rc = launch_gemm(G_TMA_IM2COL, EPI_STD, tm, tm, ta, ta, q, grid, st);
+      if (rc) return rc;
+    }
+  return VAR_OK;
 }
 
 // Two independent linear dgrads of identical shape in one launch (grid.z = 2):
@@ -313,17 +453,23 @@ int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
   ConvShape cs{M, 1, 1, Cin, Cout, 1, 1, 1, 1, 0, 0, 1, 1};
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  CUtensorMap tm[2];
+  CUtensorMap tm[2], ta[2];
   const int kpad = round_up32(Cin);
+  const bool tma = gather_mode() == 1;
   for (int z = 0; z < ndir; ++z) {
     int rc = fill_dgrad(p, z, cs, dy[z], dx[z], nullptr, addsrc[z], round_out);
     if (rc) return rc;
     rc = get_tmap_2d(w[z], Cout, kpad, kpad, 32, mn_cfg().tma_swizzle, &tm[z]);
     if (rc) return rc;
+    ta[z] = tm[z];
+    if (tma) {
+      rc = get_tmap_2d(dy[z], M, Cout, Cout, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta[z]);
+      if (rc) return rc;
+    }
   }
-  if (ndir == 1) tm[1] = tm[0];
+  if (ndir == 1) { tm[1] = tm[0]; ta[1] = ta[0]; }
   dim3 grid((M + 127) / 128, Cin / p.bn, ndir);
-  return launch_gemm(G_VEC_DGRAD, EPI_STD, tm[0], tm[1], p, grid, st);
+  return launch_gemm(tma ? G_TMA_TILED : G_VEC_DGRAD, EPI_STD, tm[0], tm[1], ta[0], ta[1], p, grid, st);
 }
 
 // One GRU time step for up to two directions: gates = hprev @ W_hh^T fused with the
@@ -334,7 +480,8 @@ int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const f
   const int jb = 64;
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  CUtensorMap tm[2];
+  CUtensorMap tm[2], ta[2];
+  const bool tma = gather_mode() == 1;
   for (int z = 0; z < ndir; ++z) {
     GatherGeom& g = p.g[z];
     g.src = hprev_r[z];
@@ -345,15 +492,20 @@ int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const f
     p.gru[z].Hdim = Hd;
     int rc = get_tmap_2d(whh[z], 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[z]);
     if (rc) return rc;
+    ta[z] = tm[z];
+    if (tma) {
+      rc = get_tmap_2d(hprev_r[z], B, Hd, Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta[z]);
+      if (rc) return rc;
+    }
   }
-  if (ndir == 1) tm[1] = tm[0];
+  if (ndir == 1) { tm[1] = tm[0]; ta[1] = ta[0]; }
   p.bn = 3 * jb;
   p.nbox = 3; p.box_rows = jb;
   p.boxbase[0] = 0; p.boxbase[1] = Hd; p.boxbase[2] = 2 * Hd;
   p.num_kb = Hd / 32;
   p.stages = 4; p.lookahead = 2;
   dim3 grid((B + 127) / 128, Hd / jb, ndir);
-  return launch_gemm(G_VEC_FWD, EPI_GRU_FWD, tm[0], tm[1], p, grid, st);
+  return launch_gemm(tma ? G_TMA_TILED : G_VEC_FWD, EPI_GRU_FWD, tm[0], tm[1], ta[0], ta[1], p, grid, st);
 }
 
 // ---- bias gradient: column sums of dY [M, ld] over a slab of C <= 256 columns

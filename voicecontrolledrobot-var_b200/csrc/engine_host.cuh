@@ -15,6 +15,9 @@ MnCfg& mn_cfg();  // process-wide (selftest may override to probe the hardware)
 // `pitch` elements; box = {32 cols, box_rows}.  Cached by value of all args.
 int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_rows, int swizzle,
                 CUtensorMap* out);
+int get_tmap_im2col(const float* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w,
+                    int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out);
+int gather_mode();  // 1: TMA-fed A operands (default), 0: cp.async gather (VAR_GATHER=cp_async)
 
 struct ConvShape {
   int N, H, W, Cin;       // input  (H, W spatial)

@@ -239,6 +239,10 @@ static std::vector<Case> cases() {
   v.push_back({"conv3x3 s1 p1 64->128", mk(2, 12, 12, 64, 128, 3, 3, 1, 1, 1, 1), SRC_NHWC_F32, 0});
   v.push_back({"conv11x5 s2 p5 64->64", mk(1, 30, 20, 64, 64, 11, 5, 2, 2, 5, 5), SRC_NHWC_F32, 0});
   v.push_back({"conv3x1 s(2,1) 32->32", mk(4, 48, 1, 32, 32, 3, 1, 2, 1, 0, 0), SRC_NHWC_F32, 0});
+  v.push_back({"linear 4x576->128 (tiny M)", mk(4, 1, 1, 576, 128, 1, 1, 1, 1, 0, 0), SRC_NHWC_F32, 0});
+  v.push_back({"conv7x3 s2 p1 odd 64->64", mk(2, 31, 13, 64, 64, 7, 3, 2, 2, 1, 1), SRC_NHWC_F32, 0});
+  v.push_back({"conv3x3 s2 p1 128->128 6x6", mk(5, 6, 6, 128, 128, 3, 3, 2, 2, 1, 1), SRC_NHWC_F32, 0});
+  v.push_back({"conv3x3 s1 p1 32->32 20x20", mk(3, 20, 20, 32, 32, 3, 3, 1, 1, 1, 1), SRC_NHWC_F32, 0});
   v.push_back({"scalar f32 nchw c3 s2", mk(2, 16, 16, 3, 32, 3, 3, 2, 2, 1, 1), SRC_STRIDED_F32, 1});
   v.push_back({"scalar u8 nchw c3 s1", mk(2, 16, 16, 3, 32, 3, 3, 1, 1, 1, 1), SRC_STRIDED_U8, 1});
   v.push_back({"scalar f32 c1 5x40", mk(2, 100, 40, 1, 32, 5, 40, 2, 1, 0, 0), SRC_STRIDED_F32, 1});

@@ -27,8 +27,12 @@ enum GatherMode : int {
   G_VEC_FWD = 0,    // NHWC source, C % 32 == 0, forward im2col
   G_VEC_DGRAD = 1,  // NHWC dY source, rows are input pixels (transposed conv)
   G_SCALAR_F32 = 2, // generic strides, float source (C in {1,3}), forward im2col
-  G_SCALAR_U8 = 3   // generic strides, uint8 source scaled by `scale`
+  G_SCALAR_U8 = 3,  // generic strides, uint8 source scaled by `scale`
+  G_TMA_IM2COL = 4, // NHWC source, C % 32 == 0: A tiles by im2col-mode TMA (one instruction / k-block)
+  G_TMA_TILED = 5   // plain [M, K] row-major source (Linear / GRU step): A tiles by tiled TMA
 };
+
+constexpr int kMaxTaps = 64;
 
 struct GatherGeom {
   const void* src;
@@ -44,6 +48,15 @@ struct GatherGeom {
 
 enum EpiKind : int { EPI_STD = 0, EPI_GRU_FWD = 1 };
 
+// Output-row remapping of the stride-2 dgrad sub-problems: GEMM row m enumerates the pixels
+// (n, h2, w2) of one parity class, stored at pixel (h2*sh + oh, w2*sw + ow) of the full map.
+struct RowMap {
+  int on;
+  int P2, Q2;   // sub-grid extents
+  int H, W;     // full extents
+  int sh, sw, oh, ow;
+};
+
 struct EpiParams {
   float* out;            // [M, ldo]
   long long ldo;
@@ -55,6 +68,7 @@ struct EpiParams {
   int ncols;             // total valid output columns
   int relu;
   int round_out;         // store tf32-rounded values
+  RowMap map;
 };
 
 // GRU cell epilogue (forward): columns of the tile are [r | z | n] blocks of
@@ -86,6 +100,12 @@ struct GemmParams {
   int stages;
   int lookahead;
   int mn_lbo, mn_sbo, mn_type;  // MN-major descriptor fields (bytes, bytes, layout type)
+  // TMA im2col A operand: k-block -> (tap, channel chunk); per tap the im2col offsets and the
+  // tap id (r*S + s) that addresses the packed weights
+  int ntaps, cpb;              // taps, 32-channel chunks per tap
+  int base_w, base_h;          // base-pixel coordinate of output (p, q) = (0, 0)
+  int step_w, step_h;          // base-pixel step per output pixel (= traversal stride)
+  uint8_t tap_w[kMaxTaps], tap_h[kMaxTaps], tap_id[kMaxTaps];
 };
 
 constexpr int kTileM = 128;
@@ -181,10 +201,13 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 template <int GMODE, int EPI>
 __global__ void __launch_bounds__(160)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int z = blockIdx.z;
   const CUtensorMap* tmB = z == 0 ? &tmB0 : &tmB1;
+  const CUtensorMap* tmA = z == 0 ? &tmA0 : &tmA1;
+  constexpr bool kTmaA = (GMODE == G_TMA_IM2COL || GMODE == G_TMA_TILED);
   const GatherGeom& g = p.g[z];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = p.stages, bn = p.bn, num_kb = p.num_kb;
@@ -199,9 +222,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
   const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
   const uint32_t tslot = tfull_bar + 8u;
 
-  __shared__ int lut_off[(GMODE >= G_SCALAR_F32) ? 256 : 1];
-  __shared__ int lut_rs[(GMODE >= G_SCALAR_F32) ? 256 : 1];
-  if constexpr (GMODE >= G_SCALAR_F32) {
+  constexpr bool kScalar = (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8);
+  __shared__ int lut_off[kScalar ? 256 : 1];
+  __shared__ int lut_rs[kScalar ? 256 : 1];
+  if constexpr (kScalar) {
     for (int k = tid; k < g.K && k < 256; k += blockDim.x) {
       const int c = k % g.C, rs = k / g.C, s = rs % g.S, r = rs / g.S;
       lut_off[k] = (int)(r * g.sH + s * g.sW + c * g.sC);
@@ -211,12 +235,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(full_bar(s), kTmaA ? 1 : 128 + 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
     mbar_fence_init();
     tma_prefetch_desc(tmB);
+    if constexpr (kTmaA) tma_prefetch_desc(tmA);
   }
   const uint32_t ncols = (uint32_t)tmem_cols_for(bn);
   if (warp == 4) tmem_alloc(tslot, ncols);
@@ -244,36 +269,77 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
       rc.q = rem - rc.p * g.Q;
       rc.base = (long long)rc.n * g.sN;
     }
-    const int la = p.lookahead;
-    int st_issue = 0, ph_issue = 0, st_arr = 0;
-    for (int it = 0; it < num_kb + la; ++it) {
-      if (it < num_kb) {
-        mbar_wait(empty_bar(st_issue), (uint32_t)(ph_issue ^ 1));
-        if (tid == 0) {
-          mbar_arrive_expect_tx(full_bar(st_issue), tileB_bytes);
-          const uint32_t dstB = sB + (uint32_t)st_issue * tileB_bytes;
+    if constexpr (kTmaA) {
+      // one elected thread feeds both operands with TMA; everyone else goes straight to the
+      // epilogue wait
+      if (tid == 0) {
+        int st = 0, ph = 0;
+        int w0 = 0, h0 = 0, n0 = 0;
+        if constexpr (GMODE == G_TMA_IM2COL) {
+          w0 = rc.q * p.step_w + p.base_w;
+          h0 = rc.p * p.step_h + p.base_h;
+          n0 = rc.n;
+        }
+        for (int it = 0; it < num_kb; ++it) {
+          mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
+          mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
+          const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
+          const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
+          int tap = 0, c0 = it << 5;
+          if constexpr (GMODE == G_TMA_IM2COL) {
+            tap = it / p.cpb;
+            c0 = (it - tap * p.cpb) << 5;
+            tma_load_im2col_4d(dstA, tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
+          } else {
+            tma_load_2d(dstA, tmA, full_bar(st), it * 32, m0);
+          }
           if (!p.b_mn_major) {
             for (int b = 0; b < p.nbox; ++b)
-              tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st_issue),
-                          it * 32, p.boxbase[b] + ntile * p.box_rows);
+              tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st), it * 32,
+                          p.boxbase[b] + ntile * p.box_rows);
           } else {
-            // MN-major: k-block `it` -> tap rs and k0; box = {32 n, 32 k}
-            const int rs = it / p.kb_per_rs;
-            const int k0 = (it - rs * p.kb_per_rs) << 5;
+            const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
+            const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
             for (int gidx = 0; gidx < (bn >> 5); ++gidx)
-              tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st_issue),
+              tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st),
                           rs * p.cin_total + ntile * bn + gidx * 32, k0);
           }
+          if (++st == stages) { st = 0; ph ^= 1; }
         }
-        gather_row<GMODE>(g, rc, it, sA + (uint32_t)st_issue * kTileABytes, row, lut_off, lut_rs);
-        if (++st_issue == stages) { st_issue = 0; ph_issue ^= 1; }
       }
-      cp_async_commit();
-      if (it >= la) {
-        cp_async_wait_dyn(la);
-        fence_proxy_async_smem();
-        mbar_arrive(full_bar(st_arr));
-        if (++st_arr == stages) st_arr = 0;
+      __syncwarp();
+    } else {
+    const int la = p.lookahead;
+      int st_issue = 0, ph_issue = 0, st_arr = 0;
+      for (int it = 0; it < num_kb + la; ++it) {
+        if (it < num_kb) {
+          mbar_wait(empty_bar(st_issue), (uint32_t)(ph_issue ^ 1));
+          if (tid == 0) {
+            mbar_arrive_expect_tx(full_bar(st_issue), tileB_bytes);
+            const uint32_t dstB = sB + (uint32_t)st_issue * tileB_bytes;
+            if (!p.b_mn_major) {
+              for (int b = 0; b < p.nbox; ++b)
+                tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st_issue),
+                            it * 32, p.boxbase[b] + ntile * p.box_rows);
+            } else {
+              // MN-major: k-block `it` -> tap rs and k0; box = {32 n, 32 k}
+              const int rs = it / p.kb_per_rs;
+              const int k0 = (it - rs * p.kb_per_rs) << 5;
+              for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+                tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st_issue),
+                            rs * p.cin_total + ntile * bn + gidx * 32, k0);
+            }
+          }
+          gather_row<GMODE>(g, rc, it, sA + (uint32_t)st_issue * kTileABytes, row, lut_off, lut_rs);
+          if (++st_issue == stages) { st_issue = 0; ph_issue ^= 1; }
+        }
+        cp_async_commit();
+        if (it >= la) {
+          cp_async_wait_dyn(la);
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar(st_arr));
+          if (++st_arr == stages) st_arr = 0;
+        }
       }
     }
 
@@ -290,7 +356,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
         tmem_ld_wait();
         const int col0 = ntile * bn + c;
         if (m < g.M && col0 < e.ncols) {
-          float* o = e.out + (long long)m * e.ldo + col0;
+          long long orow = m;
+          if (e.map.on) {
+            const int pq2 = e.map.P2 * e.map.Q2;
+            const int n_ = m / pq2, rem_ = m - n_ * pq2;
+            const int h2 = rem_ / e.map.Q2, w2 = rem_ - h2 * e.map.Q2;
+            orow = ((long long)n_ * e.map.H + h2 * e.map.sh + e.map.oh) * e.map.W + w2 * e.map.sw +
+                   e.map.ow;
+          }
+          float* o = e.out + orow * e.ldo + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -300,7 +374,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
             }
             if (e.addsrc) {
               const float4 a4 =
-                  *reinterpret_cast<const float4*>(e.addsrc + (long long)m * e.lda + col0 + j);
+                  *reinterpret_cast<const float4*>(e.addsrc + orow * e.lda + col0 + j);
               r4.x += a4.x; r4.y += a4.y; r4.z += a4.z; r4.w += a4.w;
             }
             if (e.relu) {
@@ -309,7 +383,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
             }
             if (e.mask) {
               const float4 k4 =
-                  *reinterpret_cast<const float4*>(e.mask + (long long)m * e.ldm + col0 + j);
+                  *reinterpret_cast<const float4*>(e.mask + orow * e.ldm + col0 + j);
               r4.x = k4.x > 0.f ? r4.x : 0.f; r4.y = k4.y > 0.f ? r4.y : 0.f;
               r4.z = k4.z > 0.f ? r4.z : 0.f; r4.w = k4.w > 0.f ? r4.w : 0.f;
             }
