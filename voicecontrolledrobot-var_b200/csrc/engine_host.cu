@@ -541,8 +541,70 @@ int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStr
   return VAR_OK;
 }
 
+static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, float* dw, cudaStream_t st) {
+  WgradTmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = cs.N * cs.P * cs.Q;
+  p.K = cs.R * cs.S * cs.Cin;
+  p.kpad = round_up32(p.K);
+  p.stages = 4;
+  p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
+  p.P = cs.P; p.Q = cs.Q;
+  p.a_tiled = is_linear(cs) ? 1 : 0;
+  CUtensorMap tx, tdy;
+  int rc;
+  if (p.a_tiled) {
+    rc = get_tmap_2d(x, p.M, cs.Cin, cs.Cin, 32, mn_cfg().tma_swizzle, &tx);
+  } else {
+    p.cpb = cs.Cin / 32;
+    p.base_w = -cs.pw; p.base_h = -cs.ph; p.step_w = cs.sw; p.step_h = cs.sh;
+    for (int r = 0; r < cs.R; ++r)
+      for (int s_ = 0; s_ < cs.S; ++s_) { p.tap_w[r * cs.S + s_] = (uint8_t)s_; p.tap_h[r * cs.S + s_] = (uint8_t)r; }
+    rc = get_tmap_im2col(x, cs.N, cs.H, cs.W, cs.Cin, -cs.pw, -cs.ph, cs.pw - (cs.S - 1),
+                         cs.ph - (cs.R - 1), cs.sw, cs.sh, 32, mn_cfg().tma_swizzle, &tx);
+  }
+  if (rc) return rc;
+  const int ktiles = (p.K + 127) / 128;
+  const int slab = pick_bn(cs.Cout);
+  if (slab == 0 || slab % 32) return VAR_ERR_UNSUPPORTED;
+  const int nslab = cs.Cout / slab;
+  int splits = (4 * kNumSMs + ktiles * nslab - 1) / (ktiles * nslab);
+  int ppc = (p.M + splits - 1) / splits;
+  ppc = ((ppc + 31) / 32) * 32;
+  if (ppc < 256) ppc = 256;
+  splits = (p.M + ppc - 1) / ppc;
+  p.pix_per_cta = ppc;
+  p.cout = slab;
+  const size_t smem = wgrad_smem_bytes(slab, p.stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = smem;
+  }
+  dim3 grid(ktiles, splits, 1);
+  for (int c0 = 0; c0 < cs.Cout; c0 += slab) {
+    rc = get_tmap_2d(dy + c0, p.M, slab, cs.Cout, 32, mn_cfg().tma_swizzle, &tdy);
+    if (rc) return rc;
+    p.dw = dw + (long long)c0 * p.kpad;
+    {
+      LaunchScope sc(T_WGRAD, 2.0 * p.M * (double)slab * p.K, st);
+      tc_wgrad_tma_kernel<0><<<grid, 160, smem, st>>>(tx, tdy, p);
+    }
+    VAR_CUDA_CHECK(cudaGetLastError());
+  }
+  return VAR_OK;
+}
+
 int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
                const float* dy, float* dw, float* db, cudaStream_t st) {
+  if (src_kind == SRC_NHWC_F32 && gather_mode() == 1 && cs.Cin % 32 == 0 && cs.Cout % 32 == 0 &&
+      cs.R * cs.S <= kMaxTaps) {
+    const int rc = conv_wgrad_tma(cs, reinterpret_cast<const float*>(x), dy, dw, st);
+    if (rc) return rc;
+    if (db) return colsum(dy, (long long)cs.N * cs.P * cs.Q, cs.Cout, cs.Cout, db, st);
+    return VAR_OK;
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_fwd_geom(&p.g, cs, x, src_kind, sl);

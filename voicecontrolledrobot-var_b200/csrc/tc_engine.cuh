@@ -687,4 +687,146 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// TMA-fed weight gradient: same D tile / split as tc_wgrad_kernel, but both MN-major
+// operands arrive by TMA issued from one thread -- X^T groups by im2col-mode loads of
+// 32 pixels x 32 channels (or tiled loads when X is a plain matrix), dY groups by tiled
+// loads -- in the 32-byte-atom 128B swizzle the MN-major UMMA descriptors expect.
+// grid = (ceil(K/128), splits), block = 160.
+// ---------------------------------------------------------------------------
+struct WgradTmaParams {
+  int M, K, cout, kpad;
+  float* dw;          // [cout, kpad]
+  int pix_per_cta;    // multiple of 32
+  int stages;
+  int mn_lbo, mn_sbo, mn_type;
+  int a_tiled;        // 1: X is a plain [M, K] matrix (Linear)
+  int P, Q;           // output extents: pixel m -> (n, p, q)
+  int cpb, base_w, base_h, step_w, step_h;
+  uint8_t tap_w[kMaxTaps], tap_h[kMaxTaps];
+};
+
+template <int kVariant>
+__global__ void __launch_bounds__(160)
+tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                    const __grid_constant__ WgradTmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages;
+  const int bgroups = p.cout >> 5;
+  const uint32_t tileA_bytes = 4u * 4096u;
+  const uint32_t tileB_bytes = (uint32_t)bgroups * 4096u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + (uint32_t)stages * tileA_bytes;
+  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
+  const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
+  const uint32_t tslot = tfull_bar + 8u;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  const uint32_t ncols = (uint32_t)tmem_cols_for(p.cout);
+  if (warp == 4) tmem_alloc(tslot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int ktile = blockIdx.x;
+  const int pix0 = blockIdx.y * p.pix_per_cta;
+  const int pix1 = min(pix0 + p.pix_per_cta, p.M);
+  const int num_kb = (pix1 - pix0 + 31) / 32;
+  const int kgroups = min(4, (p.K - ktile * 128 + 31) / 32);  // valid 32-row groups of this k tile
+
+  if (num_kb > 0) {
+    if (warp < 4) {
+      if (tid == 0) {
+        const int pq = p.P * p.Q;
+        int st = 0, ph = 0;
+        for (int it = 0; it < num_kb; ++it) {
+          mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
+          mbar_arrive_expect_tx(full_bar(st), (uint32_t)kgroups * 4096u + tileB_bytes);
+          const int m = pix0 + it * 32;
+          const uint32_t dA = sA + (uint32_t)st * tileA_bytes;
+          const uint32_t dB = sB + (uint32_t)st * tileB_bytes;
+          if (p.a_tiled) {
+            for (int gq = 0; gq < kgroups; ++gq)
+              tma_load_2d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), ktile * 128 + gq * 32, m);
+          } else {
+            const int n = m / pq;
+            const int rem = m - n * pq;
+            const int pp = rem / p.Q, qq = rem - pp * p.Q;
+            const int w0 = qq * p.step_w + p.base_w, h0 = pp * p.step_h + p.base_h;
+            for (int gq = 0; gq < kgroups; ++gq) {
+              const int kb = ktile * 4 + gq;
+              const int tap = kb / p.cpb;
+              const int c0 = (kb - tap * p.cpb) << 5;
+              tma_load_im2col_4d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), c0, w0, h0, n,
+                                 p.tap_w[tap], p.tap_h[tap]);
+            }
+          }
+          for (int bg = 0; bg < bgroups; ++bg)
+            tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), bg * 32, m);
+          if (++st == stages) { st = 0; ph ^= 1; }
+        }
+      }
+      __syncwarp();
+      // ---- epilogue: row = k index, columns = output channel
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const int k = ktile * 128 + warp * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int c = 0; c < p.cout; c += 32) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (k < p.K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + (long long)(c + j) * p.kpad + k, v[j]);
+        }
+      }
+      tc_fence_before();
+    } else {
+      const uint32_t idesc = make_idesc_tf32(p.cout, 1, 1);
+      const uint32_t lbo = (uint32_t)p.mn_lbo, sbo = (uint32_t)p.mn_sbo, lt = (uint32_t)p.mn_type;
+      int st = 0, ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(st), (uint32_t)ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = sA + (uint32_t)st * tileA_bytes;
+          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 1024u, lbo, sbo, lt);
+            const uint64_t bd = make_smem_desc(b0 + (uint32_t)j * 1024u, lbo, sbo, lt);
+            umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+          }
+          umma_commit(empty_bar(st));
+          if (kb == num_kb - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
 }  // namespace var
