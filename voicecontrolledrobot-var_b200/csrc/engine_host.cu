@@ -19,8 +19,12 @@ namespace var {
 // ---------------------------------------------------------------------------
 // launch accounting / per-kernel event profiler
 // ---------------------------------------------------------------------------
+static thread_local char g_prof_note[48] = "";
+void prof_note(const char* fmt, int a, int b, int c, int d, int e) {
+  snprintf(g_prof_note, sizeof(g_prof_note), fmt, a, b, c, d, e);
+}
 namespace {
-struct ProfRec { int tag; double flops; cudaEvent_t e0, e1; };
+struct ProfRec { int tag; double flops; cudaEvent_t e0, e1; char note[48]; };
 struct Prof {
   std::mutex mu;
   bool on = false;
@@ -40,7 +44,8 @@ LaunchScope::LaunchScope(int tag, double flops, cudaStream_t s) : idx(-1), st(s)
   std::lock_guard<std::mutex> lk(p.mu);
   ++p.launches;
   if (!p.on) return;
-  ProfRec r{tag, flops, p.get(), p.get()};
+  ProfRec r{tag, flops, p.get(), p.get(), {0}};
+  snprintf(r.note, sizeof(r.note), "%s", g_prof_note);
   cudaEventRecord(r.e0, st);
   idx = (int)p.recs.size();
   p.recs.push_back(r);
@@ -272,6 +277,14 @@ static int pick_bn(int n) {
     if (n % bn == 0) return bn;
   return 0;
 }
+// Narrow the N tile while the grid would leave most SMs idle (small-M GEMMs: Linear heads,
+// GRU recurrences).  `mult` keeps the tile a multiple of the operand's box granule.
+static int widen_grid_bn(int bn, int n, int m_tiles, int instances, int mult) {
+  while (bn % 2 == 0 && (bn / 2) % mult == 0 && n % (bn / 2) == 0 &&
+         (long long)m_tiles * (n / bn) * instances < kNumSMs)
+    bn /= 2;
+  return bn;
+}
 
 static int fill_fwd_geom(GatherGeom* g, const ConvShape& cs, const void* x, int src_kind,
                          const SrcLayout* sl) {
@@ -302,13 +315,15 @@ static int gmode_of(int src_kind) {
 
 int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
              const float* bias, float* y, int relu, int round_out, cudaStream_t st) {
+  prof_note("fwd N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_fwd_geom(&p.g[0], cs, x, src_kind, sl);
   if (rc) return rc;
   const int K = p.g[0].K, kpad = round_up32(K);
-  const int bn = pick_bn(cs.Cout);
+  int bn = pick_bn(cs.Cout);
   if (bn == 0 || bn % 16) return VAR_ERR_UNSUPPORTED;
+  bn = widen_grid_bn(bn, cs.Cout, (p.g[0].M + 127) / 128, 1, 32);  // epilogue works in 32-column chunks
   p.bn = bn;
   p.nbox = 1; p.box_rows = bn; p.boxbase[0] = 0;
   p.num_kb = kpad / 32;
@@ -364,8 +379,9 @@ static int fill_dgrad(GemmParams& p, int z, const ConvShape& cs, const float* dy
   g.sN = (long long)cs.P * cs.Q * cs.Cout;
   g.K = cs.R * cs.S * cs.Cout;
   g.scale = 1.f;
-  const int bn = pick_bn(cs.Cin);
+  int bn = pick_bn(cs.Cin);
   if (bn == 0) return VAR_ERR_UNSUPPORTED;
+  bn = widen_grid_bn(bn, cs.Cin, (g.M + 127) / 128, 2, 32);
   p.bn = bn;
   p.b_mn_major = 1;
   p.num_kb = g.K / 32;
@@ -386,6 +402,7 @@ static bool is_linear(const ConvShape& cs) {
 
 int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, const float* mask,
                const float* addsrc, int round_out, cudaStream_t st) {
+  prof_note("dgrad N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_dgrad(p, 0, cs, dy, dx, mask, addsrc, round_out);
@@ -450,6 +467,7 @@ int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, 
 int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
                   const float* const w[2], float* const dx[2], const float* const addsrc[2],
                   int round_out, cudaStream_t st) {
+  prof_note("gru_dgrad2 M%d Ci%d Co%d %d%d", M, Cin, Cout, 0, 0);
   ConvShape cs{M, 1, 1, Cin, Cout, 1, 1, 1, 1, 0, 0, 1, 1};
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -477,7 +495,8 @@ int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
 int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const float* const whh[2],
                  const GruEpiParams q[2], cudaStream_t st) {
   if (Hd % 64) return VAR_ERR_UNSUPPORTED;
-  const int jb = 64;
+  // hidden units per CTA: 32 (N = 96) doubles the grid when the batch gives few M tiles
+  const int jb = ((B + 127) / 128) * (Hd / 64) * ndir < kNumSMs ? 32 : 64;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap tm[2], ta[2];
@@ -508,36 +527,47 @@ int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const f
   return launch_gemm(tma ? G_TMA_TILED : G_VEC_FWD, EPI_GRU_FWD, tm[0], tm[1], ta[0], ta[1], p, grid, st);
 }
 
-// ---- bias gradient: column sums of dY [M, ld] over a slab of C <= 256 columns
-__global__ void colsum_kernel(const float* __restrict__ dy, long long M, long long ld, int C,
-                              float* __restrict__ db, int rows_per_cta) {
-  extern __shared__ float red[];
-  const int lanes = blockDim.x / C;
-  const int col = threadIdx.x % C, rl = threadIdx.x / C;
+// ---- bias gradient: column sums of dY [M, ld].  CTA = 8 row lanes x 32 float4 columns
+// (a 128-column slab), grid = (row chunks, slabs); 128-bit coalesced loads, one atomic per
+// column per CTA.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dy, long long M, long long ld, int C, float* __restrict__ db,
+              int rows_per_cta) {
+  __shared__ float4 red[256];
+  const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.y * 128 + c4 * 4;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(r0 + (long long)rows_per_cta, M);
-  float acc = 0.f;
-  for (long long r = r0 + rl; r < r1; r += lanes) acc += dy[r * ld + col];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < C) {
+    for (long long r = r0 + rl; r < r1; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(dy + r * ld + col);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
   red[threadIdx.x] = acc;
   __syncthreads();
-  if (rl == 0) {
-    for (int l = 1; l < lanes; ++l) acc += red[l * C + col];
-    atomicAdd(db + col, acc);
+  if (rl == 0 && col < C) {
+#pragma unroll
+    for (int l = 1; l < 8; ++l) {
+      const float4 v = red[l * 32 + c4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(db + col, acc.x); atomicAdd(db + col + 1, acc.y);
+    atomicAdd(db + col + 2, acc.z); atomicAdd(db + col + 3, acc.w);
   }
 }
 
 int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st) {
-  for (int c0 = 0; c0 < C; c0 += 256) {
-    const int cs = C - c0 < 256 ? C - c0 : 256;
-    const int threads = (256 / cs) * cs;
-    long long rp = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);
-    if (rp < 64) rp = 64;
-    const int grid = (int)((M + rp - 1) / rp);
-    LaunchScope sc(T_COLSUM, 0, st);
-    colsum_kernel<<<grid, threads, threads * sizeof(float), st>>>(dy + c0, M, ld, cs, db + c0,
-                                                                  (int)rp);
-    VAR_CUDA_CHECK(cudaGetLastError());
-  }
+  if ((C & 3) || (ld & 3)) return VAR_ERR_UNSUPPORTED;
+  const int slabs = (C + 127) / 128;
+  long long chunks = (4 * kNumSMs + slabs - 1) / slabs;
+  long long rp = (M + chunks - 1) / chunks;
+  if (rp < 64) rp = 64;
+  dim3 grid((unsigned)((M + rp - 1) / rp), slabs);
+  LaunchScope sc(T_COLSUM, 0, st);
+  colsum_kernel<<<grid, 256, 0, st>>>(dy, M, ld, C, db, (int)rp);
+  VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
 
@@ -598,6 +628,7 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
 
 int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
                const float* dy, float* dw, float* db, cudaStream_t st) {
+  prof_note("wgrad N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
   if (src_kind == SRC_NHWC_F32 && gather_mode() == 1 && cs.Cin % 32 == 0 && cs.Cout % 32 == 0 &&
       cs.R * cs.S <= kMaxTaps) {
     const int rc = conv_wgrad_tma(cs, reinterpret_cast<const float*>(x), dy, dw, st);
@@ -673,4 +704,23 @@ int var_prof_end(double* ms, double* flops, long long* count, int ntags) {
   return VAR_OK;
 }
 int var_prof_num_tags(void) { return var::T_NUM_TAGS; }
+// Like var_prof_end but writes one CSV line per launch (tag, ms, flops, note) to `path`.
+int var_prof_dump(const char* path) {
+  auto& p = var::prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  p.on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return VAR_ERR_CUDA;
+  FILE* f = fopen(path, "w");
+  if (!f) return VAR_ERR_ARG;
+  fprintf(f, "tag,ms,flops,note\n");
+  for (auto& r : p.recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    fprintf(f, "%d,%.5f,%.0f,%s\n", r.tag, t, r.flops, r.note);
+    p.pool.push_back(r.e0); p.pool.push_back(r.e1);
+  }
+  p.recs.clear();
+  fclose(f);
+  return VAR_OK;
+}
 }
