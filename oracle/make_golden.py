@@ -238,13 +238,37 @@ def gold_adam():
     print("adam ok")
 
 
+def gold_init():
+    """Seeded construction of the reference modules: per-tensor checksums pin that the host
+    mirror reproduces the reference's initial weights (same layer construction order and RNG use)."""
+    out = {}
+    from models.pretext.arm_pretext_model import VARPretextNet as KukaNet
+    torch.manual_seed(453)
+    m = KukaNet(kuka_cfg())
+    for k, v in m.state_dict().items():
+        out["kuka." + k] = np.array([v.double().sum().item(), v.double().abs().sum().item(), v.flatten()[0].item()])
+    from models.pretext.ai2thor_pretext_model import VARPretextNet as ThorNet
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.manual_seed(977)
+    m = ThorNet(ithor_cfg())
+    for k, v in m.state_dict().items():
+        out["ithor." + k] = np.array([v.double().sum().item(), v.double().abs().sum().item(), v.flatten()[0].item()])
+    np.savez_compressed(os.path.join(GOLD, "init.npz"), **out)
+    print("init ok", len(out))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     install_stubs()
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: python oracle/make_golden.py gold_init ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     gold_mfcc()
     gold_sampler()
     gold_adam()
     gold_reward()
     gold_model(omodel.KUKA, 4, 7)
     gold_model(omodel.ITHOR, 2, 9)
+    gold_init()

@@ -1,0 +1,89 @@
+"""CPU, world_size 2 over gloo: the host-side data-parallel logic of VAR_Pretext.train_epoch --
+identical global index stream on every rank, rank slices that tile the batch, per-rank loss /
+gradient scaling by the GLOBAL batch, one all-reduce(sum) of the flat gradient buffer, identical
+weights afterwards.  The device engine is replaced by a tiny numpy stand-in with the same
+interface (the kernels themselves need a GPU and are covered by the -m gpu tests)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeEngine:
+    """Linear 'model' y = w . x with hinge-free loss sum(x @ w) / denom: gradient is data dependent,
+    so wrong slicing or scaling shows up in the weights."""
+
+    def __init__(self, n):
+        self.params = torch.arange(n, dtype=torch.float32) / n
+        self.grads = torch.zeros(n)
+        self.steps = 0
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def triplet_step(self, img, snd, margin=1.0, loss_denominator=None):
+        x = img.float().reshape(img.shape[0], -1)[:, : self.params.numel()]
+        self.grads += x.sum(0) / loss_denominator
+        return (x @ self.params).sum() / loss_denominator
+
+    def adam_step(self, lr, weight_decay=0.0):
+        self.params -= lr * self.grads
+        self.steps += 1
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import sampler as osampler
+    # every rank draws the same global stream (device sampler semantics, restated by the oracle)
+    gen = osampler.TorchCPUGenerator(977)
+    n_items, B = 64, 16
+    batches = osampler.epoch_batches(gen, n_items, B)
+    data = torch.arange(n_items * 8, dtype=torch.float32).reshape(n_items, 8) % 7
+    eng = FakeEngine(8)
+    losses = []
+    for batch in batches:
+        lo, hi = (len(batch) * rank) // world, (len(batch) * (rank + 1)) // world
+        idx = torch.tensor(batch[lo:hi])
+        eng.zero_grad()
+        loss = eng.triplet_step(data[idx], None, loss_denominator=len(batch))
+        dist.all_reduce(eng.grads)
+        dist.all_reduce(loss)
+        eng.adam_step(0.01)
+        losses.append(float(loss))
+    torch.save({"params": eng.params, "losses": losses, "batches": batches}, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_dp_slices_sum_to_single_process_run(tmp_path):
+    world = 2
+    out = str(tmp_path / "res")
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    r = [torch.load(out + f".{i}") for i in range(world)]
+    assert r[0]["batches"] == r[1]["batches"]                      # identical index stream
+    assert torch.equal(r[0]["params"], r[1]["params"])             # replicas stay in lock step
+    # single-process reference over the same stream
+    sys.path.insert(0, ROOT)
+    data = torch.arange(64 * 8, dtype=torch.float32).reshape(64, 8) % 7
+    eng = FakeEngine(8)
+    for batch, l in zip(r[0]["batches"], r[0]["losses"]):
+        eng.zero_grad()
+        loss = eng.triplet_step(data[torch.tensor(batch)], None, loss_denominator=len(batch))
+        eng.adam_step(0.01)
+        assert abs(float(loss) - l) < 1e-4 * max(1.0, abs(l))
+    assert torch.allclose(eng.params, r[0]["params"], atol=1e-5)
+
+
+def test_rank_slices_tile_every_batch_size():
+    for B in (1, 7, 64, 255, 8192):
+        for world in (1, 2, 3, 4, 8):
+            cuts = [((B * r) // world, (B * (r + 1)) // world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == B
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))

@@ -1,0 +1,139 @@
+// Kuka sound branch forward in full fp32 (models/pretext/arm_pretext_model.py:21-34,51-55):
+//   conv(5x40, s(2,1)) 1->32, 3 x conv(3x1, s(2,1)) 32->32, ReLU each, flatten, Linear 160->128, ReLU.
+// The branch is 0.43 M MAC per clip on 16 KB of input with M = 48/23/11/5 rows per layer: far
+// too small for 128-row MMA tiles, and its first layer multiplies MFCC values of magnitude
+// 1e1-1e2 where tf32 rounding alone costs ~1e-3 of the embedding.  One CTA per clip keeps the
+// clip, every activation and the conv weights in shared memory and uses plain FFMA, so the
+// forward embedding is exact to fp32 round-off.  Activations are also written to HBM (NHWC,
+// tf32-rounded) because the backward pass reuses the tcgen05 engine on them.
+#include "kuka_sound.cuh"
+
+namespace var {
+
+namespace {
+constexpr int kF = 100, kMelW = 40, kC = 32;
+constexpr int kP1 = 48, kP2 = 23, kP3 = 11, kP4 = 5;
+constexpr int kK1 = 200, kK1Pad = 224, kK2 = 96, kHid = 128, kFlat = 160;
+constexpr int kThreads = 256;
+
+// out[p][c] = relu(b[c] + sum_{r<3, ci<32} in[(2p+r)][ci] * wt[(r*32+ci)][c]); lane = c
+template <int PIN, int POUT>
+__device__ __forceinline__ void conv3x1(const float* __restrict__ in, const float* __restrict__ wt,
+                                        const float* __restrict__ bias, float* __restrict__ out,
+                                        int warp, int lane) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int J = (POUT + kWarps - 1) / kWarps;
+  float acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) acc[j] = bias[lane];
+#pragma unroll 4
+  for (int k = 0; k < kK2; ++k) {
+    const float w = wt[k * kC + lane];
+    const int r = k >> 5, ci = k & 31;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int p = warp + kWarps * j;
+      if (p < POUT) acc[j] = fmaf(in[(2 * p + r) * kC + ci], w, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int p = warp + kWarps * j;
+    if (p < POUT) out[p * kC + lane] = fmaxf(acc[j], 0.f);
+  }
+}
+
+__device__ __forceinline__ void store_rounded(const float* __restrict__ s, float* __restrict__ g, int n) {
+  if (!g) return;
+  for (int i = threadIdx.x; i < n; i += kThreads) g[i] = round_tf32(s[i]);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 2) kuka_sound_fwd_kernel(KukaSoundArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* sx = sm;                       // [100*40]
+  float* w1t = sx + kF * kMelW;         // [200][32]
+  float* w2t = w1t + kK1 * kC;          // 3 x [96][32]
+  float* a1 = w2t + 3 * kK2 * kC;       // [48*32]
+  float* a2 = a1 + kP1 * kC;            // [23*32]
+  float* a3 = a2 + kP2 * kC;            // [11*32]
+  float* a4 = a3 + kP3 * kC;            // [5*32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x;
+
+  // stage the clip (128-bit loads) and the transposed conv weights
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.x + (long long)n * kF * kMelW);
+    float4* dst = reinterpret_cast<float4*>(sx);
+    for (int i = tid; i < kF * kMelW / 4; i += kThreads) dst[i] = src[i];
+    for (int i = tid; i < kK1 * kC; i += kThreads) {
+      const int c = i / kK1, k = i - c * kK1;  // coalesced read of packed [32][224]
+      w1t[k * kC + c] = a.w1[c * kK1Pad + k];
+    }
+    for (int l = 0; l < 3; ++l) {
+      const float* w = l == 0 ? a.w2 : (l == 1 ? a.w3 : a.w4);
+      for (int i = tid; i < kK2 * kC; i += kThreads) {
+        const int c = i / kK2, k = i - c * kK2;
+        w2t[(l * kK2 + k) * kC + c] = w[c * kK2 + k];
+      }
+    }
+  }
+  __syncthreads();
+
+  // conv1: out[p][c] = relu(b + sum_{k<200} x[2p*40 + k] * w1t[k][c])   (5x40 window is contiguous)
+  {
+    constexpr int J = kP1 / 8;  // 6 rows per warp
+    float acc[J];
+    const float b = a.b1[lane];
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = b;
+#pragma unroll 4
+    for (int k = 0; k < kK1; ++k) {
+      const float w = w1t[k * kC + lane];
+#pragma unroll
+      for (int j = 0; j < J; ++j) acc[j] = fmaf(sx[(2 * (warp + 8 * j)) * kMelW + k], w, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) a1[(warp + 8 * j) * kC + lane] = fmaxf(acc[j], 0.f);
+  }
+  __syncthreads();
+  conv3x1<kP1, kP2>(a1, w2t, a.b2, a2, warp, lane);
+  __syncthreads();
+  conv3x1<kP2, kP3>(a2, w2t + kK2 * kC, a.b3, a3, warp, lane);
+  __syncthreads();
+  conv3x1<kP3, kP4>(a3, w2t + 2 * kK2 * kC, a.b4, a4, warp, lane);
+  __syncthreads();
+
+  store_rounded(a1, a.act1 ? a.act1 + (long long)n * kP1 * kC : nullptr, kP1 * kC);
+  store_rounded(a2, a.act2 ? a.act2 + (long long)n * kP2 * kC : nullptr, kP2 * kC);
+  store_rounded(a3, a.act3 ? a.act3 + (long long)n * kP3 * kC : nullptr, kP3 * kC);
+  store_rounded(a4, a.act4 + (long long)n * kP4 * kC, kP4 * kC);
+
+  // Linear 160 -> 128 + ReLU: 16 outputs per warp, lanes split k (weights stream from L2)
+  for (int o = warp * 16; o < warp * 16 + 16; ++o) {
+    const float* w = a.wl + (long long)o * kFlat;
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < kFlat / 32; ++u) acc = fmaf(a4[lane + 32 * u], w[lane + 32 * u], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) a.hidden[(long long)n * kHid + o] = fmaxf(acc + a.bl[o], 0.f);
+  }
+}
+
+int kuka_sound_fwd(const KukaSoundArgs& a, int N, cudaStream_t st) {
+  if (N <= 0) return VAR_OK;
+  const size_t smem = (size_t)(kF * kMelW + kK1 * kC + 3 * kK2 * kC + (kP1 + kP2 + kP3 + kP4) * kC) * 4;
+  static bool configured = false;
+  if (!configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(kuka_sound_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = true;
+  }
+  LaunchScope sc(T_MISC, 2.0 * N * 447872.0, st);
+  kuka_sound_fwd_kernel<<<N, kThreads, smem, st>>>(a);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+}  // namespace var

@@ -12,6 +12,7 @@
 #include "../../include/var_b200.h"
 #include "aux_kernels.cuh"
 #include "engine_host.cuh"
+#include "kuka_sound.cuh"
 #include "triplet.cuh"
 
 namespace var {
@@ -301,6 +302,40 @@ struct Net {
     return concat2(g.h32[0][kGruT & 1], g.h32[1][kGruT & 1], g.out, g.out_r, B, kGruH, st);
   }
 
+  // Kuka sound branch: one fused fp32 kernel (kuka_sound.cu).  Buffers are laid out and the
+  // per-layer run state is filled exactly as run_layers_fwd would, so the tcgen05 backward
+  // path works on them unchanged.
+  bool fp32_sound = true;
+  int kuka_sound_forward(const float* sounds, const SrcLayout& sl, int N, bool train, Arena& ar,
+                         cudaStream_t st) {
+    const void* cur = sounds;
+    int kind_ = SRC_STRIDED_F32;
+    for (auto* L : {&snd_trunk, &snd_head})
+      for (Layer& l : *L) {
+        l.in = cur; l.in_kind = kind_; l.in_sl = sl; l.N = N;
+        l.out = ar.alloc((long long)N * l.P * l.Q * l.Cout);
+        cur = l.out;
+        kind_ = SRC_NHWC_F32;
+      }
+    snd_raw = snd_trunk.back().out;
+    h_snd = snd_head.back().out;
+    if (!ar.base) return VAR_OK;
+    if (ar.overflow) return VAR_ERR_WORKSPACE;
+    KukaSoundArgs a;
+    a.x = sounds;
+    a.w1 = wm(snd_trunk[0].tw); a.b1 = wm(snd_trunk[0].tb);
+    a.w2 = wm(snd_trunk[1].tw); a.b2 = wm(snd_trunk[1].tb);
+    a.w3 = wm(snd_trunk[2].tw); a.b3 = wm(snd_trunk[2].tb);
+    a.w4 = wm(snd_trunk[3].tw); a.b4 = wm(snd_trunk[3].tb);
+    a.wl = wm(snd_head[0].tw); a.bl = wm(snd_head[0].tb);
+    a.act1 = train ? snd_trunk[0].out : nullptr;
+    a.act2 = train ? snd_trunk[1].out : nullptr;
+    a.act3 = train ? snd_trunk[2].out : nullptr;
+    a.act4 = snd_trunk[3].out;
+    a.hidden = snd_head[0].out;
+    return kuka_sound_fwd(a, N, st);
+  }
+
   int forward(const void* images, int image_kind, int n_images, const float* sounds, int n_sounds,
               void* ws, long long ws_bytes, bool train, cudaStream_t st) {
     Arena ar(ws, ws_bytes);
@@ -323,7 +358,14 @@ struct Net {
       sl.sC = 0; sl.sW = 1; sl.sH = 40; sl.sN = (long long)F * 40;
       sl.scale = 1.f;
       float* t;
-      int rc = run_layers_fwd(snd_trunk, sounds, SRC_STRIDED_F32, sl, n_sounds, ar, st, &t);
+      int rc;
+      if (kind == 0 && fp32_sound) {
+        rc = kuka_sound_forward(sounds, sl, n_sounds, train, ar, st);
+        if (rc) return rc;
+        fwd_used = ar.used;
+        return VAR_OK;
+      }
+      rc = run_layers_fwd(snd_trunk, sounds, SRC_STRIDED_F32, sl, n_sounds, ar, st, &t);
       if (rc) return rc;
       if (has_gru) {
         rc = gru_forward(t, n_sounds, train, ar, st);
