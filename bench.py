@@ -176,7 +176,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     import var_b200 as vb
     from importlib import import_module
     al = import_module("voicecontrolledrobot-var_b200.Envs.audioLoader")
@@ -213,7 +214,7 @@ def run_b200(args):
         perm_holder["pos"] += global_b
         return perm_holder["perm"][s:s + global_b]
 
-    def step_resident():
+    def step_resident(comm=True):
         rec = sampler.sample(next_items())
         lo, hi = local_b * rank, local_b * (rank + 1)
         off = torch.cat([rec["off"][lo:hi], rec["off"][global_b + lo:global_b + hi]])
@@ -222,7 +223,7 @@ def run_b200(args):
         img = pool[(rec["item"][lo:hi] % IMAGE_POOL).long()]
         eng.zero_grad()
         eng.triplet_step(img, sounds, margin=1.0, loss_denominator=global_b, loss_out=loss_acc)
-        if world > 1:
+        if world > 1 and comm:
             dist.all_reduce(eng.grads)
         eng.adam_step(1e-4, weight_decay=1e-6)
 
@@ -292,7 +293,7 @@ def run_b200(args):
         lib.var_prof_begin()
         prof_steps = 3
         for _ in range(prof_steps):
-            step_resident()
+            step_resident(comm=False)  # rank 0 only: no collective inside the profiled steps
         prof = vb._lib.prof_end()
         step_kernel_ms = sum(v[0] for v in prof.values()) / prof_steps
         hbm, bf16_burst, bf16_sus, src = measured_peaks()

@@ -207,7 +207,9 @@ int gather_mode() {  // VAR_GATHER=cp_async keeps the LSU gather kernels (A/B te
 template <int GMODE, int EPI>
 static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& a0,
                          const CUtensorMap& a1, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  if (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8)
+    smem += (size_t)p.g[0].C * p.sc_nh * p.sc_wpad * 4 + 16;  // staged input patch
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<GMODE, EPI>,
@@ -360,6 +362,19 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
     }
   }
   dim3 grid((M + 127) / 128, cs.Cout / bn, 1);
+  if (gmode == G_SCALAR_F32 || gmode == G_SCALAR_U8) {
+    // tiles of whole output rows of one image (<= 128 pixels) over a smem-staged input patch
+    if (cs.Q > 128) return VAR_ERR_UNSUPPORTED;
+    p.sc_rpt = 128 / cs.Q < cs.P ? 128 / cs.Q : cs.P;
+    p.sc_tpi = (cs.P + p.sc_rpt - 1) / p.sc_rpt;
+    p.sc_nh = (p.sc_rpt - 1) * cs.sh + cs.R;
+    p.sc_wpad = cs.W + 2 * cs.pw;
+    grid.x = (unsigned)(cs.N * p.sc_tpi);
+    // few k-blocks per tile, no global latency to hide: a shallow pipeline keeps the CTA small
+    // so several tiles overlap their stage / build / MMA / epilogue phases on one SM
+    p.stages = p.num_kb < 2 ? 1 : 2;
+    p.lookahead = 0;
+  }
   return launch_gemm(gmode, EPI_STD, tm, tm, ta, ta, p, grid, st);
 }
 

@@ -5,6 +5,7 @@
 // Activations are NHWC fp32 (tf32-representable values) in a caller-provided
 // workspace; parameters live in one flat packed buffer (see include/var_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -90,6 +91,40 @@ struct Net {
   GruState gru;
   float *h_img = nullptr, *h_snd = nullptr;  // inputs of the tail
   float *img_raw_nhwc = nullptr, *snd_raw = nullptr;
+  // The image and sound branches are independent until the tail: the image branch runs on a
+  // side stream so its large-grid kernels fill the SMs the sound branch's small sequential
+  // launches (GRU time steps) leave idle.  VAR_OVERLAP=0 serialises them on the caller's stream.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;
+
+  ~Net() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
+  // Returns the stream the image branch should use (forked from st) or st itself.
+  cudaStream_t fork_side(bool both, cudaStream_t st) {
+    if (!both || !overlap) return st;
+    if (!side) {
+      const char* e = getenv("VAR_OVERLAP");
+      if (e && e[0] == '0') { overlap = false; return st; }
+      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        overlap = false;
+        return st;
+      }
+    }
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    return side;
+  }
+  void join_side(cudaStream_t used, cudaStream_t st) {
+    if (used == st) return;
+    cudaEventRecord(ev_join, used);
+    cudaStreamWaitEvent(st, ev_join, 0);
+  }
 
   int add_tensor(const std::string& name, int ndim, const int* shape, int O, int I, int R, int S,
                  int kpad) {
@@ -341,16 +376,22 @@ struct Net {
     Arena ar(ws, ws_bytes);
     n_img = n_images; n_snd = n_sounds;
     h_img = h_snd = img_raw_nhwc = snd_raw = nullptr;
+    cudaStream_t st_main = st;
+    cudaStream_t st_img = ar.base ? fork_side(n_images > 0 && n_sounds > 0, st) : st;
+    struct Joiner {  // joins the side stream on every exit path
+      Net* n; cudaStream_t a, b;
+      ~Joiner() { n->join_side(a, b); }
+    } joiner{this, st_img, st_main};
     if (n_images > 0) {
       SrcLayout sl;
       sl.sW = 1; sl.sH = 96; sl.sC = 96 * 96; sl.sN = 3 * 96 * 96;  // NCHW
       sl.scale = image_kind == 0 ? 1.f / 255.f : 1.f;
       float* t;
       int rc = run_layers_fwd(img_trunk, images, image_kind == 0 ? SRC_STRIDED_U8 : SRC_STRIDED_F32,
-                              sl, n_images, ar, st, &t);
+                              sl, n_images, ar, st_img, &t);
       if (rc) return rc;
       img_raw_nhwc = t;
-      rc = run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st, &h_img);
+      rc = run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st_img, &h_img);
       if (rc) return rc;
     }
     if (n_sounds > 0) {
@@ -479,15 +520,19 @@ struct Net {
   int backward_from_dh(float* dh_img, float* dh_snd, void* ws, long long ws_bytes, cudaStream_t st) {
     Arena ar(ws, ws_bytes);
     ar.used = fwd_used;
-    const long long mark = ar.used;
+    cudaStream_t st_img = fork_side(n_img > 0 && dh_img && n_snd > 0 && dh_snd, st);
+    struct Joiner {
+      Net* n; cudaStream_t a, b;
+      ~Joiner() { n->join_side(a, b); }
+    } joiner{this, st_img, st};
     if (n_img > 0 && dh_img) {
       float* d;
-      int rc = run_layers_bwd(img_head, dh_img, ar, st, &d);
+      int rc = run_layers_bwd(img_head, dh_img, ar, st_img, &d);
       if (rc) return rc;
-      rc = run_layers_bwd(img_trunk, d, ar, st, &d);
+      rc = run_layers_bwd(img_trunk, d, ar, st_img, &d);
       if (rc) return rc;
     }
-    ar.used = mark;  // the two branches reuse the same gradient scratch
+    // the branches run concurrently: each keeps its own gradient scratch region
     if (n_snd > 0 && dh_snd) {
       float* d;
       int rc = run_layers_bwd(snd_head, dh_snd, ar, st, &d);
@@ -517,7 +562,6 @@ struct Net {
       run_layers_bwd(img_trunk, nullptr, ar, 0, &d);
       best = ar.used;
     }
-    ar.used = 0;
     if (n_sounds > 0) {
       for (auto& l : snd_head) { l.N = n_sounds; l.in_kind = SRC_NHWC_F32; }
       for (size_t i = 0; i < snd_trunk.size(); ++i) {
@@ -527,7 +571,7 @@ struct Net {
       run_layers_bwd(snd_head, nullptr, ar, 0, &d);
       if (has_gru) { gru.B = n_sounds; gru_backward(nullptr, ar, 0, &d); }
       run_layers_bwd(snd_trunk, nullptr, ar, 0, &d);
-      if (ar.used > best) best = ar.used;
+      best = ar.used;  // image + sound regions (disjoint: the branches overlap in time)
     }
     return best;
   }

@@ -106,6 +106,10 @@ struct GemmParams {
   int base_w, base_h;          // base-pixel coordinate of output (p, q) = (0, 0)
   int step_w, step_h;          // base-pixel step per output pixel (= traversal stride)
   uint8_t tap_w[kMaxTaps], tap_h[kMaxTaps], tap_id[kMaxTaps];
+  // scalar (first-layer) mode: M tiles are whole output rows of one image; the input patch of the
+  // tile is staged once in shared memory
+  int sc_rpt, sc_tpi;          // output rows per tile, tiles per image
+  int sc_nh, sc_wpad;          // staged rows / padded row width
 };
 
 constexpr int kTileM = 128;
@@ -157,27 +161,17 @@ __device__ __forceinline__ void gather_row(const GatherGeom& g, const RowCtx& rc
 #pragma unroll
     for (int c = 0; c < 8; ++c) cp_async_16(tile + swz128(row, c), src + (ok ? c * 4 : 0), nb);
   } else {
-    // scalar im2col: k = (r*S + s)*C + c ; lut_off[k] = r*sH + s*sW + c*sC, lut_rs[k] = r<<16|s
-    const int h0 = rc.p * g.sh - g.ph, w0 = rc.q * g.sw - g.pw;
-    const long long b0 = rc.base + (long long)h0 * g.sH + (long long)w0 * g.sW;
+    // scalar im2col from the staged patch: lut_off[k] = (c*nh + r)*wpad + s (or -1 beyond K);
+    // rc.base = offset of the row's window origin in the patch (or -1: row not in this tile)
+    const float* sin = reinterpret_cast<const float*>(lut_rs);
+    const int b0 = (int)rc.base;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int k = kb * 32 + c * 4 + j;
-        float x = 0.f;
-        if (rc.valid && k < g.K) {
-          const int rs = lut_rs[k];
-          const int h = h0 + (rs >> 16), w = w0 + (rs & 0xFFFF);
-          if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
-            if constexpr (GMODE == G_SCALAR_U8)
-              x = (float)reinterpret_cast<const uint8_t*>(g.src)[b0 + lut_off[k]] * g.scale;
-            else
-              x = reinterpret_cast<const float*>(g.src)[b0 + lut_off[k]] * g.scale;
-          }
-        }
-        v[j] = round_tf32(x);
+        const int o = lut_off[kb * 32 + c * 4 + j];
+        v[j] = (b0 >= 0 && o >= 0) ? sin[b0 + o] : 0.f;
       }
       st_shared_v4(tile + swz128(row, c), v[0], v[1], v[2], v[3]);
     }
@@ -224,12 +218,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
 
   constexpr bool kScalar = (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8);
   __shared__ int lut_off[kScalar ? 256 : 1];
-  __shared__ int lut_rs[kScalar ? 256 : 1];
+  const float* s_patch = reinterpret_cast<const float*>(smem_raw + (((tslot + 23u) & ~15u) - smem_u32(smem_raw)));
+  int sc_n = 0, sc_p0 = 0, sc_rows = 0;
   if constexpr (kScalar) {
-    for (int k = tid; k < g.K && k < 256; k += blockDim.x) {
-      const int c = k % g.C, rs = k / g.C, s = rs % g.S, r = rs / g.S;
-      lut_off[k] = (int)(r * g.sH + s * g.sW + c * g.sC);
-      lut_rs[k] = (r << 16) | s;
+    // tile = up to sc_rpt output rows of image sc_n; stage their input rows (zero padded borders,
+    // scale and tf32 rounding applied once per element)
+    sc_n = blockIdx.x / p.sc_tpi;
+    sc_p0 = (blockIdx.x - sc_n * p.sc_tpi) * p.sc_rpt;
+    sc_rows = min(p.sc_rpt, g.P - sc_p0);
+    const int kpad = num_kb * 32;
+    for (int k = tid; k < kpad; k += blockDim.x) {
+      int o = -1;
+      if (k < g.K) {
+        const int c = k % g.C, rs = k / g.C, s = rs % g.S, r = rs / g.S;
+        o = (c * p.sc_nh + r) * p.sc_wpad + s;
+      }
+      lut_off[k] = o;
+    }
+    float* patch = const_cast<float*>(s_patch);
+    const int h_lo = sc_p0 * g.sh - g.ph;
+    const int nh = (sc_rows - 1) * g.sh + g.R;
+    const int total = g.C * nh * p.sc_wpad;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int ww = i % p.sc_wpad;
+      const int t = i / p.sc_wpad;
+      const int hh = t % nh, c = t / nh;
+      const int h = h_lo + hh, w = ww - g.pw;
+      float x = 0.f;
+      if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+        const long long idx = (long long)sc_n * g.sN + (long long)h * g.sH + (long long)w * g.sW +
+                              (long long)c * g.sC;
+        if constexpr (GMODE == G_SCALAR_U8)
+          x = (float)reinterpret_cast<const uint8_t*>(g.src)[idx] * g.scale;
+        else
+          x = reinterpret_cast<const float*>(g.src)[idx] * g.scale;
+      }
+      patch[(c * p.sc_nh + hh) * p.sc_wpad + ww] = round_tf32(x);
     }
   }
 
@@ -251,14 +275,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
-  const int m0 = blockIdx.x * kTileM;
+  const int m0 = kScalar ? (sc_n * g.P + sc_p0) * g.Q : blockIdx.x * kTileM;
+  const int m_end = kScalar ? m0 + sc_rows * g.Q : g.M;
   const int ntile = blockIdx.y;
 
   if (warp < 4) {
     // ===================== producers (then epilogue) =====================
     const int row = tid;
     RowCtx rc;
-    {
+    if constexpr (kScalar) {
+      const int pr = row / g.Q, q = row - pr * g.Q;
+      rc.valid = pr < sc_rows;
+      rc.n = sc_n; rc.p = sc_p0 + pr; rc.q = q;
+      rc.base = rc.valid ? (long long)(pr * g.sh) * p.sc_wpad + q * g.sw : -1;
+    } else {
       const int m = m0 + row;
       rc.valid = m < g.M;
       const int pq = g.P * g.Q;
@@ -330,7 +360,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
                             rs * p.cin_total + ntile * bn + gidx * 32, k0);
             }
           }
-          gather_row<GMODE>(g, rc, it, sA + (uint32_t)st_issue * kTileABytes, row, lut_off, lut_rs);
+          gather_row<GMODE>(g, rc, it, sA + (uint32_t)st_issue * kTileABytes, row, lut_off,
+                            reinterpret_cast<const int*>(s_patch));
           if (++st_issue == stages) { st_issue = 0; ph_issue ^= 1; }
         }
         cp_async_commit();
@@ -355,7 +386,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
         tmem_ld32(trow + (uint32_t)c, v);
         tmem_ld_wait();
         const int col0 = ntile * bn + c;
-        if (m < g.M && col0 < e.ncols) {
+        if (m < m_end && col0 < e.ncols) {
           long long orow = m;
           if (e.map.on) {
             const int pq2 = e.map.P2 * e.map.Q2;
