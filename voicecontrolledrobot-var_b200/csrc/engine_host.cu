@@ -613,7 +613,11 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
   const int slab = pick_bn(cs.Cout);
   if (slab == 0 || slab % 32) return VAR_ERR_UNSUPPORTED;
   const int nslab = cs.Cout / slab;
-  int splits = (4 * kNumSMs + ktiles * nslab - 1) / (ktiles * nslab);
+  // 2 CTAs fit per SM: size the pixel split so the grid is a whole number of 296-CTA waves
+  // (a 616-CTA grid runs three waves for 2.08 waves of work)
+  const int per_split = ktiles * nslab;
+  int splits = (2 * 2 * kNumSMs) / per_split;
+  if (splits < 1) splits = 1;
   int ppc = (p.M + splits - 1) / splits;
   ppc = ((ppc + 31) / 32) * 32;
   if (ppc < 256) ppc = 256;

@@ -376,13 +376,13 @@ struct Net {
     Arena ar(ws, ws_bytes);
     n_img = n_images; n_snd = n_sounds;
     h_img = h_snd = img_raw_nhwc = snd_raw = nullptr;
-    cudaStream_t st_main = st;
-    cudaStream_t st_img = ar.base ? fork_side(n_images > 0 && n_sounds > 0, st) : st;
+    const bool both = n_images > 0 && n_sounds > 0;
+    cudaStream_t st_img = st;
     struct Joiner {  // joins the side stream on every exit path
-      Net* n; cudaStream_t a, b;
-      ~Joiner() { n->join_side(a, b); }
-    } joiner{this, st_img, st_main};
-    if (n_images > 0) {
+      Net* n; cudaStream_t* a; cudaStream_t b;
+      ~Joiner() { n->join_side(*a, b); }
+    } joiner{this, &st_img, st};
+    auto image_branch = [&]() -> int {
       SrcLayout sl;
       sl.sW = 1; sl.sH = 96; sl.sC = 96 * 96; sl.sN = 3 * 96 * 96;  // NCHW
       sl.scale = image_kind == 0 ? 1.f / 255.f : 1.f;
@@ -391,7 +391,14 @@ struct Net {
                               sl, n_images, ar, st_img, &t);
       if (rc) return rc;
       img_raw_nhwc = t;
-      rc = run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st_img, &h_img);
+      return run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st_img, &h_img);
+    };
+    // With a GRU the sound trunk's big convs go first and the image branch is forked right after
+    // them, so it overlaps the 73 small GRU-step launches instead of competing with the convs.
+    const bool late_fork = both && has_gru;
+    if (n_images > 0 && !late_fork) {
+      if (ar.base) st_img = fork_side(both, st);
+      const int rc = image_branch();
       if (rc) return rc;
     }
     if (n_sounds > 0) {
@@ -408,6 +415,11 @@ struct Net {
       }
       rc = run_layers_fwd(snd_trunk, sounds, SRC_STRIDED_F32, sl, n_sounds, ar, st, &t);
       if (rc) return rc;
+      if (late_fork) {
+        if (ar.base) st_img = fork_side(true, st);
+        rc = image_branch();
+        if (rc) return rc;
+      }
       if (has_gru) {
         rc = gru_forward(t, n_sounds, train, ar, st);
         if (rc) return rc;
