@@ -70,6 +70,23 @@ def test_mfcc_edge_cases_vs_oracle(vb):
             assert ok.all(), (params, F, i, float(np.abs(out[i] - ref).max()))
 
 
+def test_mfcc_psf_flavour_vs_oracle(vb):
+    """python_speech_features flavour (iTHOR env path, Envs/audioLoader.py:159-161).  PARITY UNPINNED:
+    the package is not in this image, so the oracle restates v0.6's algorithm (oracle/mfcc.py)."""
+    rng = np.random.default_rng(3)
+    clips = synth.make_clips(77, 3, (16000, 40000)) + [np.zeros(8000, np.int16),
+                                                        rng.integers(-32768, 32767, 300).astype(np.int16),
+                                                        rng.integers(-3000, 3000, 16000).astype(np.int16)]
+    for F in (600, 100):
+        out = _mfcc_gpu(vb, clips, (512, 400, 160), F, flavour=1)
+        for i, c in enumerate(clips):
+            ref = omfcc.mfcc_psf(c, 16000, 0.025, 0.01, 40, 40, 512)
+            nf = min(F, ref.shape[0])
+            ok = _mfcc_close(out[i, :nf], ref[:nf].astype(np.float32))
+            assert ok.all(), (F, i, float(np.abs(out[i, :nf] - ref[:nf]).max()))
+            assert not out[i, nf:].any()  # zero padded beyond the clip (processSoundFeat)
+
+
 def test_mfcc_empty_class_rows_are_zero(vb):
     from importlib import import_module
     al = import_module("voicecontrolledrobot-var_b200.Envs.audioLoader")

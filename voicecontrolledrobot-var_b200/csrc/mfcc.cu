@@ -34,10 +34,12 @@ struct MfccTables {       // device pointers
   const int* foff;        // [40] offset into fweights
   const float* fweights;  // [nnz]
   const float* dct;       // [40 f][40 k]
+  const float* lifter;    // [40] cepstral lifter (flavour 1)
   int nnz;
 };
 
 struct MfccPlan {
+  int flavour;            // 0 torchaudio, 1 python_speech_features
   int fs, n_fft, win_length, hop;
   MfccTables t;
   void* dev_blob;
@@ -49,6 +51,7 @@ struct MfccArgs {
   const long long* offsets;  // [B] sample offset of clip b in wav, < 0 => all-zero feature
   const int* lengths;        // [B] samples
   int B, F, hop;
+  int flavour, win_length;
   float* out;                // [B, F, 40]
   MfccTables t;
 };
@@ -116,7 +119,12 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
   float* outp = a.out + ((long long)b * F + f0) * kMel;
   const long long off = a.offsets[b];
   const int S = a.lengths[b];
-  const int T = off < 0 ? 0 : 1 + S / a.hop;  // valid frames (centre padded)
+  // valid frames: torchaudio centre-pads (1 + S/hop); python_speech_features frames from sample 0
+  // and zero-pads the tail (1 + ceil((S - win)/hop))
+  const bool psf = a.flavour == 1;
+  const int T = off < 0 ? 0
+                        : (!psf ? 1 + S / a.hop
+                                : (S <= a.win_length ? 1 : 1 + (S - a.win_length + a.hop - 1) / a.hop));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int nvalid = max(0, min(nfr, T - f0));
@@ -129,12 +137,13 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
   const int span = (nvalid - 1) * a.hop + NFFT;  // samples needed by this chunk
   const int span2 = (span + 1) & ~1;
   int16_t* s_wav = reinterpret_cast<int16_t*>(sm_raw);
-  size_t o = ((size_t)span2 * 2 + 15) & ~(size_t)15;
+  size_t o = ((size_t)(span2 + 2) * 2 + 15) & ~(size_t)15;
   float* s_win = reinterpret_cast<float*>(sm_raw + o); o += NFFT * 4;
   float2* s_tw = reinterpret_cast<float2*>(sm_raw + o); o += NFFT * 8;
   float* s_fw = reinterpret_cast<float*>(sm_raw + o); o += ((a.t.nnz + 3) & ~3) * 4;
   float* s_dct = reinterpret_cast<float*>(sm_raw + o); o += kMel * kMel * 4;
   float* s_lm = reinterpret_cast<float*>(sm_raw + o); o += kMel * (kFramesPerCta + 4) * 4;  // [f][frame]
+  float* s_le = reinterpret_cast<float*>(sm_raw + o); o += (kFramesPerCta + 4) * 4;          // log frame energy
   float* s_scr = reinterpret_cast<float*>(sm_raw + o);  // per warp: re[SCR], im[SCR], pw[NBIN+..]
   constexpr int WSCR = 2 * SCR + ((NBIN + 7) & ~3);
   float* sre = s_scr + warp * WSCR;
@@ -144,11 +153,14 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
   // ---- stage samples (reflect padding at the clip ends), tables
   {
     const int16_t* w = a.wav + off;
-    const int base = f0 * a.hop - NFFT / 2;  // logical sample index of s_wav[0]
-    for (int i = tid; i < span2; i += kMfccThreads) {
+    // logical sample index of s_wav[0]; flavour 1 keeps one extra leading sample for the pre-emphasis
+    const int base = psf ? f0 * a.hop - 2 : f0 * a.hop - NFFT / 2;
+    for (int i = tid; i < span2 + (psf ? 2 : 0); i += kMfccThreads) {
       int idx = base + i;
-      if (idx < 0) idx = -idx;
-      if (idx >= S) idx = 2 * (S - 1) - idx;
+      if (!psf) {  // reflect padding at the clip ends
+        if (idx < 0) idx = -idx;
+        if (idx >= S) idx = 2 * (S - 1) - idx;
+      }
       int16_t v = 0;
       if (idx >= 0 && idx < S) v = w[idx];
       s_wav[i] = v;
@@ -165,7 +177,8 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
   const int fof1 = lane < kMel - 32 ? a.t.foff[lane + 32] : 0;
 
   for (int fr = warp; fr < nvalid; fr += kWarps) {
-    const int16_t* x = s_wav + fr * a.hop;  // frame element e -> x[e]
+    const int16_t* x = s_wav + fr * a.hop + (psf ? 2 : 0);  // frame element e -> x[e]
+    const int lim = S - (f0 + fr) * a.hop;                   // clip samples left from the frame start
     float2 z[NB];
     // ---------------- pass 1: radix 8, Ns = 1 (reads windowed samples) -------------
 #pragma unroll
@@ -177,7 +190,15 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
         const int e = 2 * (j + (N / 8) * t);
         const short2 s2 = *reinterpret_cast<const short2*>(x + e);
         const float2 w2 = *reinterpret_cast<const float2*>(s_win + e);
-        v[t] = make_float2((float)s2.x * (1.f / 32768.f) * w2.x, (float)s2.y * (1.f / 32768.f) * w2.y);
+        if (!psf) {
+          v[t] = make_float2((float)s2.x * (1.f / 32768.f) * w2.x, (float)s2.y * (1.f / 32768.f) * w2.y);
+        } else {  // pre-emphasis 0.97 on the raw int16 scale (sigproc.preemphasis); the zero
+          // padding of the last frame is appended AFTER the pre-emphasis, so samples >= S are 0
+          const float xm1 = (float)x[e - 1];
+          const float y0 = e < lim ? (float)s2.x - 0.97f * xm1 : 0.f;
+          const float y1 = e + 1 < lim ? (float)s2.y - 0.97f * (float)s2.x : 0.f;
+          v[t] = make_float2(y0 * w2.x, y1 * w2.y);
+        }
       }
       dft8(v);
 #pragma unroll
@@ -239,6 +260,8 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
     __syncwarp();
     // ---------------- real-FFT split, power spectrum ----------------
     {
+      const float pscale = psf ? 1.f / (float)NFFT : 1.f;
+      float esum = 0.f;
       const int src = (32 - lane) & 31;
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
@@ -253,11 +276,19 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
         const float2 w = s_tw[lane + 32 * u];  // exp(-2 pi i m / NFFT)
         const float xr = er + (orr * w.x - oi * w.y);
         const float xi = ei + (orr * w.y + oi * w.x);
-        spw[lane + 32 * u] = xr * xr + xi * xi;
+        const float pw = (xr * xr + xi * xi) * pscale;
+        spw[lane + 32 * u] = pw;
+        esum += pw;
       }
       if (lane == 0) {
         const float ny = z[0].x - z[0].y;
-        spw[N] = ny * ny;
+        spw[N] = ny * ny * pscale;
+        esum += ny * ny * pscale;
+      }
+      if (psf) {  // frame energy -> c0 (base.mfcc appendEnergy=True)
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, sft);
+        if (lane == 0) s_le[fr] = logf(esum == 0.f ? 2.220446049250313e-16f : esum);
       }
     }
     __syncwarp();
@@ -265,11 +296,13 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
     {
       float acc = 0.f;
       for (int i = 0; i < fcn0; ++i) acc = fmaf(spw[fst0 + i], s_fw[fof0 + i], acc);
-      s_lm[lane * (kFramesPerCta + 4) + fr] = logf(acc + kLogEps);
+      s_lm[lane * (kFramesPerCta + 4) + fr] =
+          psf ? logf(acc == 0.f ? 2.220446049250313e-16f : acc) : logf(acc + kLogEps);
       if (lane < kMel - 32) {
         float acc1 = 0.f;
         for (int i = 0; i < fcn1; ++i) acc1 = fmaf(spw[fst1 + i], s_fw[fof1 + i], acc1);
-        s_lm[(lane + 32) * (kFramesPerCta + 4) + fr] = logf(acc1 + kLogEps);
+        s_lm[(lane + 32) * (kFramesPerCta + 4) + fr] =
+            psf ? logf(acc1 == 0.f ? 2.220446049250313e-16f : acc1) : logf(acc1 + kLogEps);
       }
     }
     __syncwarp();
@@ -291,6 +324,13 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
         acc.z = fmaf(l4.z, d, acc.z); acc.w = fmaf(l4.w, d, acc.w);
       }
       const int fr = 4 * g;
+      if (psf) {  // lifter, then c0 := log frame energy
+        const float lf = a.t.lifter[k];
+        acc.x *= lf; acc.y *= lf; acc.z *= lf; acc.w *= lf;
+        if (k == 0) {
+          acc.x = s_le[fr]; acc.y = s_le[fr + 1]; acc.z = s_le[fr + 2]; acc.w = s_le[fr + 3];
+        }
+      }
       if (fr < nvalid) outp[(fr)*kMel + k] = acc.x;
       if (fr + 1 < nvalid) outp[(fr + 1) * kMel + k] = acc.y;
       if (fr + 2 < nvalid) outp[(fr + 2) * kMel + k] = acc.z;
@@ -305,9 +345,10 @@ static size_t mfcc_smem_bytes(int hop, int nnz) {
   constexpr int SCR = N + (N >> 5) + 40;
   constexpr int NBIN = N + 1;
   constexpr int WSCR = 2 * SCR + ((NBIN + 7) & ~3);
-  size_t span = (size_t)(kFramesPerCta - 1) * hop + NFFT + 2;
+  size_t span = (size_t)(kFramesPerCta - 1) * hop + NFFT + 4;
   size_t o = (span * 2 + 15) & ~(size_t)15;
   o += NFFT * 4 + NFFT * 8 + ((nnz + 3) & ~3) * 4 + kMel * kMel * 4 + kMel * (kFramesPerCta + 4) * 4;
+  o += (kFramesPerCta + 4) * 4;
   o += (size_t)(kMfccThreads / 32) * WSCR * 4;
   return o + 16;
 }
@@ -323,46 +364,81 @@ static void linspace_f32(float start, float end, int steps, std::vector<float>& 
     out[i] = i < half ? start + step * (float)i : end - step * (float)(steps - 1 - i);
 }
 
-int mfcc_num_frames(const MfccPlan* p, int n_samples) { return 1 + n_samples / p->hop; }
+int mfcc_num_frames(const MfccPlan* p, int n_samples) {
+  if (p->flavour == 0) return 1 + n_samples / p->hop;
+  if (n_samples <= p->win_length) return 1;
+  return 1 + (n_samples - p->win_length + p->hop - 1) / p->hop;
+}
 
 int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, MfccPlan** out) {
-  if (flavour != 0) return VAR_ERR_UNSUPPORTED;
-  if ((n_fft != 512 && n_fft != 1024) || win_length > n_fft || hop <= 0) return VAR_ERR_UNSUPPORTED;
+  if (flavour != 0 && flavour != 1) return VAR_ERR_UNSUPPORTED;
+  if ((n_fft != 512 && n_fft != 1024) || win_length > n_fft || hop <= 0 || (hop & 1)) return VAR_ERR_UNSUPPORTED;
   const int nfreq = n_fft / 2 + 1;
   std::vector<float> window(n_fft, 0.f);
-  const int left = (n_fft - win_length) / 2;
-  for (int k = 0; k < win_length; ++k)
-    window[left + k] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * (double)k / (double)win_length));
+  if (flavour == 0) {
+    // torch.hamming_window (periodic), centred in the n_fft frame by torch.stft
+    const int left = (n_fft - win_length) / 2;
+    for (int k = 0; k < win_length; ++k)
+      window[left + k] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * (double)k / (double)win_length));
+  } else {
+    // np.hamming (symmetric) on the first win_length samples; the rFFT zero-pads the tail
+    for (int k = 0; k < win_length; ++k)
+      window[k] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * (double)k / (double)(win_length - 1)));
+  }
   std::vector<float2> tw(n_fft);
   for (int q = 0; q < n_fft; ++q) {
     const double ang = -2.0 * M_PI * (double)q / (double)n_fft;
     tw[q] = make_float2((float)cos(ang), (float)sin(ang));
   }
-  // melscale_fbanks(n_freqs, 0, fs/2, 40, fs, norm=None, 'htk')
-  std::vector<float> all_freqs, m_pts;
-  linspace_f32(0.f, (float)(fs / 2), nfreq, all_freqs);
-  const float m_min = 2595.0f * log10f(1.0f + 0.f / 700.0f);
-  const float m_max = (float)(2595.0 * log10(1.0 + (double)(fs / 2) / 700.0));
-  linspace_f32(m_min, m_max, kMel + 2, m_pts);
-  std::vector<float> f_pts(kMel + 2);
-  for (int i = 0; i < kMel + 2; ++i) f_pts[i] = 700.0f * (powf(10.0f, m_pts[i] / 2595.0f) - 1.0f);
   std::vector<int> fstart(kMel), fcount(kMel), foff(kMel);
   std::vector<float> fw;
   int maxbins = 0;
-  for (int f = 0; f < kMel; ++f) {
-    int first = -1, last = -1;
-    std::vector<float> col(nfreq);
-    for (int m = 0; m < nfreq; ++m) {
-      const float down = -(f_pts[f] - all_freqs[m]) / (f_pts[f + 1] - f_pts[f]);
-      const float up = (f_pts[f + 2] - all_freqs[m]) / (f_pts[f + 2] - f_pts[f + 1]);
-      const float v = fmaxf(0.f, fminf(down, up));
-      col[m] = v;
-      if (v > 0.f) { if (first < 0) first = m; last = m; }
+  if (flavour == 0) {
+    // melscale_fbanks(n_freqs, 0, fs/2, 40, fs, norm=None, 'htk'), float32 like torch
+    std::vector<float> all_freqs, m_pts;
+    linspace_f32(0.f, (float)(fs / 2), nfreq, all_freqs);
+    const float m_min = 2595.0f * log10f(1.0f + 0.f / 700.0f);
+    const float m_max = (float)(2595.0 * log10(1.0 + (double)(fs / 2) / 700.0));
+    linspace_f32(m_min, m_max, kMel + 2, m_pts);
+    std::vector<float> f_pts(kMel + 2);
+    for (int i = 0; i < kMel + 2; ++i) f_pts[i] = 700.0f * (powf(10.0f, m_pts[i] / 2595.0f) - 1.0f);
+    for (int f = 0; f < kMel; ++f) {
+      int first = -1, last = -1;
+      std::vector<float> col(nfreq);
+      for (int m = 0; m < nfreq; ++m) {
+        const float down = -(f_pts[f] - all_freqs[m]) / (f_pts[f + 1] - f_pts[f]);
+        const float up = (f_pts[f + 2] - all_freqs[m]) / (f_pts[f + 2] - f_pts[f + 1]);
+        const float v = fmaxf(0.f, fminf(down, up));
+        col[m] = v;
+        if (v > 0.f) { if (first < 0) first = m; last = m; }
+      }
+      if (first < 0) { first = 0; last = -1; }
+      fstart[f] = first; fcount[f] = last - first + 1; foff[f] = (int)fw.size();
+      for (int m = first; m <= last; ++m) fw.push_back(col[m]);
+      if (fcount[f] > maxbins) maxbins = fcount[f];
     }
-    if (first < 0) { first = 0; last = -1; }
-    fstart[f] = first; fcount[f] = last - first + 1; foff[f] = (int)fw.size();
-    for (int m = first; m <= last; ++m) fw.push_back(col[m]);
-    if (fcount[f] > maxbins) maxbins = fcount[f];
+  } else {
+    // python_speech_features.base.get_filterbanks: triangles on FFT-bin indices (float64)
+    const double lowmel = 2595.0 * log10(1.0 + 0.0 / 700.0);
+    const double highmel = 2595.0 * log10(1.0 + (fs / 2.0) / 700.0);
+    std::vector<double> bins(kMel + 2);
+    for (int i = 0; i < kMel + 2; ++i) {
+      const double mel = lowmel + (highmel - lowmel) * (double)i / (double)(kMel + 1);
+      bins[i] = floor((n_fft + 1) * (700.0 * (pow(10.0, mel / 2595.0) - 1.0)) / fs);
+    }
+    for (int f = 0; f < kMel; ++f) {
+      std::vector<double> col(nfreq, 0.0);
+      for (int i = (int)bins[f]; i < (int)bins[f + 1]; ++i) col[i] = (i - bins[f]) / (bins[f + 1] - bins[f]);
+      for (int i = (int)bins[f + 1]; i < (int)bins[f + 2]; ++i)
+        col[i] = (bins[f + 2] - i) / (bins[f + 2] - bins[f + 1]);
+      int first = -1, last = -1;
+      for (int m = 0; m < nfreq; ++m)
+        if (col[m] != 0.0) { if (first < 0) first = m; last = m; }
+      if (first < 0) { first = 0; last = -1; }
+      fstart[f] = first; fcount[f] = last - first + 1; foff[f] = (int)fw.size();
+      for (int m = first; m <= last; ++m) fw.push_back((float)col[m]);
+      if (fcount[f] > maxbins) maxbins = fcount[f];
+    }
   }
   // create_dct(40, 40, 'ortho') -> [n_mels f][n_mfcc k]
   std::vector<float> dct(kMel * kMel);
@@ -373,10 +449,14 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
       v *= (float)sqrt(2.0 / kMel);
       dct[f * kMel + k] = v;
     }
+  std::vector<float> lifter(kMel, 1.f);
+  if (flavour == 1)
+    for (int n = 0; n < kMel; ++n) lifter[n] = (float)(1.0 + 11.0 * sin(M_PI * (double)n / 22.0));
   // pack into one device blob
   size_t o_win = 0, o_tw = o_win + window.size() * 4, o_fs = o_tw + tw.size() * 8,
          o_fc = o_fs + kMel * 4, o_fo = o_fc + kMel * 4, o_fw = o_fo + kMel * 4,
-         o_dct = o_fw + ((fw.size() + 3) & ~(size_t)3) * 4, total = o_dct + dct.size() * 4;
+         o_dct = o_fw + ((fw.size() + 3) & ~(size_t)3) * 4, o_lf = o_dct + dct.size() * 4,
+         total = o_lf + kMel * 4;
   std::vector<uint8_t> blob(total, 0);
   memcpy(&blob[o_win], window.data(), window.size() * 4);
   memcpy(&blob[o_tw], tw.data(), tw.size() * 8);
@@ -385,10 +465,12 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
   memcpy(&blob[o_fo], foff.data(), kMel * 4);
   memcpy(&blob[o_fw], fw.data(), fw.size() * 4);
   memcpy(&blob[o_dct], dct.data(), dct.size() * 4);
+  memcpy(&blob[o_lf], lifter.data(), kMel * 4);
   uint8_t* dev = nullptr;
   VAR_CUDA_CHECK(cudaMalloc(&dev, total));
   VAR_CUDA_CHECK(cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice));
   MfccPlan* p = new MfccPlan();
+  p->flavour = flavour;
   p->fs = fs; p->n_fft = n_fft; p->win_length = win_length; p->hop = hop;
   p->dev_blob = dev; p->max_filter_bins = maxbins;
   p->t.window = reinterpret_cast<float*>(dev + o_win);
@@ -398,6 +480,7 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
   p->t.foff = reinterpret_cast<int*>(dev + o_fo);
   p->t.fweights = reinterpret_cast<float*>(dev + o_fw);
   p->t.dct = reinterpret_cast<float*>(dev + o_dct);
+  p->t.lifter = reinterpret_cast<float*>(dev + o_lf);
   p->t.nnz = (int)fw.size();
   *out = p;
   return VAR_OK;
@@ -414,6 +497,7 @@ int mfcc_fwd(const MfccPlan* p, const int16_t* wav, const long long* offsets, co
   if (B <= 0 || F <= 0) return VAR_OK;
   MfccArgs a;
   a.wav = wav; a.offsets = offsets; a.lengths = lengths; a.B = B; a.F = F; a.hop = p->hop;
+  a.flavour = p->flavour; a.win_length = p->win_length;
   a.out = out; a.t = p->t;
   dim3 grid((F + kFramesPerCta - 1) / kFramesPerCta, B);
   LaunchScope sc(T_MFCC, 0, st);
