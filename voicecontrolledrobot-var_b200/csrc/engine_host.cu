@@ -252,7 +252,9 @@ int launch_gemm(int gmode, int epi, const CUtensorMap& t0, const CUtensorMap& t1
 
 template <int GMODE>
 static int launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = wgrad_smem_bytes(p.cout, p.stages);
+  size_t smem = wgrad_smem_bytes(p.cout, p.stages);
+  if (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8)
+    smem += (size_t)p.g.C * p.sc_nh * p.sc_wpad * 4 + 16;  // staged input patch
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<GMODE>,
@@ -670,14 +672,29 @@ int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout
   const int M = p.g.M;
   const int slab = pick_bn(cs.Cout);
   if (slab == 0) return VAR_ERR_UNSUPPORTED;
-  const int nslab = cs.Cout / slab;
-  int splits = (4 * kNumSMs + ktiles * nslab - 1) / (ktiles * nslab);
-  int ppc = (M + splits - 1) / splits;
-  ppc = ((ppc + 31) / 32) * 32;
-  if (ppc < 256) ppc = 256;
-  splits = (M + ppc - 1) / ppc;
-  p.pix_per_cta = ppc;
-  dim3 grid(ktiles, splits, 1);
+  dim3 grid(ktiles, 1, 1);
+  if (src_kind != SRC_NHWC_F32) {
+    // first layers: a CTA owns whole output rows of one image; the largest row tile whose staged
+    // input patch stays under 64 KB (2 CTAs per SM with a 2-stage operand pipeline)
+    p.sc_wpad = cs.W + 2 * cs.pw;
+    int rpt = cs.P;
+    while (rpt > 1 && (size_t)cs.Cin * ((rpt - 1) * cs.sh + cs.R) * p.sc_wpad * 4 > 64 * 1024) rpt = (rpt + 1) / 2;
+    p.sc_rpt = rpt;
+    p.sc_tpi = (cs.P + rpt - 1) / rpt;
+    p.sc_nh = (rpt - 1) * cs.sh + cs.R;
+    p.stages = 2; p.lookahead = 1;
+    p.pix_per_cta = rpt * cs.Q;
+    grid.y = (unsigned)(cs.N * p.sc_tpi);
+  } else {
+    const int nslab = cs.Cout / slab;
+    int splits = (4 * kNumSMs + ktiles * nslab - 1) / (ktiles * nslab);
+    int ppc = (M + splits - 1) / splits;
+    ppc = ((ppc + 31) / 32) * 32;
+    if (ppc < 256) ppc = 256;
+    splits = (M + ppc - 1) / ppc;
+    p.pix_per_cta = ppc;
+    grid.y = (unsigned)splits;
+  }
   const int gm = gmode_of(src_kind);
   for (int c0 = 0; c0 < cs.Cout; c0 += slab) {
     p.dy = dy + c0; p.cout = slab; p.dw = dw + (long long)c0 * p.kpad;

@@ -531,6 +531,9 @@ struct WgradParams {
   int lookahead;
   int mn_lbo, mn_sbo, mn_type;  // MN-major descriptor fields
   int mn_swz32;       // 1: 32-byte-granule swizzle (BASE32B), 0: 16-byte (plain 128B)
+  // scalar (first-layer) mode: a CTA owns `sc_rpt` output rows of one image and stages their
+  // input rows in shared memory once (blockIdx.y = image * sc_tpi + row tile)
+  int sc_rpt, sc_tpi, sc_nh, sc_wpad;
 };
 
 __host__ __device__ inline size_t wgrad_smem_bytes(int cout, int stages) {
@@ -558,13 +561,41 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
   const uint32_t tslot = tfull_bar + 8u;
 
-  __shared__ int lut_off[(GMODE >= G_SCALAR_F32) ? 256 : 1];
-  __shared__ int lut_rs[(GMODE >= G_SCALAR_F32) ? 256 : 1];
-  if constexpr (GMODE >= G_SCALAR_F32) {
-    for (int k = tid; k < g.K && k < 256; k += blockDim.x) {
-      const int c = k % g.C, rs = k / g.C, s = rs % g.S, r = rs / g.S;
-      lut_off[k] = (int)(r * g.sH + s * g.sW + c * g.sC);
-      lut_rs[k] = (r << 16) | s;
+  constexpr bool kScalar = (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8);
+  __shared__ int lut_off[kScalar ? 256 : 1];
+  const float* s_patch = reinterpret_cast<const float*>(smem_raw + (((tslot + 23u) & ~15u) - smem_u32(smem_raw)));
+  int sc_n = 0, sc_p0 = 0, sc_rows = 0;
+  if constexpr (kScalar) {
+    sc_n = blockIdx.y / p.sc_tpi;
+    sc_p0 = (blockIdx.y - sc_n * p.sc_tpi) * p.sc_rpt;
+    sc_rows = min(p.sc_rpt, g.P - sc_p0);
+    for (int k = tid; k < 256; k += blockDim.x) {
+      int o = -1;
+      if (k < g.K) {
+        const int c = k % g.C, rs = k / g.C, s_ = rs % g.S, r = rs / g.S;
+        o = (c * p.sc_nh + r) * p.sc_wpad + s_;
+      }
+      lut_off[k] = o;
+    }
+    float* patch = const_cast<float*>(s_patch);
+    const int h_lo = sc_p0 * g.sh - g.ph;
+    const int nh = (sc_rows - 1) * g.sh + g.R;
+    const int total = g.C * nh * p.sc_wpad;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int ww = i % p.sc_wpad;
+      const int t = i / p.sc_wpad;
+      const int hh = t % nh, c = t / nh;
+      const int h = h_lo + hh, w = ww - g.pw;
+      float x = 0.f;
+      if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+        const long long idx = (long long)sc_n * g.sN + (long long)h * g.sH + (long long)w * g.sW +
+                              (long long)c * g.sC;
+        if constexpr (GMODE == G_SCALAR_U8)
+          x = (float)reinterpret_cast<const uint8_t*>(g.src)[idx] * g.scale;
+        else
+          x = reinterpret_cast<const float*>(g.src)[idx] * g.scale;
+      }
+      patch[(c * p.sc_nh + hh) * p.sc_wpad + ww] = round_tf32(x);
     }
   }
   if (tid == 0) {
@@ -584,8 +615,8 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
   const int ktile = blockIdx.x;  // 128 k-rows
-  const int pix0 = blockIdx.y * p.pix_per_cta;
-  const int pix1 = min(pix0 + p.pix_per_cta, g.M);
+  const int pix0 = kScalar ? (sc_n * g.P + sc_p0) * g.Q : blockIdx.y * p.pix_per_cta;
+  const int pix1 = kScalar ? pix0 + sc_rows * g.Q : min(pix0 + p.pix_per_cta, g.M);
   const int num_kb = (pix1 - pix0 + 31) / 32;  // may be <= 0 for trailing CTAs
 
   if (num_kb > 0) {
@@ -624,26 +655,18 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) cp_async_16(tA + swz(row, c), src + (ok ? c * 4 : 0), nb);
           } else {
-            const int h0 = pp * g.sh - g.ph, w0 = qq * g.sw - g.pw;
-            const long long b0 = (long long)n * g.sN + (long long)h0 * g.sH + (long long)w0 * g.sW;
+            // from the staged patch: pixel i of this CTA -> window origin (pr*sh, q*sw)
+            const int i = it * 32 + row;
+            const int pr = i / g.Q, q = i - pr * g.Q;
+            const int b0 = mv ? (pr * g.sh) * p.sc_wpad + q * g.sw : -1;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               float v[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int k = k0 + c * 4 + j;
-                float x = 0.f;
-                if (mv && k < g.K) {
-                  const int rs = lut_rs[k];
-                  const int h = h0 + (rs >> 16), w = w0 + (rs & 0xFFFF);
-                  if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
-                    if constexpr (GMODE == G_SCALAR_U8)
-                      x = (float)reinterpret_cast<const uint8_t*>(g.src)[b0 + lut_off[k]] * g.scale;
-                    else
-                      x = reinterpret_cast<const float*>(g.src)[b0 + lut_off[k]] * g.scale;
-                  }
-                }
-                v[j] = round_tf32(x);
+                const int o = k < 256 ? lut_off[k] : -1;
+                v[j] = (b0 >= 0 && o >= 0) ? s_patch[b0 + o] : 0.f;
               }
               st_shared_v4(tA + swz(row, c), v[0], v[1], v[2], v[3]);
             }
