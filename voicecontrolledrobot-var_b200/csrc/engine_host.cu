@@ -219,9 +219,9 @@ static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const CUt
   {
     double flops = 0;
     for (unsigned z = 0; z < grid.z; ++z)
-      flops += 2.0 * p.g[z].M * (double)(EPI == EPI_GRU_FWD ? p.bn * grid.y : p.e[z].ncols) * p.g[z].K;
+      flops += 2.0 * p.g[z].M * (double)(EPI != EPI_STD ? p.bn * grid.y : p.e[z].ncols) * p.g[z].K;
     int tag = T_GEMM_SCALAR;
-    if (EPI == EPI_GRU_FWD) tag = T_GRU_STEP;
+    if (EPI != EPI_STD) tag = T_GRU_STEP;
     else if (p.b_mn_major) tag = T_GEMM_DGRAD;
     else if (GMODE == G_VEC_FWD || GMODE == G_TMA_IM2COL || GMODE == G_TMA_TILED) tag = T_GEMM_FWD;
     LaunchScope sc(tag, flops, st);
@@ -237,6 +237,10 @@ int launch_gemm(int gmode, int epi, const CUtensorMap& t0, const CUtensorMap& t1
   if (epi == EPI_GRU_FWD) {
     if (gmode == G_VEC_FWD) return launch_gemm_t<G_VEC_FWD, EPI_GRU_FWD>(t0, t1, a0, a1, p, grid, st);
     if (gmode == G_TMA_TILED) return launch_gemm_t<G_TMA_TILED, EPI_GRU_FWD>(t0, t1, a0, a1, p, grid, st);
+    return VAR_ERR_UNSUPPORTED;
+  }
+  if (epi == EPI_GRU_BWD) {
+    if (gmode == G_TMA_TILED) return launch_gemm_t<G_TMA_TILED, EPI_GRU_BWD>(t0, t1, a0, a1, p, grid, st);
     return VAR_ERR_UNSUPPORTED;
   }
   switch (gmode) {
@@ -505,6 +509,31 @@ int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
   if (ndir == 1) { tm[1] = tm[0]; ta[1] = ta[0]; }
   dim3 grid((M + 127) / 128, Cin / p.bn, ndir);
   return launch_gemm(tma ? G_TMA_TILED : G_VEC_DGRAD, EPI_STD, tm[0], tm[1], ta[0], ta[1], p, grid, st);
+}
+
+// One BPTT step for up to two directions: dh_{s-1} = dgh_s @ W_hh + dh_s * z_s with the cell
+// backward of step s-1 in the epilogue (EPI_GRU_BWD).  TMA-fed operands only.
+int gru_step_bwd(int ndir, int B, int Hd, const float* const dgh[2], const float* const whh[2],
+                 const GruBwdEpiParams q[2], cudaStream_t st) {
+  if (gather_mode() != 1) return VAR_ERR_UNSUPPORTED;
+  prof_note("gru_bwd_step M%d H%d %d%d%d", B, Hd, 0, 0, 0);
+  ConvShape cs{B, 1, 1, Hd, 3 * Hd, 1, 1, 1, 1, 0, 0, 1, 1};
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap tm[2], ta[2];
+  for (int z = 0; z < ndir; ++z) {
+    int rc = fill_dgrad(p, z, cs, dgh[z], nullptr, nullptr, nullptr, 0);
+    if (rc) return rc;
+    p.grub[z] = q[z];
+    p.grub[z].Hdim = Hd;
+    rc = get_tmap_2d(whh[z], 3 * Hd, Hd, Hd, 32, mn_cfg().tma_swizzle, &tm[z]);
+    if (rc) return rc;
+    rc = get_tmap_2d(dgh[z], B, 3 * Hd, 3 * Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta[z]);
+    if (rc) return rc;
+  }
+  if (ndir == 1) { tm[1] = tm[0]; ta[1] = ta[0]; }
+  dim3 grid((B + 127) / 128, Hd / p.bn, ndir);
+  return launch_gemm(G_TMA_TILED, EPI_GRU_BWD, tm[0], tm[1], ta[0], ta[1], p, grid, st);
 }
 
 // One GRU time step for up to two directions: gates = hprev @ W_hh^T fused with the

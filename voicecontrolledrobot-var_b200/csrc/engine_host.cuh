@@ -49,6 +49,8 @@ int linear_dgrad2(int ndir, int M, int Cin, int Cout, const float* const dy[2],
                   int round_out, cudaStream_t st);
 int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const float* const whh[2],
                  const GruEpiParams q[2], cudaStream_t st);
+int gru_step_bwd(int ndir, int B, int Hd, const float* const dgh[2], const float* const whh[2],
+                 const GruBwdEpiParams q[2], cudaStream_t st);
 int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st);
 
 // dw[Cout, Kpad] += im2col(x)^T dy ; db[Cout] += colsum(dy) (db may be null).

@@ -486,30 +486,56 @@ struct Net {
     if (ar.overflow) return VAR_ERR_WORKSPACE;
     int rc = split2(d_out, dh[0][0], dh[1][0], B, kGruH, st);
     if (rc) return rc;
-    for (int s = kGruT - 1; s >= 0; --s) {
-      const int cur = (kGruT - 1 - s) & 1;
+    auto slot_t = [&](int d, int s) { return d == 0 ? s : kGruT - 1 - s; };
+    {  // last step: stand-alone cell backward
+      const int s = kGruT - 1;
       GruBwdArgs a[2];
       for (int d = 0; d < 2; ++d) {
-        const int t = d == 0 ? s : kGruT - 1 - s;
-        a[d].dh = dh[d][cur];
+        a[d].dh = dh[d][0];
         a[d].gates = g.gates[d] + (long long)s * B * 3 * kGruH;
         a[d].hn_save = g.hn_save[d] + (long long)s * slot;
         a[d].hprev = g.h_r[d] + (long long)s * slot;
-        a[d].dgi = dgi[d] + (long long)t * 3 * kGruH;
+        a[d].dgi = dgi[d] + (long long)slot_t(d, s) * 3 * kGruH;
         a[d].ldgi = (long long)kGruT * 3 * kGruH;
         a[d].dgh = dgh[d] + (long long)s * B * 3 * kGruH;
         a[d].dhd = dhd[d];
       }
       rc = gru_cell_bwd(a[0], a[1], 2, B, kGruH, st);
       if (rc) return rc;
-      if (s > 0) {
-        const float* dy2[2] = {a[0].dgh, a[1].dgh};
-        const float* w2[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
-        float* dx2[2] = {dh[0][cur ^ 1], dh[1][cur ^ 1]};
-        const float* add2[2] = {dhd[0], dhd[1]};
+    }
+    // steps T-1 .. 1: recurrence GEMM with the cell backward of the previous step fused in
+    float* dhd_pp[2][2] = {{dhd[0], dh[0][1]}, {dhd[1], dh[1][1]}};
+    for (int s = kGruT - 1; s >= 1; --s) {
+      const int cur = (kGruT - 1 - s) & 1;
+      const float* dy2[2];
+      const float* w2[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
+      GruBwdEpiParams q[2];
+      for (int d = 0; d < 2; ++d) {
+        dy2[d] = dgh[d] + (long long)s * B * 3 * kGruH;
+        q[d].dhd_in = dhd_pp[d][cur];
+        q[d].gates = g.gates[d] + (long long)(s - 1) * B * 3 * kGruH;
+        q[d].hn_save = g.hn_save[d] + (long long)(s - 1) * slot;
+        q[d].hprev = g.h_r[d] + (long long)(s - 1) * slot;
+        q[d].dgi = dgi[d] + (long long)slot_t(d, s - 1) * 3 * kGruH;
+        q[d].ldgi = (long long)kGruT * 3 * kGruH;
+        q[d].dgh = dgh[d] + (long long)(s - 1) * B * 3 * kGruH;
+        q[d].dhd_out = dhd_pp[d][cur ^ 1];
+        q[d].Hdim = kGruH;
+      }
+      rc = gru_step_bwd(2, B, kGruH, dy2, w2, q, st);
+      if (rc == VAR_ERR_UNSUPPORTED) {  // cp.async gather mode: unfused GEMM + cell kernel
+        float* dx2[2] = {dh[0][0], dh[1][0]};
+        const float* add2[2] = {q[0].dhd_in, q[1].dhd_in};
         rc = linear_dgrad2(2, B, kGruH, 3 * kGruH, dy2, w2, dx2, add2, 0, st);
         if (rc) return rc;
+        GruBwdArgs a[2];
+        for (int d = 0; d < 2; ++d) {
+          a[d].dh = dh[d][0]; a[d].gates = q[d].gates; a[d].hn_save = q[d].hn_save; a[d].hprev = q[d].hprev;
+          a[d].dgi = q[d].dgi; a[d].ldgi = q[d].ldgi; a[d].dgh = q[d].dgh; a[d].dhd = q[d].dhd_out;
+        }
+        rc = gru_cell_bwd(a[0], a[1], 2, B, kGruH, st);
       }
+      if (rc) return rc;
     }
     for (int d = 0; d < 2; ++d) {
       // dW_hh += dgh^T h_prev ; db_hh += colsum(dgh)      (rows: step-major)

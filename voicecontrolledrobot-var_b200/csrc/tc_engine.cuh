@@ -46,7 +46,7 @@ struct GatherGeom {
   float scale;        // scalar path multiplier (1/255 for u8 images)
 };
 
-enum EpiKind : int { EPI_STD = 0, EPI_GRU_FWD = 1 };
+enum EpiKind : int { EPI_STD = 0, EPI_GRU_FWD = 1, EPI_GRU_BWD = 2 };
 
 // Output-row remapping of the stride-2 dgrad sub-problems: GEMM row m enumerates the pixels
 // (n, h2, w2) of one parity class, stored at pixel (h2*sh + oh, w2*sw + ow) of the full map.
@@ -85,10 +85,25 @@ struct GruEpiParams {
   int Hdim;
 };
 
+// GRU BPTT epilogue: the tile holds dgh_s . W_hh for a slice of hidden units; adding dh_s * z_s
+// gives dh_{s-1}, and the cell backward of step s-1 follows in registers (elementwise per unit).
+struct GruBwdEpiParams {
+  const float* dhd_in;   // [B, H]  dh_s * z_s
+  const float* gates;    // [B, 3H] saved r, z, n of step s-1
+  const float* hn_save;  // [B, H]
+  const float* hprev;    // [B, H]  h before step s-1
+  float* dgi;            // [B, ldgi] slot of step s-1 in the batch-major [B, T, 3H] buffer
+  long long ldgi;
+  float* dgh;            // [B, 3H] of step s-1
+  float* dhd_out;        // [B, H]  dh_{s-1} * z_{s-1}
+  int Hdim;
+};
+
 struct GemmParams {
   GatherGeom g[2];
   EpiParams e[2];
   GruEpiParams gru[2];
+  GruBwdEpiParams grub[2];
   int bn;          // UMMA N / tile columns
   int b_mn_major;  // 0: B K-major boxes {32k, box_rows}; 1: MN-major boxes {32n, 32k}
   int nbox;        // K-major: number of row boxes (1 or 3)
@@ -426,58 +441,129 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
           }
         }
       }
-    } else {
-      // GRU forward cell: tile columns = [r(jb) | z(jb) | n(jb)], jb = bn/3
+    } else if constexpr (EPI == EPI_GRU_FWD) {
+      // GRU forward cell: tile columns = [r(jb) | z(jb) | n(jb)], jb = bn/3.  The accumulator
+      // chunk is transposed through shared memory (the operand stages are free once tfull_bar
+      // fired) so that each warp-level global access covers 32 consecutive hidden units of one
+      // row: 128-byte coalesced instead of 32 rows x 16 bytes.
       const GruEpiParams& q = p.gru[z];
       const int jb = bn / 3;
       const int Hd = q.Hdim;
+      float* scr = reinterpret_cast<float*>(smem_raw + (sA - smem_u32(smem_raw))) + warp * (3 * 32 * 33);
       for (int c = 0; c < jb; c += 32) {
-        float vr[32], vz[32], vn[32];
-        tmem_ld32(trow + (uint32_t)c, vr);
-        tmem_ld32(trow + (uint32_t)(jb + c), vz);
-        tmem_ld32(trow + (uint32_t)(2 * jb + c), vn);
-        tmem_ld_wait();
-        if (m < g.M) {
-          const int j0 = ntile * jb + c;
-          const float* xp = q.xproj + (long long)m * q.ldx;
-          const float* hp = q.hprev + (long long)m * Hd + j0;
-          float* hn = q.hnew + (long long)m * Hd + j0;
+        {
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 xr = *reinterpret_cast<const float4*>(xp + j0 + j);
-            const float4 xz = *reinterpret_cast<const float4*>(xp + Hd + j0 + j);
-            const float4 xn = *reinterpret_cast<const float4*>(xp + 2 * Hd + j0 + j);
-            const float4 br = *reinterpret_cast<const float4*>(q.bhh + j0 + j);
-            const float4 bz = *reinterpret_cast<const float4*>(q.bhh + Hd + j0 + j);
-            const float4 bq = *reinterpret_cast<const float4*>(q.bhh + 2 * Hd + j0 + j);
-            const float4 h4 = *reinterpret_cast<const float4*>(hp + j);
-            float rr[4], zz[4], nn[4], hh[4], hnv[4];
-            const float xr_[4] = {xr.x, xr.y, xr.z, xr.w}, xz_[4] = {xz.x, xz.y, xz.z, xz.w},
-                        xn_[4] = {xn.x, xn.y, xn.z, xn.w}, br_[4] = {br.x, br.y, br.z, br.w},
-                        bz_[4] = {bz.x, bz.y, bz.z, bz.w}, bn_[4] = {bq.x, bq.y, bq.z, bq.w},
-                        hp_[4] = {h4.x, h4.y, h4.z, h4.w};
+          for (int gq = 0; gq < 3; ++gq) {
+            tmem_ld32(trow + (uint32_t)(gq * jb + c), v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              rr[u] = sigmoidf_(xr_[u] + vr[j + u] + br_[u]);
-              zz[u] = sigmoidf_(xz_[u] + vz[j + u] + bz_[u]);
-              hnv[u] = vn[j + u] + bn_[u];
-              nn[u] = tanhf(xn_[u] + rr[u] * hnv[u]);
-              hh[u] = (1.f - zz[u]) * nn[u] + zz[u] * hp_[u];
-            }
-            *reinterpret_cast<float4*>(hn + j) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-            if (q.hnew_r)
-              *reinterpret_cast<float4*>(q.hnew_r + (long long)m * Hd + j0 + j) = make_float4(
-                  round_tf32(hh[0]), round_tf32(hh[1]), round_tf32(hh[2]), round_tf32(hh[3]));
-            if (q.gates) {
-              float* gs = q.gates + (long long)m * 3 * Hd + j0 + j;
-              *reinterpret_cast<float4*>(gs) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-              *reinterpret_cast<float4*>(gs + Hd) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-              *reinterpret_cast<float4*>(gs + 2 * Hd) = make_float4(nn[0], nn[1], nn[2], nn[3]);
-              *reinterpret_cast<float4*>(q.hn_save + (long long)m * Hd + j0 + j) =
-                  make_float4(hnv[0], hnv[1], hnv[2], hnv[3]);
+            for (int j = 0; j < 32; ++j) scr[(gq * 32 + lane) * 33 + j] = v[j];
+          }
+        }
+        __syncwarp();
+        const int j = ntile * jb + c + lane;  // this lane's hidden unit
+        const float br = __ldg(q.bhh + j), bz = __ldg(q.bhh + Hd + j), bq = __ldg(q.bhh + 2 * Hd + j);
+        const int mrow0 = m0 + warp * 32;
+        const float* __restrict__ xproj = q.xproj;
+        const float* __restrict__ hprev = q.hprev;
+        constexpr int RB = 8;  // rows in flight: all loads of a batch are issued before any store
+        for (int r0 = 0; r0 < 32; r0 += RB) {
+          float xr[RB], xz[RB], xn[RB], hp[RB];
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int mr = mrow0 + r0 + u;
+            const bool ok = mr < g.M;
+            const float* xp = xproj + (long long)(ok ? mr : 0) * q.ldx;
+            xr[u] = ok ? __ldg(xp + j) : 0.f;
+            xz[u] = ok ? __ldg(xp + Hd + j) : 0.f;
+            xn[u] = ok ? __ldg(xp + 2 * Hd + j) : 0.f;
+            hp[u] = ok ? __ldg(hprev + (long long)mr * Hd + j) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int rr = r0 + u;
+            const int mr = mrow0 + rr;
+            if (mr < g.M) {
+              const float vr = scr[(0 * 32 + rr) * 33 + lane], vz = scr[(1 * 32 + rr) * 33 + lane],
+                          vn = scr[(2 * 32 + rr) * 33 + lane];
+              const float r_ = sigmoidf_(xr[u] + vr + br);
+              const float z_ = sigmoidf_(xz[u] + vz + bz);
+              const float hnv = vn + bq;
+              const float n_ = tanhf(xn[u] + r_ * hnv);
+              const float h_ = (1.f - z_) * n_ + z_ * hp[u];
+              q.hnew[(long long)mr * Hd + j] = h_;
+              if (q.hnew_r) q.hnew_r[(long long)mr * Hd + j] = round_tf32(h_);
+              if (q.gates) {
+                float* gs = q.gates + (long long)mr * 3 * Hd + j;
+                gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
+                q.hn_save[(long long)mr * Hd + j] = hnv;
+              }
             }
           }
         }
+        __syncwarp();
+      }
+    } else {
+      // GRU BPTT: dh_{s-1} = acc + dh_s * z_s, then the cell backward of step s-1 (same maths as
+      // gru_cell_bwd_kernel), transposed through shared memory like the forward epilogue.
+      const GruBwdEpiParams& q = p.grub[z];
+      const int Hd = q.Hdim;
+      float* scr = reinterpret_cast<float*>(smem_raw + (sA - smem_u32(smem_raw))) + warp * (32 * 33);
+      for (int c = 0; c < bn; c += 32) {
+        {
+          float v[32];
+          tmem_ld32(trow + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = v[j];
+        }
+        __syncwarp();
+        const int j = ntile * bn + c + lane;
+        const int mrow0 = m0 + warp * 32;
+        const float* __restrict__ dhd_in = q.dhd_in;
+        const float* __restrict__ gates = q.gates;
+        const float* __restrict__ hn_save = q.hn_save;
+        const float* __restrict__ hprev = q.hprev;
+        constexpr int RB = 8;
+        for (int r0 = 0; r0 < 32; r0 += RB) {
+          float din[RB], gr_[RB], gz_[RB], gn_[RB], hnv[RB], hp[RB];
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int mr = mrow0 + r0 + u;
+            const bool ok = mr < g.M;
+            const long long hoff = (long long)(ok ? mr : 0) * Hd + j;
+            const float* gt = gates + (long long)(ok ? mr : 0) * 3 * Hd + j;
+            din[u] = ok ? __ldg(dhd_in + hoff) : 0.f;
+            gr_[u] = ok ? __ldg(gt) : 0.f;
+            gz_[u] = ok ? __ldg(gt + Hd) : 0.f;
+            gn_[u] = ok ? __ldg(gt + 2 * Hd) : 0.f;
+            hnv[u] = ok ? __ldg(hn_save + hoff) : 0.f;
+            hp[u] = ok ? __ldg(hprev + hoff) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int rr = r0 + u;
+            const int mr = mrow0 + rr;
+            if (mr < g.M) {
+              const long long hoff = (long long)mr * Hd + j;
+              const float dh = scr[rr * 33 + lane] + din[u];
+              const float r_ = gr_[u], z_ = gz_[u], n_ = gn_[u];
+              const float dnn = dh * (1.f - z_);
+              const float dzz = dh * (hp[u] - n_);
+              const float dnp = dnn * (1.f - n_ * n_);
+              const float dzp = dzz * z_ * (1.f - z_);
+              const float drp = dnp * hnv[u] * r_ * (1.f - r_);
+              const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
+              float* gi = q.dgi + (long long)mr * q.ldgi + j;
+              gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
+              float* gh = q.dgh + (long long)mr * 3 * Hd + j;
+              gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = round_tf32(dnp * r_);
+              q.dhd_out[hoff] = dh * z_;
+            }
+          }
+        }
+        __syncwarp();
       }
     }
     tc_fence_before();
