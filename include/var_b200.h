@@ -120,6 +120,16 @@ int var_net_reward(void* net, const void* d_images, int image_kind, const float*
                    int64_t ws_bytes, float* d_img_feat, float* d_goal_feat, float* d_dot,
                    float* d_reward, void* stream);
 
+/* Reward post-processing of VecPretextNormalize.step_wait (vec_pretext_normalize.py:53-59,
+ * running_mean_std.py:16-35) on the device, in float64 like the reference: orig = rew;
+ * ret = ret*gamma + rew; RunningMeanStd update with the batch moments of ret; out =
+ * clip(rew / sqrt(var + eps), +-cliprew); ret[done] = 0.  d_ret: double[N]; d_rms: double[3] =
+ * {mean, var, count} (initialise to {0, 1, 1e-4}).  update_rms = 0 passes rew through unscaled
+ * (the wrapper's ret=False mode). */
+int var_reward_normalize(const float* d_rew, const uint8_t* d_done, int N, double* d_ret, double* d_rms,
+                         double gamma, double eps, double cliprew, int update_rms, float* d_orig,
+                         float* d_out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Optimizer.  torch.optim.Adam(lr, weight_decay) exactly as configured at
  * VAR/pretext_VAR.py:33-35 (L2 folded into the gradient, default betas/eps), on the flat

@@ -178,6 +178,51 @@ def test_reward_wrapper_matches_reference_golden(vb, golden):
     assert np.abs(f_goal - g[f"goal_sound_feat{steps - 1}"]).max() < 1e-3
 
 
+@pytest.mark.gpu
+def test_reward_wrapper_device_path_matches_reference_golden(vb, golden):
+    """step_wait_device(): reward query + float64 return normalisation on the device, same golden run."""
+    g = golden("reward")
+    vpn = import_module(f"{PKG}.Envs.vec_env.vec_pretext_normalize")
+    cfg = kuka_cfg()
+    N, steps = int(g["N"]), int(g["steps"])
+    m = _net("kuka", cfg)
+    m.load_state_dict(omodel.init_state_dict(omodel.KUKA, 11))
+    m.to(DEV).eval()
+    rng = np.random.default_rng(5)
+    seq = []
+    for t in range(steps + 1):
+        seq.append(({"image": rng.integers(0, 256, (N, 3, 96, 96)).astype(np.uint8),
+                     "goal_sound": (rng.standard_normal((N, 1, 100, 40)) * 5).astype(np.float32),
+                     "robot_pose": rng.standard_normal((N, 4)).astype(np.float32)},
+                    rng.standard_normal(N), rng.random(N) < 0.3))
+
+    class Venv:
+        num_envs = N
+        observation_space = types.SimpleNamespace(shape=(1,))
+        action_space = None
+        t = 0
+
+        def reset(self):
+            return seq[0][0]
+
+        def step_wait(self):
+            self.t += 1
+            return seq[self.t][0], seq[self.t][1].copy(), seq[self.t][2].copy(), ({},) * N
+
+    w = vpn.VecPretextNormalize(Venv(), ob=False, ret=True, gamma=0.99, config=cfg,
+                                pretextObj=types.SimpleNamespace(pretextModel=m))
+    w.reset()
+    for t in range(steps):
+        o, r, d, _ = w.step_wait_device()
+        assert r.is_cuda and r.shape == (N, 1) and all(v.is_cuda for v in o.values())
+        assert np.abs(r[:, 0].cpu().numpy() - g[f"rew{t}"]).max() < 3e-3
+        assert np.abs(o["image_feat"].cpu().numpy() - g[f"image_feat{t}"]).max() < 1e-3
+        w.sync_device_stats()
+        assert np.abs(w.origStepReward - g[f"orig{t}"]).max() < 3e-3
+    assert abs(float(w.ret_rms.var) - float(g["ret_var"])) < 1e-2 * float(g["ret_var"])
+    assert abs(float(w.ret_rms.mean) - float(g["ret_mean"])) < 1e-2 * max(1.0, abs(float(g["ret_mean"])))
+
+
 def _write_dataset(root, cfg, n_items=48, clips_per_class=5):
     from scipy.io import wavfile
     words = ["up", "down", "left", "right"]

@@ -9,6 +9,7 @@ path); the 1/255 scale is applied inside the first conv's loader."""
 import numpy as np
 import torch
 
+from ..._lib import check, lib, ptr, stream_ptr
 from .running_mean_std import RunningMeanStd
 
 
@@ -144,7 +145,60 @@ class VecPretextNormalize(VecEnvWrapper):
                            self.clipob)
         return obs
 
+    # ------------------------------------------------------------------ device-resident variant
+    def step_wait_device(self):
+        """`step_wait` without the host round trip of the reference (GPU -> numpy dot -> numpy RMS ->
+        torch -> GPU, vec_pretext_normalize.py:47-61 + envs.py:90-98): the reward query, the
+        discounted-return RunningMeanStd update and the clipping all stay on the device
+        (`var_net_reward` + `var_reward_normalize`).  Returns what `VecPyTorch.step_wait` would hand
+        to the policy: a dict of float32 device tensors, rewards [N, 1] on the device, `news`, `infos`.
+        `origStepReward` is refreshed lazily from the device copy."""
+        O, env_rews, news, infos = self.venv.step_wait()
+        dev, N = self.device, self.num_envs
+        model = self.pretextModel
+        eng = model._get_engine(dev)
+        img_u8 = torch.from_numpy(np.ascontiguousarray(O['image'][:, :3], dtype=np.uint8)).to(dev, non_blocking=True)
+        goal = O['goal_sound']
+        F = self.config.sound_dim[1]
+        fresh = goal is not None and not bool(np.isinf(goal.flat[0]) and np.isinf(goal).all())
+        env_r = torch.from_numpy(np.asarray(env_rews, dtype=np.float32)).to(dev, non_blocking=True)
+        if fresh:
+            snd = torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float32).reshape(-1, F, 40)).to(dev, non_blocking=True)
+            img_feat, goal_feat, _, rew = eng.reward(img_u8, goal_sounds=snd, env_reward=env_r)
+            model.cached_sound = goal_feat
+        else:
+            img_feat, goal_feat, _, rew = eng.reward(img_u8, goal_feat_cached=model.cached_sound.float().contiguous(),
+                                                     env_reward=env_r)
+        if not hasattr(self, "_ret_dev"):
+            self._ret_dev = torch.from_numpy(self.ret.astype(np.float64)).to(dev)
+            rms = self.ret_rms
+            init = [float(rms.mean), float(rms.var), float(rms.count)] if rms else [0.0, 1.0, 1e-4]
+            self._rms_dev = torch.tensor(init, dtype=torch.float64, device=dev)
+        done = torch.from_numpy(np.asarray(news, dtype=np.uint8)).to(dev, non_blocking=True)
+        orig = torch.empty(N, dtype=torch.float32, device=dev)
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+        check(lib.var_reward_normalize(ptr(rew), ptr(done), N, ptr(self._ret_dev), ptr(self._rms_dev), float(self.gamma),
+                                       float(self.epsilon), float(self.cliprew), 1 if self.ret_rms else 0, ptr(orig),
+                                       ptr(out), stream_ptr()), "var_reward_normalize")
+        self._orig_dev = orig
+        extra = 'robot_pose' if self.config.name == 'ArmConfig' else 'occupancy'
+        ex = torch.from_numpy(np.asarray(O[extra], dtype=np.float32)).to(dev, non_blocking=True)
+        obs = {extra: ex if extra == 'robot_pose' else ex / 255., 'goal_sound_feat': goal_feat,
+               'image': img_u8.float() / 255., 'image_feat': img_feat}
+        return obs, out.unsqueeze(1), news, infos
+
+    def sync_device_stats(self):
+        """Pull the device-side return / RMS state back into the numpy attributes of the reference."""
+        if hasattr(self, "_ret_dev"):
+            self.ret = self._ret_dev.cpu().numpy()
+            m, v, c = self._rms_dev.cpu().tolist()
+            if self.ret_rms:
+                self.ret_rms.mean, self.ret_rms.var, self.ret_rms.count = np.float64(m), np.float64(v), c
+            self.origStepReward = self._orig_dev.cpu().numpy().astype(np.float64)
+
     def reset(self):
+        if hasattr(self, "_ret_dev"):
+            self._ret_dev.zero_()
         self.ret = np.zeros(self.num_envs)
         obs = self.venv.reset()
         obs, _ = self.processing_func[self.config.name](obs, np.zeros((self.num_envs,)),

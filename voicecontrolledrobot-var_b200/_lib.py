@@ -54,6 +54,7 @@ PROTOTYPES = {
     "var_net_backward": (_i, [_p, _p, _p, _p, _i64, _p]),
     "var_net_triplet_step": (_i, [_p, _p, _i, _p, _i, _f, _f, _p, _i64, _p, _p, _p]),
     "var_net_reward": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _p]),
+    "var_reward_normalize": (_i, [_p, _p, _i, _p, _p, C.c_double, C.c_double, C.c_double, _i, _p, _p, _p]),
     "var_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i64, _f, _p]),
     "var_pack_weight": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "var_unpack_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),

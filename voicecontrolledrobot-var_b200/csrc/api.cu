@@ -85,6 +85,12 @@ int var_adam_step(float* p, const float* g, float* m, float* v, float* p_mma, in
   return adam_step(p, g, m, v, p_mma, n, lr, beta1, beta2, eps, wd, step, grad_scale, ST(stream));
 }
 
+int var_reward_normalize(const float* rew, const uint8_t* done, int N, double* ret, double* rms, double gamma,
+                         double eps, double cliprew, int update_rms, float* orig, float* out, void* stream) {
+  if (!rew || !done || !ret || !rms || !out) return VAR_ERR_ARG;
+  return reward_normalize(rew, done, N, ret, rms, gamma, eps, cliprew, update_rms, orig, out, ST(stream));
+}
+
 int var_pack_weight(const float* ref, float* packed, float* packed_mma, int Cout, int Cin, int R,
                     int S, int kpad, void* stream) {
   return pack_weight(ref, packed, packed_mma, Cout, Cin, R, S, kpad, ST(stream));

@@ -336,4 +336,69 @@ int split2(const float* x, float* a, float* c, int B, int Hd, cudaStream_t st) {
   return VAR_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Reward post-processing of VecPretextNormalize.step_wait (vec_pretext_normalize.py:53-59) on
+// the device, float64 like the reference: origStepReward copy, discounted return, RunningMeanStd
+// parallel-variance update (running_mean_std.py:16-35), rews / sqrt(var + eps) clipped, and
+// ret[done] = 0.  One CTA (N = number of envs, <= a few thousand); state = {mean, var, count}.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+reward_norm_kernel(const float* __restrict__ rew, const unsigned char* __restrict__ done, int N,
+                   double* __restrict__ ret, double* __restrict__ rms, double gamma, double eps,
+                   double cliprew, int update_rms, float* __restrict__ orig, float* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double r = ret[i] * gamma + (double)rew[i];
+    ret[i] = r;
+    s += r;
+    if (orig) orig[i] = rew[i];
+  }
+  double var = rms[1];
+  if (update_rms) {
+    const double bmean = block_sum(s, red) / N;
+    double q = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double d = ret[i] - bmean;
+      q += d * d;
+    }
+    const double bvar = block_sum(q, red) / N;
+    const double mean = rms[0], cnt = rms[2];
+    const double delta = bmean - mean, tot = cnt + N;
+    const double m2 = var * cnt + bvar * N + delta * delta * cnt * N / tot;
+    var = m2 / tot;
+    __syncthreads();
+    if (threadIdx.x == 0) { rms[0] = mean + delta * N / tot; rms[1] = var; rms[2] = tot; }
+  }
+  const double inv = 1.0 / sqrt(var + eps);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double v = update_rms ? (double)rew[i] * inv : (double)rew[i];
+    if (update_rms) v = fmin(fmax(v, -cliprew), cliprew);
+    out[i] = (float)v;
+    if (done[i]) ret[i] = 0.0;
+  }
+}
+
+int reward_normalize(const float* rew, const unsigned char* done, int N, double* ret, double* rms,
+                     double gamma, double eps, double cliprew, int update_rms, float* orig, float* out,
+                     cudaStream_t st) {
+  if (N <= 0) return VAR_OK;
+  LaunchScope sc(T_MISC, 0, st);
+  reward_norm_kernel<<<1, 256, 0, st>>>(rew, done, N, ret, rms, gamma, eps, cliprew, update_rms, orig, out);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
 }  // namespace var

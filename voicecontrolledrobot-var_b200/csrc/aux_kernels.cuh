@@ -31,6 +31,9 @@ int adam_step(float* p, const float* g, float* m, float* v, float* p_mma, long l
               float beta1, float beta2, float eps, float wd, long long step, float gscale,
               cudaStream_t st);
 
+int reward_normalize(const float* rew, const unsigned char* done, int N, double* ret, double* rms,
+                     double gamma, double eps, double cliprew, int update_rms, float* orig, float* out,
+                     cudaStream_t st);
 int nhwc_to_nchw(const float* x, float* y, int B, int HW, int C, cudaStream_t st);
 int concat2(const float* a, const float* c, float* out, float* out_r, int B, int Hd,
             cudaStream_t st);
