@@ -292,6 +292,10 @@ def test_trainer_end_to_end(vb, tmp_path):
     assert len(prog) == 3 and np.isfinite(prog["avg_loss"]).all() and prog["avg_loss"].iloc[-1] < prog["avg_loss"].iloc[0]
     sd = torch.load(os.path.join(cfg.pretextModelSaveDir, "2.pt"))
     assert list(sd.keys()) == list(omodel.param_shapes("kuka").keys())
+    cfg.plotNumBatch = 1
+    fp = trainer.project2representation_with_ground_truth(gen_loader)   # pretext.py:147-203
+    assert fp['img'].shape == (32, 4) and fp['sound'].shape == (32, 4)
+    assert np.allclose(np.linalg.norm(fp['img'][:, :3], axis=1), 1.0, atol=1e-5)
     trainer.pretextModel = None
     trainer.loadPretextModel()                                   # pretext.py:102-111
     with torch.no_grad():

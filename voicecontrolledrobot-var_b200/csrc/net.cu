@@ -91,9 +91,10 @@ struct Net {
   GruState gru;
   float *h_img = nullptr, *h_snd = nullptr;  // inputs of the tail
   float *img_raw_nhwc = nullptr, *snd_raw = nullptr;
-  // The image and sound branches are independent until the tail: the image branch runs on a
-  // side stream so its large-grid kernels fill the SMs the sound branch's small sequential
-  // launches (GRU time steps) leave idle.  VAR_OVERLAP=0 serialises them on the caller's stream.
+  // The image and sound branches are independent until the tail.  The sound branch (the critical
+  // path: big convs, then 73 + 72 small dependent GRU launches) runs on a HIGH-priority side stream,
+  // the image branch stays on the caller's stream: its large-grid kernels fill whatever SMs the
+  // sound branch leaves idle without delaying the GRU chain.  VAR_OVERLAP=0 serialises them.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;
@@ -103,13 +104,15 @@ struct Net {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
   }
-  // Returns the stream the image branch should use (forked from st) or st itself.
+  // Returns the stream the sound branch should use (forked from st) or st itself.
   cudaStream_t fork_side(bool both, cudaStream_t st) {
     if (!both || !overlap) return st;
     if (!side) {
       const char* e = getenv("VAR_OVERLAP");
       if (e && e[0] == '0') { overlap = false; return st; }
-      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically smallest = greatest priority
+      if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess ||
           cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
         overlap = false;
@@ -377,30 +380,11 @@ struct Net {
     n_img = n_images; n_snd = n_sounds;
     h_img = h_snd = img_raw_nhwc = snd_raw = nullptr;
     const bool both = n_images > 0 && n_sounds > 0;
-    cudaStream_t st_img = st;
+    cudaStream_t st_snd = (ar.base && both) ? fork_side(true, st) : st;
     struct Joiner {  // joins the side stream on every exit path
-      Net* n; cudaStream_t* a; cudaStream_t b;
-      ~Joiner() { n->join_side(*a, b); }
-    } joiner{this, &st_img, st};
-    auto image_branch = [&]() -> int {
-      SrcLayout sl;
-      sl.sW = 1; sl.sH = 96; sl.sC = 96 * 96; sl.sN = 3 * 96 * 96;  // NCHW
-      sl.scale = image_kind == 0 ? 1.f / 255.f : 1.f;
-      float* t;
-      int rc = run_layers_fwd(img_trunk, images, image_kind == 0 ? SRC_STRIDED_U8 : SRC_STRIDED_F32,
-                              sl, n_images, ar, st_img, &t);
-      if (rc) return rc;
-      img_raw_nhwc = t;
-      return run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st_img, &h_img);
-    };
-    // With a GRU the sound trunk's big convs go first and the image branch is forked right after
-    // them, so it overlaps the 73 small GRU-step launches instead of competing with the convs.
-    const bool late_fork = both && has_gru;
-    if (n_images > 0 && !late_fork) {
-      if (ar.base) st_img = fork_side(both, st);
-      const int rc = image_branch();
-      if (rc) return rc;
-    }
+      Net* n; cudaStream_t a, b;
+      ~Joiner() { n->join_side(a, b); }
+    } joiner{this, st_snd, st};
     if (n_sounds > 0) {
       SrcLayout sl;
       sl.sC = 0; sl.sW = 1; sl.sH = 40; sl.sN = (long long)F * 40;
@@ -408,27 +392,33 @@ struct Net {
       float* t;
       int rc;
       if (kind == 0 && fp32_sound) {
-        rc = kuka_sound_forward(sounds, sl, n_sounds, train, ar, st);
+        rc = kuka_sound_forward(sounds, sl, n_sounds, train, ar, st_snd);
         if (rc) return rc;
-        fwd_used = ar.used;
-        return VAR_OK;
-      }
-      rc = run_layers_fwd(snd_trunk, sounds, SRC_STRIDED_F32, sl, n_sounds, ar, st, &t);
-      if (rc) return rc;
-      if (late_fork) {
-        if (ar.base) st_img = fork_side(true, st);
-        rc = image_branch();
-        if (rc) return rc;
-      }
-      if (has_gru) {
-        rc = gru_forward(t, n_sounds, train, ar, st);
-        if (rc) return rc;
-        snd_raw = gru.out;
-        t = gru.out_r;
       } else {
-        snd_raw = t;
+        rc = run_layers_fwd(snd_trunk, sounds, SRC_STRIDED_F32, sl, n_sounds, ar, st_snd, &t);
+        if (rc) return rc;
+        if (has_gru) {
+          rc = gru_forward(t, n_sounds, train, ar, st_snd);
+          if (rc) return rc;
+          snd_raw = gru.out;
+          t = gru.out_r;
+        } else {
+          snd_raw = t;
+        }
+        rc = run_layers_fwd(snd_head, t, SRC_NHWC_F32, sl, n_sounds, ar, st_snd, &h_snd);
+        if (rc) return rc;
       }
-      rc = run_layers_fwd(snd_head, t, SRC_NHWC_F32, sl, n_sounds, ar, st, &h_snd);
+    }
+    if (n_images > 0) {
+      SrcLayout sl;
+      sl.sW = 1; sl.sH = 96; sl.sC = 96 * 96; sl.sN = 3 * 96 * 96;  // NCHW
+      sl.scale = image_kind == 0 ? 1.f / 255.f : 1.f;
+      float* t;
+      int rc = run_layers_fwd(img_trunk, images, image_kind == 0 ? SRC_STRIDED_U8 : SRC_STRIDED_F32,
+                              sl, n_images, ar, st, &t);
+      if (rc) return rc;
+      img_raw_nhwc = t;
+      rc = run_layers_fwd(img_head, t, SRC_NHWC_F32, sl, n_images, ar, st, &h_img);
       if (rc) return rc;
     }
     fwd_used = ar.used;
@@ -558,28 +548,28 @@ struct Net {
   int backward_from_dh(float* dh_img, float* dh_snd, void* ws, long long ws_bytes, cudaStream_t st) {
     Arena ar(ws, ws_bytes);
     ar.used = fwd_used;
-    cudaStream_t st_img = fork_side(n_img > 0 && dh_img && n_snd > 0 && dh_snd, st);
+    cudaStream_t st_snd = fork_side(n_img > 0 && dh_img && n_snd > 0 && dh_snd, st);
     struct Joiner {
       Net* n; cudaStream_t a, b;
       ~Joiner() { n->join_side(a, b); }
-    } joiner{this, st_img, st};
-    if (n_img > 0 && dh_img) {
-      float* d;
-      int rc = run_layers_bwd(img_head, dh_img, ar, st_img, &d);
-      if (rc) return rc;
-      rc = run_layers_bwd(img_trunk, d, ar, st_img, &d);
-      if (rc) return rc;
-    }
+    } joiner{this, st_snd, st};
     // the branches run concurrently: each keeps its own gradient scratch region
     if (n_snd > 0 && dh_snd) {
       float* d;
-      int rc = run_layers_bwd(snd_head, dh_snd, ar, st, &d);
+      int rc = run_layers_bwd(snd_head, dh_snd, ar, st_snd, &d);
       if (rc) return rc;
       if (has_gru) {
-        rc = gru_backward(d, ar, st, &d);
+        rc = gru_backward(d, ar, st_snd, &d);
         if (rc) return rc;
       }
-      rc = run_layers_bwd(snd_trunk, d, ar, st, &d);
+      rc = run_layers_bwd(snd_trunk, d, ar, st_snd, &d);
+      if (rc) return rc;
+    }
+    if (n_img > 0 && dh_img) {
+      float* d;
+      int rc = run_layers_bwd(img_head, dh_img, ar, st, &d);
+      if (rc) return rc;
+      rc = run_layers_bwd(img_trunk, d, ar, st, &d);
       if (rc) return rc;
     }
     return VAR_OK;

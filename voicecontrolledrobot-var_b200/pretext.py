@@ -30,6 +30,29 @@ class Pretext(object):
     def collectPretextData(self, fileName=None):
         raise NotImplementedError("data collection runs the simulators: use the reference's pretext.py:31-100")
 
+    def project2representation_with_ground_truth(self, data_generator, project_for='plot', req_grad=False):
+        """pretext.py:147-203 without the image dump / cv2 side effects: every batch of the generator
+        goes through the encoders as one batched device call; returns {'img', 'sound'} arrays of
+        [n, representationDim + 1] (embedding, ground-truth label) for plotting / medoid code."""
+        import numpy as np
+        if project_for != 'plot':
+            raise NotImplementedError
+        feat_point = {'img': [], 'sound': [], 'lastBatchNum': -1}
+        limit = getattr(self.config, "plotNumBatch", None)
+        with torch.set_grad_enabled(req_grad):
+            for n, data in enumerate(data_generator):
+                if limit is not None and n > limit:
+                    break
+                img, sp, gt = data[0], data[1], data[3]
+                features = self.pretextModel(img.to(self.device), sp.float().to(self.device), None)
+                g = gt.cpu().numpy()[:, None]
+                feat_point['img'].append(np.concatenate([features['image_feat'].detach().cpu().numpy(), g], axis=1))
+                feat_point['sound'].append(np.concatenate([features['sound_feat_positive'].detach().cpu().numpy(), g],
+                                                          axis=1))
+        feat_point['img'] = np.concatenate(feat_point['img'], axis=0)
+        feat_point['sound'] = np.concatenate(feat_point['sound'], axis=0)
+        return feat_point
+
     def plotRepresentation(self, data_generator):
         raise NotImplementedError("plotting stays with the reference (pretext.py:205-264)")
 
