@@ -35,7 +35,10 @@ struct MfccTables {       // device pointers
   const float* fweights;  // [nnz]
   const float* dct;       // [40 f][40 k]
   const float* lifter;    // [40] cepstral lifter (flavour 1)
-  int nnz;
+  const float2* tw2;      // [7][8]   pass-2 twiddles exp(-2 pi i t k / 64), t = 1..7
+  const float2* tw3;      // [R3-1][64] pass-3 twiddles exp(-2 pi i t j / N)
+  const float* fwt;       // [maxcnt][40] filter weights, i-th weight of filter f at [i*40 + f]
+  int nnz, maxcnt, maxcnt_lo;  // maxcnt_lo = longest of the first 32 filters
 };
 
 struct MfccPlan {
@@ -140,7 +143,9 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
   size_t o = ((size_t)(span2 + 2) * 2 + 15) & ~(size_t)15;
   float* s_win = reinterpret_cast<float*>(sm_raw + o); o += NFFT * 4;
   float2* s_tw = reinterpret_cast<float2*>(sm_raw + o); o += NFFT * 8;
-  float* s_fw = reinterpret_cast<float*>(sm_raw + o); o += ((a.t.nnz + 3) & ~3) * 4;
+  float* s_fwt = reinterpret_cast<float*>(sm_raw + o); o += (size_t)a.t.maxcnt * kMel * 4;
+  float2* s_tw2 = reinterpret_cast<float2*>(sm_raw + o); o += 7 * 8 * 8;
+  float2* s_tw3 = reinterpret_cast<float2*>(sm_raw + o); o += 7 * 64 * 8;
   float* s_dct = reinterpret_cast<float*>(sm_raw + o); o += kMel * kMel * 4;
   float* s_lm = reinterpret_cast<float*>(sm_raw + o); o += kMel * (kFramesPerCta + 4) * 4;  // [f][frame]
   float* s_le = reinterpret_cast<float*>(sm_raw + o); o += (kFramesPerCta + 4) * 4;          // log frame energy
@@ -155,26 +160,42 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
     const int16_t* w = a.wav + off;
     // logical sample index of s_wav[0]; flavour 1 keeps one extra leading sample for the pre-emphasis
     const int base = psf ? f0 * a.hop - 2 : f0 * a.hop - NFFT / 2;
-    for (int i = tid; i < span2 + (psf ? 2 : 0); i += kMfccThreads) {
-      int idx = base + i;
-      if (!psf) {  // reflect padding at the clip ends
-        if (idx < 0) idx = -idx;
-        if (idx >= S) idx = 2 * (S - 1) - idx;
+    // two samples per 32-bit access (clip offsets and hops are even); reflection / zero fill at
+    // the clip ends goes through the scalar path
+    const int npairs = (span2 + (psf ? 2 : 0) + 1) >> 1;
+    for (int pi = tid; pi < npairs; pi += kMfccThreads) {
+      const int i = pi * 2;
+      const int idx0 = base + i;
+      if (idx0 >= 0 && idx0 + 1 < S && !(off & 1)) {
+        *reinterpret_cast<uint32_t*>(s_wav + i) = *reinterpret_cast<const uint32_t*>(w + idx0);
+      } else {
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          int idx = idx0 + e2;
+          if (!psf) {  // reflect padding at the clip ends
+            if (idx < 0) idx = -idx;
+            if (idx >= S) idx = 2 * (S - 1) - idx;
+          }
+          int16_t v = 0;
+          if (idx >= 0 && idx < S) v = w[idx];
+          s_wav[i + e2] = v;
+        }
       }
-      int16_t v = 0;
-      if (idx >= 0 && idx < S) v = w[idx];
-      s_wav[i] = v;
     }
     for (int i = tid; i < NFFT; i += kMfccThreads) { s_win[i] = a.t.window[i]; s_tw[i] = a.t.tw[i]; }
-    for (int i = tid; i < a.t.nnz; i += kMfccThreads) s_fw[i] = a.t.fweights[i];
+    for (int i = tid; i < a.t.maxcnt * kMel; i += kMfccThreads) s_fwt[i] = a.t.fwt[i];
+    for (int i = tid; i < 7 * 8; i += kMfccThreads) s_tw2[i] = a.t.tw2[i];
+    for (int i = tid; i < (N / 64 - 1) * 64; i += kMfccThreads) s_tw3[i] = a.t.tw3[i];
     for (int i = tid; i < kMel * kMel; i += kMfccThreads) s_dct[i] = a.t.dct[i];
   }
   __syncthreads();
 
-  const int fst0 = a.t.fstart[lane], fcn0 = a.t.fcount[lane], fof0 = a.t.foff[lane];
-  const int fst1 = lane < kMel - 32 ? a.t.fstart[lane + 32] : 0;
-  const int fcn1 = lane < kMel - 32 ? a.t.fcount[lane + 32] : 0;
-  const int fof1 = lane < kMel - 32 ? a.t.foff[lane + 32] : 0;
+  // mel filters: lane f owns filter f (< 32); the 8 widest filters (32..39) are split over
+  // 4 lanes each so that both loops have short, balanced trip counts
+  const int fst0 = a.t.fstart[lane], fcn0 = a.t.fcount[lane];
+  const int fhi = 32 + (lane >> 2), part = lane & 3;
+  const int fst1 = a.t.fstart[fhi], fcn1 = a.t.fcount[fhi];
+  const int cnt_lo = a.t.maxcnt_lo, cnt_hi = (a.t.maxcnt + 3) >> 2;
 
   for (int fr = warp; fr < nvalid; fr += kWarps) {
     const int16_t* x = s_wav + fr * a.hop + (psf ? 2 : 0);  // frame element e -> x[e]
@@ -220,7 +241,7 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
         for (int t = 0; t < 8; ++t) {
           const int p = padA(j + (N / 8) * t);
           float2 u = make_float2(sre[p], sim[p]);
-          if (t) u = cmul(u, s_tw[(t * k) * (NFFT / 64)]);
+          if (t) u = cmul(u, s_tw2[(t - 1) * 8 + k]);
           v2[h][t] = u;
         }
         dft8(v2[h]);
@@ -249,7 +270,7 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
         for (int t = 0; t < R3; ++t) {
           const int p = padB(j + 64 * t);
           float2 u = make_float2(sre[p], sim[p]);
-          if (t) u = cmul(u, s_tw[(t * j) * (NFFT / N)]);
+          if (t) u = cmul(u, s_tw3[(t - 1) * 64 + j]);
           v[t] = u;
         }
         if constexpr (R3 == 4) dft4(v); else dft8(v);
@@ -295,15 +316,20 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
     // ---------------- mel filterbank + log ----------------
     {
       float acc = 0.f;
-      for (int i = 0; i < fcn0; ++i) acc = fmaf(spw[fst0 + i], s_fw[fof0 + i], acc);
+      for (int i = 0; i < cnt_lo; ++i)
+        if (i < fcn0) acc = fmaf(spw[fst0 + i], s_fwt[i * kMel + lane], acc);
       s_lm[lane * (kFramesPerCta + 4) + fr] =
           psf ? logf(acc == 0.f ? 2.220446049250313e-16f : acc) : logf(acc + kLogEps);
-      if (lane < kMel - 32) {
-        float acc1 = 0.f;
-        for (int i = 0; i < fcn1; ++i) acc1 = fmaf(spw[fst1 + i], s_fw[fof1 + i], acc1);
-        s_lm[(lane + 32) * (kFramesPerCta + 4) + fr] =
-            psf ? logf(acc1 == 0.f ? 2.220446049250313e-16f : acc1) : logf(acc1 + kLogEps);
+      float acc1 = 0.f;
+      for (int q4 = 0; q4 < cnt_hi; ++q4) {
+        const int i = q4 * 4 + part;
+        if (i < fcn1) acc1 = fmaf(spw[fst1 + i], s_fwt[i * kMel + fhi], acc1);
       }
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+      if (part == 0)
+        s_lm[fhi * (kFramesPerCta + 4) + fr] =
+            psf ? logf(acc1 == 0.f ? 2.220446049250313e-16f : acc1) : logf(acc1 + kLogEps);
     }
     __syncwarp();
   }
@@ -340,14 +366,15 @@ mfcc_kernel(const __grid_constant__ MfccArgs a) {
 }
 
 template <int NFFT>
-static size_t mfcc_smem_bytes(int hop, int nnz) {
+static size_t mfcc_smem_bytes(int hop, int maxcnt) {
   constexpr int N = NFFT / 2;
   constexpr int SCR = N + (N >> 5) + 40;
   constexpr int NBIN = N + 1;
   constexpr int WSCR = 2 * SCR + ((NBIN + 7) & ~3);
   size_t span = (size_t)(kFramesPerCta - 1) * hop + NFFT + 4;
   size_t o = (span * 2 + 15) & ~(size_t)15;
-  o += NFFT * 4 + NFFT * 8 + ((nnz + 3) & ~3) * 4 + kMel * kMel * 4 + kMel * (kFramesPerCta + 4) * 4;
+  o += NFFT * 4 + NFFT * 8 + (size_t)maxcnt * kMel * 4 + 7 * 8 * 8 + 7 * 64 * 8 + kMel * kMel * 4 +
+       kMel * (kFramesPerCta + 4) * 4;
   o += (kFramesPerCta + 4) * 4;
   o += (size_t)(kMfccThreads / 32) * WSCR * 4;
   return o + 16;
@@ -449,6 +476,25 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
       v *= (float)sqrt(2.0 / kMel);
       dct[f * kMel + k] = v;
     }
+  // compact, conflict-free twiddle tables of FFT passes 2 and 3, transposed filter weights
+  const int Nc = n_fft / 2, R3 = Nc / 64;
+  std::vector<float2> tw2(7 * 8), tw3((size_t)7 * 64, make_float2(1.f, 0.f));
+  for (int t = 1; t < 8; ++t)
+    for (int k = 0; k < 8; ++k) {
+      const double ang = -2.0 * M_PI * (double)(t * k) / 64.0;
+      tw2[(t - 1) * 8 + k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  for (int t = 1; t < R3; ++t)
+    for (int j = 0; j < 64; ++j) {
+      const double ang = -2.0 * M_PI * (double)(t * j) / (double)Nc;
+      tw3[(t - 1) * 64 + j] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  int maxcnt_lo = 1;
+  for (int f = 0; f < 32; ++f) if (fcount[f] > maxcnt_lo) maxcnt_lo = fcount[f];
+  if (maxbins < 1) maxbins = 1;
+  std::vector<float> fwt((size_t)maxbins * kMel, 0.f);
+  for (int f = 0; f < kMel; ++f)
+    for (int i = 0; i < fcount[f]; ++i) fwt[(size_t)i * kMel + f] = fw[foff[f] + i];
   std::vector<float> lifter(kMel, 1.f);
   if (flavour == 1)
     for (int n = 0; n < kMel; ++n) lifter[n] = (float)(1.0 + 11.0 * sin(M_PI * (double)n / 22.0));
@@ -456,7 +502,8 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
   size_t o_win = 0, o_tw = o_win + window.size() * 4, o_fs = o_tw + tw.size() * 8,
          o_fc = o_fs + kMel * 4, o_fo = o_fc + kMel * 4, o_fw = o_fo + kMel * 4,
          o_dct = o_fw + ((fw.size() + 3) & ~(size_t)3) * 4, o_lf = o_dct + dct.size() * 4,
-         total = o_lf + kMel * 4;
+         o_tw2 = o_lf + kMel * 4, o_tw3 = o_tw2 + tw2.size() * 8, o_fwt = o_tw3 + tw3.size() * 8,
+         total = o_fwt + fwt.size() * 4;
   std::vector<uint8_t> blob(total, 0);
   memcpy(&blob[o_win], window.data(), window.size() * 4);
   memcpy(&blob[o_tw], tw.data(), tw.size() * 8);
@@ -466,6 +513,9 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
   memcpy(&blob[o_fw], fw.data(), fw.size() * 4);
   memcpy(&blob[o_dct], dct.data(), dct.size() * 4);
   memcpy(&blob[o_lf], lifter.data(), kMel * 4);
+  memcpy(&blob[o_tw2], tw2.data(), tw2.size() * 8);
+  memcpy(&blob[o_tw3], tw3.data(), tw3.size() * 8);
+  memcpy(&blob[o_fwt], fwt.data(), fwt.size() * 4);
   uint8_t* dev = nullptr;
   VAR_CUDA_CHECK(cudaMalloc(&dev, total));
   VAR_CUDA_CHECK(cudaMemcpy(dev, blob.data(), total, cudaMemcpyHostToDevice));
@@ -481,7 +531,12 @@ int mfcc_plan_create(int flavour, int fs, int n_fft, int win_length, int hop, Mf
   p->t.fweights = reinterpret_cast<float*>(dev + o_fw);
   p->t.dct = reinterpret_cast<float*>(dev + o_dct);
   p->t.lifter = reinterpret_cast<float*>(dev + o_lf);
+  p->t.tw2 = reinterpret_cast<float2*>(dev + o_tw2);
+  p->t.tw3 = reinterpret_cast<float2*>(dev + o_tw3);
+  p->t.fwt = reinterpret_cast<float*>(dev + o_fwt);
   p->t.nnz = (int)fw.size();
+  p->t.maxcnt = maxbins;
+  p->t.maxcnt_lo = maxcnt_lo;
   *out = p;
   return VAR_OK;
 }
@@ -502,7 +557,7 @@ int mfcc_fwd(const MfccPlan* p, const int16_t* wav, const long long* offsets, co
   dim3 grid((F + kFramesPerCta - 1) / kFramesPerCta, B);
   LaunchScope sc(T_MFCC, 0, st);
   if (p->n_fft == 512) {
-    const size_t smem = mfcc_smem_bytes<512>(p->hop, p->t.nnz);
+    const size_t smem = mfcc_smem_bytes<512>(p->hop, p->t.maxcnt);
     static bool cfg = false;
     if (!cfg) {
       VAR_CUDA_CHECK(cudaFuncSetAttribute(mfcc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -510,7 +565,7 @@ int mfcc_fwd(const MfccPlan* p, const int16_t* wav, const long long* offsets, co
     }
     mfcc_kernel<512><<<grid, kMfccThreads, smem, st>>>(a);
   } else {
-    const size_t smem = mfcc_smem_bytes<1024>(p->hop, p->t.nnz);
+    const size_t smem = mfcc_smem_bytes<1024>(p->hop, p->t.maxcnt);
     static size_t cfg = 0;
     if (smem > cfg) {
       VAR_CUDA_CHECK(cudaFuncSetAttribute(mfcc_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
