@@ -315,39 +315,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
       rc.base = (long long)rc.n * g.sN;
     }
     if constexpr (kTmaA) {
-      // one elected thread feeds both operands with TMA; everyone else goes straight to the
-      // epilogue wait
-      if (tid == 0) {
+      // lane 0 of the four epilogue warps share the TMA issue of every k-block (warp 0: the A
+      // tile and the expect_tx arm; warps 1-3: the weight boxes round-robin) -- a single issuing
+      // thread becomes the bottleneck once a k-block needs more than two TMA instructions.
+      // A warp without a box to load must stay out of the loop: an idle waiter can fall two
+      // phases behind an mbarrier and then never sees its parity flip.
+      const int nb_boxes = p.b_mn_major ? (bn >> 5) : p.nbox;
+      const bool multi = nb_boxes >= 3;  // up to 3 instructions per k-block: one issuer is fastest
+      if (lane == 0 && (warp == 0 || (multi && warp - 1 < nb_boxes))) {
         int st = 0, ph = 0;
         int w0 = 0, h0 = 0, n0 = 0;
         if constexpr (GMODE == G_TMA_IM2COL) {
-          w0 = rc.q * p.step_w + p.base_w;
-          h0 = rc.p * p.step_h + p.base_h;
-          n0 = rc.n;
+          const int pq0 = g.P * g.Q;
+          const int mm0 = m0 < g.M ? m0 : 0;
+          n0 = mm0 / pq0;
+          const int rem0 = mm0 - n0 * pq0;
+          const int p0 = rem0 / g.Q;
+          w0 = (rem0 - p0 * g.Q) * p.step_w + p.base_w;
+          h0 = p0 * p.step_h + p.base_h;
         }
         for (int it = 0; it < num_kb; ++it) {
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-          mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
           const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
           const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
           int tap = 0, c0 = it << 5;
           if constexpr (GMODE == G_TMA_IM2COL) {
             tap = it / p.cpb;
             c0 = (it - tap * p.cpb) << 5;
-            tma_load_im2col_4d(dstA, tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
-          } else {
-            tma_load_2d(dstA, tmA, full_bar(st), it * 32, m0);
+          }
+          if (warp == 0) {
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
+            if constexpr (GMODE == G_TMA_IM2COL)
+              tma_load_im2col_4d(dstA, tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
+            else
+              tma_load_2d(dstA, tmA, full_bar(st), it * 32, m0);
           }
           if (!p.b_mn_major) {
             for (int b = 0; b < p.nbox; ++b)
-              tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st), it * 32,
-                          p.boxbase[b] + ntile * p.box_rows);
+              if (warp == (multi ? 1 + (b % 3) : 0))
+                tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st), it * 32,
+                            p.boxbase[b] + ntile * p.box_rows);
           } else {
             const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
             const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
             for (int gidx = 0; gidx < (bn >> 5); ++gidx)
-              tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st),
-                          rs * p.cin_total + ntile * bn + gidx * 32, k0);
+              if (warp == (multi ? 1 + (gidx % 3) : 0))
+                tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st),
+                            rs * p.cin_total + ntile * bn + gidx * 32, k0);
           }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
@@ -891,24 +905,28 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
   if (num_kb > 0) {
     if (warp < 4) {
-      if (tid == 0) {
+      // Four producer threads (lane 0 of warps 0-3) share the TMA issue work of a k-block: warp w
+      // loads X^T group w and dY groups w, w+4, ...  One thread alone spends about as long issuing
+      // the 6+ small boxes as the tensor core needs for the k-block.
+      // (a warp with nothing to load stays out: an idle waiter could fall two phases behind)
+      if (lane == 0 && (warp == 0 || warp < kgroups || warp < bgroups)) {
         const int pq = p.P * p.Q;
         int st = 0, ph = 0;
         for (int it = 0; it < num_kb; ++it) {
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-          mbar_arrive_expect_tx(full_bar(st), (uint32_t)kgroups * 4096u + tileB_bytes);
+          if (warp == 0) mbar_arrive_expect_tx(full_bar(st), (uint32_t)kgroups * 4096u + tileB_bytes);
           const int m = pix0 + it * 32;
           const uint32_t dA = sA + (uint32_t)st * tileA_bytes;
           const uint32_t dB = sB + (uint32_t)st * tileB_bytes;
-          if (p.a_tiled) {
-            for (int gq = 0; gq < kgroups; ++gq)
+          const int gq = warp;
+          if (gq < kgroups) {
+            if (p.a_tiled) {
               tma_load_2d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), ktile * 128 + gq * 32, m);
-          } else {
-            const int n = m / pq;
-            const int rem = m - n * pq;
-            const int pp = rem / p.Q, qq = rem - pp * p.Q;
-            const int w0 = qq * p.step_w + p.base_w, h0 = pp * p.step_h + p.base_h;
-            for (int gq = 0; gq < kgroups; ++gq) {
+            } else {
+              const int n = m / pq;
+              const int rem = m - n * pq;
+              const int pp = rem / p.Q, qq = rem - pp * p.Q;
+              const int w0 = qq * p.step_w + p.base_w, h0 = pp * p.step_h + p.base_h;
               const int kb = ktile * 4 + gq;
               const int tap = kb / p.cpb;
               const int c0 = (kb - tap * p.cpb) << 5;
@@ -916,7 +934,7 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                                  p.tap_w[tap], p.tap_h[tap]);
             }
           }
-          for (int bg = 0; bg < bgroups; ++bg)
+          for (int bg = warp; bg < bgroups; bg += 4)
             tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), bg * 32, m);
           if (++st == stages) { st = 0; ph ^= 1; }
         }
