@@ -88,6 +88,9 @@ int var_net_store_tensor(void* net, int index, int which, float* d_dst, void* st
 int var_net_refresh_mma(void* net, void* stream);
 int64_t var_net_workspace_bytes(void* net, int n_images, int n_sounds, int train);
 int var_net_raw_dims(void* net, int* img_raw, int* snd_raw);
+/* on = 0 serialises the image and sound branches on the caller's stream (default: the sound branch runs on a
+ * high-priority side stream so the branches overlap); used by bench.py for uncontended per-kernel timings. */
+int var_net_set_overlap(void* net, int on);
 
 /* VARPretextNet.forward (models/pretext/pretext_base.py:10-42) for a batch.
  *   d_images : [n_images, 3, 96, 96] NCHW; image_kind 0 = uint8 (scaled by 1/255 in the first

@@ -103,12 +103,16 @@ def test_first_layer_conv_vs_torch(vb, case):
     lib = vb._lib.lib
     kind, N, H, W, Cin, Cout, R, S, sh, sw, ph, pw = case
     g = torch.Generator().manual_seed(7)
+    # the 3 -> 32 channel 3x3 conv1 runs as a direct fp32 kernel (exact input values); the other
+    # first layers go through the tensor path, which rounds the loaded value to tf32
+    direct = Cin == 3 and Cout == 32 and R == 3 and S == 3
+    rnd = (lambda t: t) if direct else tf32
     if kind == "u8":
         xu = torch.randint(0, 256, (N, Cin, H, W), generator=g, dtype=torch.uint8)
-        x = tf32(xu.float() * np.float32(1.0 / 255.0))  # the kernel rounds the scaled value to tf32
+        x = rnd(xu.float() * np.float32(1.0 / 255.0))
         src, src_kind, scale = xu.to(DEV), 2, 1.0 / 255.0
     else:
-        x = tf32(torch.randn(N, Cin, H, W, generator=g))
+        x = rnd(torch.randn(N, Cin, H, W, generator=g))
         src, src_kind, scale = x.to(DEV), 1, 1.0
     w = tf32(torch.randn(Cout, Cin, R, S, generator=g) / (R * S * Cin) ** 0.5).requires_grad_(True)
     b = torch.randn(Cout, generator=g)
@@ -134,6 +138,7 @@ def test_first_layer_conv_vs_torch(vb, case):
     dw_ref = torch.empty(Cout, Cin, R, S, device=DEV)
     assert lib.var_unpack_weight(dw.data_ptr(), dw_ref.data_ptr(), Cout, Cin, R, S, kpad, None) == 0
     assert rel_to_max(dw_ref.cpu().numpy(), w.grad.numpy()) < 2e-5
+    assert rel_to_max(db.cpu().numpy(), (dy * (y_ref > 0)).sum(dim=(0, 2, 3)).numpy()) < 2e-5
 
 
 @pytest.mark.parametrize("shape", [(3, 96, 96, 32), (2, 12, 12, 128), (5, 6, 10, 64)])

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "var_net_store_tensor": (_i, [_p, _i, _i, _p, _p]),
     "var_net_refresh_mma": (_i, [_p, _p]),
     "var_net_workspace_bytes": (_i64, [_p, _i, _i, _i]),
+    "var_net_set_overlap": (_i, [_p, _i]),
     "var_net_raw_dims": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
     "var_net_forward": (_i, [_p, _p, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _p, _p, _p]),
     "var_net_backward": (_i, [_p, _p, _p, _p, _i64, _p]),

@@ -1,5 +1,6 @@
 // Host launchers for the tcgen05 engine (see tc_engine.cuh).
 #include "engine_host.cuh"
+#include "first_conv.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -316,6 +317,14 @@ static int fill_fwd_geom(GatherGeom* g, const ConvShape& cs, const void* x, int 
   return VAR_OK;
 }
 
+// image conv1 of both encoders: 3 -> 32 channels, 3x3, pad 1, stride 1 or 2, strided source
+static bool is_first_conv(const ConvShape& cs, int src_kind) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAR_FIRST_CONV"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on && src_kind != SRC_NHWC_F32 && cs.Cin == 3 && cs.Cout == 32 && cs.R == 3 && cs.S == 3 &&
+         cs.ph == 1 && cs.pw == 1 && cs.sh == cs.sw && (cs.sh == 1 || cs.sh == 2);
+}
+
 static int gmode_of(int src_kind) {
   return src_kind == SRC_NHWC_F32 ? G_VEC_FWD
                                   : (src_kind == SRC_STRIDED_F32 ? G_SCALAR_F32 : G_SCALAR_U8);
@@ -324,6 +333,14 @@ static int gmode_of(int src_kind) {
 int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
              const float* bias, float* y, int relu, int round_out, cudaStream_t st) {
   prof_note("fwd N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (is_first_conv(cs, src_kind) && sl) {
+    FirstConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.sN = sl->sN; a.sH = sl->sH; a.sW = sl->sW; a.sC = sl->sC; a.scale = sl->scale;
+    a.N = cs.N; a.H = cs.H; a.W = cs.W; a.P = cs.P; a.Q = cs.Q; a.stride = cs.sh;
+    a.w = w; a.kpad = round_up32(27); a.bias = bias; a.y = y; a.relu = relu; a.round_out = round_out;
+    return first_conv_fwd(a, src_kind == SRC_STRIDED_U8, st);
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_fwd_geom(&p.g[0], cs, x, src_kind, sl);
@@ -679,6 +696,14 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
 int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
                const float* dy, float* dw, float* db, cudaStream_t st) {
   prof_note("wgrad N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (is_first_conv(cs, src_kind) && sl) {
+    FirstConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.sN = sl->sN; a.sH = sl->sH; a.sW = sl->sW; a.sC = sl->sC; a.scale = sl->scale;
+    a.N = cs.N; a.H = cs.H; a.W = cs.W; a.P = cs.P; a.Q = cs.Q; a.stride = cs.sh;
+    a.kpad = round_up32(27); a.dy = dy; a.dw = dw; a.db = db;
+    return first_conv_wgrad(a, src_kind == SRC_STRIDED_U8, st);
+  }
   if (src_kind == SRC_NHWC_F32 && gather_mode() == 1 && cs.Cin % 32 == 0 && cs.Cout % 32 == 0 &&
       cs.R * cs.S <= kMaxTaps) {
     const int rc = conv_wgrad_tma(cs, reinterpret_cast<const float*>(x), dy, dw, st);

@@ -676,6 +676,10 @@ int var_net_refresh_mma(void* net, void* stream) {
   if (!n->P || !n->PR) return VAR_ERR_ARG;
   return var::round_copy(n->P, n->PR, n->nparams, ST(stream));
 }
+int var_net_set_overlap(void* net, int on) {
+  NET(net)->overlap = on != 0;
+  return VAR_OK;
+}
 int var_net_raw_dims(void* net, int* img_raw, int* snd_raw) {
   if (img_raw) *img_raw = NET(net)->img_raw_dim;
   if (snd_raw) *snd_raw = NET(net)->snd_raw_dim;

@@ -85,6 +85,10 @@ class VarEngine:
     def grad_dict(self):
         return self._store(1)
 
+    def set_overlap(self, on):
+        """Image / sound branch overlap on two streams (default on)."""
+        check(lib.var_net_set_overlap(self._net, 1 if on else 0), "var_net_set_overlap")
+
     def zero_grad(self):
         self.grads.zero_()
 
