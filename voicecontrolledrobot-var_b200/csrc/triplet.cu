@@ -111,9 +111,11 @@ __global__ void sampler_seed_kernel(uint32_t* state, uint32_t seed) {
 // second seeds a private mt19937 whose Fisher-Yates randperm(n) is the epoch
 // order.  perm lives in global memory; thread 0 performs the dependent swaps.
 __global__ void sampler_epoch_kernel(uint32_t* state, int n, int* perm) {
+  extern __shared__ uint16_t s_perm[];  // [n] when n <= 65536 (the dependent swaps then stay on chip)
   __shared__ uint32_t s[MT_N];
   __shared__ uint32_t d[4];
   __shared__ uint32_t buf[MT_N];
+  const bool in_smem = n <= 65536;
   for (int i = threadIdx.x; i < MT_N; i += blockDim.x) s[i] = state[i];
   __syncthreads();
   int pos = (int)state[MT_N];
@@ -124,23 +126,35 @@ __global__ void sampler_epoch_kernel(uint32_t* state, int n, int* perm) {
   // sampler seed = ((d[2] << 32) | d[3]) mod 2^63 ; at::mt19937 seeds with the low 32 bits
   const uint32_t seed = d[3];
   mt_seed(s, seed);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
+  if (in_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) s_perm[i] = (uint16_t)i;
+  else for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
   __syncthreads();
   int ppos = MT_N;
   for (int base = 0; base < n - 1; base += MT_N) {
     const int cnt = min(MT_N, n - 1 - base);
     ppos = mt_fill(s, ppos, buf, cnt);
     if (threadIdx.x == 0) {
-      for (int i = 0; i < cnt; ++i) {
-        const int ii = base + i;
-        const int z = (int)(buf[i] % (uint32_t)(n - ii));
-        const int t = perm[ii];
-        perm[ii] = perm[z + ii];
-        perm[z + ii] = t;
+      if (in_smem) {
+        for (int i = 0; i < cnt; ++i) {
+          const int ii = base + i;
+          const int z = (int)(buf[i] % (uint32_t)(n - ii));
+          const uint16_t t = s_perm[ii];
+          s_perm[ii] = s_perm[z + ii];
+          s_perm[z + ii] = t;
+        }
+      } else {
+        for (int i = 0; i < cnt; ++i) {
+          const int ii = base + i;
+          const int z = (int)(buf[i] % (uint32_t)(n - ii));
+          const int t = perm[ii];
+          perm[ii] = perm[z + ii];
+          perm[z + ii] = t;
+        }
       }
     }
     __syncthreads();
   }
+  if (in_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = (int)s_perm[i];
 }
 
 // One batch of triplets.  item i = items[i] (index into gt / stored_sn).
@@ -258,8 +272,15 @@ int sampler_seed(uint32_t* state, unsigned long long seed, cudaStream_t st) {
 }
 int sampler_epoch(uint32_t* state, int n, int* perm, cudaStream_t st) {
   if (n <= 0) return VAR_ERR_ARG;
+  const size_t smem = n <= 65536 ? (size_t)n * 2 + 16 : 0;
+  static size_t configured = 0;
+  if (smem > configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(sampler_epoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = smem;
+  }
   LaunchScope sc(T_SAMPLER, 0, st);
-  sampler_epoch_kernel<<<1, 256, 0, st>>>(state, n, perm);
+  sampler_epoch_kernel<<<1, 256, smem, st>>>(state, n, perm);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
