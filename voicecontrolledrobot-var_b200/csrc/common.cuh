@@ -133,6 +133,18 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       : "memory");
 }
 
+// ---- programmatic dependent launch --------------------------------------------
+// launch_dependents: lets the next kernel of the stream (if it was launched with the
+// programmatic-stream-serialization attribute) start its prologue while this grid runs;
+// wait: blocks until the prerequisite grid has completed and its writes are visible.
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void griddep_launch() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

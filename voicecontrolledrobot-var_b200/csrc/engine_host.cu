@@ -195,6 +195,15 @@ int get_tmap_im2col(const float* ptr, int N, int H, int W, int C, int low_w, int
   return VAR_OK;
 }
 
+// VAR_PDL=1 launches the GRU steps with programmatic dependent launch.  Measured on B200: no gain
+// (16.8 vs 16.4 ms/step) -- a step is bound by its TMA round trips and epilogue, not by launch or
+// prologue latency -- so ordinary stream-ordered launches stay the default.
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAR_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+
 int gather_mode() {  // VAR_GATHER=cp_async keeps the LSU gather kernels (A/B testing)
   static int mode = -1;
   if (mode < 0) {
@@ -226,7 +235,20 @@ static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const CUt
     else if (p.b_mn_major) tag = T_GEMM_DGRAD;
     else if (GMODE == G_VEC_FWD || GMODE == G_TMA_IM2COL || GMODE == G_TMA_TILED) tag = T_GEMM_FWD;
     LaunchScope sc(tag, flops, st);
-    tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, a0, a1, p);
+    if (EPI != EPI_STD && pdl_enabled()) {
+      // GRU time steps: 145 small dependent launches per training step.  Programmatic dependent
+      // launch lets step s+1 set up (barriers, TMEM, descriptors) while step s is still running.
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = grid; cfg.blockDim = dim3(160, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      VAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<GMODE, EPI>, t0, t1, a0, a1, p));
+    } else {
+      tc_gemm_kernel<GMODE, EPI><<<grid, 160, smem, st>>>(t0, t1, a0, a1, p);
+    }
   }
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;

@@ -213,6 +213,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  griddep_launch();  // PDL: the next GRU step may run its prologue under this grid
+  if constexpr (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8) griddep_wait();  // stages inputs first
   const int z = blockIdx.z;
   const CUtensorMap* tmB = z == 0 ? &tmB0 : &tmB1;
   const CUtensorMap* tmA = z == 0 ? &tmA0 : &tmA1;
@@ -289,6 +291,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+  griddep_wait();  // everything above overlapped the previous kernel; its results are read below
 
   const int m0 = kScalar ? (sc_n * g.P + sc_p0) * g.Q : blockIdx.x * kTileM;
   const int m_end = kScalar ? m0 + sc_rows * g.Q : g.M;
