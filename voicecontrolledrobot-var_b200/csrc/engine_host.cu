@@ -1,6 +1,7 @@
 // Host launchers for the tcgen05 engine (see tc_engine.cuh).
 #include "engine_host.cuh"
 #include "first_conv.cuh"
+#include "gru_persist.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -573,6 +574,92 @@ int gru_step_bwd(int ndir, int B, int Hd, const float* const dgh[2], const float
   if (ndir == 1) { tm[1] = tm[0]; ta[1] = ta[0]; }
   dim3 grid((B + 127) / 128, Hd / p.bn, ndir);
   return launch_gemm(G_TMA_TILED, EPI_GRU_BWD, tm[0], tm[1], ta[0], ta[1], p, grid, st);
+}
+
+bool gru_persist_enabled() {  // VAR_GRU_PERSIST=0 falls back to one launch per time step
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAR_GRU_PERSIST"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+template <int BWD>
+static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3 grid, cudaStream_t st) {
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_persist_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = smem;
+  }
+  static int max_ctas = -1;
+  if (max_ctas < 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_persist_kernel<BWD>, 160, smem);
+    max_ctas = per_sm * sms;
+  }
+  if ((long long)grid.x * grid.y * grid.z > max_ctas) return VAR_ERR_UNSUPPORTED;  // not co-resident
+  VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * grid.x * grid.z, st));
+  void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
+  const int nsteps = BWD ? p.T - 1 : p.T;
+  LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)(p.bn * grid.y) * (p.num_kb * 32.0) * grid.z * nsteps, st);
+  VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD>, grid, dim3(160, 1, 1), args, smem, st));
+  return VAR_OK;
+}
+
+// All T forward steps of both directions in one cooperative launch (gru_persist.cuh).
+// h_r: [(T+1), B, H] with slot 0 zeroed; h32[d][0] zeroed.  Returns VAR_ERR_UNSUPPORTED when the
+// grid cannot be co-resident (caller falls back to per-step launches).
+int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long ldx, const float* const whh[2],
+                    const float* const bhh[2], float* const h32[2][2], float* const h_r[2],
+                    float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st) {
+  if (!gru_persist_enabled() || gather_mode() != 1 || Hd % 64) return VAR_ERR_UNSUPPORTED;
+  prof_note("gru_persist_fwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
+  GruPersistParams p;
+  memset(&p, 0, sizeof(p));
+  const int jb = 32;
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / 32; p.stages = 4;
+  p.counters = counters; p.ldx = ldx;
+  CUtensorMap tm[4];
+  for (int d = 0; d < 2; ++d) {
+    p.xproj[d] = xproj[d]; p.bhh[d] = bhh[d];
+    p.h32[d][0] = h32[d][0]; p.h32[d][1] = h32[d][1];
+    p.h_r[d] = h_r[d]; p.gates[d] = gates[d]; p.hn_save[d] = hn_save[d];
+    int rc = get_tmap_2d(whh[d], 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[d]);
+    if (rc) return rc;
+    rc = get_tmap_2d(h_r[d], (T + 1) * B, Hd, Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    if (rc) return rc;
+  }
+  dim3 grid((B + 127) / 128, Hd / jb, 2);
+  p.arrivals = 4 * (int)grid.y;
+  return launch_gru_persist<0>(tm, p, grid, st);
+}
+
+// BPTT steps T-1 .. 1 of both directions in one cooperative launch: dgh[T-1] and dhd[d][0] must hold
+// the cell backward of the last step (gru_cell_bwd).
+int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float* const gates[2],
+                    const float* const hn_save[2], const float* const h_r[2], float* const dgh[2],
+                    float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st) {
+  if (!gru_persist_enabled() || gather_mode() != 1 || Hd % 32) return VAR_ERR_UNSUPPORTED;
+  prof_note("gru_persist_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
+  GruPersistParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 32; p.num_kb = 3 * Hd / 32; p.stages = 4;
+  p.counters = counters;
+  p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
+  CUtensorMap tm[4];
+  for (int d = 0; d < 2; ++d) {
+    p.gates_c[d] = gates[d]; p.hn_save_c[d] = hn_save[d]; p.h_r_c[d] = h_r[d];
+    p.dgh[d] = dgh[d]; p.dgi[d] = dgi[d]; p.dhd[d][0] = dhd[d][0]; p.dhd[d][1] = dhd[d][1];
+    int rc = get_tmap_2d(whh[d], 3 * Hd, Hd, Hd, 32, mn_cfg().tma_swizzle, &tm[d]);
+    if (rc) return rc;
+    rc = get_tmap_2d(dgh[d], T * B, 3 * Hd, 3 * Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    if (rc) return rc;
+  }
+  dim3 grid((B + 127) / 128, Hd / p.bn, 2);
+  p.arrivals = 4 * (int)grid.y;
+  return launch_gru_persist<1>(tm, p, grid, st);
 }
 
 // One GRU time step for up to two directions: gates = hprev @ W_hh^T fused with the

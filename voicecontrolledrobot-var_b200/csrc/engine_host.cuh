@@ -51,6 +51,12 @@ int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const f
                  const GruEpiParams q[2], cudaStream_t st);
 int gru_step_bwd(int ndir, int B, int Hd, const float* const dgh[2], const float* const whh[2],
                  const GruBwdEpiParams q[2], cudaStream_t st);
+int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long ldx, const float* const whh[2],
+                    const float* const bhh[2], float* const h32[2][2], float* const h_r[2],
+                    float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st);
+int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float* const gates[2],
+                    const float* const hn_save[2], const float* const h_r[2], float* const dgh[2],
+                    float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st);
 int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st);
 
 // dw[Cout, Kpad] += im2col(x)^T dy ; db[Cout] += colsum(dy) (db may be null).

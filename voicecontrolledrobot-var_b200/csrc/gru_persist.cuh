@@ -1,0 +1,306 @@
+// Persistent GRU kernels: all time steps of torch.nn.GRU(448 -> 512, bidirectional)
+// (models/pretext/ai2thor_pretext_model.py:6,33-38) in ONE cooperative launch per pass.
+//
+// A step-per-launch GRU spends more on launch gaps, barrier / TMEM set-up and cold TMA round
+// trips than on its 1.6 GFLOP.  Here every CTA keeps its role for the whole sequence: tile =
+// (128 batch rows) x (a slice of hidden units, all three gates) x (direction); barriers, TMEM and
+// tensor-map prefetches are set up once; per step the CTA streams h_{s} (A, K-major, tiled TMA)
+// and its W_hh slice (B) through the tcgen05 pipeline, runs the GRU cell (or the fused BPTT
+// cell backward) in the epilogue and publishes its slice of h_{s+1}.  The only cross-CTA
+// dependency is "all hidden slices of my (row tile, direction) are written": a monotonic global
+// counter per group, release = __threadfence + atomicAdd by each epilogue warp, acquire =
+// ld.acquire spin by the A-operand producer followed by a proxy fence before the TMA reads.
+// Launched with cudaLaunchCooperativeKernel so all CTAs are co-resident (spin-waits are safe).
+#pragma once
+#include "tc_engine.cuh"
+
+namespace var {
+
+struct GruPersistParams {
+  int B, Hd, T;
+  int bn;             // fwd: 3 * jb ; bwd: hidden units per CTA
+  int num_kb;         // k-blocks per step: fwd Hd/32, bwd 3*Hd/32
+  int stages;
+  int arrivals;       // epilogue-warp arrivals per group per step = 4 * gridDim.y
+  unsigned int* counters;  // [gridDim.x * gridDim.z], zero before launch
+  int mn_lbo, mn_sbo, mn_type;
+  // forward
+  const float* xproj[2];  // [B, T, 3H] incl. b_ih
+  long long ldx;
+  const float* bhh[2];
+  float* h32[2][2];       // fp32 hidden state ping-pong [B, H]
+  float* h_r[2];          // [(T+1), B, H] tf32-rounded hidden states (slot 0 = zeros): A operand
+  float* gates[2];        // [T][B, 3H] (nullptr = inference)
+  float* hn_save[2];      // [T][B, H]
+  // backward (step s = T-1 .. 1 computes the cell backward of step s-1)
+  const float* gates_c[2];
+  const float* hn_save_c[2];
+  const float* h_r_c[2];
+  float* dgh[2];          // [T][B, 3H]: A operand (slot s), written for slot s-1
+  float* dgi[2];          // [B, T, 3H] batch-major
+  float* dhd[2][2];       // dh * z ping-pong [B, H]
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// grid = (row tiles, hidden tiles, directions), block = 160.
+template <int BWD>
+__global__ void __launch_bounds__(160)
+gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                   const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ GruPersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int z = blockIdx.z;
+  const CUtensorMap* tmB = z == 0 ? &tmB0 : &tmB1;
+  const CUtensorMap* tmA = z == 0 ? &tmA0 : &tmA1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages, bn = p.bn, num_kb = p.num_kb;
+  const int Hd = p.Hd, B = p.B, T = p.T;
+  const uint32_t tileB_bytes = (uint32_t)bn * 128u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + (uint32_t)stages * kTileABytes;
+  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
+  const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
+  const uint32_t tslot = tfull_bar + 8u;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tmB);
+    tma_prefetch_desc(tmA);
+  }
+  const uint32_t ncols = (uint32_t)tmem_cols_for(bn);
+  if (warp == 4) tmem_alloc(tslot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int m0 = blockIdx.x * kTileM;
+  const int ntile = blockIdx.y;
+  unsigned int* counter = p.counters + (blockIdx.z * gridDim.x + blockIdx.x);
+  const int nsteps = BWD ? T - 1 : T;
+  const int jb = BWD ? bn : bn / 3;
+  const int nb_boxes = BWD ? (bn >> 5) : 3;
+  const bool multi = nb_boxes >= 3;
+
+  if (warp < 4) {
+    int st = 0, ph = 0;  // producer ring position (kept by every issuing lane)
+    const bool issuer = lane == 0 && (warp == 0 || (multi && warp - 1 < nb_boxes));
+    float* scr = reinterpret_cast<float*>(smem_raw + (sA - smem_u32(smem_raw))) +
+                 warp * (BWD ? 32 * 33 : 3 * 32 * 33);
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int it_s = 0; it_s < nsteps; ++it_s) {
+      const int s = BWD ? T - 1 - it_s : it_s;  // fwd: step index; bwd: slot whose dgh is the A operand
+      // ------------------------------------------------------------ producers
+      if (issuer) {
+        if (warp == 0 && it_s > 0) {
+          const unsigned int target = (unsigned int)(p.arrivals * it_s);
+          while (ld_acquire_gpu(counter) < target) {
+          }
+          fence_proxy_async_all();  // the generic-proxy writes just acquired are read by TMA below
+        }
+        const int arow = s * B + m0;  // row of the A tile in the [slots * B, K] matrix
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
+          const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
+          const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
+          if (warp == 0) {
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
+            tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
+          }
+          if constexpr (!BWD) {
+            for (int b = 0; b < 3; ++b)
+              if (warp == 1 + b)
+                tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * 32, b * Hd + ntile * jb);
+          } else {
+            for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+              if (warp == (multi ? 1 + (gidx % 3) : 0))
+                tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st), ntile * bn + gidx * 32, kb * 32);
+          }
+          if (++st == stages) { st = 0; ph ^= 1; }
+        }
+      }
+      __syncwarp();
+      // ------------------------------------------------------------- epilogue
+      mbar_wait(tfull_bar, (uint32_t)(it_s & 1));
+      tc_fence_after();
+      const int mrow0 = m0 + warp * 32;
+      constexpr int RB = 8;
+      if constexpr (!BWD) {
+        const int t = z == 0 ? s : T - 1 - s;
+        const float* __restrict__ xproj = p.xproj[z] + (long long)t * 3 * Hd;
+        const float* __restrict__ hprev = p.h32[z][s & 1];
+        float* hnew = p.h32[z][(s + 1) & 1];
+        float* hnew_r = p.h_r[z] + (long long)(s + 1) * B * Hd;
+        float* gates = p.gates[z] ? p.gates[z] + (long long)s * B * 3 * Hd : nullptr;
+        float* hn_save = p.hn_save[z] ? p.hn_save[z] + (long long)s * B * Hd : nullptr;
+        for (int c = 0; c < jb; c += 32) {
+          {
+            float v[32];
+#pragma unroll
+            for (int gq = 0; gq < 3; ++gq) {
+              tmem_ld32(trow + (uint32_t)(gq * jb + c), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) scr[(gq * 32 + lane) * 33 + j] = v[j];
+            }
+          }
+          __syncwarp();
+          const int j = ntile * jb + c + lane;
+          const float br = __ldg(p.bhh[z] + j), bz = __ldg(p.bhh[z] + Hd + j), bq = __ldg(p.bhh[z] + 2 * Hd + j);
+          for (int r0 = 0; r0 < 32; r0 += RB) {
+            float xr[RB], xz[RB], xn[RB], hp[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+              const int mr = mrow0 + r0 + u;
+              const bool ok = mr < B;
+              const float* xp = xproj + (long long)(ok ? mr : 0) * p.ldx;
+              xr[u] = ok ? __ldg(xp + j) : 0.f;
+              xz[u] = ok ? __ldg(xp + Hd + j) : 0.f;
+              xn[u] = ok ? __ldg(xp + 2 * Hd + j) : 0.f;
+              hp[u] = ok ? hprev[(long long)mr * Hd + j] : 0.f;  // written by this CTA last step
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+              const int rr = r0 + u, mr = mrow0 + rr;
+              if (mr < B) {
+                const float vr = scr[(0 * 32 + rr) * 33 + lane], vz = scr[(1 * 32 + rr) * 33 + lane],
+                            vn = scr[(2 * 32 + rr) * 33 + lane];
+                const float r_ = sigmoidf_(xr[u] + vr + br);
+                const float z_ = sigmoidf_(xz[u] + vz + bz);
+                const float hnv = vn + bq;
+                const float n_ = tanhf(xn[u] + r_ * hnv);
+                const float h_ = (1.f - z_) * n_ + z_ * hp[u];
+                const long long ho = (long long)mr * Hd + j;
+                hnew[ho] = h_;
+                hnew_r[ho] = round_tf32(h_);
+                if (gates) {
+                  float* gs = gates + (long long)mr * 3 * Hd + j;
+                  gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
+                  hn_save[ho] = hnv;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // acc = dgh_s . W_hh ; dh_{s-1} = acc + dh_s * z_s ; then the cell backward of step s-1
+        const int sp = s - 1;
+        const int t = z == 0 ? sp : T - 1 - sp;
+        const float* __restrict__ dhd_in = p.dhd[z][it_s & 1];
+        float* dhd_out = p.dhd[z][(it_s + 1) & 1];
+        const float* __restrict__ gates = p.gates_c[z] + (long long)sp * B * 3 * Hd;
+        const float* __restrict__ hn_save = p.hn_save_c[z] + (long long)sp * B * Hd;
+        const float* __restrict__ hprev = p.h_r_c[z] + (long long)sp * B * Hd;
+        float* dgi = p.dgi[z] + (long long)t * 3 * Hd;
+        const long long ldgi = (long long)T * 3 * Hd;
+        float* dgh = p.dgh[z] + (long long)sp * B * 3 * Hd;
+        for (int c = 0; c < bn; c += 32) {
+          {
+            float v[32];
+            tmem_ld32(trow + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = v[j];
+          }
+          __syncwarp();
+          const int j = ntile * bn + c + lane;
+          for (int r0 = 0; r0 < 32; r0 += RB) {
+            float din[RB], gr_[RB], gz_[RB], gn_[RB], hnv[RB], hp[RB];
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+              const int mr = mrow0 + r0 + u;
+              const bool ok = mr < B;
+              const long long hoff = (long long)(ok ? mr : 0) * Hd + j;
+              const float* gt = gates + (long long)(ok ? mr : 0) * 3 * Hd + j;
+              din[u] = ok ? dhd_in[hoff] : 0.f;  // written by this CTA last step
+              gr_[u] = ok ? __ldg(gt) : 0.f;
+              gz_[u] = ok ? __ldg(gt + Hd) : 0.f;
+              gn_[u] = ok ? __ldg(gt + 2 * Hd) : 0.f;
+              hnv[u] = ok ? __ldg(hn_save + hoff) : 0.f;
+              hp[u] = ok ? __ldg(hprev + hoff) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+              const int rr = r0 + u, mr = mrow0 + rr;
+              if (mr < B) {
+                const long long hoff = (long long)mr * Hd + j;
+                const float dh = scr[rr * 33 + lane] + din[u];
+                const float r_ = gr_[u], z_ = gz_[u], n_ = gn_[u];
+                const float dnn = dh * (1.f - z_);
+                const float dzz = dh * (hp[u] - n_);
+                const float dnp = dnn * (1.f - n_ * n_);
+                const float dzp = dzz * z_ * (1.f - z_);
+                const float drp = dnp * hnv[u] * r_ * (1.f - r_);
+                const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
+                float* gi = dgi + (long long)mr * ldgi + j;
+                gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
+                float* gh = dgh + (long long)mr * 3 * Hd + j;
+                gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = round_tf32(dnp * r_);
+                dhd_out[hoff] = dh * z_;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // publish this warp's slice of the new state (release), order the TMEM reads before the
+      // next step's MMAs
+      tc_fence_before();
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(counter, 1u);
+    }
+  } else {
+    // ===================== MMA issuer (warp 4) =====================
+    const uint32_t idesc = make_idesc_tf32(bn, 0, BWD ? 1 : 0);
+    int st = 0, ph = 0;
+    for (int it_s = 0; it_s < nsteps; ++it_s) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(st), (uint32_t)ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = sA + (uint32_t)st * kTileABytes;
+          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
+            const uint64_t bd = BWD ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
+                                                     (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                    : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
+            umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+          }
+          umma_commit(empty_bar(st));
+          if (kb == num_kb - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+}  // namespace var

@@ -70,6 +70,7 @@ struct GruState {
   float* h32[2][2];     // ping-pong fp32 hidden state
   float* out;           // [B, 1024]
   float* out_r;
+  unsigned int* counters;  // [row tiles * 2] persistent-kernel group barriers
 };
 
 }  // namespace
@@ -296,12 +297,13 @@ struct Net {
       g.xproj[d] = ar.alloc(BT * 3 * kGruH);
       g.gates[d] = train ? ar.alloc(BT * 3 * kGruH) : nullptr;
       g.hn_save[d] = train ? ar.alloc(BT * kGruH) : nullptr;
-      g.h_r[d] = ar.alloc((train ? (long long)(kGruT + 1) : 2) * B * kGruH);
+      g.h_r[d] = ar.alloc((long long)(kGruT + 1) * B * kGruH);
       g.h32[d][0] = ar.alloc((long long)B * kGruH);
       g.h32[d][1] = ar.alloc((long long)B * kGruH);
     }
     g.out = ar.alloc((long long)B * 2 * kGruH);
     g.out_r = ar.alloc((long long)B * 2 * kGruH);
+    g.counters = reinterpret_cast<unsigned int*>(ar.alloc(256));
     if (!ar.base) return VAR_OK;
     if (ar.overflow) return VAR_ERR_WORKSPACE;
     for (int d = 0; d < 2; ++d) {
@@ -314,13 +316,28 @@ struct Net {
       VAR_CUDA_CHECK(cudaMemsetAsync(g.h32[d][0], 0, (size_t)B * kGruH * 4, st));
     }
     const long long slot = (long long)B * kGruH;
+    {  // all 73 steps in one cooperative launch when the grid fits the device
+      const float* xp[2] = {g.xproj[0], g.xproj[1]};
+      const float* whh[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
+      const float* bhh[2] = {wm(t_gru[0][3]), wm(t_gru[1][3])};
+      float* h32[2][2] = {{g.h32[0][0], g.h32[0][1]}, {g.h32[1][0], g.h32[1][1]}};
+      float* hr[2] = {g.h_r[0], g.h_r[1]};
+      float* gt[2] = {g.gates[0], g.gates[1]};
+      float* hs[2] = {g.hn_save[0], g.hn_save[1]};
+      const int rc = gru_persist_fwd(B, kGruH, kGruT, xp, (long long)kGruT * 3 * kGruH, whh, bhh, h32, hr, gt, hs,
+                                     g.counters, st);
+      if (rc == VAR_OK)
+        return concat2(g.h32[0][kGruT & 1], g.h32[1][kGruT & 1], g.out, g.out_r, B, kGruH, st);
+      if (rc != VAR_ERR_UNSUPPORTED) return rc;
+    }
+    const bool keep_all = true;  // h_r always holds all T+1 slots
     for (int s = 0; s < kGruT; ++s) {
       const float* hp[2];
       const float* whh[2];
       GruEpiParams q[2];
       for (int d = 0; d < 2; ++d) {
         const int t = d == 0 ? s : kGruT - 1 - s;
-        const int cur_slot = train ? s : (s & 1), nxt_slot = train ? s + 1 : ((s + 1) & 1);
+        const int cur_slot = keep_all ? s : (s & 1), nxt_slot = keep_all ? s + 1 : ((s + 1) & 1);
         hp[d] = g.h_r[d] + cur_slot * slot;
         whh[d] = wr(t_gru[d][1]);
         memset(&q[d], 0, sizeof(GruEpiParams));
@@ -495,7 +512,19 @@ struct Net {
     }
     // steps T-1 .. 1: recurrence GEMM with the cell backward of the previous step fused in
     float* dhd_pp[2][2] = {{dhd[0], dh[0][1]}, {dhd[1], dh[1][1]}};
-    for (int s = kGruT - 1; s >= 1; --s) {
+    bool persistent_done = false;
+    {
+      const float* whh[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
+      const float* gt[2] = {g.gates[0], g.gates[1]};
+      const float* hs[2] = {g.hn_save[0], g.hn_save[1]};
+      const float* hr[2] = {g.h_r[0], g.h_r[1]};
+      float* dgh2[2] = {dgh[0], dgh[1]};
+      float* dgi2[2] = {dgi[0], dgi[1]};
+      rc = gru_persist_bwd(B, kGruH, kGruT, whh, gt, hs, hr, dgh2, dgi2, dhd_pp, g.counters, st);
+      if (rc == VAR_OK) persistent_done = true;
+      else if (rc != VAR_ERR_UNSUPPORTED) return rc;
+    }
+    for (int s = kGruT - 1; s >= 1 && !persistent_done; --s) {
       const int cur = (kGruT - 1 - s) & 1;
       const float* dy2[2];
       const float* w2[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
