@@ -1,34 +1,21 @@
 """Host mirror of models/pretext/arm_pretext_model.py (Kuka VAR encoders).
 
-Parameter containers reproduce the reference module tree (names, shapes, construction order
-and the two `torch.rand` shape probes of arm_pretext_model.py:44,50), so a seeded
-construction yields the reference's initial weights and checkpoints load both ways.  The
-nn layers are never called: forward/backward run in libvar_b200.so."""
+The module tree is rebuilt from layer specs (`_layers.py`) with the reference's names, shapes and
+construction order, and the constructor consumes the global RNG exactly where the reference's two
+shape probes do (`get_layer_output_shape` at arm_pretext_model.py:44 and the sound-branch probe at
+:50), so `torch.manual_seed(s); VARPretextNet(config)` yields the reference's initial weights and
+checkpoints load both ways.  The torch layers are parameter containers only: forward / backward
+run in libvar_b200.so."""
 import torch
-import torch.nn as nn
 
 from ...engine import KUKA
+from ._layers import conv_stack, mlp_head
 from .pretext_base import PretextNetBase
 
-
-class Flatten(nn.Module):  # utils.py:9-11 (parameter-free placeholder, keeps Sequential indices)
-    def forward(self, x):
-        return x.view(x.size(0), -1)
-
-
-def buildCNN(nn_module, config=None):
-    chans = [3, 32, 32, 64, 64, 64]
-    mods = []
-    for i in range(5):
-        mods += [nn.Conv2d(chans[i], chans[i + 1], 3, stride=2, padding=1), nn.ReLU()]
-    nn_module.imgBranch = nn.Sequential(*mods, Flatten())
-
-
-def buildSoundBranch(nn_module, config=None):
-    mods = [nn.Conv2d(1, 32, (5, 40), stride=(2, 1)), nn.ReLU()]
-    for _ in range(3):
-        mods += [nn.Conv2d(32, 32, (3, 1), stride=(2, 1)), nn.ReLU()]
-    nn_module.soundCNN = nn.Sequential(*mods, Flatten())
+# image: five 3x3 stride-2 convs 96 -> 3;  sound: a 5x40 conv over the MFCC, then three 3x1 convs
+IMG_SPEC = [("c", cin, cout, 3, 2, 1) for cin, cout in ((3, 32), (32, 32), (32, 64), (64, 64), (64, 64))]
+SND_SPEC = [("c", 1, 32, (5, 40), (2, 1), 0)] + [("c", 32, 32, (3, 1), (2, 1), 0)] * 3
+IMG_FLAT, SND_FLAT, HIDDEN = 64 * 3 * 3, 32 * 5, 128
 
 
 class VARPretextNet(PretextNetBase):
@@ -39,14 +26,14 @@ class VARPretextNet(PretextNetBase):
         self.config = config
         if tuple(config.img_dim) != (3, 96, 96) or tuple(config.sound_dim) != (1, 100, 40):
             raise ValueError("Kuka VARPretextNet is built for img_dim (3,96,96), sound_dim (1,100,40)")
-        buildCNN(self, config)
-        buildSoundBranch(self, config)
-        torch.rand((1, *config.img_dim))  # RNG parity with get_layer_output_shape (arm_pretext_model.py:44)
-        self.imgCNN_outputShape = torch.Size([1, 576])
-        self.imgTriplet = nn.Sequential(nn.Linear(576, 128), nn.ReLU(), nn.Linear(128, config.representationDim))
-        torch.rand(*config.sound_dim)  # RNG parity with the sound-branch probe (arm_pretext_model.py:50)
-        self.soundBranch_outputShape = torch.Size([1, 160])
-        self.soundTriplet = nn.Sequential(nn.Linear(160, 128), nn.ReLU(), nn.Linear(128, config.representationDim))
+        self.imgBranch = conv_stack(IMG_SPEC)
+        self.soundCNN = conv_stack(SND_SPEC)
+        torch.rand((1, *config.img_dim))       # RNG parity: image-branch shape probe
+        self.imgCNN_outputShape = torch.Size([1, IMG_FLAT])
+        self.imgTriplet = mlp_head([IMG_FLAT, HIDDEN, config.representationDim])
+        torch.rand(*config.sound_dim)          # RNG parity: sound-branch shape probe
+        self.soundBranch_outputShape = torch.Size([1, SND_FLAT])
+        self.soundTriplet = mlp_head([SND_FLAT, HIDDEN, config.representationDim])
 
     def forward(self, image, sound_positive, sound_negative, is_train=False):
         return self.VAR_forward(image, sound_positive, sound_negative, is_train=False)
