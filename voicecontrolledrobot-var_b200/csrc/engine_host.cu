@@ -1,6 +1,7 @@
 // Host launchers for the tcgen05 engine (see tc_engine.cuh).
 #include "engine_host.cuh"
 #include "first_conv.cuh"
+#include "gemm_persist.cuh"
 #include "gru_persist.cuh"
 
 #include <cstdio>
@@ -255,9 +256,42 @@ static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const CUt
   return VAR_OK;
 }
 
+static bool gemm_persist_enabled() {  // VAR_GEMM_PERSIST=0 keeps one CTA per tile
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAR_GEMM_PERSIST"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+template <int GMODE>
+static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, const GemmParams& p, int m_tiles,
+                                 int n_tiles, cudaStream_t st) {
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_persist_kernel<GMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = smem;
+  }
+  const long long total = (long long)m_tiles * n_tiles;
+  const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
+  int grid = kNumSMs * per_sm;
+  if (grid > total) grid = (int)total;
+  const double flops = 2.0 * p.g[0].M * (double)p.e[0].ncols * p.g[0].K;
+  LaunchScope sc(p.b_mn_major ? T_GEMM_DGRAD : T_GEMM_FWD, flops, st);
+  tc_gemm_persist_kernel<GMODE><<<grid, 192, smem, st>>>(tb, ta, p, m_tiles, n_tiles);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
 int launch_gemm(int gmode, int epi, const CUtensorMap& t0, const CUtensorMap& t1,
                 const CUtensorMap& a0, const CUtensorMap& a1, const GemmParams& p, dim3 grid,
                 cudaStream_t st) {
+  if (epi == EPI_STD && grid.z == 1 && gemm_persist_enabled() && (gmode == G_TMA_IM2COL || gmode == G_TMA_TILED) &&
+      (long long)grid.x * grid.y > 2 * kNumSMs) {
+    // more tiles than CTA slots: resident CTAs walking the tile list beat one CTA per tile
+    if (gmode == G_TMA_IM2COL) return launch_gemm_persist_t<G_TMA_IM2COL>(t0, a0, p, (int)grid.x, (int)grid.y, st);
+    return launch_gemm_persist_t<G_TMA_TILED>(t0, a0, p, (int)grid.x, (int)grid.y, st);
+  }
   if (epi == EPI_GRU_FWD) {
     if (gmode == G_VEC_FWD) return launch_gemm_t<G_VEC_FWD, EPI_GRU_FWD>(t0, t1, a0, a1, p, grid, st);
     if (gmode == G_TMA_TILED) return launch_gemm_t<G_TMA_TILED, EPI_GRU_FWD>(t0, t1, a0, a1, p, grid, st);

@@ -1,0 +1,210 @@
+// Persistent form of the TMA-fed implicit GEMM (tc_engine.cuh) for the standard epilogue.
+//
+// One launch of tc_gemm_kernel pays, per 128-row tile, a CTA launch, barrier initialisation, a
+// TMEM allocation, a cold pipeline fill and a fully exposed epilogue -- about as long as 45
+// k-blocks of MMA work, i.e. more than the main loop of every dgrad sub-problem (20-36
+// k-blocks) and of the 3x3 image convs (9-18).  Here a CTA (192 threads) is resident for the
+// whole GEMM and walks tiles blockIdx.x, +gridDim.x, ...:
+//   warp 5      TMA producer (lane 0; lanes 1-3 help when a k-block needs >= 4 instructions)
+//   warp 4      MMA issuer, alternating between two TMEM accumulators
+//   warps 0-3   epilogue of tile i (tcgen05.ld -> bias / add / ReLU / mask / round -> HBM) while
+//               the producer and the tensor core already work on tile i+1
+// Barriers: full/empty per smem stage (ring shared by all tiles), tfull/tempty per accumulator.
+#pragma once
+#include "tc_engine.cuh"
+
+namespace var {
+
+template <int GMODE>
+__global__ void __launch_bounds__(192)
+tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA,
+                       const __grid_constant__ GemmParams p, int m_tiles, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const GatherGeom& g = p.g[0];
+  const EpiParams& e = p.e[0];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = p.stages, bn = p.bn, num_kb = p.num_kb;
+  const uint32_t tileB_bytes = (uint32_t)bn * 128u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + (uint32_t)stages * kTileABytes;
+  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
+  auto tfull_bar = [&](int a) { return bars + (uint32_t)(2 * stages + a) * 8u; };
+  auto tempty_bar = [&](int a) { return bars + (uint32_t)(2 * stages + 2 + a) * 8u; };
+  const uint32_t tslot = bars + (uint32_t)(2 * stages + 4) * 8u;
+
+  const uint32_t acc_cols = (uint32_t)tmem_cols_for(bn);
+  const int nacc = acc_cols * 2 <= 256 ? 2 : 1;  // 2 CTAs per SM share the 512 TMEM columns
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmA);
+  }
+  if (warp == 4) tmem_alloc(tslot, acc_cols * (uint32_t)nacc);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int total = m_tiles * n_tiles;
+  if (warp == 5) {
+    // ===================== TMA producer =====================
+    const int nb_boxes = p.b_mn_major ? (bn >> 5) : p.nbox;
+    const bool multi = nb_boxes >= 3;
+    if (lane == 0 || (multi && lane <= 3 && lane - 1 < nb_boxes)) {
+      int st = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int ntile = tile % n_tiles, mtile = tile / n_tiles;
+        const int m0 = mtile * kTileM;
+        int w0 = 0, h0 = 0, n0 = 0;
+        if constexpr (GMODE == G_TMA_IM2COL) {
+          const int pq0 = g.P * g.Q;
+          n0 = m0 / pq0;
+          const int rem0 = m0 - n0 * pq0;
+          const int p0 = rem0 / g.Q;
+          w0 = (rem0 - p0 * g.Q) * p.step_w + p.base_w;
+          h0 = p0 * p.step_h + p.base_h;
+        }
+        for (int it = 0; it < num_kb; ++it) {
+          mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
+          const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
+          const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
+          int tap = 0, c0 = it << 5;
+          if constexpr (GMODE == G_TMA_IM2COL) {
+            tap = it / p.cpb;
+            c0 = (it - tap * p.cpb) << 5;
+          }
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
+            if constexpr (GMODE == G_TMA_IM2COL)
+              tma_load_im2col_4d(dstA, &tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
+            else
+              tma_load_2d(dstA, &tmA, full_bar(st), it * 32, m0);
+          }
+          if (!p.b_mn_major) {
+            for (int b = 0; b < p.nbox; ++b)
+              if (lane == (multi ? 1 + (b % 3) : 0))
+                tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it * 32,
+                            p.boxbase[b] + ntile * p.box_rows);
+          } else {
+            const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
+            const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
+            for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+              if (lane == (multi ? 1 + (gidx % 3) : 0))
+                tma_load_2d(dstB + (uint32_t)gidx * 4096u, &tmB, full_bar(st),
+                            rs * p.cin_total + ntile * bn + gidx * 32, k0);
+          }
+          if (++st == stages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_tf32(bn, 0, p.b_mn_major);
+    int st = 0, ph = 0, i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+      const int acc = nacc == 2 ? (i & 1) : 0;
+      const int use = nacc == 2 ? (i >> 1) : i;            // how often this accumulator was used
+      mbar_wait(tempty_bar(acc), (uint32_t)((use & 1) ^ 1));  // epilogue drained it
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(st), (uint32_t)ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = sA + (uint32_t)st * kTileABytes;
+          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
+            const uint64_t bd = p.b_mn_major ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
+                                                              (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                             : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
+            umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+          }
+          umma_commit(empty_bar(st));
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== epilogue warps 0-3 =====================
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+      const int ntile = tile % n_tiles, mtile = tile / n_tiles;
+      const int acc = nacc == 2 ? (i & 1) : 0;
+      const int use = nacc == 2 ? (i >> 1) : i;
+      mbar_wait(tfull_bar(acc), (uint32_t)(use & 1));
+      tc_fence_after();
+      const int m = mtile * kTileM + warp * 32 + lane;
+      const uint32_t trow = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(warp * 32) << 16);
+      for (int c = 0; c < bn; c += 32) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int col0 = ntile * bn + c;
+        if (m < g.M && col0 < e.ncols) {
+          long long orow = m;
+          if (e.map.on) {
+            const int pq2 = e.map.P2 * e.map.Q2;
+            const int n_ = m / pq2, rem_ = m - n_ * pq2;
+            const int h2 = rem_ / e.map.Q2, w2 = rem_ - h2 * e.map.Q2;
+            orow = ((long long)n_ * e.map.H + h2 * e.map.sh + e.map.oh) * e.map.W + w2 * e.map.sw + e.map.ow;
+          }
+          float* o = e.out + orow * e.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (e.bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(e.bias + col0 + j);
+              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+            }
+            if (e.addsrc) {
+              const float4 a4 = *reinterpret_cast<const float4*>(e.addsrc + orow * e.lda + col0 + j);
+              r4.x += a4.x; r4.y += a4.y; r4.z += a4.z; r4.w += a4.w;
+            }
+            if (e.relu) {
+              r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
+              r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+            }
+            if (e.mask) {
+              const float4 k4 = *reinterpret_cast<const float4*>(e.mask + orow * e.ldm + col0 + j);
+              r4.x = k4.x > 0.f ? r4.x : 0.f; r4.y = k4.y > 0.f ? r4.y : 0.f;
+              r4.z = k4.z > 0.f ? r4.z : 0.f; r4.w = k4.w > 0.f ? r4.w : 0.f;
+            }
+            if (e.round_out) {
+              r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+              r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+            }
+            *reinterpret_cast<float4*>(o + j) = r4;
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, acc_cols * (uint32_t)nacc);
+  }
+}
+
+}  // namespace var
