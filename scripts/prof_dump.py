@@ -9,6 +9,8 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 F = 600 if net == "ithor" else 100
 eng = vb.VarEngine(vb.ITHOR if net == "ithor" else vb.KUKA, F, 3, "cuda:0")
 eng.load_state_dict(omodel.init_state_dict(net, 0))
+if len(sys.argv) > 3 and sys.argv[3] == "serial":
+    eng.set_overlap(False)
 img = torch.randint(0, 256, (B, 3, 96, 96), dtype=torch.uint8, device="cuda")
 snd = torch.randn(2 * B, F, 40, device="cuda") * 4
 for _ in range(2):

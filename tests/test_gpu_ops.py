@@ -94,7 +94,12 @@ FIRST_LAYER_CASES = [  # strided (NCHW / single channel) sources
     ("u8", 2, 96, 96, 3, 32, 3, 3, 1, 1, 1, 1),
     ("f32", 4, 40, 40, 3, 32, 3, 3, 2, 2, 1, 1),
     ("f32", 5, 100, 40, 1, 32, 5, 40, 2, 1, 0, 0),
-    ("f32", 2, 120, 40, 1, 64, 11, 11, 2, 2, 5, 5),
+    ("f32", 2, 120, 40, 1, 64, 11, 11, 2, 2, 5, 5),   # thor.snd.conv1: persistent kernels (cin1_conv.cu)
+    ("f32", 3, 600, 40, 1, 64, 11, 11, 2, 2, 5, 5),   # full-height map, 150 tiles
+    ("f32", 2, 50, 40, 1, 64, 11, 11, 2, 2, 5, 5),    # P = 25: last tile of an image has one row
+    ("f32", 1, 7, 40, 1, 64, 11, 11, 2, 2, 5, 5),     # shorter than the filter
+    ("f32raw", 90, 120, 40, 1, 64, 11, 11, 2, 2, 5, 5),  # 900 tiles: >= 6 per resident CTA; unrounded input
+    ("f32", 2, 120, 24, 1, 64, 11, 11, 2, 2, 5, 5),   # other width: generic first-layer path
 ]
 
 
@@ -111,6 +116,10 @@ def test_first_layer_conv_vs_torch(vb, case):
         xu = torch.randint(0, 256, (N, Cin, H, W), generator=g, dtype=torch.uint8)
         x = rnd(xu.float() * np.float32(1.0 / 255.0))
         src, src_kind, scale = xu.to(DEV), 2, 1.0 / 255.0
+    elif kind == "f32raw":  # the kernel rounds the loaded value itself
+        xr = torch.randn(N, Cin, H, W, generator=g)
+        x = rnd(xr)
+        src, src_kind, scale = xr.to(DEV), 1, 1.0
     else:
         x = rnd(torch.randn(N, Cin, H, W, generator=g))
         src, src_kind, scale = x.to(DEV), 1, 1.0

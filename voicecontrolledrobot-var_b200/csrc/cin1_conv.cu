@@ -1,0 +1,397 @@
+// iTHOR sound conv1 (1 -> 64 channels, 11x11, stride 2, pad 5 over [N, H, 40] MFCC maps;
+// models/pretext/ai2thor_pretext_model.py:27) as persistent tcgen05 kernels.
+//
+// With one input channel the im2col matrix has no channel vectors to copy: every element of the
+// [128 pixels x 128 taps] operand tile is a separate 4-byte pick from the input map, so the layer
+// is bound by how fast the SM can build that tile in shared memory, not by the tensor core
+// (16 MMAs per tile) or HBM (the 256 B per pixel output).  The generic first-layer kernels
+// (tc_engine.cuh, G_SCALAR_*) pay a CTA launch, a TMEM allocation, barrier set-up, a weight
+// reload and a look-up-table walk per tile; here a CTA is resident for the whole layer:
+//
+//   tile      = 6 output rows of one image (120 pixels) over a zero-padded 21 x 52 input patch
+//   warps 0-3 / 4-7   two builder groups, one tile each in flight: the patch of the group's NEXT
+//               tile is prefetched into registers (9 coalesced loads per thread) while the
+//               current tile drains, rounded to tf32 and stored to shared memory once; then
+//               thread = pixel reads its 11x11 window with compile-time offsets (66 LDS.64)
+//               and writes its operand row (32 STS.128, swizzled, conflict-free)
+//   warp 8    lane 0: TMA issue (weights / dY) + the 16 (forward) / 15 (wgrad) MMAs of a tile
+//   forward   weights stay in shared memory for the whole kernel; two TMEM accumulators; the
+//             builder group runs the epilogue of its own tile while the other group builds
+//   wgrad     D[tap, cout] accumulates in ONE TMEM tile over all tiles of the CTA (dY arrives
+//             by TMA as the MN-major B operand); tap row 121 is all ones, so row 121 of D is
+//             the bias gradient; one coalesced red.add pass per CTA at the end
+#include "cin1_conv.cuh"
+#include "engine_host.cuh"
+
+#include <cstdlib>
+
+namespace var {
+
+namespace {
+constexpr int kR = 11, kS = 11, kW = 40, kQ = 20, kCout = 64, kTaps = kR * kS, kKpad = 128;
+constexpr int kRows = 6;                       // output rows per tile
+constexpr int kPix = kRows * kQ;               // 120 of the 128 MMA rows
+constexpr int kNH = (kRows - 1) * 2 + kR;      // 21 input rows per tile
+constexpr int kWP = 52;                        // patch row pitch in floats: 5 + 40 + 7 (16-byte multiple)
+constexpr uint32_t kPatchSlot = 4608;          // 128-byte aligned slot per patch
+constexpr uint32_t kABytes = 4 * 16384;        // operand tile: 128 pixels x 128 taps
+constexpr uint32_t kWBytes = kCout * kKpad * 4;
+constexpr uint32_t kDyBytes = 4 * 2 * 4096;    // 4 pixel blocks x 2 channel groups
+constexpr int kThreads = 288;
+constexpr size_t kSmemFwd = 1024 + 2 * kABytes + kWBytes + 2 * kPatchSlot + 128;
+constexpr size_t kSmemWgrad = 1024 + 2 * kABytes + 2 * kDyBytes + 2 * kPatchSlot + 128;
+
+__device__ __forceinline__ void group_sync(int g) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+}
+
+// Patch element e = hh*52 + ww of the tile at (n, p0) <-> input (h, w) = (2 p0 - 5 + hh, ww - 5);
+// thread r of a builder group owns elements r, r + 128, ... (9 of them).
+constexpr int kPatchRegs = (kNH * kWP + 127) / 128;
+__device__ __forceinline__ void patch_prefetch(const float* __restrict__ x, int H, int n, int p0, int r,
+                                               float (&pre)[kPatchRegs]) {
+#pragma unroll
+  for (int u = 0; u < kPatchRegs; ++u) {
+    const int e = r + u * 128;
+    const int hh = e / kWP, ww = e - hh * kWP;
+    const int h = p0 * 2 - 5 + hh, w = ww - 5;
+    pre[u] = (e < kNH * kWP && h >= 0 && h < H && w >= 0 && w < kW) ? __ldg(x + ((long long)n * H + h) * kW + w)
+                                                                     : 0.f;
+  }
+}
+__device__ __forceinline__ void patch_store(float* patch, int r, const float (&pre)[kPatchRegs]) {
+#pragma unroll
+  for (int u = 0; u < kPatchRegs; ++u) {
+    const int e = r + u * 128;
+    if (e < kNH * kWP) patch[e] = round_tf32(pre[u]);
+  }
+}
+
+// Operand row of pixel `r`: taps k = rr*11 + s of the window whose origin is `win` (patch pitch
+// kWP).  Forward: K-major rows of 128 B per 32-tap block.  Weight gradient: MN-major, per
+// 32-pixel block four 4 KB groups of 32 taps, 32-byte-granule swizzle; tap 121 = 1 (bias row).
+template <bool WG>
+__device__ __forceinline__ void build_row(const float* win, uint32_t sA, int r, bool valid) {
+  const float one = valid ? 1.f : 0.f;
+  // two halves of 16 chunks (taps 0-63: window rows 0-5, taps 64-127: rows 5-10) keep the live
+  // window at 72 registers
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r0 = half * 5;
+    float xr[6][12];
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        float2 t = make_float2(0.f, 0.f);
+        if (valid) t = *reinterpret_cast<const float2*>(win + (r0 + rr) * kWP + 2 * u);
+        xr[rr][2 * u] = t.x;
+        xr[rr][2 * u + 1] = t.y;
+      }
+#pragma unroll
+    for (int cc = half * 16; cc < half * 16 + 16; ++cc) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = cc * 4 + j;
+        v[j] = k < kTaps ? xr[k / kS - r0][k % kS] : ((WG && k == kTaps) ? one : 0.f);
+      }
+      uint32_t dst;
+      if constexpr (WG)
+        dst = sA + (uint32_t)(r >> 5) * 16384u + (uint32_t)(cc >> 3) * 4096u + swz128_32((uint32_t)(r & 31), cc & 7);
+      else
+        dst = sA + (uint32_t)(cc >> 3) * 16384u + swz128((uint32_t)r, cc & 7);
+      st_shared_v4(dst, v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+struct TilePos { int n, p0; };
+__device__ __forceinline__ TilePos tile_pos(int i, int tpi) {
+  const int t = blockIdx.x + i * gridDim.x;
+  TilePos tp;
+  tp.n = t / tpi;
+  tp.p0 = (t - tp.n * tpi) * kRows;
+  return tp;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int tiles, int tpi) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sW = sA + 2 * kABytes, sP = sW + kWBytes;
+  const uint32_t bars = sP + 2 * kPatchSlot;
+  auto a_full = [&](int g) { return bars + 16u + (uint32_t)g * 8u; };
+  auto acc_full = [&](int g) { return bars + 32u + (uint32_t)g * 8u; };
+  const uint32_t w_full = bars + 48u, tslot = bars + 56u;
+  const int nt = (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+
+  if (tid == 0) {
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(a_full(g), 128);
+      mbar_init(acc_full(g), 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 8) tmem_alloc(tslot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, kWBytes);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + (uint32_t)kb * 8192u, &tmW, w_full, kb * 32, 0);
+      mbar_wait(w_full, 0);
+      const uint32_t idesc = make_idesc_tf32(kCout, 0, 0);
+      for (int i = 0; i < nt; ++i) {
+        const int g = i & 1;
+        mbar_wait(a_full(g), (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        const uint32_t a0 = sA + (uint32_t)g * kABytes;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)kb * 16384u + (uint32_t)j * 32u, 16u, 1024u);
+            const uint64_t bd = make_smem_desc(sW + (uint32_t)kb * 8192u + (uint32_t)j * 32u, 16u, 1024u);
+            umma_tf32(tmem_base + (uint32_t)g * 64u, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+          }
+        umma_commit(acc_full(g));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int g = warp >> 2, r = tid & 127, wq = warp & 3;
+    const int pr = r / kQ, q = r - pr * kQ;
+    float* patch = reinterpret_cast<float*>(gbase + 2 * kABytes + kWBytes + (uint32_t)g * kPatchSlot);
+    const uint32_t a0 = sA + (uint32_t)g * kABytes;
+    float pre[kPatchRegs];
+    if (g < nt) { const TilePos t0 = tile_pos(g, tpi); patch_prefetch(a.x, a.H, t0.n, t0.p0, r, pre); }
+    for (int i = g; i < nt; i += 2) {
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const TilePos tp = tile_pos(i, tpi);
+      // (every thread of the group passed acc_full of the previous tile: nobody reads the patch)
+      patch_store(patch, r, pre);
+      group_sync(g);
+      if (r < kPix) build_row<false>(patch + pr * 2 * kWP + q * 2, a0, r, true);
+      fence_proxy_async_smem();
+      mbar_arrive(a_full(g));
+      if (i + 2 < nt) { const TilePos t2 = tile_pos(i + 2, tpi); patch_prefetch(a.x, a.H, t2.n, t2.p0, r, pre); }
+      // ---- epilogue of the same tile: bias, ReLU, tf32 rounding, 256 B per pixel
+      mbar_wait(acc_full(g), ph);
+      tc_fence_after();
+      const bool store = r < kPix && tp.p0 + pr < a.P;
+      float* out = a.y + ((long long)(tp.n * a.P + tp.p0) * kQ + r) * kCout;
+#pragma unroll
+      for (int c = 0; c < kCout; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t)g * 64u + (uint32_t)c + ((uint32_t)(wq * 32) << 16), v);
+        tmem_ld_wait();
+        if (store) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (a.bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c + j));
+              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+            }
+            if (a.relu) {
+              r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
+              r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+            }
+            if (a.round_out) {
+              r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+              r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+            }
+            *reinterpret_cast<float4*>(out + c + j) = r4;
+          }
+        }
+      }
+      tc_fence_before();  // orders the TMEM reads before the next a_full arrival
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+cin1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin1Args a, int tiles, int tpi, int mn_lbo, int mn_sbo, int mn_type) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = sA + 2 * kABytes, sP = sB + 2 * kDyBytes;
+  const uint32_t bars = sP + 2 * kPatchSlot;
+  auto a_full = [&](int g) { return bars + 16u + (uint32_t)g * 8u; };
+  auto dy_full = [&](int g) { return bars + 32u + (uint32_t)g * 8u; };
+  auto mma_done = [&](int g) { return bars + 48u + (uint32_t)g * 8u; };
+  const uint32_t final_bar = bars + 64u, tslot = bars + 72u;
+  const int nt = (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+
+  if (tid == 0) {
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(a_full(g), 128);
+      mbar_init(dy_full(g), 1);
+      mbar_init(mma_done(g), 1);
+    }
+    mbar_init(final_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 8) tmem_alloc(tslot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  if (warp == 8) {
+    if (lane == 0) {
+      auto issue_dy = [&](int i) {
+        const TilePos tp = tile_pos(i, tpi);
+        const int g = i & 1;
+        const int m0 = (tp.n * a.P + tp.p0) * kQ;
+        mbar_arrive_expect_tx(dy_full(g), kDyBytes);
+        for (int pb = 0; pb < 4; ++pb)
+          for (int cg = 0; cg < 2; ++cg)
+            tma_load_2d(sB + (uint32_t)g * kDyBytes + (uint32_t)pb * 8192u + (uint32_t)cg * 4096u, &tmDY,
+                        dy_full(g), cg * 32, m0 + pb * 32);
+      };
+      for (int i = 0; i < 2 && i < nt; ++i) issue_dy(i);
+      const uint32_t idesc = make_idesc_tf32(kCout, 1, 1);
+      const uint32_t lbo = (uint32_t)mn_lbo, sbo = (uint32_t)mn_sbo, lt = (uint32_t)mn_type;
+      for (int i = 0; i < nt; ++i) {
+        const int g = i & 1;
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        mbar_wait(a_full(g), ph);
+        mbar_wait(dy_full(g), ph);
+        tc_fence_after();
+        const uint32_t a0 = sA + (uint32_t)g * kABytes, b0 = sB + (uint32_t)g * kDyBytes;
+#pragma unroll
+        for (int pb = 0; pb < 4; ++pb)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (pb * 32 + j * 8 >= kPix) continue;  // 15 steps of 8 pixels
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)pb * 16384u + (uint32_t)j * 1024u, lbo, sbo, lt);
+            const uint64_t bd = make_smem_desc(b0 + (uint32_t)pb * 8192u + (uint32_t)j * 1024u, lbo, sbo, lt);
+            umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((i | pb | j) != 0));
+          }
+        umma_commit(mma_done(g));
+        if (i >= 1 && i + 1 < nt) {  // the other group's dY buffer is free once tile i-1 retired
+          mbar_wait(mma_done(g ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
+          issue_dy(i + 1);
+        }
+      }
+      umma_commit(final_bar);
+    }
+    __syncwarp();
+  } else {
+    const int g = warp >> 2, r = tid & 127, wq = warp & 3;
+    const int pr = r / kQ, q = r - pr * kQ;
+    float* patch = reinterpret_cast<float*>(gbase + 2 * kABytes + 2 * kDyBytes + (uint32_t)g * kPatchSlot);
+    const uint32_t a0 = sA + (uint32_t)g * kABytes;
+    float pre[kPatchRegs];
+    if (g < nt) { const TilePos t0 = tile_pos(g, tpi); patch_prefetch(a.x, a.H, t0.n, t0.p0, r, pre); }
+    for (int i = g; i < nt; i += 2) {
+      const TilePos tp = tile_pos(i, tpi);
+      // tile i-2 retired: its MMAs needed every a_full arrival of the group, so nobody still reads
+      // the patch, and the operand buffer is free
+      if (i >= 2) mbar_wait(mma_done(g), (uint32_t)(((i >> 1) - 1) & 1));
+      patch_store(patch, r, pre);
+      group_sync(g);
+      if (i + 2 < nt) { const TilePos t2 = tile_pos(i + 2, tpi); patch_prefetch(a.x, a.H, t2.n, t2.p0, r, pre); }
+      if (r < kPix) build_row<true>(patch + pr * 2 * kWP + q * 2, a0, r, tp.p0 + pr < a.P);
+      fence_proxy_async_smem();
+      mbar_arrive(a_full(g));
+    }
+    if (g == 0) {
+      // ---- D rows = taps (row 121 = bias gradient), columns = output channels
+      mbar_wait(final_bar, 0);
+      tc_fence_after();
+      const int tap = wq * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < kCout; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t)c + ((uint32_t)(wq * 32) << 16), v);
+        tmem_ld_wait();
+        if (tap < kTaps) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(a.dw + (long long)(c + j) * kKpad + tap, v[j]);
+        } else if (tap == kTaps && a.db) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(a.db + c + j, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+bool enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VAR_CIN1"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+}  // namespace
+
+bool cin1_conv_match(int H, int W, int Cin, int Cout, int R, int S, int sh, int sw, int ph, int pw,
+                     long long sN, long long sH, long long sW, float scale, const void* x) {
+  return enabled() && W == kW && Cin == 1 && Cout == kCout && R == kR && S == kS && sh == 2 && sw == 2 &&
+         ph == 5 && pw == 5 && H >= 1 && sW == 1 && sH == kW && sN == (long long)H * kW && scale == 1.f &&
+         (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+int cin1_conv_fwd(const Cin1Args& a, cudaStream_t st) {
+  const int tpi = (a.P + kRows - 1) / kRows, tiles = a.N * tpi;
+  if (tiles <= 0) return VAR_OK;
+  CUtensorMap tw;
+  int rc = get_tmap_2d(a.w, kCout, kKpad, kKpad, kCout, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
+    configured = true;
+  }
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  LaunchScope sc(T_GEMM_SCALAR, 2.0 * a.N * a.P * kQ * kCout * (double)kTaps, st);
+  cin1_fwd_kernel<<<grid, kThreads, kSmemFwd, st>>>(tw, a, tiles, tpi);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+int cin1_conv_wgrad(const Cin1Args& a, cudaStream_t st) {
+  const int tpi = (a.P + kRows - 1) / kRows, tiles = a.N * tpi;
+  if (tiles <= 0) return VAR_OK;
+  CUtensorMap tdy;
+  int rc = get_tmap_2d(a.dy, a.N * a.P * kQ, kCout, kCout, 32, mn_cfg().tma_swizzle, &tdy);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWgrad));
+    configured = true;
+  }
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  LaunchScope sc(T_WGRAD, 2.0 * a.N * a.P * kQ * kCout * (double)kTaps, st);
+  cin1_wgrad_kernel<<<grid, kThreads, kSmemWgrad, st>>>(tdy, a, tiles, tpi, mn_cfg().lbo, mn_cfg().sbo,
+                                                       mn_cfg().type);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+}  // namespace var

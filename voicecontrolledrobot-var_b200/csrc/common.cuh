@@ -118,6 +118,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// 3-D tiled load (coordinates innermost first); out-of-tensor elements are zero filled.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // 4-D im2col load (NHWC tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` base
 // pixels starting at (w, h, n), walked in W-then-H-then-N order inside the map's bounding
 // box with the map's traversal strides; each loads `channelsPerPixel` channels from c of the

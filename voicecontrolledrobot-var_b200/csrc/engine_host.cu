@@ -1,6 +1,7 @@
 // Host launchers for the tcgen05 engine (see tc_engine.cuh).
 #include "engine_host.cuh"
 #include "first_conv.cuh"
+#include "cin1_conv.cuh"
 #include "gemm_persist.cuh"
 #include "gru_persist.cuh"
 
@@ -147,6 +148,30 @@ int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_r
     cache[key] = m;
   }
   *out = m;
+  return VAR_OK;
+}
+
+int get_tmap_3d(const float* ptr, int d0, int d1, int d2, int b0, int b1, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    var_set_last_error("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((d0 * 4) & 15) || ((b0 * 4) & 15)) return VAR_ERR_ARG;
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(3d) failed: %d (dims %d %d %d box %d %d)", (int)r, d0, d1,
+             d2, b0, b1);
+    var_set_last_error(buf, __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
   return VAR_OK;
 }
 
@@ -397,6 +422,15 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
     a.N = cs.N; a.H = cs.H; a.W = cs.W; a.P = cs.P; a.Q = cs.Q; a.stride = cs.sh;
     a.w = w; a.kpad = round_up32(27); a.bias = bias; a.y = y; a.relu = relu; a.round_out = round_out;
     return first_conv_fwd(a, src_kind == SRC_STRIDED_U8, st);
+  }
+  if (src_kind == SRC_STRIDED_F32 && sl &&
+      cin1_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, sl->sN, sl->sH, sl->sW,
+                      sl->scale, x)) {
+    Cin1Args a;
+    memset(&a, 0, sizeof(a));
+    a.x = reinterpret_cast<const float*>(x); a.N = cs.N; a.H = cs.H; a.P = cs.P;
+    a.w = w; a.bias = bias; a.y = y; a.relu = relu; a.round_out = round_out;
+    return cin1_conv_fwd(a, st);
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -846,6 +880,15 @@ int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout
     a.N = cs.N; a.H = cs.H; a.W = cs.W; a.P = cs.P; a.Q = cs.Q; a.stride = cs.sh;
     a.kpad = round_up32(27); a.dy = dy; a.dw = dw; a.db = db;
     return first_conv_wgrad(a, src_kind == SRC_STRIDED_U8, st);
+  }
+  if (src_kind == SRC_STRIDED_F32 && sl &&
+      cin1_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, sl->sN, sl->sH, sl->sW,
+                      sl->scale, x)) {
+    Cin1Args a;  // bias gradient comes out of the same kernel (all-ones tap row)
+    memset(&a, 0, sizeof(a));
+    a.x = reinterpret_cast<const float*>(x); a.N = cs.N; a.H = cs.H; a.P = cs.P;
+    a.dy = dy; a.dw = dw; a.db = db;
+    return cin1_conv_wgrad(a, st);
   }
   if (src_kind == SRC_NHWC_F32 && gather_mode() == 1 && cs.Cin % 32 == 0 && cs.Cout % 32 == 0 &&
       cs.R * cs.S <= kMaxTaps) {

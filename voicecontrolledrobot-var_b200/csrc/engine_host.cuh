@@ -17,6 +17,8 @@ int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_r
                 CUtensorMap* out);
 int get_tmap_im2col(const float* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w,
                     int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out);
+// 3-D fp32 tensor map over a dense [d2][d1][d0] array, box {b0, b1, 1}, no swizzle (not cached).
+int get_tmap_3d(const float* ptr, int d0, int d1, int d2, int b0, int b1, CUtensorMap* out);
 int gather_mode();  // 1: TMA-fed A operands (default), 0: cp.async gather (VAR_GATHER=cp_async)
 
 struct ConvShape {
