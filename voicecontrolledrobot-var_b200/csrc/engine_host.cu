@@ -650,9 +650,14 @@ bool gru_persist_enabled() {  // VAR_GRU_PERSIST=0 falls back to one launch per 
   return on == 1;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 template <int BWD>
 static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages) + gru_scr_bytes(BWD) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_persist_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -664,7 +669,7 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_persist_kernel<BWD>, 160, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_persist_kernel<BWD>, kGruThreads, smem);
     max_ctas = per_sm * sms;
   }
   if ((long long)grid.x * grid.y * grid.z > max_ctas) return VAR_ERR_UNSUPPORTED;  // not co-resident
@@ -672,7 +677,28 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
   const int nsteps = BWD ? p.T - 1 : p.T;
   LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)(p.bn * grid.y) * (p.num_kb * 32.0) * grid.z * nsteps, st);
-  VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD>, grid, dim3(160, 1, 1), args, smem, st));
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("VAR_GRU_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
+  static long long* d_trace = nullptr;
+  if (trace_on) {  // debugging aid: per-step clock64 samples of CTA (0,0,0), dumped after a sync
+    if (!d_trace) VAR_CUDA_CHECK(cudaMalloc(&d_trace, sizeof(long long) * 8 * 128));
+    VAR_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 128, st));
+    p.trace = d_trace;
+  }
+  VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD>, grid, dim3(kGruThreads, 1, 1), args, smem, st));
+  if (trace_on) {
+    std::vector<long long> h(8 * 128);
+    VAR_CUDA_CHECK(cudaStreamSynchronize(st));
+    VAR_CUDA_CHECK(cudaMemcpy(h.data(), d_trace, sizeof(long long) * 8 * 128, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(BWD ? "gpurun_out/gru_trace_bwd.csv" : "gpurun_out/gru_trace_fwd.csv", "w");
+    if (f) {
+      fprintf(f, "step,start,acquired,issued,tfull,epi_done,released\n");
+      for (int i = 0; i < nsteps && i < 128; ++i)
+        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld\n", i, h[i * 8] - h[0], h[i * 8 + 1] - h[0], h[i * 8 + 2] - h[0],
+                h[i * 8 + 3] - h[0], h[i * 8 + 4] - h[0], h[i * 8 + 5] - h[0]);
+      fclose(f);
+    }
+  }
   return VAR_OK;
 }
 
@@ -687,7 +713,7 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
   GruPersistParams p;
   memset(&p, 0, sizeof(p));
   const int jb = 32;
-  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / 32; p.stages = 4;
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / 32; p.stages = env_int("VAR_GRU_STAGES_FWD", 4);
   p.counters = counters; p.ldx = ldx;
   CUtensorMap tm[4];
   for (int d = 0; d < 2; ++d) {
@@ -700,7 +726,7 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
     if (rc) return rc;
   }
   dim3 grid((B + 127) / 128, Hd / jb, 2);
-  p.arrivals = 4 * (int)grid.y;
+  p.arrivals = kGruEpiWarps * (int)grid.y;
   return launch_gru_persist<0>(tm, p, grid, st);
 }
 
@@ -713,7 +739,7 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
   prof_note("gru_persist_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
   GruPersistParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.Hd = Hd; p.T = T; p.bn = 32; p.num_kb = 3 * Hd / 32; p.stages = 4;
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 32; p.num_kb = 3 * Hd / 32; p.stages = env_int("VAR_GRU_STAGES_BWD", 4);
   p.counters = counters;
   p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
   CUtensorMap tm[4];
@@ -726,7 +752,7 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
     if (rc) return rc;
   }
   dim3 grid((B + 127) / 128, Hd / p.bn, 2);
-  p.arrivals = 4 * (int)grid.y;
+  p.arrivals = kGruEpiWarps * (int)grid.y;
   return launch_gru_persist<1>(tm, p, grid, st);
 }
 

@@ -39,6 +39,7 @@ struct GruPersistParams {
   float* dgh[2];          // [T][B, 3H]: A operand (slot s), written for slot s-1
   float* dgi[2];          // [B, T, 3H] batch-major
   float* dhd[2][2];       // dh * z ping-pong [B, H]
+  long long* trace;       // optional [steps][8] clock64 samples of CTA (0,0,0) (VAR_GRU_TRACE=1)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -50,9 +51,26 @@ __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-// grid = (row tiles, hidden tiles, directions), block = 160.
+// grid = (row tiles, hidden tiles, directions), block = kGruThreads.
+//   warps 0-3   TMA issue (lane 0) and TMEM -> smem transposition of their 32-row quarter
+//   warps 4-15  epilogue helpers: quarter q is finished by 4 warps (the TMEM warp + 3 helpers),
+//               8 rows each, lane = hidden unit (128-byte coalesced global rows)
+//   warp 4      additionally issues the MMAs of the step between its prefetch and its rows
+// Every epilogue warp issues the global loads of its cell inputs (x-projection and h_{s-1}, or
+// the saved gates for BPTT) at the TOP of the step, so they fly while the operands stream in
+// and the MMAs run; after the accumulator is ready only TMEM -> smem, the gate maths and the
+// stores are left.  (One epilogue warp per scheduler with loads after the MMA cost 12.8 of
+// the 19.9 us per forward step.)
+constexpr int kGruThreads = 512;
+constexpr int kGruEpiWarps = 16;
+__host__ __device__ inline size_t gru_scr_bytes(int bwd) { return (size_t)4 * (bwd ? 32 * 33 : 3 * 32 * 33) * 4; }
+
+__device__ __forceinline__ void quarter_sync(int q) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+}
+
 template <int BWD>
-__global__ void __launch_bounds__(160)
+__global__ void __launch_bounds__(kGruThreads, 1)
 gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                    const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ GruPersistParams p) {
@@ -72,6 +90,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
   auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
   const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
   const uint32_t tslot = tfull_bar + 8u;
+  float* scr_base = reinterpret_cast<float*>(smem_raw + (((tslot + 8u + 15u) & ~15u) - smem_u32(smem_raw)));
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -95,207 +114,202 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
   const int ntile = blockIdx.y;
   unsigned int* counter = p.counters + (blockIdx.z * gridDim.x + blockIdx.x);
   const int nsteps = BWD ? T - 1 : T;
-  const int jb = BWD ? bn : bn / 3;
+  const int jb = BWD ? bn : bn / 3;  // == 32: one 32-column chunk per gate
   const int nb_boxes = BWD ? (bn >> 5) : 3;
   const bool multi = nb_boxes >= 3;
 
-  if (warp < 4) {
+  {
+    const int quarter = warp & 3;
+    const int sub = warp >> 2;
+    const uint32_t idesc = make_idesc_tf32(bn, 0, BWD ? 1 : 0);
+    int mst = 0, mph = 0;  // MMA ring position (warp 4)
+    constexpr int RB = 8;                         // rows per epilogue warp
+    const int mrow0 = m0 + quarter * 32 + sub * RB;
+    const int j = ntile * jb + lane;
+    float* scr = scr_base + quarter * (BWD ? 32 * 33 : 3 * 32 * 33);
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int st = 0, ph = 0;  // producer ring position (kept by every issuing lane)
-    const bool issuer = lane == 0 && (warp == 0 || (multi && warp - 1 < nb_boxes));
-    float* scr = reinterpret_cast<float*>(smem_raw + (sA - smem_u32(smem_raw))) +
-                 warp * (BWD ? 32 * 33 : 3 * 32 * 33);
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool issuer = warp < 4 && lane == 0 && (warp == 0 || (multi && warp - 1 < nb_boxes));
+    const bool tracer = p.trace && tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    float br = 0.f, bz = 0.f, bq = 0.f;
+    if constexpr (!BWD) { br = __ldg(p.bhh[z] + j); bz = __ldg(p.bhh[z] + Hd + j); bq = __ldg(p.bhh[z] + 2 * Hd + j); }
     for (int it_s = 0; it_s < nsteps; ++it_s) {
       const int s = BWD ? T - 1 - it_s : it_s;  // fwd: step index; bwd: slot whose dgh is the A operand
-      // ------------------------------------------------------------ producers
-      if (issuer) {
-        if (warp == 0 && it_s > 0) {
-          const unsigned int target = (unsigned int)(p.arrivals * it_s);
-          while (ld_acquire_gpu(counter) < target) {
-          }
-          fence_proxy_async_all();  // the generic-proxy writes just acquired are read by TMA below
-        }
-        const int arow = s * B + m0;  // row of the A tile in the [slots * B, K] matrix
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-          const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
-          const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
-          if (warp == 0) {
-            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
-            tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
-          }
-          if constexpr (!BWD) {
-            for (int b = 0; b < 3; ++b)
-              if (warp == 1 + b)
-                tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * 32, b * Hd + ntile * jb);
-          } else {
-            for (int gidx = 0; gidx < (bn >> 5); ++gidx)
-              if (warp == (multi ? 1 + (gidx % 3) : 0))
-                tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st), ntile * bn + gidx * 32, kb * 32);
-          }
-          if (++st == stages) { st = 0; ph ^= 1; }
-        }
-      }
-      __syncwarp();
-      // ------------------------------------------------------------- epilogue
-      mbar_wait(tfull_bar, (uint32_t)(it_s & 1));
-      tc_fence_after();
-      const int mrow0 = m0 + warp * 32;
-      constexpr int RB = 8;
+      if (tracer) p.trace[it_s * 8 + 0] = clock64();
+      // ---------------------------------------- cell inputs: in flight during the main loop
+      float in0[RB], in1[RB], in2[RB], in3[RB], in4[RB], in5[RB];
       if constexpr (!BWD) {
         const int t = z == 0 ? s : T - 1 - s;
         const float* __restrict__ xproj = p.xproj[z] + (long long)t * 3 * Hd;
-        const float* __restrict__ hprev = p.h32[z][s & 1];
+        const float* hprev = p.h32[z][s & 1];  // rows of this warp: written by this very thread last step
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int mr = mrow0 + u;
+          const bool ok = mr < B;
+          const float* xp = xproj + (long long)(ok ? mr : 0) * p.ldx;
+          in0[u] = ok ? __ldg(xp + j) : 0.f;
+          in1[u] = ok ? __ldg(xp + Hd + j) : 0.f;
+          in2[u] = ok ? __ldg(xp + 2 * Hd + j) : 0.f;
+          in3[u] = ok ? hprev[(long long)mr * Hd + j] : 0.f;
+          in4[u] = 0.f; in5[u] = 0.f;
+        }
+      } else {
+        const int sp = s - 1;
+        const float* dhd_in = p.dhd[z][it_s & 1];  // written by this very thread last step
+        const float* __restrict__ gates = p.gates_c[z] + (long long)sp * B * 3 * Hd;
+        const float* __restrict__ hn_save = p.hn_save_c[z] + (long long)sp * B * Hd;
+        const float* __restrict__ hprev = p.h_r_c[z] + (long long)sp * B * Hd;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int mr = mrow0 + u;
+          const bool ok = mr < B;
+          const long long hoff = (long long)(ok ? mr : 0) * Hd + j;
+          const float* gt = gates + (long long)(ok ? mr : 0) * 3 * Hd + j;
+          in0[u] = ok ? dhd_in[hoff] : 0.f;
+          in1[u] = ok ? __ldg(gt) : 0.f;
+          in2[u] = ok ? __ldg(gt + Hd) : 0.f;
+          in3[u] = ok ? __ldg(gt + 2 * Hd) : 0.f;
+          in4[u] = ok ? __ldg(hn_save + hoff) : 0.f;
+          in5[u] = ok ? __ldg(hprev + hoff) : 0.f;
+        }
+      }
+      if (warp < 4) {
+        // ---------------------------------------------------------- producers
+        if (issuer) {
+          if (warp == 0 && it_s > 0) {
+            const unsigned int target = (unsigned int)(p.arrivals * it_s);
+            while (ld_acquire_gpu(counter) < target) {
+            }
+            fence_proxy_async_all();  // the generic-proxy writes just acquired are read by TMA below
+          }
+          if (tracer) p.trace[it_s * 8 + 1] = clock64();
+          const int arow = s * B + m0;  // row of the A tile in the [slots * B, K] matrix
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
+            const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
+            const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
+            if (warp == 0) {
+              mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
+              tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
+            }
+            if constexpr (!BWD) {
+              for (int b = 0; b < 3; ++b)
+                if (warp == 1 + b)
+                  tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * 32, b * Hd + ntile * jb);
+            } else {
+              for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+                if (warp == (multi ? 1 + (gidx % 3) : 0))
+                  tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st), ntile * bn + gidx * 32, kb * 32);
+            }
+            if (++st == stages) { st = 0; ph ^= 1; }
+          }
+        }
+        __syncwarp();
+        if (tracer) p.trace[it_s * 8 + 2] = clock64();
+        // -------------------------------------- accumulator quarter -> shared memory (transposed use)
+        mbar_wait(tfull_bar, (uint32_t)(it_s & 1));
+        tc_fence_after();
+        if (tracer) p.trace[it_s * 8 + 3] = clock64();
+        float v[32];
+#pragma unroll
+        for (int gq = 0; gq < (BWD ? 1 : 3); ++gq) {
+          tmem_ld32(trow + (uint32_t)(gq * jb), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) scr[(gq * 32 + lane) * 33 + c] = v[c];
+        }
+        tc_fence_before();
+      } else if (warp == 4) {
+        // ---------------------------------------------------------- MMA issue for this step
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(mst), (uint32_t)mph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a0 = sA + (uint32_t)mst * kTileABytes;
+            const uint32_t b0 = sB + (uint32_t)mst * tileB_bytes;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint64_t ad = make_smem_desc(a0 + (uint32_t)jj * 32u, 16u, 1024u);
+              const uint64_t bd = BWD ? make_smem_desc(b0 + (uint32_t)jj * 1024u, (uint32_t)p.mn_lbo,
+                                                       (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                      : make_smem_desc(b0 + (uint32_t)jj * 32u, 16u, 1024u);
+              umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | jj) != 0));
+            }
+            umma_commit(empty_bar(mst));
+            if (kb == num_kb - 1) umma_commit(tfull_bar);
+          }
+          __syncwarp();
+          if (++mst == stages) { mst = 0; mph ^= 1; }
+        }
+      }
+      quarter_sync(quarter);
+      // --------------------------------------------------------------- cell maths, 8 rows
+      if constexpr (!BWD) {
         float* hnew = p.h32[z][(s + 1) & 1];
         float* hnew_r = p.h_r[z] + (long long)(s + 1) * B * Hd;
         float* gates = p.gates[z] ? p.gates[z] + (long long)s * B * 3 * Hd : nullptr;
         float* hn_save = p.hn_save[z] ? p.hn_save[z] + (long long)s * B * Hd : nullptr;
-        for (int c = 0; c < jb; c += 32) {
-          {
-            float v[32];
 #pragma unroll
-            for (int gq = 0; gq < 3; ++gq) {
-              tmem_ld32(trow + (uint32_t)(gq * jb + c), v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) scr[(gq * 32 + lane) * 33 + j] = v[j];
+        for (int u = 0; u < RB; ++u) {
+          const int rr = sub * RB + u, mr = mrow0 + u;
+          if (mr < B) {
+            const float vr = scr[(0 * 32 + rr) * 33 + lane], vz = scr[(1 * 32 + rr) * 33 + lane],
+                        vn = scr[(2 * 32 + rr) * 33 + lane];
+            const float r_ = sigmoidf_(in0[u] + vr + br);
+            const float z_ = sigmoidf_(in1[u] + vz + bz);
+            const float hnv = vn + bq;
+            const float n_ = tanhf(in2[u] + r_ * hnv);
+            const float h_ = (1.f - z_) * n_ + z_ * in3[u];
+            const long long ho = (long long)mr * Hd + j;
+            hnew[ho] = h_;
+            hnew_r[ho] = round_tf32(h_);
+            if (gates) {
+              float* gs = gates + (long long)mr * 3 * Hd + j;
+              gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
+              hn_save[ho] = hnv;
             }
           }
-          __syncwarp();
-          const int j = ntile * jb + c + lane;
-          const float br = __ldg(p.bhh[z] + j), bz = __ldg(p.bhh[z] + Hd + j), bq = __ldg(p.bhh[z] + 2 * Hd + j);
-          for (int r0 = 0; r0 < 32; r0 += RB) {
-            float xr[RB], xz[RB], xn[RB], hp[RB];
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-              const int mr = mrow0 + r0 + u;
-              const bool ok = mr < B;
-              const float* xp = xproj + (long long)(ok ? mr : 0) * p.ldx;
-              xr[u] = ok ? __ldg(xp + j) : 0.f;
-              xz[u] = ok ? __ldg(xp + Hd + j) : 0.f;
-              xn[u] = ok ? __ldg(xp + 2 * Hd + j) : 0.f;
-              hp[u] = ok ? hprev[(long long)mr * Hd + j] : 0.f;  // written by this CTA last step
-            }
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-              const int rr = r0 + u, mr = mrow0 + rr;
-              if (mr < B) {
-                const float vr = scr[(0 * 32 + rr) * 33 + lane], vz = scr[(1 * 32 + rr) * 33 + lane],
-                            vn = scr[(2 * 32 + rr) * 33 + lane];
-                const float r_ = sigmoidf_(xr[u] + vr + br);
-                const float z_ = sigmoidf_(xz[u] + vz + bz);
-                const float hnv = vn + bq;
-                const float n_ = tanhf(xn[u] + r_ * hnv);
-                const float h_ = (1.f - z_) * n_ + z_ * hp[u];
-                const long long ho = (long long)mr * Hd + j;
-                hnew[ho] = h_;
-                hnew_r[ho] = round_tf32(h_);
-                if (gates) {
-                  float* gs = gates + (long long)mr * 3 * Hd + j;
-                  gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
-                  hn_save[ho] = hnv;
-                }
-              }
-            }
-          }
-          __syncwarp();
         }
       } else {
         // acc = dgh_s . W_hh ; dh_{s-1} = acc + dh_s * z_s ; then the cell backward of step s-1
         const int sp = s - 1;
         const int t = z == 0 ? sp : T - 1 - sp;
-        const float* __restrict__ dhd_in = p.dhd[z][it_s & 1];
         float* dhd_out = p.dhd[z][(it_s + 1) & 1];
-        const float* __restrict__ gates = p.gates_c[z] + (long long)sp * B * 3 * Hd;
-        const float* __restrict__ hn_save = p.hn_save_c[z] + (long long)sp * B * Hd;
-        const float* __restrict__ hprev = p.h_r_c[z] + (long long)sp * B * Hd;
         float* dgi = p.dgi[z] + (long long)t * 3 * Hd;
         const long long ldgi = (long long)T * 3 * Hd;
         float* dgh = p.dgh[z] + (long long)sp * B * 3 * Hd;
-        for (int c = 0; c < bn; c += 32) {
-          {
-            float v[32];
-            tmem_ld32(trow + (uint32_t)c, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = v[j];
+        for (int u = 0; u < RB; ++u) {
+          const int rr = sub * RB + u, mr = mrow0 + u;
+          if (mr < B) {
+            const long long hoff = (long long)mr * Hd + j;
+            const float dh = scr[rr * 33 + lane] + in0[u];
+            const float r_ = in1[u], z_ = in2[u], n_ = in3[u];
+            const float dnn = dh * (1.f - z_);
+            const float dzz = dh * (in5[u] - n_);
+            const float dnp = dnn * (1.f - n_ * n_);
+            const float dzp = dzz * z_ * (1.f - z_);
+            const float drp = dnp * in4[u] * r_ * (1.f - r_);
+            const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
+            float* gi = dgi + (long long)mr * ldgi + j;
+            gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
+            float* gh = dgh + (long long)mr * 3 * Hd + j;
+            gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = round_tf32(dnp * r_);
+            dhd_out[hoff] = dh * z_;
           }
-          __syncwarp();
-          const int j = ntile * bn + c + lane;
-          for (int r0 = 0; r0 < 32; r0 += RB) {
-            float din[RB], gr_[RB], gz_[RB], gn_[RB], hnv[RB], hp[RB];
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-              const int mr = mrow0 + r0 + u;
-              const bool ok = mr < B;
-              const long long hoff = (long long)(ok ? mr : 0) * Hd + j;
-              const float* gt = gates + (long long)(ok ? mr : 0) * 3 * Hd + j;
-              din[u] = ok ? dhd_in[hoff] : 0.f;  // written by this CTA last step
-              gr_[u] = ok ? __ldg(gt) : 0.f;
-              gz_[u] = ok ? __ldg(gt + Hd) : 0.f;
-              gn_[u] = ok ? __ldg(gt + 2 * Hd) : 0.f;
-              hnv[u] = ok ? __ldg(hn_save + hoff) : 0.f;
-              hp[u] = ok ? __ldg(hprev + hoff) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-              const int rr = r0 + u, mr = mrow0 + rr;
-              if (mr < B) {
-                const long long hoff = (long long)mr * Hd + j;
-                const float dh = scr[rr * 33 + lane] + din[u];
-                const float r_ = gr_[u], z_ = gz_[u], n_ = gn_[u];
-                const float dnn = dh * (1.f - z_);
-                const float dzz = dh * (hp[u] - n_);
-                const float dnp = dnn * (1.f - n_ * n_);
-                const float dzp = dzz * z_ * (1.f - z_);
-                const float drp = dnp * hnv[u] * r_ * (1.f - r_);
-                const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
-                float* gi = dgi + (long long)mr * ldgi + j;
-                gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
-                float* gh = dgh + (long long)mr * 3 * Hd + j;
-                gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = round_tf32(dnp * r_);
-                dhd_out[hoff] = dh * z_;
-              }
-            }
-          }
-          __syncwarp();
         }
       }
-      // publish this warp's slice of the new state (release), order the TMEM reads before the
-      // next step's MMAs
-      tc_fence_before();
+      if (tracer) p.trace[it_s * 8 + 4] = clock64();
+      // publish this warp's rows of the new state (release).  The next write of this quarter's
+      // scratch comes after the next accumulator is ready, i.e. after every warp of the group
+      // -- including this quarter's helpers -- has arrived here.
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicAdd(counter, 1u);
+      if (tracer) p.trace[it_s * 8 + 5] = clock64();
     }
-  } else {
-    // ===================== MMA issuer (warp 4) =====================
-    const uint32_t idesc = make_idesc_tf32(bn, 0, BWD ? 1 : 0);
-    int st = 0, ph = 0;
-    for (int it_s = 0; it_s < nsteps; ++it_s) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(st), (uint32_t)ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a0 = sA + (uint32_t)st * kTileABytes;
-          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
-            const uint64_t bd = BWD ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
-                                                     (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
-                                    : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
-            umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | j) != 0));
-          }
-          umma_commit(empty_bar(st));
-          if (kb == num_kb - 1) umma_commit(tfull_bar);
-        }
-        __syncwarp();
-        if (++st == stages) { st = 0; ph ^= 1; }
-      }
-    }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
