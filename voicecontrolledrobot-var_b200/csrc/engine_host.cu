@@ -824,8 +824,55 @@ colsum_kernel(const float* __restrict__ dy, long long M, long long ld, int C, fl
   }
 }
 
+// Narrow dense matrices (ld == C, C | 1024): the slab kernel would leave 3/4 (C = 32) of its lanes
+// idle.  Here dY is one flat float4 stream; with a grid stride that is a multiple of C/4 every
+// thread stays on its own 4 columns, keeps 4 independent loads in flight, and the CTA folds its
+// 256 partial sums per column group through shared memory.
+__global__ void __launch_bounds__(256)
+colsum_flat_kernel(const float4* __restrict__ dy, long long total4, int C4, float* __restrict__ db) {
+  __shared__ float4 red[256];
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  for (; i + 3 * stride < total4; i += 4 * stride) {
+    const float4 v0 = dy[i], v1 = dy[i + stride], v2 = dy[i + 2 * stride], v3 = dy[i + 3 * stride];
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+    a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+    a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+  }
+  for (; i < total4; i += stride) {
+    const float4 v0 = dy[i];
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+  }
+  a0.x += a1.x + (a2.x + a3.x); a0.y += a1.y + (a2.y + a3.y);
+  a0.z += a1.z + (a2.z + a3.z); a0.w += a1.w + (a2.w + a3.w);
+  red[threadIdx.x] = a0;
+  __syncthreads();
+  if (threadIdx.x < C4) {  // 256 % C4 == 0: thread t and t + k*C4 share their 4 columns
+    float4 acc = red[threadIdx.x];
+    for (int l = threadIdx.x + C4; l < 256; l += C4) {
+      const float4 v = red[l];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const int col = threadIdx.x * 4;
+    atomicAdd(db + col, acc.x); atomicAdd(db + col + 1, acc.y);
+    atomicAdd(db + col + 2, acc.z); atomicAdd(db + col + 3, acc.w);
+  }
+}
+
 int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st) {
   if ((C & 3) || (ld & 3)) return VAR_ERR_UNSUPPORTED;
+  if (ld == C && C < 128 && 1024 % C == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const long long total4 = M * C / 4;
+    long long ctas = (total4 + 256 * 8 - 1) / (256 * 8);
+    if (ctas > 8 * kNumSMs) ctas = 8 * kNumSMs;
+    if (ctas < 1) ctas = 1;
+    LaunchScope sc(T_COLSUM, 0, st);
+    colsum_flat_kernel<<<(unsigned)ctas, 256, 0, st>>>(reinterpret_cast<const float4*>(dy), total4, C / 4, db);
+    VAR_CUDA_CHECK(cudaGetLastError());
+    return VAR_OK;
+  }
   const int slabs = (C + 127) / 128;
   long long chunks = (4 * kNumSMs + slabs - 1) / slabs;
   long long rp = (M + chunks - 1) / chunks;
