@@ -92,6 +92,10 @@ def test_conv_fwd_dgrad_wgrad_vs_torch(vb, case):
 FIRST_LAYER_CASES = [  # strided (NCHW / single channel) sources
     ("u8", 3, 96, 96, 3, 32, 3, 3, 2, 2, 1, 1),
     ("u8", 2, 96, 96, 3, 32, 3, 3, 1, 1, 1, 1),
+    ("u8", 40, 96, 96, 3, 32, 3, 3, 1, 1, 1, 1),      # 3840 tiles: 13 per resident CTA (cin3_conv.cu)
+    ("u8", 3, 64, 64, 3, 32, 3, 3, 1, 1, 1, 1),       # 2 output rows per tile
+    ("u8", 5, 66, 64, 3, 32, 3, 3, 2, 2, 1, 1),       # 4 rows per tile, P = 33: ragged last tile
+    ("u8", 2, 40, 40, 3, 32, 3, 3, 2, 2, 1, 1),       # narrow frame: direct fp32 kernel
     ("f32", 4, 40, 40, 3, 32, 3, 3, 2, 2, 1, 1),
     ("f32", 5, 100, 40, 1, 32, 5, 40, 2, 1, 0, 0),
     ("f32", 2, 120, 40, 1, 64, 11, 11, 2, 2, 5, 5),   # thor.snd.conv1: persistent kernels (cin1_conv.cu)

@@ -2,6 +2,7 @@
 #include "engine_host.cuh"
 #include "first_conv.cuh"
 #include "cin1_conv.cuh"
+#include "cin3_conv.cuh"
 #include "gemm_persist.cuh"
 #include "gru_persist.cuh"
 
@@ -415,6 +416,16 @@ static int gmode_of(int src_kind) {
 int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
              const float* bias, float* y, int relu, int round_out, cudaStream_t st) {
   prof_note("fwd N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (src_kind == SRC_STRIDED_U8 && sl &&
+      cin3_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, cs.P, cs.Q, sl->sN, sl->sH,
+                      sl->sW, sl->sC, x)) {
+    Cin3Args a;
+    memset(&a, 0, sizeof(a));
+    a.x = reinterpret_cast<const unsigned char*>(x); a.scale = sl->scale;
+    a.N = cs.N; a.H = cs.H; a.W = cs.W; a.P = cs.P; a.Q = cs.Q; a.stride = cs.sh;
+    a.w = w; a.bias = bias; a.y = y; a.relu = relu; a.round_out = round_out;
+    return cin3_conv_fwd(a, st);
+  }
   if (is_first_conv(cs, src_kind) && sl) {
     FirstConvArgs a;
     memset(&a, 0, sizeof(a));
@@ -946,6 +957,16 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
 int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
                const float* dy, float* dw, float* db, cudaStream_t st) {
   prof_note("wgrad N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (src_kind == SRC_STRIDED_U8 && sl &&
+      cin3_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, cs.P, cs.Q, sl->sN, sl->sH,
+                      sl->sW, sl->sC, x)) {
+    Cin3Args a;
+    memset(&a, 0, sizeof(a));
+    a.x = reinterpret_cast<const unsigned char*>(x); a.scale = sl->scale;
+    a.N = cs.N; a.H = cs.H; a.W = cs.W; a.P = cs.P; a.Q = cs.Q; a.stride = cs.sh;
+    a.dy = dy; a.dw = dw; a.db = db;
+    return cin3_conv_wgrad(a, st);
+  }
   if (is_first_conv(cs, src_kind) && sl) {
     FirstConvArgs a;
     memset(&a, 0, sizeof(a));
