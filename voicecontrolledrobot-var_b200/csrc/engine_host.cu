@@ -737,7 +737,7 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
     if (rc) return rc;
   }
   dim3 grid((B + 127) / 128, Hd / jb, 2);
-  p.arrivals = kGruEpiWarps * (int)grid.y;
+  p.arrivals = (int)grid.y;
   return launch_gru_persist<0>(tm, p, grid, st);
 }
 
@@ -763,7 +763,7 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
     if (rc) return rc;
   }
   dim3 grid((B + 127) / 128, Hd / p.bn, 2);
-  p.arrivals = kGruEpiWarps * (int)grid.y;
+  p.arrivals = (int)grid.y;
   return launch_gru_persist<1>(tm, p, grid, st);
 }
 

@@ -21,7 +21,7 @@ struct GruPersistParams {
   int bn;             // fwd: 3 * jb ; bwd: hidden units per CTA
   int num_kb;         // k-blocks per step: fwd Hd/32, bwd 3*Hd/32
   int stages;
-  int arrivals;       // epilogue-warp arrivals per group per step = 4 * gridDim.y
+  int arrivals;       // CTA arrivals per group per step = gridDim.y
   unsigned int* counters;  // [gridDim.x * gridDim.z], zero before launch
   int mn_lbo, mn_sbo, mn_type;
   // forward
@@ -133,11 +133,11 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
     const bool tracer = p.trace && tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     float br = 0.f, bz = 0.f, bq = 0.f;
     if constexpr (!BWD) { br = __ldg(p.bhh[z] + j); bz = __ldg(p.bhh[z] + Hd + j); bq = __ldg(p.bhh[z] + 2 * Hd + j); }
-    for (int it_s = 0; it_s < nsteps; ++it_s) {
-      const int s = BWD ? T - 1 - it_s : it_s;  // fwd: step index; bwd: slot whose dgh is the A operand
-      if (tracer) p.trace[it_s * 8 + 0] = clock64();
-      // ---------------------------------------- cell inputs: in flight during the main loop
-      float in0[RB], in1[RB], in2[RB], in3[RB], in4[RB], in5[RB];
+    // ---------------------------------------- cell inputs of a step: issued one step ahead so
+    // the loads fly during the release / wait for peers / operand stream of the next step
+    float in0[RB], in1[RB], in2[RB], in3[RB], in4[RB], in5[RB];
+    auto prefetch = [&](int it) {
+      const int s = BWD ? T - 1 - it : it;
       if constexpr (!BWD) {
         const int t = z == 0 ? s : T - 1 - s;
         const float* __restrict__ xproj = p.xproj[z] + (long long)t * 3 * Hd;
@@ -155,7 +155,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         }
       } else {
         const int sp = s - 1;
-        const float* dhd_in = p.dhd[z][it_s & 1];  // written by this very thread last step
+        const float* dhd_in = p.dhd[z][it & 1];  // written by this very thread last step
         const float* __restrict__ gates = p.gates_c[z] + (long long)sp * B * 3 * Hd;
         const float* __restrict__ hn_save = p.hn_save_c[z] + (long long)sp * B * Hd;
         const float* __restrict__ hprev = p.h_r_c[z] + (long long)sp * B * Hd;
@@ -173,6 +173,11 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
           in5[u] = ok ? __ldg(hprev + hoff) : 0.f;
         }
       }
+    };
+    if (nsteps > 0) prefetch(0);
+    for (int it_s = 0; it_s < nsteps; ++it_s) {
+      const int s = BWD ? T - 1 - it_s : it_s;  // fwd: step index; bwd: slot whose dgh is the A operand
+      if (tracer) p.trace[it_s * 8 + 0] = clock64();
       if (warp < 4) {
         // ---------------------------------------------------------- producers
         if (issuer) {
@@ -300,12 +305,17 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         }
       }
       if (tracer) p.trace[it_s * 8 + 4] = clock64();
-      // publish this warp's rows of the new state (release).  The next write of this quarter's
-      // scratch comes after the next accumulator is ready, i.e. after every warp of the group
-      // -- including this quarter's helpers -- has arrived here.
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicAdd(counter, 1u);
+      if (it_s + 1 < nsteps) prefetch(it_s + 1);
+      // publish the CTA's slice of the new state: ONE release per CTA per step (256 same-address
+      // atomics per group and step -- one per epilogue warp -- serialise in L2 for ~3 us).  All
+      // warps pass the barrier after their stores; thread 0's fence is cumulative over them.
+      // The next write of a quarter's scratch comes after the next accumulator is ready, i.e.
+      // after every CTA of the group has arrived here.
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+      }
       if (tracer) p.trace[it_s * 8 + 5] = clock64();
     }
   }
