@@ -133,8 +133,9 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
     const bool tracer = p.trace && tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     float br = 0.f, bz = 0.f, bq = 0.f;
     if constexpr (!BWD) { br = __ldg(p.bhh[z] + j); bz = __ldg(p.bhh[z] + Hd + j); bq = __ldg(p.bhh[z] + 2 * Hd + j); }
-    // ---------------------------------------- cell inputs of a step: issued one step ahead so
-    // the loads fly during the release / wait for peers / operand stream of the next step
+    // ---------------------------------------- cell inputs of a step: issued at the top of the step
+    // (after the previous release: a fence behind outstanding loads would wait for them) so the
+    // loads fly during the wait for peers, the operand stream and the MMAs
     float in0[RB], in1[RB], in2[RB], in3[RB], in4[RB], in5[RB];
     auto prefetch = [&](int it) {
       const int s = BWD ? T - 1 - it : it;
@@ -174,10 +175,10 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         }
       }
     };
-    if (nsteps > 0) prefetch(0);
     for (int it_s = 0; it_s < nsteps; ++it_s) {
       const int s = BWD ? T - 1 - it_s : it_s;  // fwd: step index; bwd: slot whose dgh is the A operand
       if (tracer) p.trace[it_s * 8 + 0] = clock64();
+      prefetch(it_s);
       if (warp < 4) {
         // ---------------------------------------------------------- producers
         if (issuer) {
@@ -305,7 +306,6 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         }
       }
       if (tracer) p.trace[it_s * 8 + 4] = clock64();
-      if (it_s + 1 < nsteps) prefetch(it_s + 1);
       // publish the CTA's slice of the new state: ONE release per CTA per step (256 same-address
       // atomics per group and step -- one per epilogue warp -- serialise in L2 for ~3 us).  All
       // warps pass the barrier after their stores; thread 0's fence is cumulative over them.
