@@ -45,6 +45,8 @@ CONV_CASES = [  # N, H, W, Cin, Cout, R, S, sh, sw, ph, pw
     (41, 1, 1, 1024, 128, 1, 1, 1, 1, 0, 0),
     (130, 1, 1, 128, 64, 1, 1, 1, 1, 0, 0),
     (146, 1, 1, 448, 1536, 1, 1, 1, 1, 0, 0),  # GRU input projection
+    (19000, 1, 1, 448, 1536, 1, 1, 1, 1, 0, 0),  # same at training size: persistent tile loop, coalescing epilogue
+    (70, 60, 20, 64, 64, 11, 5, 2, 2, 5, 5),   # thor.snd.conv2 with > 296 tiles: persistent im2col path
 ]
 
 

@@ -104,6 +104,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t dst, float a, float b, flo
                : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t src) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src));
+  return v;
+}
+
 // ---- TMA ------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

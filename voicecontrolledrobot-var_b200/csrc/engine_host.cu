@@ -289,9 +289,20 @@ static bool gemm_persist_enabled() {  // VAR_GEMM_PERSIST=0 keeps one CTA per ti
 }
 
 template <int GMODE>
-static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, const GemmParams& p, int m_tiles,
+static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, const GemmParams& p_in, int m_tiles,
                                  int n_tiles, cudaStream_t st) {
-  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  GemmParams p = p_in;
+  size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  // wide tiles run one CTA per SM and are epilogue bound: spend spare smem on a coalescing stage
+  static int coal = -1;
+  if (coal < 0) { const char* e = getenv("VAR_EPI_COALESCE"); coal = (e && e[0] == '0') ? 0 : 1; }
+  // (direct stores cost ~32 * bn cycles of line transactions per tile; worth hiding only when that is
+  // at least half of the tile's operand stream at ~50 B/clk -- short K, wide N)
+  const long long stream_clk = (long long)p.num_kb * (kTileABytes + p.bn * 128) / 50;
+  if (coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
+    p.epi_coalesce = 1;
+    smem += 4 * 4352;
+  }
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_persist_kernel<GMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -34,6 +34,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
   auto tfull_bar = [&](int a) { return bars + (uint32_t)(2 * stages + a) * 8u; };
   auto tempty_bar = [&](int a) { return bars + (uint32_t)(2 * stages + 2 + a) * 8u; };
   const uint32_t tslot = bars + (uint32_t)(2 * stages + 4) * 8u;
+  const uint32_t stage_base = bars + 128u;  // epi_coalesce: 4 x (32 rows x 128 B + 32 row offsets)
 
   const uint32_t acc_cols = (uint32_t)tmem_cols_for(bn);
   const int nacc = acc_cols * 2 <= 256 ? 2 : 1;  // 2 CTAs per SM share the 512 TMEM columns
@@ -152,19 +153,70 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
       tc_fence_after();
       const int m = mtile * kTileM + warp * 32 + lane;
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(warp * 32) << 16);
+      long long orow = m;
+      if (e.map.on) {
+        const int pq2 = e.map.P2 * e.map.Q2;
+        const int n_ = m / pq2, rem_ = m - n_ * pq2;
+        const int h2 = rem_ / e.map.Q2, w2 = rem_ - h2 * e.map.Q2;
+        orow = ((long long)n_ * e.map.H + h2 * e.map.sh + e.map.oh) * e.map.W + w2 * e.map.sw + e.map.ow;
+      }
+      if (p.epi_coalesce) {
+        // thread = row after tcgen05.ld; a direct store would touch 32 different 128-byte lines per
+        // instruction.  The 32 x 32 chunk goes through a swizzled smem tile so that 8 lanes cover
+        // one 128-byte row segment: 4 lines per store instruction, same for the mask / add loads.
+        const uint32_t stg = stage_base + (uint32_t)warp * 4352u;
+        const uint32_t srow = stg + 4096u;
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(srow + (uint32_t)lane * 8u), "l"(m < g.M ? orow : -1LL) : "memory");
+        const int chunk = lane & 7, rsub = lane >> 3;
+        for (int c = 0; c < bn; c += 32) {
+          float v[32];
+          tmem_ld32(trow + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(stg + swz128((uint32_t)lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const int col = ntile * bn + c + chunk * 4;
+          if (col < e.ncols) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias) b4 = *reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const int row = i2 * 4 + rsub;
+              long long orw;
+              asm volatile("ld.shared.b64 %0, [%1];" : "=l"(orw) : "r"(srow + (uint32_t)row * 8u));
+              if (orw < 0) continue;
+              float4 r4 = ld_shared_v4(stg + swz128((uint32_t)row, chunk));
+              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+              if (e.addsrc) {
+                const float4 a4 = *reinterpret_cast<const float4*>(e.addsrc + orw * e.lda + col);
+                r4.x += a4.x; r4.y += a4.y; r4.z += a4.z; r4.w += a4.w;
+              }
+              if (e.relu) {
+                r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
+                r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+              }
+              if (e.mask) {
+                const float4 k4 = *reinterpret_cast<const float4*>(e.mask + orw * e.ldm + col);
+                r4.x = k4.x > 0.f ? r4.x : 0.f; r4.y = k4.y > 0.f ? r4.y : 0.f;
+                r4.z = k4.z > 0.f ? r4.z : 0.f; r4.w = k4.w > 0.f ? r4.w : 0.f;
+              }
+              if (e.round_out) {
+                r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+                r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+              }
+              *reinterpret_cast<float4*>(e.out + orw * e.ldo + col) = r4;
+            }
+          }
+          __syncwarp();
+        }
+      } else
       for (int c = 0; c < bn; c += 32) {
         float v[32];
         tmem_ld32(trow + (uint32_t)c, v);
         tmem_ld_wait();
         const int col0 = ntile * bn + c;
         if (m < g.M && col0 < e.ncols) {
-          long long orow = m;
-          if (e.map.on) {
-            const int pq2 = e.map.P2 * e.map.Q2;
-            const int n_ = m / pq2, rem_ = m - n_ * pq2;
-            const int h2 = rem_ / e.map.Q2, w2 = rem_ - h2 * e.map.Q2;
-            orow = ((long long)n_ * e.map.H + h2 * e.map.sh + e.map.oh) * e.map.W + w2 * e.map.sw + e.map.ow;
-          }
           float* o = e.out + orow * e.ldo + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {

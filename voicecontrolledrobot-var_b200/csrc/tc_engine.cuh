@@ -125,6 +125,7 @@ struct GemmParams {
   // tile is staged once in shared memory
   int sc_rpt, sc_tpi;          // output rows per tile, tiles per image
   int sc_nh, sc_wpad;          // staged rows / padded row width
+  int epi_coalesce;            // persistent kernel: transpose the accumulator through smem (512 B per store instr.)
 };
 
 constexpr int kTileM = 128;
