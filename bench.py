@@ -335,6 +335,8 @@ def run_b200(args):
         if not args.no_reward:
             reward = bench_reward(vb, eng, net, wl, dev, pool, al, arena)
         cpu = None if args.no_cpu_baseline else cpu_baseline(wl, net, sample_steps=1)
+        if reward is not None and not args.no_cpu_baseline:
+            reward["cpu_baseline"] = cpu_reward_baseline(wl, net)
         out = {
             "metric": "VAR train triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -430,6 +432,36 @@ def cpu_step_fn(wl, net, B):
         opt.step()
         return float(loss.detach())
     return step
+
+
+def cpu_reward_baseline(wl, net, N=16, iters=3):
+    """Oracle port of getEmbeddings + calcReward (vec_pretext_normalize.py:82-101) for N envs on the host:
+    uint8 frames -> /255 -> image branch (+ goal-sound branch for Kuka, cached for iTHOR) -> dot + envReward.
+    Timed with one torch thread (RL.py:75 pins the reference to one) and with all host threads."""
+    from oracle import model as omodel, reward as oreward, synth
+    sd = omodel.init_state_dict(net, 0)
+    o = omodel.OracleVAR(net, sd)
+    img_u8 = synth.make_images(3, N)
+    snd = torch.randn(N, 1, wl["F"], 40) * 4
+    inf = torch.full((N, 1, wl["F"], 40), float("inf"))
+    env_r = np.zeros(N, np.float32)
+    out = {}
+
+    def query(first):
+        with torch.no_grad():
+            image = torch.from_numpy(img_u8.astype(np.float64) / 255.0).float()
+            d = o(image, snd if (first or net == "kuka") else inf, None)
+            return oreward.calc_reward(env_r, d["image_feat"].numpy(), d["sound_feat_positive"].numpy())[0]
+    for threads in (1, os.cpu_count() or 1):
+        torch.set_num_threads(threads)
+        query(True)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            query(False)
+        dt = (time.perf_counter() - t0) / iters
+        out[f"threads_{threads}"] = {"queries_per_s": N / dt, "ms": dt * 1e3}
+    torch.set_num_threads(os.cpu_count() or 1)
+    return {"kind": "port", "n_envs": N, "sample": f"{iters} queries of {N} envs, oracle port on the host", **out}
 
 
 def cpu_baseline(wl, net, sample_steps=1):
