@@ -679,7 +679,7 @@ static int env_int(const char* name, int dflt) {
 
 template <int BWD>
 static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = gemm_smem_bytes(p.bn, p.stages) + gru_scr_bytes(BWD) + 16;
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + gru_scr_bytes(BWD) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_persist_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -735,7 +735,9 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
   GruPersistParams p;
   memset(&p, 0, sizeof(p));
   const int jb = 32;
-  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / 32; p.stages = env_int("VAR_GRU_STAGES_FWD", 4);
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / 32; p.stages = env_int("VAR_GRU_STAGES_FWD", 2);
+  p.kps = env_int("VAR_GRU_KPS_FWD", 2);
+  p.a_split = env_int("VAR_GRU_ASPLIT", 0);
   p.counters = counters; p.ldx = ldx;
   CUtensorMap tm[4];
   for (int d = 0; d < 2; ++d) {
@@ -744,7 +746,7 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
     p.h_r[d] = h_r[d]; p.gates[d] = gates[d]; p.hn_save[d] = hn_save[d];
     int rc = get_tmap_2d(whh[d], 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[d]);
     if (rc) return rc;
-    rc = get_tmap_2d(h_r[d], (T + 1) * B, Hd, Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    rc = get_tmap_2d(h_r[d], (T + 1) * B, Hd, Hd, p.a_split ? 32 : 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
     if (rc) return rc;
   }
   dim3 grid((B + 127) / 128, Hd / jb, 2);
@@ -761,7 +763,9 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
   prof_note("gru_persist_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
   GruPersistParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.Hd = Hd; p.T = T; p.bn = 32; p.num_kb = 3 * Hd / 32; p.stages = env_int("VAR_GRU_STAGES_BWD", 4);
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 32; p.num_kb = 3 * Hd / 32; p.stages = env_int("VAR_GRU_STAGES_BWD", 3);
+  p.kps = env_int("VAR_GRU_KPS_BWD", 2);
+  p.a_split = env_int("VAR_GRU_ASPLIT", 0);
   p.counters = counters;
   p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
   CUtensorMap tm[4];
@@ -770,7 +774,7 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
     p.dgh[d] = dgh[d]; p.dgi[d] = dgi[d]; p.dhd[d][0] = dhd[d][0]; p.dhd[d][1] = dhd[d][1];
     int rc = get_tmap_2d(whh[d], 3 * Hd, Hd, Hd, 32, mn_cfg().tma_swizzle, &tm[d]);
     if (rc) return rc;
-    rc = get_tmap_2d(dgh[d], T * B, 3 * Hd, 3 * Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    rc = get_tmap_2d(dgh[d], T * B, 3 * Hd, 3 * Hd, p.a_split ? 32 : 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
     if (rc) return rc;
   }
   dim3 grid((B + 127) / 128, Hd / p.bn, 2);

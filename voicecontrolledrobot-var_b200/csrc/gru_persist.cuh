@@ -21,6 +21,8 @@ struct GruPersistParams {
   int bn;             // fwd: 3 * jb ; bwd: hidden units per CTA
   int num_kb;         // k-blocks per step: fwd Hd/32, bwd 3*Hd/32
   int stages;
+  int kps;            // k-blocks (32 columns) per pipeline stage: 1 or 2
+  int a_split;        // 1: the A tile arrives as four 32-row boxes issued by four threads
   int arrivals;       // CTA arrivals per group per step = gridDim.y
   unsigned int* counters;  // [gridDim.x * gridDim.z], zero before launch
   int mn_lbo, mn_sbo, mn_type;
@@ -82,10 +84,12 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
   const int stages = p.stages, bn = p.bn, num_kb = p.num_kb;
   const int Hd = p.Hd, B = p.B, T = p.T;
   const uint32_t tileB_bytes = (uint32_t)bn * 128u;
+  const int kps = p.kps;
+  const uint32_t stageA = (uint32_t)kps * kTileABytes, stageB = (uint32_t)kps * tileB_bytes;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
-  const uint32_t sB = base + (uint32_t)stages * kTileABytes;
-  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  const uint32_t sB = base + (uint32_t)stages * stageA;
+  const uint32_t bars = sB + (uint32_t)stages * stageB;
   auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
   auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
   const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
@@ -129,7 +133,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
     float* scr = scr_base + quarter * (BWD ? 32 * 33 : 3 * 32 * 33);
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int st = 0, ph = 0;  // producer ring position (kept by every issuing lane)
-    const bool issuer = warp < 4 && lane == 0 && (warp == 0 || (multi && warp - 1 < nb_boxes));
+    const bool issuer = warp < 4 && lane == 0 && (p.a_split || warp == 0 || (multi && warp - 1 < nb_boxes));
     const bool tracer = p.trace && tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
     float br = 0.f, bz = 0.f, bq = 0.f;
     if constexpr (!BWD) { br = __ldg(p.bhh[z] + j); bz = __ldg(p.bhh[z] + Hd + j); bq = __ldg(p.bhh[z] + 2 * Hd + j); }
@@ -190,22 +194,24 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
           }
           if (tracer) p.trace[it_s * 8 + 1] = clock64();
           const int arow = s * B + m0;  // row of the A tile in the [slots * B, K] matrix
-          for (int kb = 0; kb < num_kb; ++kb) {
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kps) {
             mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-            const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
-            const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
-            if (warp == 0) {
-              mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
-              tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
-            }
-            if constexpr (!BWD) {
-              for (int b = 0; b < 3; ++b)
-                if (warp == 1 + b)
-                  tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * 32, b * Hd + ntile * jb);
-            } else {
-              for (int gidx = 0; gidx < (bn >> 5); ++gidx)
-                if (warp == (multi ? 1 + (gidx % 3) : 0))
-                  tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st), ntile * bn + gidx * 32, kb * 32);
+            if (warp == 0) mbar_arrive_expect_tx(full_bar(st), stageA + stageB);
+            for (int sub = 0; sub < kps; ++sub) {
+              const int kb = kb0 + sub;
+              const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
+              const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
+              if (p.a_split) tma_load_2d(dstA + (uint32_t)warp * 4096u, tmA, full_bar(st), kb * 32, arow + warp * 32);
+              else if (warp == 0) tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
+              if constexpr (!BWD) {
+                for (int b = 0; b < 3; ++b)
+                  if (warp == 1 + b)
+                    tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * 32, b * Hd + ntile * jb);
+              } else {
+                for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+                  if (warp == ((multi || p.a_split) ? 1 + (gidx % 3) : 0))
+                    tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st), ntile * bn + gidx * 32, kb * 32);
+              }
             }
             if (++st == stages) { st = 0; ph ^= 1; }
           }
@@ -227,22 +233,24 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         tc_fence_before();
       } else if (warp == 4) {
         // ---------------------------------------------------------- MMA issue for this step
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += kps) {
           mbar_wait(full_bar(mst), (uint32_t)mph);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a0 = sA + (uint32_t)mst * kTileABytes;
-            const uint32_t b0 = sB + (uint32_t)mst * tileB_bytes;
+            for (int sub = 0; sub < kps; ++sub) {
+              const uint32_t a0 = sA + (uint32_t)mst * stageA + (uint32_t)sub * kTileABytes;
+              const uint32_t b0 = sB + (uint32_t)mst * stageB + (uint32_t)sub * tileB_bytes;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const uint64_t ad = make_smem_desc(a0 + (uint32_t)jj * 32u, 16u, 1024u);
-              const uint64_t bd = BWD ? make_smem_desc(b0 + (uint32_t)jj * 1024u, (uint32_t)p.mn_lbo,
-                                                       (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
-                                      : make_smem_desc(b0 + (uint32_t)jj * 32u, 16u, 1024u);
-              umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | jj) != 0));
+              for (int jj = 0; jj < 4; ++jj) {
+                const uint64_t ad = make_smem_desc(a0 + (uint32_t)jj * 32u, 16u, 1024u);
+                const uint64_t bd = BWD ? make_smem_desc(b0 + (uint32_t)jj * 1024u, (uint32_t)p.mn_lbo,
+                                                         (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                        : make_smem_desc(b0 + (uint32_t)jj * 32u, 16u, 1024u);
+                umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb0 | sub | jj) != 0));
+              }
             }
             umma_commit(empty_bar(mst));
-            if (kb == num_kb - 1) umma_commit(tfull_bar);
+            if (kb0 + kps >= num_kb) umma_commit(tfull_bar);
           }
           __syncwarp();
           if (++mst == stages) { mst = 0; mph ^= 1; }
