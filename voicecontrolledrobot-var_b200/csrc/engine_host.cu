@@ -707,7 +707,41 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
     VAR_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 128, st));
     p.trace = d_trace;
   }
-  VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD>, grid, dim3(kGruThreads, 1, 1), args, smem, st));
+  // Optional placement experiment: launch the 16 CTAs of a (row tile, direction) group as one
+  // thread-block cluster so that they share a GPC (VAR_GRU_CLUSTER=8|16); the kernel itself uses no
+  // cluster feature.
+  static int cluster = -1;
+  if (cluster < 0) cluster = env_int("VAR_GRU_CLUSTER", 0);
+  bool launched = false;
+  if (cluster > 1 && grid.y % cluster == 0) {
+    static bool np_set = false;
+    if (!np_set) {
+      cudaFuncSetAttribute(gru_persist_kernel<BWD>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      np_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cluster; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, gru_persist_kernel<BWD>, &cfg) == cudaSuccess &&
+        (long long)nclusters * cluster >= (long long)grid.x * grid.y * grid.z) {
+      cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gru_persist_kernel<BWD>, args);
+      if (e == cudaSuccess) launched = true;
+      else (void)cudaGetLastError();
+    } else {
+      (void)cudaGetLastError();
+    }
+    static bool said = false;
+    if (!said) { fprintf(stderr, "[var] gru cluster %d: max active clusters %d, launched=%d\n", cluster, nclusters, (int)launched); said = true; }
+  }
+  if (!launched)
+    VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD>, grid, dim3(kGruThreads, 1, 1), args, smem, st));
   if (trace_on) {
     std::vector<long long> h(8 * 128);
     VAR_CUDA_CHECK(cudaStreamSynchronize(st));
