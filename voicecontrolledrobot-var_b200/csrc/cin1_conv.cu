@@ -187,21 +187,35 @@ cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int t
       // ---- epilogue of the same tile: bias, ReLU, tf32 rounding, 256 B per pixel
       mbar_wait(acc_full(g), ph);
       tc_fence_after();
-      const bool store = r < kPix && tp.p0 + pr < a.P;
-      float* out = a.y + ((long long)(tp.n * a.P + tp.p0) * kQ + r) * kCout;
+      // After tcgen05.ld a thread owns one pixel row (256 B): a direct store would touch 32 different
+      // lines per instruction.  The rows go through the group's operand buffer (idle until the
+      // next build, which starts behind the group barrier) so that 16 lanes cover one row: every
+      // store instruction writes 512 contiguous bytes.
+      const uint32_t stg = a0 + (uint32_t)(wq * 32) * 256u;  // this warp's 32 rows x 256 B
 #pragma unroll
       for (int c = 0; c < kCout; c += 32) {
         float v[32];
         tmem_ld32(tmem_base + (uint32_t)g * 64u + (uint32_t)c + ((uint32_t)(wq * 32) << 16), v);
         tmem_ld_wait();
-        if (store) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (a.bias) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c + j));
-              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
-            }
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(stg + (uint32_t)lane * 256u + (uint32_t)(((c >> 2) + j) ^ (lane & 7)) * 16u, v[4 * j],
+                       v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      __syncwarp();
+      {
+        const int chunk = lane & 15, rsub = lane >> 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) b4 = __ldg(reinterpret_cast<const float4*>(a.bias + chunk * 4));
+        float* out = a.y + ((long long)(tp.n * a.P + tp.p0) * kQ + wq * 32) * kCout + chunk * 4;
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          const int row = i2 * 2 + rsub;           // row within the warp's 32
+          const int rt = wq * 32 + row;            // pixel within the tile
+          const int prow = rt / kQ;
+          if (rt < kPix && tp.p0 + prow < a.P) {
+            float4 r4 = ld_shared_v4(stg + (uint32_t)row * 256u + (uint32_t)(chunk ^ (row & 7)) * 16u);
+            r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
             if (a.relu) {
               r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
               r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
@@ -210,7 +224,7 @@ cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int t
               r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
               r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
             }
-            *reinterpret_cast<float4*>(out + c + j) = r4;
+            *reinterpret_cast<float4*>(out + (long long)row * kCout) = r4;
           }
         }
       }
