@@ -187,27 +187,41 @@ cin3_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin3Args a, const
       // ---- epilogue: scale (1/255), bias, ReLU, tf32 rounding, 128 B per pixel
       mbar_wait(acc_full(g), ph);
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_base + (uint32_t)g * 32u + ((uint32_t)(wq * 32) << 16), v);
-      tmem_ld_wait();
-      if (valid) {
-        float* out = a.y + ((long long)(tp.n * a.P + tp.p0) * a.Q + r) * kCout;
+      // thread = pixel row (128 B) after tcgen05.ld; the rows go through the group's idle operand
+      // buffer so that 8 lanes cover one row and a store instruction writes 512 contiguous bytes
+      const uint32_t stg = a0 + (uint32_t)(wq * 32) * 128u;
+      {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t)g * 32u + ((uint32_t)(wq * 32) << 16), v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 r4 = make_float4(v[j] * a.scale, v[j + 1] * a.scale, v[j + 2] * a.scale, v[j + 3] * a.scale);
-          if (a.bias) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + j));
-            r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(stg + swz128((uint32_t)lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      __syncwarp();
+      {
+        const int chunk = lane & 7, rsub = lane >> 3;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) b4 = __ldg(reinterpret_cast<const float4*>(a.bias + chunk * 4));
+        float* out = a.y + ((long long)(tp.n * a.P + tp.p0) * a.Q + wq * 32) * kCout + chunk * 4;
+        const int npix = min(ge.rt, a.P - tp.p0) * a.Q;  // valid pixels of this tile
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+          const int row = i2 * 4 + rsub;
+          if (wq * 32 + row < npix) {
+            float4 r4 = ld_shared_v4(stg + swz128((uint32_t)row, chunk));
+            r4.x = r4.x * a.scale + b4.x; r4.y = r4.y * a.scale + b4.y;
+            r4.z = r4.z * a.scale + b4.z; r4.w = r4.w * a.scale + b4.w;
+            if (a.relu) {
+              r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
+              r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+            }
+            if (a.round_out) {
+              r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+              r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+            }
+            *reinterpret_cast<float4*>(out + (long long)row * kCout) = r4;
           }
-          if (a.relu) {
-            r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
-            r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
-          }
-          if (a.round_out) {
-            r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
-            r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
-          }
-          *reinterpret_cast<float4*>(out + j) = r4;
         }
       }
       tc_fence_before();  // orders the TMEM reads before the next a_full arrival
