@@ -293,11 +293,13 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
                                  int n_tiles, cudaStream_t st) {
   GemmParams p = p_in;
   size_t smem = gemm_smem_bytes(p.bn, p.stages);
-  // wide tiles run one CTA per SM and are epilogue bound: spend spare smem on a coalescing stage
+  // Wide short-K tiles (one CTA per SM) are epilogue bound: after tcgen05.ld a thread owns a row, so
+  // direct stores touch 32 different 128-byte lines per instruction (~32 * bn cycles per tile).  When
+  // that is at least half of the tile's operand stream (~50 B/clk) the accumulator is transposed
+  // through a swizzled smem tile instead.  (Measured: GRU input projection 198 -> 272 TF/s; for the
+  // two-CTA-per-SM configurations -- masked dgrads of the small convs -- it costs 10-25 %.)
   static int coal = -1;
   if (coal < 0) { const char* e = getenv("VAR_EPI_COALESCE"); coal = (e && e[0] == '0') ? 0 : 1; }
-  // (direct stores cost ~32 * bn cycles of line transactions per tile; worth hiding only when that is
-  // at least half of the tile's operand stream at ~50 B/clk -- short K, wide N)
   const long long stream_clk = (long long)p.num_kb * (kTileABytes + p.bn * 128) / 50;
   if (coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
     p.epi_coalesce = 1;
@@ -989,17 +991,17 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
                                         (int)smem));
     configured = smem;
   }
-  dim3 grid(ktiles, splits, 1);
-  for (int c0 = 0; c0 < cs.Cout; c0 += slab) {
-    rc = get_tmap_2d(dy + c0, p.M, slab, cs.Cout, 32, mn_cfg().tma_swizzle, &tdy);
-    if (rc) return rc;
-    p.dw = dw + (long long)c0 * p.kpad;
-    {
-      LaunchScope sc(T_WGRAD, 2.0 * p.M * (double)slab * p.K, st);
-      tc_wgrad_tma_kernel<0><<<grid, 160, smem, st>>>(tx, tdy, p);
-    }
-    VAR_CUDA_CHECK(cudaGetLastError());
+  // all slabs of output channels in one launch (grid.z): one slab alone is ktiles * splits CTAs and
+  // would leave a third of the SMs idle for wide layers (GRU: 6 slabs of 96 CTAs)
+  dim3 grid(ktiles, splits, nslab);
+  rc = get_tmap_2d(dy, p.M, cs.Cout, cs.Cout, 32, mn_cfg().tma_swizzle, &tdy);
+  if (rc) return rc;
+  p.dw = dw;
+  {
+    LaunchScope sc(T_WGRAD, 2.0 * p.M * (double)cs.Cout * p.K, st);
+    tc_wgrad_tma_kernel<0><<<grid, 160, smem, st>>>(tx, tdy, p);
   }
+  VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
 

@@ -939,7 +939,7 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
           }
           for (int bg = warp; bg < bgroups; bg += 4)
-            tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), bg * 32, m);
+            tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), (int)blockIdx.z * p.cout + bg * 32, m);
           if (++st == stages) { st = 0; ph ^= 1; }
         }
       }
@@ -948,6 +948,7 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       const int k = ktile * 128 + warp * 32 + lane;
+      float* dw_slab = p.dw + (long long)blockIdx.z * p.cout * p.kpad;  // grid.z = slab of cout columns
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
       for (int c = 0; c < p.cout; c += 32) {
         float v[32];
@@ -955,7 +956,7 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_ld_wait();
         if (k < p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + (long long)(c + j) * p.kpad + k, v[j]);
+          for (int j = 0; j < 32; ++j) atomicAdd(dw_slab + (long long)(c + j) * p.kpad + k, v[j]);
         }
       }
       tc_fence_before();
