@@ -952,7 +952,10 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
   p.M = cs.N * cs.P * cs.Q;
   p.K = cs.R * cs.S * cs.Cin;
   p.kpad = round_up32(p.K);
-  p.stages = 4;
+  // two 32-pixel blocks per pipeline stage halve the barrier round trips: +12 % for the narrow convs
+  // (Cout <= 64); wide slabs (GRU, 256 columns) lose 15 % with the coarser stages
+  p.kps = env_int("VAR_WGRAD_KPS", cs.Cout <= 64 ? 2 : 1);
+  p.stages = 4 / p.kps;
   p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
   p.P = cs.P; p.Q = cs.Q;
   p.a_tiled = is_linear(cs) ? 1 : 0;
@@ -979,12 +982,12 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
   int splits = (2 * 2 * kNumSMs) / per_split;
   if (splits < 1) splits = 1;
   int ppc = (p.M + splits - 1) / splits;
-  ppc = ((ppc + 31) / 32) * 32;
+  ppc = ((ppc + 32 * p.kps - 1) / (32 * p.kps)) * (32 * p.kps);
   if (ppc < 256) ppc = 256;
   splits = (p.M + ppc - 1) / ppc;
   p.pix_per_cta = ppc;
   p.cout = slab;
-  const size_t smem = wgrad_smem_bytes(slab, p.stages);
+  const size_t smem = wgrad_smem_bytes(slab, p.stages * p.kps);
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,

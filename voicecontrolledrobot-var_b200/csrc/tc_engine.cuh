@@ -859,6 +859,7 @@ struct WgradTmaParams {
   int stages;
   int mn_lbo, mn_sbo, mn_type;
   int a_tiled;        // 1: X is a plain [M, K] matrix (Linear)
+  int kps;            // 32-pixel blocks per pipeline stage (1 or 2)
   int P, Q;           // output extents: pixel m -> (n, p, q)
   int cpb, base_w, base_h, step_w, step_h;
   uint8_t tap_w[kMaxTaps], tap_h[kMaxTaps];
@@ -872,12 +873,14 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = p.stages;
   const int bgroups = p.cout >> 5;
+  const int kps = p.kps;  // 32-pixel blocks per pipeline stage
   const uint32_t tileA_bytes = 4u * 4096u;
   const uint32_t tileB_bytes = (uint32_t)bgroups * 4096u;
+  const uint32_t stageA = (uint32_t)kps * tileA_bytes, stageB = (uint32_t)kps * tileB_bytes;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
-  const uint32_t sB = base + (uint32_t)stages * tileA_bytes;
-  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  const uint32_t sB = base + (uint32_t)stages * stageA;
+  const uint32_t bars = sB + (uint32_t)stages * stageB;
   auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
   auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
   const uint32_t tfull_bar = bars + (uint32_t)(2 * stages) * 8u;
@@ -904,7 +907,7 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int ktile = blockIdx.x;
   const int pix0 = blockIdx.y * p.pix_per_cta;
   const int pix1 = min(pix0 + p.pix_per_cta, p.M);
-  const int num_kb = (pix1 - pix0 + 31) / 32;
+  const int num_kb = ((pix1 - pix0 + 31) / 32 + kps - 1) / kps;  // pipeline stages of kps pixel blocks
   const int kgroups = min(4, (p.K - ktile * 128 + 31) / 32);  // valid 32-row groups of this k tile
 
   if (num_kb > 0) {
@@ -918,28 +921,33 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         int st = 0, ph = 0;
         for (int it = 0; it < num_kb; ++it) {
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-          if (warp == 0) mbar_arrive_expect_tx(full_bar(st), (uint32_t)kgroups * 4096u + tileB_bytes);
-          const int m = pix0 + it * 32;
-          const uint32_t dA = sA + (uint32_t)st * tileA_bytes;
-          const uint32_t dB = sB + (uint32_t)st * tileB_bytes;
-          const int gq = warp;
-          if (gq < kgroups) {
-            if (p.a_tiled) {
-              tma_load_2d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), ktile * 128 + gq * 32, m);
-            } else {
-              const int n = m / pq;
-              const int rem = m - n * pq;
-              const int pp = rem / p.Q, qq = rem - pp * p.Q;
-              const int w0 = qq * p.step_w + p.base_w, h0 = pp * p.step_h + p.base_h;
-              const int kb = ktile * 4 + gq;
-              const int tap = kb / p.cpb;
-              const int c0 = (kb - tap * p.cpb) << 5;
-              tma_load_im2col_4d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), c0, w0, h0, n,
-                                 p.tap_w[tap], p.tap_h[tap]);
+          if (warp == 0)
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kps * ((uint32_t)kgroups * 4096u + tileB_bytes));
+          for (int sub = 0; sub < kps; ++sub) {
+            // (blocks past the pixel range are loaded too: rows beyond M are zero filled by TMA and
+            // rows of the next CTA's range cannot occur -- ranges are multiples of 32 * kps)
+            const int m = pix0 + (it * kps + sub) * 32;
+            const uint32_t dA = sA + (uint32_t)st * stageA + (uint32_t)sub * tileA_bytes;
+            const uint32_t dB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
+            const int gq = warp;
+            if (gq < kgroups) {
+              if (p.a_tiled) {
+                tma_load_2d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), ktile * 128 + gq * 32, m);
+              } else {
+                const int n = m / pq;
+                const int rem = m - n * pq;
+                const int pp = rem / p.Q, qq = rem - pp * p.Q;
+                const int w0 = qq * p.step_w + p.base_w, h0 = pp * p.step_h + p.base_h;
+                const int kb = ktile * 4 + gq;
+                const int tap = kb / p.cpb;
+                const int c0 = (kb - tap * p.cpb) << 5;
+                tma_load_im2col_4d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), c0, w0, h0, n,
+                                   p.tap_w[tap], p.tap_h[tap]);
+              }
             }
+            for (int bg = warp; bg < bgroups; bg += 4)
+              tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), (int)blockIdx.z * p.cout + bg * 32, m);
           }
-          for (int bg = warp; bg < bgroups; bg += 4)
-            tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), (int)blockIdx.z * p.cout + bg * 32, m);
           if (++st == stages) { st = 0; ph ^= 1; }
         }
       }
@@ -968,13 +976,15 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a0 = sA + (uint32_t)st * tileA_bytes;
-          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+          for (int sub = 0; sub < kps; ++sub) {
+            const uint32_t a0 = sA + (uint32_t)st * stageA + (uint32_t)sub * tileA_bytes;
+            const uint32_t b0 = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 1024u, lbo, sbo, lt);
-            const uint64_t bd = make_smem_desc(b0 + (uint32_t)j * 1024u, lbo, sbo, lt);
-            umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 1024u, lbo, sbo, lt);
+              const uint64_t bd = make_smem_desc(b0 + (uint32_t)j * 1024u, lbo, sbo, lt);
+              umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | sub | j) != 0));
+            }
           }
           umma_commit(empty_bar(st));
           if (kb == num_kb - 1) umma_commit(tfull_bar);
