@@ -62,6 +62,11 @@ LaunchScope::~LaunchScope() {
   cudaEventRecord(p.recs[idx].e1, st);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 MnCfg& mn_cfg() {
   static MnCfg c;
   return c;
@@ -292,7 +297,10 @@ template <int GMODE>
 static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, const GemmParams& p_in, int m_tiles,
                                  int n_tiles, cudaStream_t st) {
   GemmParams p = p_in;
-  size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  p.kps = env_int("VAR_GEMM_KPS", 2);
+  if (p.kps < 1 || p.stages % p.kps) p.kps = 1;
+  p.stages /= p.kps;
+  size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps);
   // Wide short-K tiles (one CTA per SM) are epilogue bound: after tcgen05.ld a thread owns a row, so
   // direct stores touch 32 different 128-byte lines per instruction (~32 * bn cycles per tile).  When
   // that is at least half of the tile's operand stream (~50 B/clk) the accumulator is transposed
@@ -672,11 +680,6 @@ bool gru_persist_enabled() {  // VAR_GRU_PERSIST=0 falls back to one launch per 
   static int on = -1;
   if (on < 0) { const char* e = getenv("VAR_GRU_PERSIST"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
 }
 
 template <int BWD>

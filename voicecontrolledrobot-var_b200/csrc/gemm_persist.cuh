@@ -25,10 +25,12 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = p.stages, bn = p.bn, num_kb = p.num_kb;
   const uint32_t tileB_bytes = (uint32_t)bn * 128u;
+  const int kps = p.kps;  // k-blocks per pipeline stage: fewer barrier round trips per byte
+  const uint32_t stageA = (uint32_t)kps * kTileABytes, stageB = (uint32_t)kps * tileB_bytes;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
-  const uint32_t sB = base + (uint32_t)stages * kTileABytes;
-  const uint32_t bars = sB + (uint32_t)stages * tileB_bytes;
+  const uint32_t sB = base + (uint32_t)stages * stageA;
+  const uint32_t bars = sB + (uint32_t)stages * stageB;
   auto full_bar = [&](int s) { return bars + (uint32_t)s * 8u; };
   auto empty_bar = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
   auto tfull_bar = [&](int a) { return bars + (uint32_t)(2 * stages + a) * 8u; };
@@ -77,34 +79,38 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
           w0 = (rem0 - p0 * g.Q) * p.step_w + p.base_w;
           h0 = p0 * p.step_h + p.base_h;
         }
-        for (int it = 0; it < num_kb; ++it) {
+        for (int it0 = 0; it0 < num_kb; it0 += kps) {
+          const int nsub = min(kps, num_kb - it0);
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-          const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
-          const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
-          int tap = 0, c0 = it << 5;
-          if constexpr (GMODE == G_TMA_IM2COL) {
-            tap = it / p.cpb;
-            c0 = (it - tap * p.cpb) << 5;
-          }
-          if (lane == 0) {
-            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
-            if constexpr (GMODE == G_TMA_IM2COL)
-              tma_load_im2col_4d(dstA, &tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
-            else
-              tma_load_2d(dstA, &tmA, full_bar(st), it * 32, m0);
-          }
-          if (!p.b_mn_major) {
-            for (int b = 0; b < p.nbox; ++b)
-              if (lane == (multi ? 1 + (b % 3) : 0))
-                tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it * 32,
-                            p.boxbase[b] + ntile * p.box_rows);
-          } else {
-            const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
-            const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
-            for (int gidx = 0; gidx < (bn >> 5); ++gidx)
-              if (lane == (multi ? 1 + (gidx % 3) : 0))
-                tma_load_2d(dstB + (uint32_t)gidx * 4096u, &tmB, full_bar(st),
-                            rs * p.cin_total + ntile * bn + gidx * 32, k0);
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(st), (uint32_t)nsub * ((uint32_t)kTileABytes + tileB_bytes));
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int it = it0 + sub;
+            const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
+            const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
+            int tap = 0, c0 = it << 5;
+            if constexpr (GMODE == G_TMA_IM2COL) {
+              tap = it / p.cpb;
+              c0 = (it - tap * p.cpb) << 5;
+            }
+            if (lane == 0) {
+              if constexpr (GMODE == G_TMA_IM2COL)
+                tma_load_im2col_4d(dstA, &tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
+              else
+                tma_load_2d(dstA, &tmA, full_bar(st), it * 32, m0);
+            }
+            if (!p.b_mn_major) {
+              for (int b = 0; b < p.nbox; ++b)
+                if (lane == (multi ? 1 + (b % 3) : 0))
+                  tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it * 32,
+                              p.boxbase[b] + ntile * p.box_rows);
+            } else {
+              const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
+              const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
+              for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+                if (lane == (multi ? 1 + (gidx % 3) : 0))
+                  tma_load_2d(dstB + (uint32_t)gidx * 4096u, &tmB, full_bar(st),
+                              rs * p.cin_total + ntile * bn + gidx * 32, k0);
+            }
           }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
@@ -120,22 +126,25 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
       mbar_wait(tempty_bar(acc), (uint32_t)((use & 1) ^ 1));  // epilogue drained it
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb0 = 0; kb0 < num_kb; kb0 += kps) {
+        const int nsub = min(kps, num_kb - kb0);
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a0 = sA + (uint32_t)st * kTileABytes;
-          const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
+          for (int sub = 0; sub < nsub; ++sub) {
+            const uint32_t a0 = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
+            const uint32_t b0 = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
-            const uint64_t bd = p.b_mn_major ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
-                                                              (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
-                                             : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
-            umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((kb | j) != 0));
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
+              const uint64_t bd = p.b_mn_major ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
+                                                                (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                               : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
+              umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((kb0 | sub | j) != 0));
+            }
           }
           umma_commit(empty_bar(st));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (kb0 + kps >= num_kb) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++st == stages) { st = 0; ph ^= 1; }

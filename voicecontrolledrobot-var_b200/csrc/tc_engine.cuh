@@ -126,6 +126,7 @@ struct GemmParams {
   int sc_rpt, sc_tpi;          // output rows per tile, tiles per image
   int sc_nh, sc_wpad;          // staged rows / padded row width
   int epi_coalesce;            // persistent kernel: transpose the accumulator through smem (512 B per store instr.)
+  int kps;                     // persistent kernel: k-blocks per pipeline stage (1 or 2)
 };
 
 constexpr int kTileM = 128;
