@@ -47,6 +47,7 @@ CONV_CASES = [  # N, H, W, Cin, Cout, R, S, sh, sw, ph, pw
     (146, 1, 1, 448, 1536, 1, 1, 1, 1, 0, 0),  # GRU input projection
     (19000, 1, 1, 448, 1536, 1, 1, 1, 1, 0, 0),  # same at training size: persistent tile loop, coalescing epilogue
     (70, 60, 20, 64, 64, 11, 5, 2, 2, 5, 5),   # thor.snd.conv2 with > 296 tiles: persistent im2col path
+    (8, 96, 96, 32, 32, 3, 3, 1, 1, 1, 1),     # thor.img.conv2, 576 tiles, odd k-block count (9) in 2-block stages
 ]
 
 
