@@ -119,6 +119,10 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_tf32(bn, 0, p.b_mn_major);
+    const uint64_t adesc0 = make_smem_desc(sA, 16u, 1024u);
+    const uint64_t bdesc0 = p.b_mn_major ? make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                         : make_smem_desc(sB, 16u, 1024u);
+    const int bstep = p.b_mn_major ? 64 : 2;  // 1024 B (8 k-rows, MN-major) or 32 B (8 columns, K-major) per MMA
     int st = 0, ph = 0, i = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
       const int acc = nacc == 2 ? (i & 1) : 0;
@@ -131,17 +135,16 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
         if (lane == 0) {
+          // descriptors differ only in their 14-bit start-address field (bytes >> 4): add offsets
+          // to a base descriptor instead of rebuilding both per MMA (the issuing thread is on the
+          // critical path: 4 MMAs of a 64-column k-block are only 128 tensor-pipe cycles)
           for (int sub = 0; sub < nsub; ++sub) {
-            const uint32_t a0 = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
-            const uint32_t b0 = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
+            const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA + (uint32_t)sub * kTileABytes) >> 4);
+            const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB + (uint32_t)sub * tileB_bytes) >> 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
-              const uint64_t bd = p.b_mn_major ? make_smem_desc(b0 + (uint32_t)j * 1024u, (uint32_t)p.mn_lbo,
-                                                                (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
-                                               : make_smem_desc(b0 + (uint32_t)j * 32u, 16u, 1024u);
-              umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((kb0 | sub | j) != 0));
-            }
+            for (int j = 0; j < 4; ++j)
+              umma_tf32(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc,
+                        (uint32_t)((kb0 | sub | j) != 0));
           }
           umma_commit(empty_bar(st));
           if (kb0 + kps >= num_kb) umma_commit(tfull_bar(acc));

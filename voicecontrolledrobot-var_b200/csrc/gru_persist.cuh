@@ -126,6 +126,9 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
     const int quarter = warp & 3;
     const int sub = warp >> 2;
     const uint32_t idesc = make_idesc_tf32(bn, 0, BWD ? 1 : 0);
+    const uint64_t adesc0 = make_smem_desc(sA, 16u, 1024u);
+    const uint64_t bdesc0 = BWD ? make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+                                : make_smem_desc(sB, 16u, 1024u);
     int mst = 0, mph = 0;  // MMA ring position (warp 4)
     constexpr int RB = 8;                         // rows per epilogue warp
     const int mrow0 = m0 + quarter * 32 + sub * RB;
@@ -237,17 +240,13 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
           mbar_wait(full_bar(mst), (uint32_t)mph);
           tc_fence_after();
           if (lane == 0) {
-            for (int sub = 0; sub < kps; ++sub) {
-              const uint32_t a0 = sA + (uint32_t)mst * stageA + (uint32_t)sub * kTileABytes;
-              const uint32_t b0 = sB + (uint32_t)mst * stageB + (uint32_t)sub * tileB_bytes;
+            for (int sub = 0; sub < kps; ++sub) {  // base descriptor + start-address offset (bytes >> 4)
+              const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)mst * stageA + (uint32_t)sub * kTileABytes) >> 4);
+              const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)mst * stageB + (uint32_t)sub * tileB_bytes) >> 4);
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const uint64_t ad = make_smem_desc(a0 + (uint32_t)jj * 32u, 16u, 1024u);
-                const uint64_t bd = BWD ? make_smem_desc(b0 + (uint32_t)jj * 1024u, (uint32_t)p.mn_lbo,
-                                                         (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
-                                        : make_smem_desc(b0 + (uint32_t)jj * 32u, 16u, 1024u);
-                umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb0 | sub | jj) != 0));
-              }
+              for (int jj = 0; jj < 4; ++jj)
+                umma_tf32(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * (BWD ? 64 : 2)), idesc,
+                          (uint32_t)((kb0 | sub | jj) != 0));
             }
             umma_commit(empty_bar(mst));
             if (kb0 + kps >= num_kb) umma_commit(tfull_bar);

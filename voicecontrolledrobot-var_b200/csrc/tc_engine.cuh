@@ -972,20 +972,19 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     } else {
       const uint32_t idesc = make_idesc_tf32(p.cout, 1, 1);
       const uint32_t lbo = (uint32_t)p.mn_lbo, sbo = (uint32_t)p.mn_sbo, lt = (uint32_t)p.mn_type;
+      const uint64_t adesc0 = make_smem_desc(sA, lbo, sbo, lt), bdesc0 = make_smem_desc(sB, lbo, sbo, lt);
       int st = 0, ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
         if (lane == 0) {
-          for (int sub = 0; sub < kps; ++sub) {
-            const uint32_t a0 = sA + (uint32_t)st * stageA + (uint32_t)sub * tileA_bytes;
-            const uint32_t b0 = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
+          for (int sub = 0; sub < kps; ++sub) {  // base descriptor + start-address offset (bytes >> 4)
+            const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA + (uint32_t)sub * tileA_bytes) >> 4);
+            const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB + (uint32_t)sub * tileB_bytes) >> 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 1024u, lbo, sbo, lt);
-              const uint64_t bd = make_smem_desc(b0 + (uint32_t)j * 1024u, lbo, sbo, lt);
-              umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((kb | sub | j) != 0));
-            }
+            for (int j = 0; j < 4; ++j)
+              umma_tf32(tmem_base, ad0 + (uint64_t)(j * 64), bd0 + (uint64_t)(j * 64), idesc,
+                        (uint32_t)((kb | sub | j) != 0));
           }
           umma_commit(empty_bar(st));
           if (kb == num_kb - 1) umma_commit(tfull_bar);
