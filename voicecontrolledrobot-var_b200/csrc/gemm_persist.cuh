@@ -79,6 +79,10 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
           w0 = (rem0 - p0 * g.Q) * p.step_w + p.base_w;
           h0 = p0 * p.step_h + p.base_h;
         }
+        // (tap, channel block) = divmod(k-block, blocks per tap), kept incrementally: this thread's
+        // instruction stream is on the critical path
+        const int period = GMODE == G_TMA_IM2COL ? p.cpb : (p.b_mn_major ? p.kb_per_rs : 1 << 30);
+        int tap = 0, cb = 0;
         for (int it0 = 0; it0 < num_kb; it0 += kps) {
           const int nsub = min(kps, num_kb - it0);
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
@@ -87,11 +91,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
             const int it = it0 + sub;
             const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
             const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
-            int tap = 0, c0 = it << 5;
-            if constexpr (GMODE == G_TMA_IM2COL) {
-              tap = it / p.cpb;
-              c0 = (it - tap * p.cpb) << 5;
-            }
+            const int c0 = GMODE == G_TMA_IM2COL ? (cb << 5) : (it << 5);
             if (lane == 0) {
               if constexpr (GMODE == G_TMA_IM2COL)
                 tma_load_im2col_4d(dstA, &tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
@@ -104,13 +104,14 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
                   tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it * 32,
                               p.boxbase[b] + ntile * p.box_rows);
             } else {
-              const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
-              const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
+              const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
+              const int k0 = cb << 5;
               for (int gidx = 0; gidx < (bn >> 5); ++gidx)
                 if (lane == (multi ? 1 + (gidx % 3) : 0))
                   tma_load_2d(dstB + (uint32_t)gidx * 4096u, &tmB, full_bar(st),
                               rs * p.cin_total + ntile * bn + gidx * 32, k0);
             }
+            if (++cb == period) { cb = 0; ++tap; }
           }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
