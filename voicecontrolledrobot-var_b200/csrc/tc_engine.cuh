@@ -918,7 +918,20 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       // the 6+ small boxes as the tensor core needs for the k-block.
       // (a warp with nothing to load stays out: an idle waiter could fall two phases behind)
       if (lane == 0 && (warp == 0 || warp < kgroups || warp < bgroups)) {
-        const int pq = p.P * p.Q;
+        // per-lane constants and an incrementally tracked base pixel (n, pp, qq): this thread's
+        // instruction stream is on the critical path, so no divisions inside the loop
+        const int gq = warp;
+        const int kbg = ktile * 4 + gq;
+        const int tap = p.a_tiled ? 0 : kbg / p.cpb;
+        const int c0 = p.a_tiled ? 0 : (kbg - tap * p.cpb) << 5;
+        int n = 0, pp = 0, qq = 0;
+        if (!p.a_tiled) {
+          const int pq = p.P * p.Q;
+          n = pix0 / pq;
+          const int rem = pix0 - n * pq;
+          pp = rem / p.Q;
+          qq = rem - pp * p.Q;
+        }
         int st = 0, ph = 0;
         for (int it = 0; it < num_kb; ++it) {
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
@@ -930,21 +943,19 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const int m = pix0 + (it * kps + sub) * 32;
             const uint32_t dA = sA + (uint32_t)st * stageA + (uint32_t)sub * tileA_bytes;
             const uint32_t dB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
-            const int gq = warp;
             if (gq < kgroups) {
               if (p.a_tiled) {
                 tma_load_2d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), ktile * 128 + gq * 32, m);
               } else {
-                const int n = m / pq;
-                const int rem = m - n * pq;
-                const int pp = rem / p.Q, qq = rem - pp * p.Q;
                 const int w0 = qq * p.step_w + p.base_w, h0 = pp * p.step_h + p.base_h;
-                const int kb = ktile * 4 + gq;
-                const int tap = kb / p.cpb;
-                const int c0 = (kb - tap * p.cpb) << 5;
                 tma_load_im2col_4d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), c0, w0, h0, n,
                                    p.tap_w[tap], p.tap_h[tap]);
               }
+            }
+            if (!p.a_tiled) {  // base pixel of the next 32-pixel block
+              qq += 32;
+              while (qq >= p.Q) { qq -= p.Q; ++pp; }
+              while (pp >= p.P) { pp -= p.P; ++n; }
             }
             for (int bg = warp; bg < bgroups; bg += 4)
               tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), (int)blockIdx.z * p.cout + bg * 32, m);
