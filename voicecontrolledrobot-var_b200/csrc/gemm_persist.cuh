@@ -125,6 +125,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
                                          : make_smem_desc(sB, 16u, 1024u);
     const int bstep = p.b_mn_major ? 64 : 2;  // 1024 B (8 k-rows, MN-major) or 32 B (8 columns, K-major) per MMA
     int st = 0, ph = 0, i = 0;
+    if (lane == 0)  // one thread runs the whole issue loop (no warp-wide spin / re-convergence per stage)
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
       const int acc = nacc == 2 ? (i & 1) : 0;
       const int use = nacc == 2 ? (i >> 1) : i;            // how often this accumulator was used
@@ -135,7 +136,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         const int nsub = min(kps, num_kb - kb0);
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           // descriptors differ only in their 14-bit start-address field (bytes >> 4): add offsets
           // to a base descriptor instead of rebuilding both per MMA (the issuing thread is on the
           // critical path: 4 MMAs of a 64-column k-block are only 128 tensor-pipe cycles)
@@ -150,10 +151,10 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
           umma_commit(empty_bar(st));
           if (kb0 + kps >= num_kb) umma_commit(tfull_bar(acc));
         }
-        __syncwarp();
         if (++st == stages) { st = 0; ph ^= 1; }
       }
     }
+    __syncwarp();
     tc_fence_before();
   } else {
     // ===================== epilogue warps 0-3 =====================

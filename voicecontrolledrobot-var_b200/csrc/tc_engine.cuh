@@ -339,15 +339,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
           w0 = (rem0 - p0 * g.Q) * p.step_w + p.base_w;
           h0 = p0 * p.step_h + p.base_h;
         }
+        // (tap, channel block) = divmod(k-block, blocks per tap), kept incrementally
+        const int period = GMODE == G_TMA_IM2COL ? p.cpb : (p.b_mn_major ? p.kb_per_rs : 1 << 30);
+        int tap = 0, cb = 0;
         for (int it = 0; it < num_kb; ++it) {
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
           const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
           const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
-          int tap = 0, c0 = it << 5;
-          if constexpr (GMODE == G_TMA_IM2COL) {
-            tap = it / p.cpb;
-            c0 = (it - tap * p.cpb) << 5;
-          }
+          const int c0 = GMODE == G_TMA_IM2COL ? (cb << 5) : (it << 5);
           if (warp == 0) {
             mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
             if constexpr (GMODE == G_TMA_IM2COL)
@@ -361,13 +360,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
                 tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st), it * 32,
                             p.boxbase[b] + ntile * p.box_rows);
           } else {
-            const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : it / p.kb_per_rs;
-            const int k0 = GMODE == G_TMA_IM2COL ? c0 : (it - rs * p.kb_per_rs) << 5;
+            const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
+            const int k0 = cb << 5;
             for (int gidx = 0; gidx < (bn >> 5); ++gidx)
               if (warp == (multi ? 1 + (gidx % 3) : 0))
                 tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st),
                             rs * p.cin_total + ntile * bn + gidx * 32, k0);
           }
+          if (++cb == period) { cb = 0; ++tap; }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
       }
@@ -985,10 +985,11 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const uint32_t lbo = (uint32_t)p.mn_lbo, sbo = (uint32_t)p.mn_sbo, lt = (uint32_t)p.mn_type;
       const uint64_t adesc0 = make_smem_desc(sA, lbo, sbo, lt), bdesc0 = make_smem_desc(sB, lbo, sbo, lt);
       int st = 0, ph = 0;
+      if (lane == 0)  // one thread runs the whole issue loop
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           for (int sub = 0; sub < kps; ++sub) {  // base descriptor + start-address offset (bytes >> 4)
             const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA + (uint32_t)sub * tileA_bytes) >> 4);
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB + (uint32_t)sub * tileB_bytes) >> 4);
@@ -1000,9 +1001,9 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           umma_commit(empty_bar(st));
           if (kb == num_kb - 1) umma_commit(tfull_bar);
         }
-        __syncwarp();
         if (++st == stages) { st = 0; ph ^= 1; }
       }
+      __syncwarp();
       tc_fence_before();
     }
   }
