@@ -5,6 +5,7 @@
 #include "cin3_conv.cuh"
 #include "gemm_persist.cuh"
 #include "gru_persist.cuh"
+#include "gru_ksplit.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -793,6 +794,41 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
   return launch_gru_persist<0>(tm, p, grid, st);
 }
 
+// K-split variant of the BPTT kernel (gru_ksplit.cuh): 2-CTA clusters, each CTA streams half of the
+// reduction dimension.  Returns VAR_ERR_UNSUPPORTED when the clusters cannot all be resident.
+static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, int nrt, cudaStream_t st) {
+  p.bn = 64; p.num_kb = (3 * p.Hd / 32) / 2; p.kps = 2; p.stages = 3;
+  if (p.num_kb % p.kps) return VAR_ERR_UNSUPPORTED;
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + 2 * gru_scr_bytes(1) + 32;
+  static bool configured = false;
+  if (!configured) {
+    VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_ksplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(2, p.Hd / 64, nrt * 2);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gru_bwd_ksplit_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    max_clusters = n;
+  }
+  if ((long long)max_clusters * 2 < (long long)grid.x * grid.y * grid.z) return VAR_ERR_UNSUPPORTED;
+  VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * nrt * 2, st));
+  void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
+  LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
+  VAR_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args));
+  return VAR_OK;
+}
+
 // BPTT steps T-1 .. 1 of both directions in one cooperative launch: dgh[T-1] and dhd[d][0] must hold
 // the cell backward of the last step (gru_cell_bwd).
 int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float* const gates[2],
@@ -815,6 +851,13 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
     if (rc) return rc;
     rc = get_tmap_2d(dgh[d], T * B, 3 * Hd, 3 * Hd, p.a_split ? 32 : 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
     if (rc) return rc;
+  }
+  if (env_int("VAR_GRU_KSPLIT", 1) && Hd % 64 == 0 && !p.a_split) {
+    prof_note("gru_ksplit_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
+    const int rc = launch_gru_bwd_ksplit(tm, p, (B + 127) / 128, st);
+    if (rc != VAR_ERR_UNSUPPORTED) return rc;
+    p.bn = 32; p.num_kb = 3 * Hd / 32;
+    p.stages = env_int("VAR_GRU_STAGES_BWD", 3); p.kps = env_int("VAR_GRU_KPS_BWD", 2);
   }
   dim3 grid((B + 127) / 128, Hd / p.bn, 2);
   p.arrivals = (int)grid.y;
