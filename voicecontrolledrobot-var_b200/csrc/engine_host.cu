@@ -809,23 +809,30 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[2];
+  // Cluster attribute only: the cooperative attribute on top of it makes the launch unprofilable
+  // (ncu aborts the application with LaunchFailed).  Co-residency -- needed for the spin waits --
+  // is checked against cudaOccupancyMaxActiveClusters instead; kernels of the other stream never
+  // wait on this one, so CTAs that start late only delay their peers.
+  cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeCooperative;
-  at[1].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = 2;
+  cfg.attrs = at; cfg.numAttrs = 1;
   static int max_clusters = -1;
   if (max_clusters < 0) {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, gru_bwd_ksplit_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     max_clusters = n;
   }
-  if ((long long)max_clusters * 2 < (long long)grid.x * grid.y * grid.z) return VAR_ERR_UNSUPPORTED;
+  static bool refused = false;  // a launch was rejected once (e.g. under a profiler that cannot replay it)
+  if (refused || (long long)max_clusters * 2 < (long long)grid.x * grid.y * grid.z) return VAR_ERR_UNSUPPORTED;
   VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * nrt * 2, st));
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
   LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
-  VAR_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args));
+  if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args) != cudaSuccess) {
+    (void)cudaGetLastError();  // not sticky: fall back to the one-CTA-per-tile kernel from now on
+    refused = true;
+    return VAR_ERR_UNSUPPORTED;
+  }
   return VAR_OK;
 }
 
