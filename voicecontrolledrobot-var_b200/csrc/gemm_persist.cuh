@@ -10,6 +10,10 @@
 //   warps 0-3   epilogue of tile i (tcgen05.ld -> bias / add / ReLU / mask / round -> HBM) while
 //               the producer and the tensor core already work on tile i+1
 // Barriers: full/empty per smem stage (ring shared by all tiles), tfull/tempty per accumulator.
+// A stage holds p.kps (1-2) k-blocks; the producer and the MMA issuer are single threads whose
+// instruction streams pace the CTA (4 MMAs of a 64-column k-block are 128 tensor-pipe cycles), so
+// they carry no divisions and no descriptor rebuilds in their loops.  Wide short-K tiles use a
+// coalescing epilogue (p.epi_coalesce): accumulator chunks transposed through a swizzled smem tile.
 #pragma once
 #include "tc_engine.cuh"
 

@@ -8,9 +8,12 @@
 // and its W_hh slice (B) through the tcgen05 pipeline, runs the GRU cell (or the fused BPTT
 // cell backward) in the epilogue and publishes its slice of h_{s+1}.  The only cross-CTA
 // dependency is "all hidden slices of my (row tile, direction) are written": a monotonic global
-// counter per group, release = __threadfence + atomicAdd by each epilogue warp, acquire =
-// ld.acquire spin by the A-operand producer followed by a proxy fence before the TMA reads.
+// counter per group, release = CTA barrier + __threadfence + ONE atomicAdd per CTA and step,
+// acquire = ld.acquire spin by the A-operand producer followed by a proxy fence before the TMA
+// reads.  A pipeline stage holds two k-blocks (fewer barrier round trips per byte).
 // Launched with cudaLaunchCooperativeKernel so all CTAs are co-resident (spin-waits are safe).
+// The backward pass normally runs as gru_bwd_ksplit_kernel (gru_ksplit.cuh); the BWD
+// instantiation here is its fallback when the 2-CTA clusters cannot all be resident.
 #pragma once
 #include "tc_engine.cuh"
 

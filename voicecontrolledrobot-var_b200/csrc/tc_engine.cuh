@@ -850,8 +850,9 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
 // TMA-fed weight gradient: same D tile / split as tc_wgrad_kernel, but both MN-major
 // operands arrive by TMA issued from one thread -- X^T groups by im2col-mode loads of
 // 32 pixels x 32 channels (or tiled loads when X is a plain matrix), dY groups by tiled
-// loads -- in the 32-byte-atom 128B swizzle the MN-major UMMA descriptors expect.
-// grid = (ceil(K/128), splits), block = 160.
+// loads -- in the 32-byte-atom 128B swizzle the MN-major UMMA descriptors expect.  Four threads
+// share the TMA issue; a pipeline stage holds p.kps 32-pixel blocks.
+// grid = (ceil(K/128), pixel splits, slabs of p.cout output channels), block = 160.
 // ---------------------------------------------------------------------------
 struct WgradTmaParams {
   int M, K, cout, kpad;
