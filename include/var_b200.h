@@ -64,6 +64,26 @@ int var_sampler_batch(uint32_t* d_state, int B, int task_num, const int32_t* d_i
                       int32_t* d_out_item, int32_t* d_out_gt, int32_t* d_out_sn, int32_t* d_out_rec,
                       int64_t* d_out_off, int32_t* d_out_len, void* stream);
 
+/* The same batch draw for the iTHOR configuration: VARDataset resolves ground truth / negative class
+ * through its task list (dataset.py:17-29, :37-53) and audioLoader.getAudioFromTask draws a location
+ * synonym, an object synonym (Envs/audioLoader.py:223-228) and then a clip of the resolved
+ * (location, object, action) list (genSoundFeatFromTask, Envs/audioLoader.py:203-209): three draws per
+ * sound.  d_n_loc_syn / d_n_obj_syn: [task_num] synonym counts of each task's location / object
+ * (config.synonym, Envs/ai2thor/env_config.py:35-42); d_nclips / d_clip_base:
+ * [task_num, max_loc_syn, max_obj_syn] clip count / first clip id of the resolved list.
+ * out_rec rows are (task, li * max_obj_syn + oi, clip) for the positive then the negative. */
+int var_sampler_batch_tasks(uint32_t* d_state, int B, int task_num, const int32_t* d_items,
+                            const int32_t* d_gt, const int32_t* d_stored_sn, const int32_t* d_n_loc_syn,
+                            const int32_t* d_n_obj_syn, const int32_t* d_nclips, const int32_t* d_clip_base,
+                            int max_loc_syn, int max_obj_syn, const int64_t* d_clip_off,
+                            const int32_t* d_clip_len, int32_t* d_scratch, int32_t* d_out_item,
+                            int32_t* d_out_gt, int32_t* d_out_sn, int32_t* d_out_rec, int64_t* d_out_off,
+                            int32_t* d_out_len, void* stream);
+/* Continue a HOST mt19937 stream on the device: words[624] + read position (624 = twist before the
+ * next draw), i.e. torch.get_rng_state() of the global CPU generator the reference's
+ * DataLoader / __getitem__ draw from (dataset.py:76, :157-162). */
+int var_sampler_set_state(uint32_t* d_state, const uint32_t* host_words, int pos, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Encoders.  A net object holds the layer plan of one VARPretextNet
  *   kind 0: models/pretext/arm_pretext_model.py:37-59   (Kuka)

@@ -41,6 +41,7 @@ def install_stubs():
     mod("gym.envs"); mod("gym.envs.registration", register=lambda **k: None)
     mod("matplotlib", use=lambda *a, **k: None); mod("matplotlib.pyplot")
     mod("python_speech_features", mfcc=None)
+    mod("ai2thor"); mod("ai2thor.controller", Controller=object); mod("ai2thor.platform", CloudRendering=object)
     sys.path.insert(0, REF)
 
 
@@ -171,6 +172,68 @@ def gold_sampler():
     print("sampler draws per epoch:", len(epochs[0][1]), len(epochs[1][1]))
 
 
+ITHOR_LIST_SIZES = {("none", "lights", "activate"): 7, ("none", "lights", "deactivate"): 3,
+                    ("none", "music", "activate"): 5, ("none", "music", "deactivate"): 11,
+                    ("none", "lamp", "activate"): 4, ("none", "lamp", "deactivate"): 6}
+
+
+def gold_sampler_ithor():
+    """The reference VARDataset under the REAL AI2ThorConfig + EnvConfig (Envs/ai2thor/config.py,
+    env_config.py), with the reference audioLoader's own getAudioFromTask / genSoundFeatFromTask
+    doing the draws; only get_mfcc is replaced (python_speech_features is absent) by a recorder that
+    identifies the chosen clip.  Also records the generator state at loader construction so the
+    `continue torch's global generator` path is pinned."""
+    import pickle
+    import tempfile
+    import torch.utils.data as D
+    from Envs.ai2thor.config import AI2ThorConfig
+    from Envs.ai2thor.env_config import EnvConfig
+    from Envs.audioLoader import audioLoader
+    from dataset import VARDataset
+    cfg = AI2ThorConfig()
+    cfg.get_env_config(EnvConfig)
+    assert cfg.taskNum == 4 and cfg.name == "AI2ThorConfig"
+    keys = list(ITHOR_LIST_SIZES)
+    rec = []
+
+    class RecAudio(audioLoader):
+        def get_mfcc(self, audioSamples, param, mfcc_from):
+            assert mfcc_from is None  # the iTHOR path never asks for torchaudio (audioLoader.py:203,234-236)
+            rec.append((int(audioSamples[0]), int(audioSamples[1])))
+            return np.zeros(cfg.sound_dim)
+
+    al = RecAudio(cfg)
+    al.fs = 16000
+    al.transcription = {}
+    for li, (loc, obj, act) in enumerate(keys):
+        n = ITHOR_LIST_SIZES[(loc, obj, act)]
+        al.words.setdefault(loc, {}).setdefault(obj, {})[act] = [np.array([li, j], np.int16) for j in range(n)]
+        al.transcription.setdefault(loc, {}).setdefault(obj, {})[act] = ["t"] * n
+    gts = synth.make_labels(77, 29)
+    items = [{"image": np.zeros((3, 2, 2), np.uint8), "ground_truth": int(g)} for g in gts]
+    with tempfile.NamedTemporaryFile(suffix=".pickle", delete=False) as f:
+        pickle.dump(items, f)
+        path = f.name
+    ds = VARDataset(path, cfg, audio=al)
+    torch.manual_seed(cfg.pretextEnvSeed)  # 977 (Envs/ai2thor/config.py:60; pretext.py:294)
+    torch.rand(37)  # the generator is NOT fresh when training starts (model init consumed it)
+    state0 = torch.get_rng_state().numpy().copy()
+    dl = D.DataLoader(ds, batch_size=6, shuffle=True, num_workers=0, drop_last=False)
+    out = {"gts": gts, "seed": cfg.pretextEnvSeed, "batch": 6, "rng_state": state0,
+           "list_keys": np.array(["/".join(k) for k in keys]),
+           "list_sizes": np.array([ITHOR_LIST_SIZES[k] for k in keys])}
+    for ep in range(2):
+        rec.clear()
+        gt_stream = []
+        for image, sp, sn, gt in dl:
+            gt_stream += gt.tolist()
+        out[f"ep{ep}_gt"] = np.array(gt_stream)
+        out[f"ep{ep}_draws"] = np.array(rec)
+    os.unlink(path)
+    np.savez_compressed(os.path.join(GOLD, "sampler_ithor.npz"), **out)
+    print("ithor sampler draws per epoch:", len(out["ep0_draws"]), len(out["ep1_draws"]))
+
+
 def gold_reward():
     from Envs.vec_env.vec_pretext_normalize import VecPretextNormalize
     from models.pretext.arm_pretext_model import VARPretextNet
@@ -267,6 +330,7 @@ if __name__ == "__main__":
         sys.exit(0)
     gold_mfcc()
     gold_sampler()
+    gold_sampler_ithor()
     gold_adam()
     gold_reward()
     gold_model(omodel.KUKA, 4, 7)

@@ -8,11 +8,16 @@ Bit-exact restatement of the integer sampling on the triplet path:
   Envs/audioLoader.py:174-176 (`rand_fn(0, len(...), size=())`);
 * the negative-class rule dataset.py:72-78 (collision -> "empty" class taskNum);
 * the per-item draw order of dataset.py:34-62 (`getImgSoundPair`);
-* DataLoader(shuffle=True, num_workers=0) batch order (RandomSampler).
+* DataLoader(shuffle=True, num_workers=0) batch order (RandomSampler);
+* the iTHOR variant: task list of dataset.py:17-29, `getAudioFromTask`
+  (Envs/audioLoader.py:223-237: location-synonym draw, object-synonym draw) and
+  `genSoundFeatFromTask` (Envs/audioLoader.py:203-209: clip draw) -- three draws per sound;
+* `from_torch_state`: continue torch's global CPU generator (torch.get_rng_state()).
 
 PINNED: oracle/make_golden.py drives the imported reference `VARDataset` /
-`DataLoader` with a recording audio stub under the same seeds and stores the
-index streams in tests/golden/sampler_*.npz.
+`DataLoader` with a recording audio stub (Kuka) and with the reference's own `audioLoader`
+methods under the real `AI2ThorConfig` + `EnvConfig` (iTHOR) under the same seeds and stores
+the index streams in tests/golden/sampler_*.npz.
 """
 import numpy as np
 
@@ -57,11 +62,28 @@ class MT19937:
         return y & 0xFFFFFFFF
 
 
+def torch_state_words(rng_state):
+    """torch.get_rng_state() bytes (the legacy THGeneratorState layout at::CPUGeneratorImpl serialises:
+    u64 the_initial_seed, i32 left, i32 seeded, u64 next, u64 state[624], normal-sample cache)
+    -> (words[624] uint32, pos) with pos = 624 when the next draw twists first."""
+    b = np.asarray(rng_state, dtype=np.uint8).tobytes()
+    left = int(np.frombuffer(b, dtype=np.int32, count=1, offset=8)[0])
+    nxt = int(np.frombuffer(b, dtype=np.uint64, count=1, offset=16)[0])
+    words = np.frombuffer(b, dtype=np.uint64, count=_N, offset=24).astype(np.uint32)
+    return words, (_N if left <= 1 else nxt)
+
+
 class TorchCPUGenerator:
     """at::CPUGeneratorImpl draws as used by the reference's sampling calls."""
 
     def __init__(self, seed):
         self.engine = MT19937(seed)
+
+    @classmethod
+    def from_torch_state(cls, rng_state):
+        g = cls(0)
+        g.engine.state, g.engine.pos = torch_state_words(rng_state)
+        return g
 
     def random(self):
         return self.engine.next_u32()
@@ -117,6 +139,50 @@ def sample_triplet_kuka(gen, gt, task_num, dataset_sizes, stored_sn_id=None):
     else:
         pos = draw_clip_kuka(gen, gt, task_num, dataset_sizes)
         neg = None if sn_id == task_num else draw_clip_kuka(gen, sn_id, task_num, dataset_sizes)
+    return sn_id, pos, neg
+
+
+def ithor_task_tables(all_tasks, synonym, obj_act, words):
+    """Flatten config.allTasks / config.synonym / soundSource['FSC_obj_act'] and the loaded
+    words[loc][obj][act] clip lists into the tables the device sampler indexes.
+    -> (n_loc[t], n_obj[t], lists[t][li][oi] = (fsc_loc, fsc_obj, fsc_act)) with the task order of
+    dataset.py:22-29 and the action resolved as Envs/audioLoader.py:230-232."""
+    n_loc, n_obj, lists = [], [], []
+    for loc in all_tasks:
+        for obj in all_tasks[loc]:
+            for act in all_tasks[loc][obj]:
+                ls, os_ = synonym[loc], synonym[obj]
+                n_loc.append(len(ls)); n_obj.append(len(os_))
+                row = []
+                for fl in ls:
+                    col = []
+                    for fo in os_:
+                        fa = sorted(set(obj_act[fo]).intersection(synonym[act]))
+                        assert len(fa) == 1, "the reference takes element [0] of a set: only one match is deterministic"
+                        assert fa[0] in words[fl][fo]
+                        col.append((fl, fo, fa[0]))
+                    row.append(col)
+                lists.append(row)
+    return n_loc, n_obj, lists
+
+
+def draw_clip_ithor(gen, task, n_loc, n_obj, sizes):
+    """getAudioFromTask + genSoundFeatFromTask: sizes[task][li][oi] = clips in the resolved list."""
+    li = gen.randint(0, n_loc[task])
+    oi = gen.randint(0, n_obj[task])
+    clip = gen.randint(0, sizes[task][li][oi])
+    return task, li, oi, clip
+
+
+def sample_triplet_ithor(gen, gt, task_num, n_loc, n_obj, sizes, stored_sn_id=None):
+    """dataset.py:64-89 + :34-62 for config.name == 'AI2ThorConfig'."""
+    sn_id = negative_class(gen, gt, task_num, stored_sn_id)
+    if gt == task_num:
+        pos = None
+        neg = draw_clip_ithor(gen, sn_id, n_loc, n_obj, sizes)
+    else:
+        pos = draw_clip_ithor(gen, gt, n_loc, n_obj, sizes)
+        neg = None if sn_id == task_num else draw_clip_ithor(gen, sn_id, n_loc, n_obj, sizes)
     return sn_id, pos, neg
 
 

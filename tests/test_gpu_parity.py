@@ -309,6 +309,85 @@ def test_sampler_large_batch_vs_oracle(vb):
                 assert sn_got[j] == sn and got[j].tolist() == exp, (ep, bi, j)
 
 
+def _ithor_words(sizes_by_key):
+    words = {}
+    for (loc, obj, act), n in sizes_by_key.items():
+        words.setdefault(loc, {}).setdefault(obj, {})[act] = [np.full(4 + 2 * j, j, np.int16) for j in range(n)]
+    return words
+
+
+def test_ithor_sampler_bit_exact_vs_reference_golden(vb, golden):
+    """dataset.py:17-53 + audioLoader.py:203-237 on the device (var_sampler_batch_tasks), continuing the
+    reference run's torch generator state; golden = the reference VARDataset under the real AI2ThorConfig."""
+    from importlib import import_module
+    from conftest import ithor_config
+    ds = import_module("voicecontrolledrobot-var_b200.dataset")
+    al = import_module("voicecontrolledrobot-var_b200.Envs.audioLoader")
+    g = golden("sampler_ithor")
+    keys = [tuple(k.split("/")) for k in g["list_keys"].tolist()]
+    cfg = ithor_config()
+    arena = al.TaskClipArena(_ithor_words(dict(zip(keys, g["list_sizes"].tolist()))), cfg, DEV)
+    assert arena.lists == keys
+    gts = g["gts"]
+    smp = ds.DeviceTripletSampler(task_num=4, dataset_sizes=None, gt=gts, stored_sn=None, seed=0, device=DEV,
+                                  clip_off=arena.clip_off, clip_len=arena.clip_len, task_tables=arena)
+    smp.adopt_torch_state(torch.from_numpy(g["rng_state"]))
+    base = np.cumsum([0] + g["list_sizes"].tolist())
+    for ep in range(2):
+        perm = smp.begin_epoch()
+        order, draws, lens = [], [], []
+        n, bs = len(gts), int(g["batch"])
+        for s in range(0, n, bs):
+            rec = smp.sample(perm[s:s + bs])
+            order += rec["gt"].cpu().tolist()
+            B = rec["gt"].numel()
+            ln = rec["len"].cpu().numpy()
+            for j, row in enumerate(rec["rec"].cpu().numpy()):
+                for part, l in ((row[:3], ln[j]), (row[3:], ln[B + j])):
+                    if part[0] >= 0:
+                        t, slot, clip = part.tolist()
+                        key = arena.resolved[(t, slot // arena.max_obj, slot % arena.max_obj)]
+                        draws.append([keys.index(key), clip])
+                        assert l == 4 + 2 * clip  # the arena offset / length of exactly that clip came back
+        assert order == g[f"ep{ep}_gt"].tolist()
+        assert draws == g[f"ep{ep}_draws"].tolist()
+
+
+def test_ithor_sampler_large_batch_vs_oracle(vb):
+    """B = 8192 crosses the 4096-item draw window of the three-draw variant; stored negative ids too."""
+    from importlib import import_module
+    from conftest import ITHOR_ALL_TASKS, ITHOR_OBJ_ACT, ITHOR_SYNONYM, ithor_config
+    ds = import_module("voicecontrolledrobot-var_b200.dataset")
+    al = import_module("voicecontrolledrobot-var_b200.Envs.audioLoader")
+    sizes = {("none", "lights", "activate"): 1000, ("none", "lights", "deactivate"): 37, ("none", "music", "activate"): 999,
+             ("none", "music", "deactivate"): 5, ("none", "lamp", "activate"): 64, ("none", "lamp", "deactivate"): 1}
+    words = _ithor_words(sizes)
+    cfg = ithor_config()
+    arena = al.TaskClipArena(words, cfg, DEV)
+    n_loc, n_obj, lists = osampler.ithor_task_tables(ITHOR_ALL_TASKS, ITHOR_SYNONYM, ITHOR_OBJ_ACT, words)
+    tsizes = [[[sizes[k] for k in col] for col in row] for row in lists]
+    n, B = 12000, 8192
+    gts = synth.make_labels(6, n)
+    st_all = np.random.default_rng(1).integers(0, 5, n)
+    st_all = np.where(gts == 4, st_all % 4, st_all)  # gt == sn == taskNum is not a record the reference can hold (tl[4])
+    for stored in (None, st_all):
+        smp = ds.DeviceTripletSampler(task_num=4, dataset_sizes=None, gt=gts, stored_sn=stored, seed=349, device=DEV,
+                                      clip_off=arena.clip_off, clip_len=arena.clip_len, task_tables=arena)
+        gen = osampler.TorchCPUGenerator(349)
+        perm = smp.begin_epoch()
+        batches = osampler.epoch_batches(gen, n, B)
+        assert perm.cpu().tolist() == [i for b in batches for i in b]
+        for bi, batch in enumerate(batches):
+            rec = smp.sample(perm[bi * B: bi * B + len(batch)])
+            got, sn_got = rec["rec"].cpu().numpy(), rec["sn"].cpu().numpy()
+            for j, idx in enumerate(batch):
+                gt = int(gts[idx])
+                st = None if stored is None else int(stored[idx])
+                sn, pos, neg = osampler.sample_triplet_ithor(gen, gt, 4, n_loc, n_obj, tsizes, st)
+                flat = lambda d: [d[0], d[1] * arena.max_obj + d[2], d[3]] if d else [-1, -1, -1]
+                assert sn_got[j] == sn and got[j].tolist() == flat(pos) + flat(neg), (bi, j)
+
+
 def test_adam_matches_torch_golden(vb, golden):
     g = golden("adam")
     n = 260  # padded to a multiple of 4

@@ -223,11 +223,13 @@ def test_reward_wrapper_device_path_matches_reference_golden(vb, golden):
     assert abs(float(w.ret_rms.mean) - float(g["ret_mean"])) < 1e-2 * max(1.0, abs(float(g["ret_mean"])))
 
 
-def _write_dataset(root, cfg, n_items=48, clips_per_class=5):
+def _write_dataset(root, cfg, n_items=48, clips_per_class=5, media_only_records=False):
     from scipy.io import wavfile
     words = ["up", "down", "left", "right"]
     media = os.path.join(root, "commonMedia")
     for c, wd in enumerate(words):
+        if media_only_records:
+            break
         d = os.path.join(media, "GoogleCommand", "train", wd)
         os.makedirs(d)
         for i, clip in enumerate(synth.make_clips(100 + c, clips_per_class, 16000)):
@@ -240,9 +242,10 @@ def _write_dataset(root, cfg, n_items=48, clips_per_class=5):
         items = [{"image": imgs[i], "ground_truth": int(gts[i])} for i in range(f, n_items, 2)]
         with open(os.path.join(data, f"data_{f}.pickle"), "wb") as fh:
             pickle.dump(items, fh)
-    cfg.commonMediaPath = media
-    cfg.soundSource = {"dataset": ["GoogleCommand"], "train_test": "train", "items": {"GoogleCommand": words},
-                       "size": {"GoogleCommand": [1000] * 4}, "max_sound_dur": {"GoogleCommand": 3.0}}
+    if not media_only_records:
+        cfg.commonMediaPath = media
+        cfg.soundSource = {"dataset": ["GoogleCommand"], "train_test": "train", "items": {"GoogleCommand": words},
+                           "size": {"GoogleCommand": [1000] * 4}, "max_sound_dur": {"GoogleCommand": 3.0}}
     cfg.pretextDataDir = [os.path.join(root, "data")]
     cfg.pretextDataFileLoadNum = ["all"]
     cfg.pretextModelSaveDir = os.path.join(root, "model")
@@ -257,33 +260,90 @@ def _write_dataset(root, cfg, n_items=48, clips_per_class=5):
     return gts
 
 
+ITHOR_CLIPS = {("none", "lights", "activate"): 4, ("none", "lights", "deactivate"): 3, ("none", "music", "activate"): 5,
+               ("none", "music", "deactivate"): 2, ("none", "lamp", "activate"): 3, ("none", "lamp", "deactivate"): 4}
+
+
+def _write_dataset_ithor(root, cfg, n_items=48):
+    """Fluent-Speech-Commands layout read by loadFSCData_ai2thor (Envs/audioLoader.py:61-98): a csv with
+    path / transcription / action / object / location columns + the wavs it names."""
+    import pandas as pd
+    from scipy.io import wavfile
+    media = os.path.join(root, "commonMedia")
+    os.makedirs(os.path.join(media, "FSC", "data"))
+    os.makedirs(os.path.join(media, "FSC", "wavs"))
+    rows = []
+    for li, ((loc, obj, act), n) in enumerate(ITHOR_CLIPS.items()):
+        for i, clip in enumerate(synth.make_clips(200 + li, n, (12000, 30000))):
+            rel = os.path.join("wavs", f"{obj}_{act}_{i}.wav")
+            wavfile.write(os.path.join(media, "FSC", rel), 16000, clip)
+            rows.append({"path": rel, "transcription": f"{act} the {obj}", "action": act, "object": obj, "location": loc})
+    rows.append({"path": "wavs/none.wav", "transcription": "x", "action": "bring", "object": "shoes", "location": "none"})
+    pd.DataFrame(rows).to_csv(os.path.join(media, "FSC", "data", "train_data.csv"))
+    gts = _write_dataset(root, cfg, n_items, media_only_records=True)
+    cfg.commonMediaPath = media
+    cfg.pretextEnvSeed = 977
+    return gts
+
+
 @pytest.mark.gpu
-def test_trainer_end_to_end(vb, tmp_path):
+@pytest.mark.parametrize("kind", ["kuka", "ithor"])
+def test_trainer_end_to_end(vb, tmp_path, kind):
     """VAR_Pretext(config).run(): wavs + pickled records on disk -> device sampler -> MFCC -> fused
-    steps -> legacy checkpoints + progress.csv, and the loader's first epoch == the oracle's stream."""
+    steps -> legacy checkpoints + progress.csv, and the loader's first epoch == the oracle's stream.
+    iTHOR: config.name == 'AI2ThorConfig' (task list, synonym draws, python_speech_features-flavoured
+    MFCC: dataset.py:17-53, audioLoader.py:203-237)."""
+    from conftest import ITHOR_ALL_TASKS, ITHOR_OBJ_ACT, ITHOR_SYNONYM, ithor_config
+    from oracle import mfcc as omfcc
     from oracle import sampler as osampler
-    cfg = kuka_cfg()
     ds = import_module(f"{PKG}.dataset")
+    if kind == "kuka":
+        cfg = kuka_cfg()
+        cfg.pretextModel = import_module(f"{PKG}.models.pretext.arm_pretext_model").VARPretextNet
+        gts = _write_dataset(str(tmp_path), cfg)
+        F = 100
+    else:
+        cfg = ithor_config()
+        cfg.pretextModel = import_module(f"{PKG}.models.pretext.ai2thor_pretext_model").VARPretextNet
+        gts = _write_dataset_ithor(str(tmp_path), cfg)
+        F = 600
     cfg.pretextDataset = ds.VARDataset
-    cfg.pretextModel = import_module(f"{PKG}.models.pretext.arm_pretext_model").VARPretextNet
-    gts = _write_dataset(str(tmp_path), cfg)
     trainer = import_module(f"{PKG}.VAR.pretext_VAR").VAR_Pretext(cfg)
-    # loader contract: reference tuple shapes / dtypes, index stream == oracle under the same seed
+    # loader contract: reference tuple shapes / dtypes, index stream == oracle continuing torch's generator
     torch.manual_seed(cfg.pretextEnvSeed)
+    torch.rand(11)  # the global generator is not fresh when the loader is built
+    ogen = osampler.TorchCPUGenerator.from_torch_state(torch.get_rng_state().numpy())
     gen_loader, final = ds.loadEnvData(cfg.pretextDataDir, cfg, 16, True, 4, False, cfg.pretextDataFileLoadNum,
                                        dtype=ds.VARDataset)
     assert len(final) == 48 and len(gen_loader) == 3
     record_gt = [int(p["ground_truth"]) for d in final.datasets for p in d.ground_truth_pair]
-    ogen = osampler.TorchCPUGenerator(cfg.pretextEnvSeed)
     batches = osampler.epoch_batches(ogen, 48, 16)
+    if kind == "ithor":
+        words = gen_loader.audio.words
+        assert {(l, o, a): len(words[l][o][a]) for l in words for o in words[l] for a in words[l][o]} == ITHOR_CLIPS
+        n_loc, n_obj, lists = osampler.ithor_task_tables(ITHOR_ALL_TASKS, ITHOR_SYNONYM, ITHOR_OBJ_ACT, words)
+        tsizes = [[[ITHOR_CLIPS[k] for k in col] for col in row] for row in lists]
+    checked = 0
     for (image, sp, sn, gt), batch in zip(gen_loader, batches):
         assert image.shape == (16, 3, 96, 96) and image.dtype == torch.float32 and float(image.max()) <= 1.0
-        assert sp.shape == (16, 1, 100, 40) and sn.shape == (16, 1, 100, 40) and gt.dtype == torch.int64
+        assert sp.shape == (16, 1, F, 40) and sn.shape == (16, 1, F, 40) and gt.dtype == torch.int64
         assert gt.cpu().tolist() == [record_gt[i] for i in batch]
         for j, i in enumerate(batch):
-            sn_id, pos, neg = osampler.sample_triplet_kuka(ogen, record_gt[i], 4, {k: [5] for k in range(4)})
+            if kind == "kuka":
+                sn_id, pos, neg = osampler.sample_triplet_kuka(ogen, record_gt[i], 4, {k: [5] for k in range(4)})
+            else:
+                sn_id, pos, neg = osampler.sample_triplet_ithor(ogen, record_gt[i], 4, n_loc, n_obj, tsizes)
             assert (float(sp[j].abs().max()) == 0.0) == (pos is None)
             assert (float(sn[j].abs().max()) == 0.0) == (neg is None)
+            if kind == "ithor" and pos is not None and checked < 4:
+                # the features are those of exactly the drawn clip, in the python_speech_features flavour
+                t, li, oi, clip = pos
+                l, o, a = lists[t][li][oi]
+                ref = omfcc.process_sound_feat(omfcc.mfcc_psf(words[l][o][a][clip]), (1, 600, 40))[0]
+                got = sp[j, 0].cpu().numpy()
+                scale = np.maximum(np.abs(ref).max(axis=-1, keepdims=True), 1.0)
+                assert (np.abs(got - ref) <= 1e-4 * np.abs(ref) + 1e-4 * scale).all()
+                checked += 1
     losses = trainer.run() or None
     files = sorted(os.listdir(cfg.pretextModelSaveDir))
     assert "progress.csv" in files and "1.pt" in files and "2.pt" in files
@@ -291,7 +351,7 @@ def test_trainer_end_to_end(vb, tmp_path):
     prog = pd.read_csv(os.path.join(cfg.pretextModelSaveDir, "progress.csv"))
     assert len(prog) == 3 and np.isfinite(prog["avg_loss"]).all() and prog["avg_loss"].iloc[-1] < prog["avg_loss"].iloc[0]
     sd = torch.load(os.path.join(cfg.pretextModelSaveDir, "2.pt"))
-    assert list(sd.keys()) == list(omodel.param_shapes("kuka").keys())
+    assert list(sd.keys()) == list(omodel.param_shapes(kind).keys())
     cfg.plotNumBatch = 1
     fp = trainer.project2representation_with_ground_truth(gen_loader)   # pretext.py:147-203
     assert fp['img'].shape == (32, 4) and fp['sound'].shape == (32, 4)

@@ -95,3 +95,49 @@ def test_reward_oracle_matches_reference(golden):
         assert np.allclose(orig, g[f"orig{t-1}"], atol=1e-6)
         assert np.allclose(out, g[f"rew{t-1}"], atol=1e-6)
     assert abs(norm.rms.var - float(g["ret_var"])) < 1e-9
+
+
+from conftest import ITHOR_ALL_TASKS, ITHOR_OBJ_ACT, ITHOR_SYNONYM  # noqa: E402
+
+
+def ithor_golden_tables(g):
+    keys = [tuple(k.split("/")) for k in g["list_keys"].tolist()]
+    sizes = dict(zip(keys, g["list_sizes"].tolist()))
+    words = {}
+    for (loc, obj, act), n in sizes.items():
+        words.setdefault(loc, {}).setdefault(obj, {})[act] = [None] * n
+    n_loc, n_obj, lists = osampler.ithor_task_tables(ITHOR_ALL_TASKS, ITHOR_SYNONYM, ITHOR_OBJ_ACT, words)
+    tsizes = [[[sizes[k] for k in col] for col in row] for row in lists]
+    return keys, n_loc, n_obj, lists, tsizes
+
+
+def test_ithor_sampler_oracle_matches_reference(golden):
+    """dataset.py:17-53 + audioLoader.py:203-237 driven through the REAL AI2ThorConfig/EnvConfig by
+    oracle/make_golden.py::gold_sampler_ithor; the stream continues a non-fresh torch generator."""
+    g = golden("sampler_ithor")
+    keys, n_loc, n_obj, lists, tsizes = ithor_golden_tables(g)
+    gts = g["gts"].tolist()
+    gen = osampler.TorchCPUGenerator.from_torch_state(g["rng_state"])
+    for ep in range(2):
+        gt_stream, draws = [], []
+        for batch in osampler.epoch_batches(gen, len(gts), int(g["batch"])):
+            for idx in batch:
+                gt_stream.append(gts[idx])
+                _, pos, neg = osampler.sample_triplet_ithor(gen, gts[idx], 4, n_loc, n_obj, tsizes)
+                for d in (pos, neg):
+                    if d is not None:
+                        t, li, oi, clip = d
+                        draws.append([keys.index(lists[t][li][oi]), clip])
+        assert gt_stream == g[f"ep{ep}_gt"].tolist()
+        assert draws == g[f"ep{ep}_draws"].tolist()
+
+
+def test_torch_state_words_continue_global_generator():
+    torch.manual_seed(5)
+    torch.rand(1000)  # crosses a twist boundary
+    gen = osampler.TorchCPUGenerator.from_torch_state(torch.get_rng_state().numpy())
+    want = [int(torch.randint(0, 1000003, size=())) for _ in range(700)]
+    assert [gen.randint(0, 1000003) for _ in range(700)] == want
+    torch.manual_seed(6)  # fresh seed: left_ == 1, twist before the first draw
+    gen = osampler.TorchCPUGenerator.from_torch_state(torch.get_rng_state().numpy())
+    assert gen.randint(0, 97) == int(torch.randint(0, 97, size=()))

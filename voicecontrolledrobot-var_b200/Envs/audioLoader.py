@@ -70,18 +70,63 @@ class ClipArena:
         self.task_num = task_num
         self.dataset_names = [list(words[i].keys()) for i in range(task_num)]
         self.dataset_sizes = [[len(words[i][k]) for k in words[i]] for i in range(task_num)]
-        offs, lens, parts, cur = [], [], [], 0
-        for i in range(task_num):
-            for k in words[i]:
-                for c in words[i][k]:
-                    c = np.ascontiguousarray(c, dtype=np.int16)
-                    offs.append(cur); lens.append(len(c)); parts.append(c)
-                    if len(c) & 1:
-                        parts.append(np.zeros(1, np.int16))
-                    cur += len(c) + (len(c) & 1)
-        self.wav = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(2, np.int16)).to(device)
-        self.clip_off = torch.tensor(offs, dtype=torch.int64, device=device)
-        self.clip_len = torch.tensor(lens, dtype=torch.int32, device=device)
+        self.wav, self.clip_off, self.clip_len = _pack_clips(
+            [words[i][k] for i in range(task_num) for k in words[i]], device)
+
+
+def _pack_clips(lists, device):
+    """Concatenate int16 clips (4-byte aligned) -> (arena, offsets, lengths) on the device."""
+    offs, lens, parts, cur = [], [], [], 0
+    for clips in lists:
+        for c in clips:
+            c = np.ascontiguousarray(c, dtype=np.int16)
+            offs.append(cur); lens.append(len(c)); parts.append(c)
+            if len(c) & 1:
+                parts.append(np.zeros(1, np.int16))
+            cur += len(c) + (len(c) & 1)
+    wav = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(2, np.int16)).to(device)
+    return wav, torch.tensor(offs, dtype=torch.int64, device=device), torch.tensor(lens, dtype=torch.int32, device=device)
+
+
+class TaskClipArena:
+    """iTHOR counterpart of ClipArena: the `words[loc][obj][act]` lists of loadFSCData_ai2thor
+    (Envs/audioLoader.py:61-98) in one int16 device buffer, plus the per-task tables of the two synonym
+    draws of getAudioFromTask (Envs/audioLoader.py:223-232) for the device sampler.  Task order is the
+    task list of dataset.py:22-29."""
+
+    def __init__(self, words, config, device):
+        syn, obj_act = config.synonym, config.soundSource['FSC_obj_act']
+        self.lists = [(loc, obj, act) for loc in words for obj in words[loc] for act in words[loc][obj]]
+        base, cur = {}, 0
+        for k in self.lists:
+            base[k] = cur
+            cur += len(words[k[0]][k[1]][k[2]])
+        self.tasks = [(loc, obj, act) for loc in config.allTasks for obj in config.allTasks[loc]
+                      for act in config.allTasks[loc][obj]]
+        self.task_num = len(self.tasks)
+        self.n_loc = [len(syn[t[0]]) for t in self.tasks]
+        self.n_obj = [len(syn[t[1]]) for t in self.tasks]
+        self.max_loc, self.max_obj = max(self.n_loc), max(self.n_obj)
+        self.nclips = np.zeros((self.task_num, self.max_loc, self.max_obj), np.int32)
+        self.clip_base = np.zeros_like(self.nclips)
+        self.resolved = {}
+        for t, (loc, obj, act) in enumerate(self.tasks):
+            for li, fl in enumerate(syn[loc]):
+                for oi, fo in enumerate(syn[obj]):
+                    acts = set(obj_act[fo]).intersection(syn[act])
+                    if len(acts) != 1:
+                        # the reference takes list(set)[0] (audioLoader.py:232): with several matches the
+                        # choice depends on the process' string-hash seed, so there is nothing to reproduce
+                        raise NotImplementedError(f"task {(loc, obj, act)}: action synonyms {sorted(acts)} are ambiguous")
+                    key = (fl, fo, acts.pop())
+                    n = len(words[key[0]][key[1]][key[2]])
+                    if n < 1:
+                        raise ValueError(f"no clips loaded for {key}")
+                    self.nclips[t, li, oi], self.clip_base[t, li, oi] = n, base[key]
+                    self.resolved[(t, li, oi)] = key
+        self.n_clips = cur
+        self.wav, self.clip_off, self.clip_len = _pack_clips([words[k[0]][k[1]][k[2]] for k in self.lists], device)
+        self.dataset_names = [[config.soundSource['dataset']]]
 
 
 class audioLoader(object):
@@ -264,6 +309,9 @@ class audioLoader(object):
 
     # ------------------------------------------------------------------ device residency
     def build_arena(self, device=None):
-        """Upload every clip of the pybullet-style `words[intent][dataset]` table once."""
+        """Upload every loaded clip once: the pybullet `words[intent][dataset]` table or the iTHOR
+        `words[loc][obj][act]` table."""
         device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        if self.env_type == 'ai2thor':
+            return TaskClipArena(self.words, self.config, device)
         return ClipArena(self.words, self.config.taskNum, device)

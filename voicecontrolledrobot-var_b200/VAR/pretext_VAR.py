@@ -45,13 +45,21 @@ class VAR_Pretext(Pretext):
                 for image, sp, sn, _ in data_generator:
                     b = image.shape[0]
                     lo, hi = (b * rank) // world, (b * (rank + 1)) // world
+                    if hi == lo:
+                        yield None, None, b
+                        continue
                     F = cfg.sound_dim[1]
                     snd = torch.cat([sp[lo:hi].reshape(-1, F, 40), sn[lo:hi].reshape(-1, F, 40)]).float()
                     yield (image[lo:hi].to(self.device).contiguous(), snd.to(self.device).contiguous(), b)
             batches = host_batches()
         for img, snd, global_b in batches:
             eng.zero_grad()
-            loss = eng.triplet_step(img, snd, margin=cfg.tripletMargin, loss_denominator=global_b)
+            if img is None or img.shape[0] == 0:
+                # ragged tail batch smaller than the world size: this rank has no triplet, but it must
+                # still take part in both collectives and in the (identical) Adam step
+                loss = torch.zeros((), dtype=torch.float32, device=self.device)
+            else:
+                loss = eng.triplet_step(img, snd, margin=cfg.tripletMargin, loss_denominator=global_b)
             if world > 1:
                 dist.all_reduce(eng.grads)
                 dist.all_reduce(loss)
@@ -69,6 +77,7 @@ class VAR_Pretext(Pretext):
         os.makedirs(cfg.pretextModelSaveDir, exist_ok=True)
         self.pretextModel.train()
         eng = self.pretextModel._get_engine(self.device)
+        eng.reset_optimizer()  # the reference builds a fresh optim.Adam per call (VAR/pretext_VAR.py:33)
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
         loss_list = []

@@ -38,6 +38,9 @@ PROTOTYPES = {
     "var_sampler_seed": (_i, [_p, C.c_uint64, _p]),
     "var_sampler_epoch": (_i, [_p, _i, _p, _p]),
     "var_sampler_batch": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "var_sampler_batch_tasks": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
+                                     _p, _p]),
+    "var_sampler_set_state": (_i, [_p, _p, _i, _p]),
     "var_net_create": (_i, [_i, _i, _i, C.POINTER(_p)]),
     "var_net_destroy": (_i, [_p]),
     "var_net_param_floats": (_i64, [_p]),

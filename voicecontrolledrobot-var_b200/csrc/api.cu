@@ -78,6 +78,30 @@ int var_sampler_batch(uint32_t* state, int B, int task_num, const int32_t* items
   return sampler_batch(a, ST(stream));
 }
 
+int var_sampler_batch_tasks(uint32_t* state, int B, int task_num, const int32_t* items, const int32_t* gt,
+                            const int32_t* stored_sn, const int32_t* n_loc_syn, const int32_t* n_obj_syn,
+                            const int32_t* nclips, const int32_t* clip_base, int max_loc_syn, int max_obj_syn,
+                            const int64_t* clip_off, const int32_t* clip_len, int32_t* scratch,
+                            int32_t* out_item, int32_t* out_gt, int32_t* out_sn, int32_t* out_rec,
+                            int64_t* out_off, int32_t* out_len, void* stream) {
+  if (!state || !gt || !n_loc_syn || !n_obj_syn || !nclips || !clip_base || !clip_off || !clip_len || !scratch ||
+      !out_item || !out_gt || !out_sn || !out_rec || !out_off || !out_len || max_loc_syn <= 0 || max_obj_syn <= 0)
+    return VAR_ERR_ARG;
+  SamplerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.state = state; a.B = B; a.task_num = task_num; a.items = items; a.gt = gt;
+  a.stored_sn = stored_sn; a.nds = n_loc_syn; a.nds2 = n_obj_syn; a.nclips = nclips; a.clip_base = clip_base;
+  a.max_ds = max_loc_syn * max_obj_syn; a.max_ds2 = max_obj_syn;
+  a.clip_off = reinterpret_cast<const long long*>(clip_off); a.clip_len = clip_len;
+  a.scratch_off = scratch; a.out_item = out_item; a.out_gt = out_gt; a.out_sn = out_sn;
+  a.out_rec = out_rec; a.out_off = reinterpret_cast<long long*>(out_off); a.out_len = out_len;
+  return sampler_batch(a, ST(stream));
+}
+int var_sampler_set_state(uint32_t* state, const uint32_t* host_words, int pos, void* stream) {
+  if (!state || !host_words || pos < 0 || pos > 624) return VAR_ERR_ARG;
+  return sampler_set_state(state, host_words, pos, ST(stream));
+}
+
 int var_adam_step(float* p, const float* g, float* m, float* v, float* p_mma, int64_t n, float lr,
                   float beta1, float beta2, float eps, float wd, int64_t step, float grad_scale,
                   void* stream) {

@@ -133,11 +133,15 @@ __global__ void sampler_epoch_kernel(uint32_t* state, int n, int* perm) {
   for (int base = 0; base < n - 1; base += MT_N) {
     const int cnt = min(MT_N, n - 1 - base);
     ppos = mt_fill(s, ppos, buf, cnt);
+    // the variable-divisor modulo of every swap is independent of the swaps: all threads reduce
+    // their draws first, the single dependent thread then only moves data
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) buf[i] = buf[i] % (uint32_t)(n - (base + i));
+    __syncthreads();
     if (threadIdx.x == 0) {
       if (in_smem) {
         for (int i = 0; i < cnt; ++i) {
           const int ii = base + i;
-          const int z = (int)(buf[i] % (uint32_t)(n - ii));
+          const int z = (int)buf[i];
           const uint16_t t = s_perm[ii];
           s_perm[ii] = s_perm[z + ii];
           s_perm[z + ii] = t;
@@ -145,7 +149,7 @@ __global__ void sampler_epoch_kernel(uint32_t* state, int n, int* perm) {
       } else {
         for (int i = 0; i < cnt; ++i) {
           const int ii = base + i;
-          const int z = (int)(buf[i] % (uint32_t)(n - ii));
+          const int z = (int)buf[i];
           const int t = perm[ii];
           perm[ii] = perm[z + ii];
           perm[z + ii] = t;
@@ -159,14 +163,20 @@ __global__ void sampler_epoch_kernel(uint32_t* state, int n, int* perm) {
 
 // One batch of triplets.  item i = items[i] (index into gt / stored_sn).
 // Draw order per item (dataset.py:64-89, :34-62; audioLoader.py:171-177):
-//   [sn draw unless stored]  then  positive (ds, clip) unless gt == taskNum,
-//   then negative (ds, clip) unless sn == taskNum.
+//   [sn draw unless stored]  then  positive sound unless gt == taskNum,
+//   then negative sound unless sn == taskNum.
+// A sound costs dps draws: 2 for the pybullet tables (dataset, clip; audioLoader.py:174-176) and
+// 3 for the iTHOR task tables (location synonym, object synonym, clip; audioLoader.py:223-237,
+// :208-209), where nds / nds2 hold the two synonym counts of a task and the clip list of the
+// resolved (location, object, action) sits at [task * max_ds + li * max_ds2 + oi].
 __global__ void sampler_batch_kernel(SamplerArgs a) {
   extern __shared__ uint32_t sm[];
   uint32_t* s = sm;            // [624]
-  uint32_t* draws = sm + MT_N; // [5 * chunk]
+  uint32_t* draws = sm + MT_N; // [(1 + 2 dps) * chunk]
   __shared__ int s_off_next;
   const int T = a.task_num;
+  const int dps = a.nds2 ? 3 : 2;
+  const int dpi = 1 + 2 * dps;  // most draws one item can consume
   for (int i = threadIdx.x; i < MT_N; i += blockDim.x) s[i] = a.state[i];
   int pos = (int)a.state[MT_N];  // uniform across the CTA
   __syncthreads();
@@ -174,10 +184,10 @@ __global__ void sampler_batch_kernel(SamplerArgs a) {
     const int nb = min(a.chunk, a.B - c0);
     // speculatively materialise the maximum this chunk can consume, from a scratch copy
     // of the state (the authoritative state is advanced by the consumed count below)
-    uint32_t* s2 = draws + 5 * a.chunk;  // [624] scratch state
+    uint32_t* s2 = draws + dpi * a.chunk;  // [624] scratch state
     for (int i = threadIdx.x; i < MT_N; i += blockDim.x) s2[i] = s[i];
     __syncthreads();
-    mt_fill(s2, pos, draws, 5 * nb);
+    mt_fill(s2, pos, draws, dpi * nb);
     // stage the chunk's labels in shared memory so the chain below never waits on HBM
     int16_t* s_lab = reinterpret_cast<int16_t*>(s2 + MT_N);  // [chunk] gt | (stored sn + 1) << 8
     for (int i = threadIdx.x; i < nb; i += blockDim.x) {
@@ -189,7 +199,7 @@ __global__ void sampler_batch_kernel(SamplerArgs a) {
     // sequential chain: where does each item's draw window start?  Everything the loop touches
     // is in shared memory and the modulo is a multiply-high (T is tiny), so one iteration is a
     // dependent LDS + ~10 ALU ops (~25 ns) instead of a global store and a 32-bit division.
-    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_lab + a.chunk);  // [chunk], offsets < 5*8192
+    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_lab + a.chunk);  // [chunk], offsets < dpi*chunk <= 40960
     if (threadIdx.x == 0) {
       const uint32_t Tm = (uint32_t)((0x100000000ull + (uint32_t)T - 1) / (uint32_t)T);
       int off = 0;
@@ -207,8 +217,8 @@ __global__ void sampler_batch_kernel(SamplerArgs a) {
           sn = r == gt ? T : r;
           used = 1;
         }
-        if (gt == T) used += 2;                      // negative only
-        else used += 2 + (sn == T ? 0 : 2);
+        if (gt == T) used += dps;                    // negative only
+        else used += dps + (sn == T ? 0 : dps);
         off += used;
       }
       s_off_next = off;
@@ -231,7 +241,8 @@ __global__ void sampler_batch_kernel(SamplerArgs a) {
       auto draw_clip = [&](int intent, int* r, long long* o, int* l) {
         if (intent > T - 1) intent = T - 1;
         const int nds = a.nds[intent];
-        const int ds = (int)(draws[off++] % (uint32_t)nds);
+        int ds = (int)(draws[off++] % (uint32_t)nds);
+        if (a.nds2) ds = ds * a.max_ds2 + (int)(draws[off++] % (uint32_t)a.nds2[intent]);
         const int cnt = a.nclips[intent * a.max_ds + ds];
         const int clip = (int)(draws[off++] % (uint32_t)cnt);
         const int cid = a.clip_base[intent * a.max_ds + ds] + clip;
@@ -270,6 +281,16 @@ int sampler_seed(uint32_t* state, unsigned long long seed, cudaStream_t st) {
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
+// Adopt a host generator state (torch.get_rng_state(): 624 words + read position) so the device
+// stream continues exactly where torch's global CPU generator stands.
+int sampler_set_state(uint32_t* state, const uint32_t* host_words, int pos, cudaStream_t st) {
+  uint32_t tmp[kSamplerStateWords];
+  for (int i = 0; i < MT_N; ++i) tmp[i] = host_words[i];
+  tmp[MT_N] = (uint32_t)pos;
+  // pageable source: the runtime stages the 2.5 KB before returning, so the stack buffer may die
+  VAR_CUDA_CHECK(cudaMemcpyAsync(state, tmp, sizeof(tmp), cudaMemcpyHostToDevice, st));
+  return VAR_OK;
+}
 int sampler_epoch(uint32_t* state, int n, int* perm, cudaStream_t st) {
   if (n <= 0) return VAR_ERR_ARG;
   const size_t smem = n <= 65536 ? (size_t)n * 2 + 16 : 0;
@@ -287,8 +308,10 @@ int sampler_epoch(uint32_t* state, int n, int* perm, cudaStream_t st) {
 int sampler_batch(const SamplerArgs& a_in, cudaStream_t st) {
   SamplerArgs a = a_in;
   if (a.B <= 0 || a.task_num <= 0 || a.task_num > 126) return VAR_ERR_ARG;
-  a.chunk = a.B < 8192 ? a.B : 8192;
-  const size_t smem = (size_t)(MT_N + 5 * a.chunk + MT_N) * 4 + (size_t)a.chunk * 4 + 16;
+  if (a.nds2 && (a.max_ds2 <= 0 || a.max_ds % a.max_ds2 != 0)) return VAR_ERR_ARG;
+  const int dpi = a.nds2 ? 7 : 5, cap = a.nds2 ? 4096 : 8192;  // keeps the draw window under the smem limit
+  a.chunk = a.B < cap ? a.B : cap;
+  const size_t smem = (size_t)(MT_N + dpi * a.chunk + MT_N) * 4 + (size_t)a.chunk * 4 + 16;
   static size_t configured = 0;
   if (smem > configured) {
     VAR_CUDA_CHECK(cudaFuncSetAttribute(sampler_batch_kernel,

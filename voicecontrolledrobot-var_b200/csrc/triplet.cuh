@@ -17,6 +17,8 @@ struct SamplerArgs {
   const int* nclips;        // [task_num * max_ds] clips per (intent, dataset)
   const int* clip_base;     // [task_num * max_ds] first clip id of (intent, dataset)
   int max_ds;
+  const int* nds2;          // iTHOR task tables: [task_num] object-synonym count (null = pybullet tables)
+  int max_ds2;              //   row pitch of the object-synonym index inside a task's max_ds slots
   const long long* clip_off;  // [n_clips] sample offset of each clip in the int16 arena
   const int* clip_len;        // [n_clips] samples
   int* scratch_off;         // [B] workspace
@@ -31,6 +33,7 @@ struct SamplerArgs {
 };
 
 int sampler_seed(uint32_t* state, unsigned long long seed, cudaStream_t st);
+int sampler_set_state(uint32_t* state, const uint32_t* host_words, int pos, cudaStream_t st);
 int sampler_epoch(uint32_t* state, int n, int* perm, cudaStream_t st);
 int sampler_batch(const SamplerArgs& a, cudaStream_t st);
 

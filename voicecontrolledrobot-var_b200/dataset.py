@@ -9,9 +9,10 @@ assembled by two launches: `var_sampler_batch` (bit-exact index draws) and `var_
 `(generator, final_dataset)`; the generator yields the reference's
 `(image, sound_positive, sound_negative, gt)` tuples, already on the device.
 
-Pybullet/Kuka sampling (intent -> dataset -> clip, audioLoader.py:166-177) is covered by the
-device sampler; the iTHOR synonym-table draw (audioLoader.py:223-237) needs the simulator's
-task tables and is out of this path's scope.
+Both sampling schemes are covered by the device sampler: pybullet/Kuka (intent -> dataset ->
+clip, audioLoader.py:166-177, torchaudio-flavoured MFCC) and iTHOR (task list of dataset.py:17-29,
+location-synonym / object-synonym / clip draws of audioLoader.py:203-237, and -- because
+getAudioFromTask leaves mfcc_from=None -- the python_speech_features-flavoured MFCC).
 """
 import glob
 import os
@@ -25,43 +26,87 @@ from ._lib import check, lib, ptr, stream_ptr
 from .Envs.audioLoader import audioLoader, mfcc_device
 
 
+def torch_generator_words(rng_state):
+    """torch.get_rng_state() of the CPU generator -> (uint32 words[624], read position).  The blob is
+    the legacy THGeneratorState at::CPUGeneratorImpl serialises: u64 seed, i32 left, i32 seeded,
+    u64 next, u64 state[624], ...; `left <= 1` means the next draw twists first (position 624)."""
+    b = rng_state.numpy().tobytes()
+    left = int(np.frombuffer(b, dtype=np.int32, count=1, offset=8)[0])
+    nxt = int(np.frombuffer(b, dtype=np.uint64, count=1, offset=16)[0])
+    words = np.ascontiguousarray(np.frombuffer(b, dtype=np.uint64, count=624, offset=24).astype(np.uint32))
+    return words, (624 if left <= 1 else nxt)
+
+
 class DeviceTripletSampler:
     """Device-resident mt19937 + the tables of one triplet dataset (see var_sampler_* in
-    include/var_b200.h).  Consumes the stream exactly like torch's global CPU generator does in
-    the reference's `for batch in DataLoader(shuffle=True, num_workers=0)` loop."""
+    include/var_b200.h).  Runs the same generator algorithm and the same draw order as the
+    reference's `for batch in DataLoader(shuffle=True, num_workers=0)` loop; `adopt_torch_state()`
+    makes it continue torch's global CPU generator from its current state (what the reference
+    draws from), `seed(s)` starts a fresh `torch.manual_seed(s)` stream.
+
+    `dataset_sizes` (pybullet): clips per (intent, dataset).  `task_tables` (iTHOR): a TaskClipArena
+    (per-task synonym counts and the [task, loc synonym, obj synonym] clip lists)."""
 
     def __init__(self, task_num, dataset_sizes, gt, stored_sn=None, seed=0, device=None, clip_off=None,
-                 clip_len=None):
+                 clip_len=None, task_tables=None):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceTripletSampler needs CUDA; there is no CPU fallback")
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.task_num = int(task_num)
         i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=self.device)
-        self.max_ds = max(1, max(len(s) for s in dataset_sizes))
-        nds = [len(s) for s in dataset_sizes]
-        if min(nds) < 1 or any(c < 1 for s in dataset_sizes for c in s):
-            raise ValueError("every intent needs at least one dataset with at least one clip")
-        nclips = np.zeros((self.task_num, self.max_ds), np.int32)
-        base = np.zeros((self.task_num, self.max_ds), np.int32)
-        cur = 0
-        for i, s in enumerate(dataset_sizes):
-            for j, c in enumerate(s):
-                nclips[i, j] = c
-                base[i, j] = cur
-                cur += c
-        self.n_clips = cur
-        self.nds, self.nclips, self.clip_base = i32(nds), i32(nclips), i32(base)
+        self.nds2 = None
+        if task_tables is not None:
+            t = task_tables
+            if t.task_num != self.task_num:
+                raise ValueError(f"config.taskNum = {self.task_num} but allTasks lists {t.task_num} tasks")
+            self.max_ds, self.max_ds2, self.n_clips = t.max_loc * t.max_obj, t.max_obj, t.n_clips
+            self.nds, self.nds2 = i32(t.n_loc), i32(t.n_obj)
+            self.nclips, self.clip_base = i32(t.nclips.reshape(self.task_num, -1)), i32(t.clip_base.reshape(self.task_num, -1))
+            cur = t.n_clips
+        else:
+            self.max_ds = max(1, max(len(s) for s in dataset_sizes))
+            nds = [len(s) for s in dataset_sizes]
+            if min(nds) < 1 or any(c < 1 for s in dataset_sizes for c in s):
+                raise ValueError("every intent needs at least one dataset with at least one clip")
+            nclips = np.zeros((self.task_num, self.max_ds), np.int32)
+            base = np.zeros((self.task_num, self.max_ds), np.int32)
+            cur = 0
+            for i, s in enumerate(dataset_sizes):
+                for j, c in enumerate(s):
+                    nclips[i, j] = c
+                    base[i, j] = cur
+                    cur += c
+            self.n_clips = cur
+            self.nds, self.nclips, self.clip_base = i32(nds), i32(nclips), i32(base)
         self.clip_off = clip_off if clip_off is not None else torch.zeros(cur, dtype=torch.int64, device=self.device)
         self.clip_len = clip_len if clip_len is not None else torch.zeros(cur, dtype=torch.int32, device=self.device)
         self.gt = i32(gt)
         self.n_items = int(self.gt.numel())
         self.stored_sn = i32(stored_sn) if stored_sn is not None else None
         self.state = torch.zeros(625, dtype=torch.int32, device=self.device)
-        self.seed(seed)
+        if seed is None:
+            self.adopt_torch_state()
+        else:
+            self.seed(seed)
         self.perm = torch.empty(self.n_items, dtype=torch.int32, device=self.device)
 
     def seed(self, seed):
         check(lib.var_sampler_seed(ptr(self.state), int(seed) & 0xFFFFFFFFFFFFFFFF, stream_ptr()), "var_sampler_seed")
+
+    def adopt_torch_state(self, rng_state=None):
+        """Continue torch's global CPU generator (or a given torch.get_rng_state() blob).  Under
+        torch.distributed rank 0's state is broadcast, so every rank draws the same global batches."""
+        import torch.distributed as dist
+        if rng_state is None:
+            rng_state = torch.get_rng_state()
+        rng_state = torch.as_tensor(rng_state, dtype=torch.uint8).clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            buf = rng_state.to(self.device) if dist.get_backend() == "nccl" else rng_state
+            dist.broadcast(buf, src=0)
+            rng_state = buf.cpu()
+        words, pos = torch_generator_words(rng_state)
+        check(lib.var_sampler_set_state(ptr(self.state), words.ctypes.data, int(pos), stream_ptr()),
+              "var_sampler_set_state")
 
     def begin_epoch(self):
         """DataLoader iterator creation + RandomSampler permutation -> int32 [n_items] on device."""
@@ -80,11 +125,17 @@ class DeviceTripletSampler:
                "len": torch.empty(2 * B, dtype=torch.int32, device=dev)}
         scratch = torch.empty(B, dtype=torch.int32, device=dev)
         items = items.contiguous()
-        check(lib.var_sampler_batch(ptr(self.state), B, self.task_num, ptr(items), ptr(self.gt), ptr(self.stored_sn),
-                                    ptr(self.nds), ptr(self.nclips), ptr(self.clip_base), self.max_ds,
-                                    ptr(self.clip_off), ptr(self.clip_len), ptr(scratch), ptr(out["item"]),
-                                    ptr(out["gt"]), ptr(out["sn"]), ptr(out["rec"]), ptr(out["off"]), ptr(out["len"]),
-                                    stream_ptr()), "var_sampler_batch")
+        tail = (ptr(self.clip_off), ptr(self.clip_len), ptr(scratch), ptr(out["item"]), ptr(out["gt"]), ptr(out["sn"]),
+                ptr(out["rec"]), ptr(out["off"]), ptr(out["len"]), stream_ptr())
+        if self.nds2 is None:
+            check(lib.var_sampler_batch(ptr(self.state), B, self.task_num, ptr(items), ptr(self.gt), ptr(self.stored_sn),
+                                        ptr(self.nds), ptr(self.nclips), ptr(self.clip_base), self.max_ds, *tail),
+                  "var_sampler_batch")
+        else:
+            check(lib.var_sampler_batch_tasks(ptr(self.state), B, self.task_num, ptr(items), ptr(self.gt),
+                                              ptr(self.stored_sn), ptr(self.nds), ptr(self.nds2), ptr(self.nclips),
+                                              ptr(self.clip_base), self.max_ds // self.max_ds2, self.max_ds2, *tail),
+                  "var_sampler_batch_tasks")
         out["_keep"] = (scratch, items)
         return out
 
@@ -100,7 +151,11 @@ class VARDataset(Dataset):
             self.ground_truth_pair = pickle.load(f)
         self.audio = kwargs['audio']
         if config.name == 'AI2ThorConfig':
-            raise NotImplementedError("iTHOR task-table sampling needs the simulator package (out of scope)")
+            from .Envs.ai2thor.RL_env_VAR import Task
+            self.Task = Task
+            # task list, dataset.py:21-29
+            self.tl = [Task(loc=loc, obj=obj, act=act) for loc in config.allTasks for obj in config.allTasks[loc]
+                       for act in config.allTasks[loc][obj]]
 
     def __len__(self):
         return len(self.ground_truth_pair)
@@ -112,10 +167,13 @@ class VARDataset(Dataset):
         return self.config.taskNum if gt == sn_id else sn_id
 
     def getImgSoundPair(self, gt, sn_id):
-        """dataset.py:34-62 for the pybullet config; features come from the GPU MFCC kernel."""
+        """dataset.py:34-62 (both configs); features come from the GPU MFCC kernel."""
         T = self.config.taskNum
         zeros = lambda: np.zeros(shape=self.config.sound_dim)
-        feat = lambda i: self.audio.genSoundFeat(intentIdx=i, featType='MFCC', rand_fn=torch.randint)[0]
+        if self.config.name == 'AI2ThorConfig':
+            feat = lambda i: self.audio.getAudioFromTask(torch, self.tl[i], self.Task)[0]
+        else:
+            feat = lambda i: self.audio.genSoundFeat(intentIdx=i, featType='MFCC', rand_fn=torch.randint)[0]
         if gt == T:
             return zeros(), feat(sn_id)
         pos = feat(gt)
@@ -152,8 +210,11 @@ class VARFineTuneDataset(VARDataset):
 class DeviceTripletLoader:
     """Iterable replacing `DataLoader(ConcatDataset, batch_size, shuffle=True, num_workers=0)` for
     VARDataset records: device-resident images / labels / clips, batches assembled by
-    var_sampler_batch + var_mfcc_fwd.  Yields the reference tuples; `raw_batches()` yields the
-    uint8 / [2B, F, 40] form the fused trainer consumes (rank-sliced under data parallelism)."""
+    var_sampler_batch[_tasks] + var_mfcc_fwd.  Yields the reference tuples; `raw_batches()` yields the
+    uint8 / [2B, F, 40] form the fused trainer consumes (rank-sliced under data parallelism).
+
+    seed=None (default) continues torch's global CPU generator from its state at construction, as the
+    reference's DataLoader does; an int starts a fresh `torch.manual_seed(seed)` stream."""
 
     def __init__(self, images_u8, gt, stored_sn, audio, arena, config, batch_size, shuffle=True, drop_last=False,
                  seed=None, device=None, rank=0, world_size=1):
@@ -171,16 +232,21 @@ class DeviceTripletLoader:
         if len(params) != 1:
             raise NotImplementedError(f"datasets {names} mix STFT parameter sets")
         self.param = params.pop()
-        if seed is None:
-            seed = torch.initial_seed()
-        self.sampler = DeviceTripletSampler(config.taskNum, arena.dataset_sizes, gt, stored_sn, seed, self.device,
-                                            arena.clip_off, arena.clip_len)
+        ithor = config.name == 'AI2ThorConfig'
+        # getAudioFromTask -> genSoundFeatFromTask(mfcc_from=None) -> python_speech_features (audioLoader.py:159-161,
+        # 203, 234-236); genSoundFeat defaults to torchaudio (audioLoader.py:187)
+        self.flavour = 1 if ithor else 0
+        self.sampler = DeviceTripletSampler(config.taskNum, None if ithor else arena.dataset_sizes, gt, stored_sn, seed,
+                                            self.device, arena.clip_off, arena.clip_len,
+                                            task_tables=arena if ithor else None)
 
     def __len__(self):
         n = self.n_items // self.batch_size
         return n if (self.drop_last or self.n_items % self.batch_size == 0) else n + 1
 
     def raw_batches(self):
+        """-> (uint8 images [b, 3, 96, 96], sounds [2b, F, 40], gt [b], global batch B, sampler record) with
+        b = this rank's slice of the global batch (may be 0 on a ragged tail: images/sounds are then None)."""
         n, bs = self.n_items, self.batch_size
         if self.shuffle:
             perm = self.sampler.begin_epoch()
@@ -195,14 +261,19 @@ class DeviceTripletLoader:
                 break
             rec = self.sampler.sample(items)  # every rank draws the GLOBAL batch: identical streams
             lo, hi = (B * self.rank) // self.world_size, (B * (self.rank + 1)) // self.world_size
+            if hi == lo:
+                yield None, None, rec["gt"][lo:hi], B, rec
+                continue
             idx = rec["item"][lo:hi].long()
             off = torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]])
             ln = torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]])
-            sounds = mfcc_device(self.arena.wav, off, ln, self.audio.fs, n_fft, win, hop, F)
+            sounds = mfcc_device(self.arena.wav, off, ln, self.audio.fs, n_fft, win, hop, F, flavour=self.flavour)
             yield self.images[idx], sounds, rec["gt"][lo:hi], B, rec
 
     def __iter__(self):
         for img_u8, sounds, gt, _, _ in self.raw_batches():
+            if img_u8 is None:
+                continue
             b = img_u8.shape[0]
             F = sounds.shape[1]
             yield ((img_u8.float() / 255.), sounds[:b].view(b, 1, F, 40), sounds[b:].view(b, 1, F, 40), gt.long())

@@ -69,6 +69,7 @@ class VarEngine:
             keep.append(src)
             check(lib.var_net_load_tensor(self._net, i, ptr(src), st), f"var_net_load_tensor({name})")
         torch.cuda.current_stream().synchronize()  # sources may be freed after return
+        self.reset_optimizer()  # moments of the replaced weights are stale
 
     def _store(self, which):
         out = {}
@@ -178,6 +179,13 @@ class VarEngine:
                                  ptr(goal_feat_cached), ptr(env_reward), N, ptr(ws), ws.numel(), ptr(img_feat),
                                  ptr(goal_feat), ptr(dot), ptr(rew), stream_ptr()), "var_net_reward")
         return img_feat, goal_feat, dot, rew
+
+    def reset_optimizer(self):
+        """Forget the Adam moments and the bias-correction step count (a fresh torch.optim.Adam)."""
+        if self.adam_m is not None:
+            self.adam_m.zero_()
+            self.adam_v.zero_()
+        self.adam_steps = 0
 
     def adam_step(self, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         if self.adam_m is None:

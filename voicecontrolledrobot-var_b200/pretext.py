@@ -60,7 +60,11 @@ class Pretext(object):
         torch.manual_seed(self.config.pretextEnvSeed)
         torch.cuda.manual_seed_all(self.config.pretextEnvSeed)
         if getattr(self.config, "pretextCollection", False):
-            self.collectPretextData()
+            # pretext.py:297-304 runs the simulators here; that stage stays with the reference, so the
+            # triplet files under config.pretextDataDir must already exist
+            import warnings
+            warnings.warn("config.pretextCollection is set: data collection drives the pybullet / Unity simulators "
+                          "and is not part of this package -- using the triplet files already on disk")
         if self.config.pretextTrain:
             self.pretextModel = self.config.pretextModel(self.config).to(self.device)
             if self.config.pretextModelFineTune:
