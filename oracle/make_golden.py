@@ -281,6 +281,51 @@ def gold_reward():
     print("reward ok, var", w.ret_rms.var)
 
 
+def gold_reward_ithor():
+    """The reference VecPretextNormalize with the iTHOR VARPretextNet (processAI2Thor, the all-inf
+    cached-goal schedule, return normalisation) on the CPU."""
+    from Envs.vec_env.vec_pretext_normalize import VecPretextNormalize
+    from models.pretext.ai2thor_pretext_model import VARPretextNet
+    torch.Tensor.cuda = lambda self, *a, **k: self  # constructor calls .cuda() (ai2thor_pretext_model.py:46)
+    cfg = ithor_cfg()
+    N, steps = 5, 7
+    m = VARPretextNet(cfg)
+    m.load_state_dict(omodel.init_state_dict(omodel.ITHOR, 13))
+    m.eval()
+    obs_seq, rew_seq, done_seq = synth.ithor_reward_case(N, steps)
+
+    class Venv:
+        num_envs = N
+        observation_space = types.SimpleNamespace(shape=(1,))
+        action_space = None
+        t = 0
+
+        def reset(self):
+            return obs_seq[0]
+
+        def step_wait(self):
+            self.t += 1
+            return obs_seq[self.t], rew_seq[self.t].copy(), done_seq[self.t].copy(), ({},) * N
+
+    w = VecPretextNormalize(Venv(), ob=False, ret=True, gamma=0.99, config=cfg,
+                            pretextObj=types.SimpleNamespace(pretextModel=m))
+    w.device = torch.device("cpu")
+    o0 = w.reset()
+    out = {"reset_image_feat": o0["image_feat"], "reset_goal_sound_feat": o0["goal_sound_feat"],
+           "reset_occupancy_sum": np.array(o0["occupancy"].sum())}
+    for t in range(steps):
+        o, r, d, _ = w.step_wait()
+        out[f"rew{t}"] = r
+        out[f"orig{t}"] = w.origStepReward
+        out[f"image_feat{t}"] = o["image_feat"]
+        out[f"goal_sound_feat{t}"] = o["goal_sound_feat"]
+        assert set(o) == {"occupancy", "goal_sound_feat", "image", "image_feat"}
+    out["ret_var"] = np.array(w.ret_rms.var)
+    out["ret_mean"] = np.array(w.ret_rms.mean)
+    np.savez_compressed(os.path.join(GOLD, "reward_ithor.npz"), N=N, steps=steps, **out)
+    print("ithor reward ok, var", w.ret_rms.var)
+
+
 def gold_adam():
     rng = np.random.default_rng(3)
     p0 = rng.standard_normal(257).astype(np.float32)
@@ -333,6 +378,7 @@ if __name__ == "__main__":
     gold_sampler_ithor()
     gold_adam()
     gold_reward()
+    gold_reward_ithor()
     gold_model(omodel.KUKA, 4, 7)
     gold_model(omodel.ITHOR, 2, 9)
     gold_init()

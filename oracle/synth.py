@@ -61,3 +61,22 @@ def model_case(net, B, seed):
     sp = snd()
     sn = snd()
     return images, sp, sn
+
+
+def ithor_reward_case(N, steps, seed=6, goal_every=3):
+    """Seeded observation stream of the iTHOR reward golden: uint8 frames, occupancy maps, env rewards,
+    dones; the goal sound is real on the reset observation and on every `goal_every`-th step and
+    all-inf otherwise (Envs/ai2thor/RL_env_VAR.py:509-510 sends inf after an episode's first step)."""
+    rng = np.random.default_rng(seed)
+    obs_seq, rew_seq, done_seq = [], [], []
+    for t in range(steps + 1):
+        snd = np.zeros((N, 1, 600, 40), np.float32)
+        if t % goal_every == 0:
+            snd[:, :, :101] = (rng.standard_normal((N, 1, 101, 40)) * 5).astype(np.float32)
+        else:
+            snd[:] = np.inf
+        obs_seq.append({"image": rng.integers(0, 256, (N, 3, 96, 96)).astype(np.uint8), "goal_sound": snd,
+                        "occupancy": rng.integers(0, 256, (N, 1, 9, 9)).astype(np.uint8)})
+        rew_seq.append(rng.standard_normal(N))
+        done_seq.append(rng.random(N) < 0.3)
+    return obs_seq, rew_seq, done_seq

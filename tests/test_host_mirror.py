@@ -223,6 +223,138 @@ def test_reward_wrapper_device_path_matches_reference_golden(vb, golden):
     assert abs(float(w.ret_rms.mean) - float(g["ret_mean"])) < 1e-2 * max(1.0, abs(float(g["ret_mean"])))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_path", [False, True])
+def test_ithor_reward_wrapper_matches_reference_golden(vb, golden, device_path):
+    """processAI2Thor + the iTHOR net + the all-inf cached-goal schedule (Envs/ai2thor/RL_env_VAR.py:509-510)
+    through step_wait (host protocol) and step_wait_device, against the reference wrapper's own run
+    (oracle/make_golden.py::gold_reward_ithor)."""
+    from conftest import ithor_config
+    g = golden("reward_ithor")
+    vpn = import_module(f"{PKG}.Envs.vec_env.vec_pretext_normalize")
+    cfg = ithor_config()
+    N, steps = int(g["N"]), int(g["steps"])
+    m = _net("ithor", cfg)
+    m.load_state_dict(omodel.init_state_dict(omodel.ITHOR, 13))
+    m.to(DEV).eval()
+    obs_seq, rew_seq, done_seq = synth.ithor_reward_case(N, steps)
+    assert np.isinf(obs_seq[1]["goal_sound"]).all() and not np.isinf(obs_seq[3]["goal_sound"]).any()
+
+    class Venv:
+        num_envs = N
+        observation_space = types.SimpleNamespace(shape=(1,))
+        action_space = None
+        t = 0
+
+        def reset(self):
+            return obs_seq[0]
+
+        def step_wait(self):
+            self.t += 1
+            return obs_seq[self.t], rew_seq[self.t].copy(), done_seq[self.t].copy(), ({},) * N
+
+    w = vpn.VecPretextNormalize(Venv(), ob=False, ret=True, gamma=0.99, config=cfg,
+                                pretextObj=types.SimpleNamespace(pretextModel=m))
+    o0 = w.reset()
+    assert set(o0) == {"occupancy", "goal_sound_feat", "image", "image_feat"}
+    assert np.abs(o0["image_feat"] - g["reset_image_feat"]).max() < 1e-3
+    assert np.abs(o0["goal_sound_feat"] - g["reset_goal_sound_feat"]).max() < 1e-3
+    assert abs(float(o0["occupancy"].sum()) - float(g["reset_occupancy_sum"])) < 1e-6 * float(g["reset_occupancy_sum"])
+    for t in range(steps):
+        if device_path:
+            o, r, d, _ = w.step_wait_device()
+            w.sync_device_stats()
+            o = {k: v.cpu().numpy() for k, v in o.items()}
+            r = r[:, 0].cpu().numpy()
+        else:
+            o, r, d, _ = w.step_wait()
+        assert np.abs(r - g[f"rew{t}"]).max() < 3e-3, t
+        assert np.abs(w.origStepReward - g[f"orig{t}"]).max() < 3e-3, t
+        assert np.abs(o["image_feat"] - g[f"image_feat{t}"]).max() < 1e-3, t
+        assert np.abs(o["goal_sound_feat"] - g[f"goal_sound_feat{t}"]).max() < 1e-3, t   # cached on the inf steps
+        assert o["occupancy"].max() <= 1.0 and o["image"].max() <= 1.0
+    assert abs(float(w.ret_rms.var) - float(g["ret_var"])) < 1e-2 * float(g["ret_var"])
+
+
+@pytest.mark.gpu
+def test_rl_var_surface(vb, tmp_path):
+    """VAR/RL_VAR.py:8-76: RL_VAR(config).run() loads the VAR weights, builds the (sharded) envs through
+    the env factory hook, and testRL rolls a policy reading `eval_envs.venv.origStepReward` after every
+    batched reward query; results land in test_<policy>.csv."""
+    rlv = import_module(f"{PKG}.VAR.RL_VAR")
+    vpn = import_module(f"{PKG}.Envs.vec_env.vec_pretext_normalize")
+    assert rlv.shard_envs(16, 1, 4) == (4, 8) and rlv.shard_envs(10, 2, 3) == (6, 10)
+    cfg = kuka_cfg()
+    cfg.pretextModel = import_module(f"{PKG}.models.pretext.arm_pretext_model").VARPretextNet
+    cfg.pretextModelLoadDir = str(tmp_path / "var.pt")
+    torch.save(omodel.init_state_dict(omodel.KUKA, 3), cfg.pretextModelLoadDir, _use_new_zipfile_serialization=False)
+    cfg.RLManualControl = False; cfg.RLManualControlLoaded = False; cfg.RLTrain = False
+    cfg.RLEnvName = "arms-RL-v2"; cfg.RLEnvSeed = 1; cfg.RLGamma = 0.99; cfg.RLDeterministic = True
+    cfg.render = False; cfg.success_threshold = 1
+    cfg.skillInfos = [{"path": str(tmp_path / "policy.pt")}]
+    rng = np.random.default_rng(2)
+
+    class BaseEnv:
+        size_per_class = [1, 1, 1, 1]
+        size_per_class_cumsum = np.cumsum([1, 1, 1, 1])
+        episodeCounter = 0
+
+    base = BaseEnv()
+
+    class Venv:  # one env, 3 steps per episode
+        num_envs = 1
+        observation_space = types.SimpleNamespace(shape=(1,))
+        action_space = None
+        unwrapped = types.SimpleNamespace(envs=[base])
+        t = 0
+
+        def _obs(self):
+            return {"image": rng.integers(0, 256, (1, 3, 96, 96)).astype(np.uint8),
+                    "goal_sound": (rng.standard_normal((1, 1, 100, 40)) * 5).astype(np.float32),
+                    "robot_pose": np.zeros((1, 4), np.float32)}
+
+        def reset(self):
+            return self._obs()
+
+        def step_async(self, a):
+            pass
+
+        def step_wait(self):
+            self.t += 1
+            done = self.t % 3 == 0
+            if done:
+                base.episodeCounter += 1
+            return self._obs(), np.array([0.25]), np.array([done]), ({"goal_area_count": self.t % 2},)
+
+        def close(self):
+            pass
+
+    made = {}
+
+    def make_vec_envs(**kw):
+        made.update(kw)
+        w = vpn.VecPretextNormalize(Venv(), ob=False, ret=True, gamma=kw["gamma"], config=kw["config"],
+                                    pretextObj=kw["pretextObj"])
+        return types.SimpleNamespace(venv=w, reset=w.reset, step=w.step, close=w.close, render=lambda: None)
+
+    class Policy:
+        recurrent_hidden_state_size = 4
+
+        def act(self, obs, h, masks, deterministic=False):
+            assert set(obs) == {"robot_pose", "goal_sound_feat", "image", "image_feat"}
+            return None, torch.zeros(1, 1), None, h
+
+    rl = rlv.RL_VAR(cfg, make_vec_envs=make_vec_envs, load_policy=lambda envs: [Policy()])
+    rl.run()
+    assert made["num_processes"] == 1 and made["pretextObj"] is rl.pretextObj and rl.pretextObj.pretextModel is not None
+    import pandas as pd
+    df = pd.read_csv(tmp_path / "test_policy.csv")
+    assert list(df.columns) == ["objIdx", "goal area count", "rewards", "results"] and len(df) == 4
+    assert df["objIdx"].tolist() == [0, 1, 2, 3] and np.isfinite(df["rewards"]).all()
+    # per-episode reward = sum over 3 steps of (img . goal dot in [-1, 1]) + 0.25 env reward
+    assert (df["rewards"].abs() <= 3 * 1.25 + 1e-6).all()
+
+
 def _write_dataset(root, cfg, n_items=48, clips_per_class=5, media_only_records=False):
     from scipy.io import wavfile
     words = ["up", "down", "left", "right"]

@@ -5,12 +5,21 @@ wrapper; `getEmbeddings` + `calcReward` (lines 82-101) are served by ONE batched
 (`var_net_reward`: image branch, goal-sound branch or its cached embedding, normalisation, dot
 product and env-reward add) instead of a model call, two D2H copies and a numpy dot.  The
 uint8 observation is uploaded as uint8 (4x fewer H2D bytes than the reference's float64->float32
-path); the 1/255 scale is applied inside the first conv's loader."""
+path); the 1/255 scale is applied inside the first conv's loader.
+
+Multi-GPU: reward queries shard by env index with NO collective -- one process per GPU, rank r of G
+owns envs [r*N/G, (r+1)*N/G) (VAR/RL_VAR.py::shard_envs), builds its venv with that many workers and
+wraps it in its own VecPretextNormalize: weights are replicated, `cached_sound` holds the rank's own
+envs, and a query is row-wise independent, so the gathered result equals the single-GPU query bit
+for bit (tests/test_gpu_parity.py::test_reward_query_sharded_by_env_is_bit_identical).  The one piece
+of state the reference shares across envs is the discounted-return RunningMeanStd (`ret_rms`); each
+rank keeps the statistics of its own envs unless `merge_ret_rms()` is called (an optional 3-double
+all_gather, off the query path)."""
 import numpy as np
 import torch
 
 from ..._lib import check, lib, ptr, stream_ptr
-from .running_mean_std import RunningMeanStd
+from .running_mean_std import RunningMeanStd, merge_moments
 
 
 class VecEnvWrapper(object):
@@ -61,33 +70,38 @@ class VecPretextNormalize(VecEnvWrapper):
 
     # ------------------------------------------------------------------ reward query
     def _query(self, O, envReward):
-        """-> image_feat, goal_sound_feat (numpy [N, D]), img_sound_dot, reward (numpy [N])."""
+        """-> image_feat, goal_sound_feat (numpy [N, D]), img_sound_dot, reward (numpy [N]).
+        The query for this wrapper's fixed N is a captured CUDA graph (engine.RewardGraph): host
+        observations are copied straight into its static input buffers, one graph launch runs the image
+        branch (+ the goal-sound branch on steps that carry a real goal sound) and the fused
+        normalise / dot / reward tail, and one D2H copy brings back [img_feat | goal_feat | dot | reward]."""
         model = self.pretextModel
         eng = model._get_engine(self.device)
         img = np.ascontiguousarray(O['image'][:, :3])
         if img.dtype != np.uint8:
             img = img.astype(np.float32) / np.float32(255.)  # non-uint8 observations keep the reference scaling
-        image = torch.from_numpy(img).to(self.device, non_blocking=True)
         goal = O['goal_sound']
-        F = self.config.sound_dim[1]
+        N, F, D = img.shape[0], self.config.sound_dim[1], self.config.representationDim
         # pretext_base.py:29-32: an all-inf goal sound means "reuse the cached embedding"
         fresh = goal is not None and not bool(np.isinf(goal.flat[0]) and np.isinf(goal).all())
-        env_r = torch.from_numpy(np.asarray(envReward, dtype=np.float32)).to(self.device, non_blocking=True)
+        g = eng.reward_graph(N, torch.uint8 if img.dtype == np.uint8 else torch.float32, fresh)
+        g.images.copy_(torch.from_numpy(img), non_blocking=True)
+        g.env_reward.copy_(torch.from_numpy(np.asarray(envReward, dtype=np.float32)), non_blocking=True)
         if fresh:
-            snd = torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float32).reshape(-1, F, 40)).to(
-                self.device, non_blocking=True)
-            img_feat, goal_feat, dot, rew = eng.reward(image, goal_sounds=snd, env_reward=env_r)
-            self._cached_goal_feat = goal_feat
-            model.cached_sound = goal_feat
+            g.goal_sounds.copy_(torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float32).reshape(-1, F, 40)),
+                                non_blocking=True)
         else:
             cached = model.cached_sound if model.cached_sound is not None else self._cached_goal_feat
             if cached is None:
                 raise RuntimeError("all-inf goal sound before any goal sound was encoded (no cached embedding)")
-            cached = cached.to(self.device).float().contiguous()
-            img_feat, goal_feat, dot, rew = eng.reward(image, goal_feat_cached=cached, env_reward=env_r)
-        out = torch.cat([img_feat, goal_feat, dot[:, None], rew[:, None]], dim=1).cpu().numpy()  # one D2H
-        D = img_feat.shape[1]
-        return out[:, :D], out[:, D:2 * D], out[:, 2 * D], out[:, 2 * D + 1]
+            g.goal_feat_cached.copy_(cached.to(self.device).float(), non_blocking=True)
+        g.launch()
+        if fresh:
+            self._cached_goal_feat = g.goal_feat.clone()  # the graph's output buffer is overwritten by the next query
+            model.cached_sound = self._cached_goal_feat
+        out = g.out.cpu().numpy()  # one D2H (synchronises)
+        return (out[:N * D].reshape(N, D), out[N * D:2 * N * D].reshape(N, D), out[2 * N * D:2 * N * D + N],
+                out[2 * N * D + N:])
 
     def getEmbeddings(self, O):
         image_feat, goal_sound_feat, _, _ = self._query(O, np.zeros(len(O['image']), np.float32))
@@ -113,9 +127,10 @@ class VecPretextNormalize(VecEnvWrapper):
             image_feat, goal_sound_feat, current_sound_feat = self.getEmbeddings(O)
             reward, _, _ = self.calcReward(envReward, image_feat, goal_sound_feat, current_sound_feat)
         else:
-            image_feat, goal_sound_feat, _, dev_reward = self._query(O, envReward)
-            # the device adds envReward in fp32; keep the reference's float64 host add for the sum
-            reward = (dev_reward - np.asarray(envReward, dtype=np.float32)).astype(np.float64) + envReward
+            image_feat, goal_sound_feat, dot, _ = self._query(O, envReward)
+            # float64 host add as in the reference (vec_pretext_normalize.py:99); the device-side fp32 sum is what
+            # step_wait_device() uses
+            reward = dot.astype(np.float64) + envReward
         s = {extra_key: O[extra_key] / extra_scale if extra_scale else O[extra_key],
              'goal_sound_feat': goal_sound_feat, 'image': O['image'] / 255., 'image_feat': image_feat}
         return self._obfilt(s), reward
@@ -137,6 +152,22 @@ class VecPretextNormalize(VecEnvWrapper):
             rews = np.clip(rews / np.sqrt(self.ret_rms.var + self.epsilon), -self.cliprew, self.cliprew)
         self.ret[news] = 0.
         return obs, rews, news, infos
+
+    def merge_ret_rms(self):
+        """Optional: make `ret_rms` the statistic over ALL ranks' envs (what a single-process run of the
+        reference would hold) by merging the per-rank (mean, var, count) with the parallel-variance rule of
+        running_mean_std.py:22-35, in rank order on every rank.  Not called by step_wait."""
+        import torch.distributed as dist
+        if not (self.ret_rms and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        mine = torch.tensor([float(self.ret_rms.mean), float(self.ret_rms.var), float(self.ret_rms.count)],
+                            dtype=torch.float64, device=self.device if dist.get_backend() == "nccl" else "cpu")
+        parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, mine)
+        mean, var, count = [float(v) for v in parts[0].cpu()]
+        for p in parts[1:]:
+            mean, var, count = merge_moments(mean, var, count, *[float(v) for v in p.cpu()])
+        self.ret_rms.mean, self.ret_rms.var, self.ret_rms.count = np.float64(mean), np.float64(var), count
 
     def _obfilt(self, obs):
         if self.ob_rms and self.config.RLTrain:

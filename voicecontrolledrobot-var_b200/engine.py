@@ -45,6 +45,7 @@ class VarEngine:
         self.img_raw_dim, self.snd_raw_dim = ir.value, sr.value
         self._ws = None
         self._ws_need = {}
+        self._reward_graphs = {}
 
     def __del__(self):
         try:
@@ -168,13 +169,14 @@ class VarEngine:
                                        stream_ptr()), "var_net_triplet_step")
         return loss_out
 
-    def reward(self, images, goal_sounds=None, goal_feat_cached=None, env_reward=None):
-        """-> (img_feat [N, D], goal_feat [N, D], img_sound_dot [N], reward [N])."""
+    def reward(self, images, goal_sounds=None, goal_feat_cached=None, env_reward=None, out=None):
+        """-> (img_feat [N, D], goal_feat [N, D], img_sound_dot [N], reward [N]); `out` = the four
+        destination tensors (else they are allocated)."""
         self._check_inputs(images, goal_sounds)
         N = images.shape[0]
         ws = self._workspace(N, N if goal_sounds is not None else 0, False)
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
-        img_feat, goal_feat, dot, rew = e(N, self.D), e(N, self.D), e(N), e(N)
+        img_feat, goal_feat, dot, rew = out if out is not None else (e(N, self.D), e(N, self.D), e(N), e(N))
         check(lib.var_net_reward(self._net, ptr(images), self._image_kind(images), ptr(goal_sounds),
                                  ptr(goal_feat_cached), ptr(env_reward), N, ptr(ws), ws.numel(), ptr(img_feat),
                                  ptr(goal_feat), ptr(dot), ptr(rew), stream_ptr()), "var_net_reward")
@@ -187,6 +189,17 @@ class VarEngine:
             self.adam_v.zero_()
         self.adam_steps = 0
 
+    def reward_graph(self, N, image_dtype=torch.uint8, fresh_goal=False):
+        """Cached RewardGraph for (N, image dtype, goal sound re-encoded or cached).  Graphs pin the
+        workspace they were captured with, so a later, larger workspace request drops them."""
+        key = (int(N), image_dtype, bool(fresh_goal))
+        g = self._reward_graphs.get(key)
+        if g is None or g.ws_ptr != (self._ws.data_ptr() if self._ws is not None else 0):
+            g = RewardGraph(self, N, image_dtype, fresh_goal)
+            g.ws_ptr = self._ws.data_ptr()
+            self._reward_graphs[key] = g
+        return g
+
     def adam_step(self, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         if self.adam_m is None:
             self.adam_m = torch.zeros_like(self.params)
@@ -196,6 +209,42 @@ class VarEngine:
                                 ptr(self.params_mma), self.nparams, float(lr), float(betas[0]), float(betas[1]),
                                 float(eps), float(weight_decay), self.adam_steps, float(grad_scale), stream_ptr()),
               "var_adam_step")
+
+
+class RewardGraph:
+    """The batched reward query for a FIXED number of envs captured once as a CUDA graph
+    (Envs/vec_env/vec_pretext_normalize.py:82-101 is issued every rollout step with the same N =
+    config.RLNumEnvs, 8 by default): a query then costs one graph launch instead of ~12 dependent
+    kernel launches, which is what bounds the latency at small N.  Inputs are written into the static
+    buffers (`images`, `goal_sounds` / `goal_feat_cached`, `env_reward`), `launch()` replays, and `out`
+    is ONE flat device buffer [img_feat | goal_feat | dot | reward] so the caller reads everything
+    back with a single D2H copy."""
+
+    def __init__(self, eng, N, image_dtype=torch.uint8, fresh_goal=False):
+        dev, D = eng.device, eng.D
+        self.eng, self.N, self.fresh = eng, int(N), bool(fresh_goal)
+        self.images = torch.zeros(N, 3, 96, 96, dtype=image_dtype, device=dev)
+        self.goal_sounds = torch.zeros(N, eng.F, 40, dtype=torch.float32, device=dev) if fresh_goal else None
+        self.goal_feat_cached = None if fresh_goal else torch.zeros(N, D, dtype=torch.float32, device=dev)
+        self.env_reward = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.out = torch.zeros(N * (2 * D + 2), dtype=torch.float32, device=dev)
+        self.img_feat = self.out[:N * D].view(N, D)
+        self.goal_feat = self.out[N * D:2 * N * D].view(N, D)
+        self.dot = self.out[2 * N * D:2 * N * D + N]
+        self.reward = self.out[2 * N * D + N:]
+        self._run()  # eager once: sizes the workspace and sets the kernels' attributes outside the capture
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._run()
+
+    def _run(self):
+        self.eng.reward(self.images, goal_sounds=self.goal_sounds, goal_feat_cached=self.goal_feat_cached,
+                        env_reward=self.env_reward, out=(self.img_feat, self.goal_feat, self.dot, self.reward))
+
+    def launch(self):
+        self.graph.replay()
+        return self.img_feat, self.goal_feat, self.dot, self.reward
 
 
 def multistep_lr(base_lr, epoch, milestones, gamma):
