@@ -87,3 +87,46 @@ def test_rank_slices_tile_every_batch_size():
             cuts = [((B * r) // world, (B * (r + 1)) // world) for r in range(world)]
             assert cuts[0][0] == 0 and cuts[-1][1] == B
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+
+
+def _trainer_worker(rank, world, port, out):
+    """The REAL VAR_Pretext.train_epoch (host-tuple path) over gloo with a ragged tail batch that leaves
+    rank 0 without a triplet: every rank must still reach both all-reduces and the optimiser step."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from importlib import import_module
+    tr = import_module("voicecontrolledrobot-var_b200.VAR.pretext_VAR")
+    t = object.__new__(tr.VAR_Pretext)  # the constructor insists on a CUDA device; train_epoch's host logic does not
+    t.device = torch.device("cpu")
+    cfg = type("C", (), {})()
+    cfg.sound_dim = (1, 2, 40); cfg.tripletMargin = 1.0; cfg.pretextAdamL2 = 0.0
+    t.config = cfg
+    n, bs = 17, 8   # 17 % 8 == 1 < world
+    images = (torch.arange(n * 8, dtype=torch.float32).reshape(n, 8) % 5)
+    batches = [(images[s:s + bs], torch.zeros(min(bs, n - s), 1, 2, 40), torch.zeros(min(bs, n - s), 1, 2, 40), None)
+               for s in range(0, n, bs)]
+    eng = FakeEngine(8)
+    seen = []
+    losses = t.train_epoch(eng, batches, 0.01, world, rank, on_step=lambda l: seen.append(float(l)))
+    assert len(losses) == 3 and seen == [float(l) for l in losses]
+    assert len(t.train_epoch(FakeEngine(8), batches, 0.01, world, rank, max_steps=2)) == 2
+    torch.save({"params": eng.params, "losses": [float(l) for l in losses], "steps": eng.steps}, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_train_epoch_ragged_tail_smaller_than_world(tmp_path):
+    world = 2
+    out = str(tmp_path / "res")
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_trainer_worker, args=(world, port, out), nprocs=world, join=True)
+    r = [torch.load(out + f".{i}") for i in range(world)]
+    assert r[0]["steps"] == r[1]["steps"] == 3
+    assert torch.equal(r[0]["params"], r[1]["params"]) and r[0]["losses"] == r[1]["losses"]
+    images = (torch.arange(17 * 8, dtype=torch.float32).reshape(17, 8) % 5)
+    eng = FakeEngine(8)
+    for s in range(0, 17, 8):
+        eng.zero_grad()
+        eng.triplet_step(images[s:s + 8], None, loss_denominator=min(8, 17 - s))
+        eng.adam_step(0.01)
+    assert torch.allclose(eng.params, r[0]["params"], atol=1e-5)

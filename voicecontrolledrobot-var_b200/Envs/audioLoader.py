@@ -63,32 +63,44 @@ def mfcc_batch(clips, fs, n_fft, win_length, hop, F, flavour=0, device=None):
                        torch.tensor(lens, dtype=torch.int32, device=device), fs, n_fft, win_length, hop, F, flavour)
 
 
-class ClipArena:
+class _ClipStore:
+    """int16 clips concatenated (4-byte aligned) into one host arena + per-clip offsets / lengths on the
+    device (what the sampler hands out).  `.wav` uploads the arena on first use (device-resident
+    loaders); streaming loaders read `wav_host` and never upload it whole."""
+
+    def _pack(self, lists, device):
+        offs, lens, parts, cur = [], [], [], 0
+        for clips in lists:
+            for c in clips:
+                c = np.ascontiguousarray(c, dtype=np.int16)
+                offs.append(cur); lens.append(len(c)); parts.append(c)
+                if len(c) & 1:
+                    parts.append(np.zeros(1, np.int16))
+                cur += len(c) + (len(c) & 1)
+        self.device = device
+        self.wav_host = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(2, np.int16))
+        self._wav = None
+        self.clip_off = torch.tensor(offs, dtype=torch.int64, device=device)
+        self.clip_len = torch.tensor(lens, dtype=torch.int32, device=device)
+
+    @property
+    def wav(self):
+        if self._wav is None:
+            self._wav = self.wav_host.to(self.device)
+        return self._wav
+
+
+class ClipArena(_ClipStore):
     """All loaded clips in one int16 device buffer + the tables the device sampler indexes."""
 
     def __init__(self, words, task_num, device):
         self.task_num = task_num
         self.dataset_names = [list(words[i].keys()) for i in range(task_num)]
         self.dataset_sizes = [[len(words[i][k]) for k in words[i]] for i in range(task_num)]
-        self.wav, self.clip_off, self.clip_len = _pack_clips(
-            [words[i][k] for i in range(task_num) for k in words[i]], device)
+        self._pack([words[i][k] for i in range(task_num) for k in words[i]], device)
 
 
-def _pack_clips(lists, device):
-    """Concatenate int16 clips (4-byte aligned) -> (arena, offsets, lengths) on the device."""
-    offs, lens, parts, cur = [], [], [], 0
-    for clips in lists:
-        for c in clips:
-            c = np.ascontiguousarray(c, dtype=np.int16)
-            offs.append(cur); lens.append(len(c)); parts.append(c)
-            if len(c) & 1:
-                parts.append(np.zeros(1, np.int16))
-            cur += len(c) + (len(c) & 1)
-    wav = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(2, np.int16)).to(device)
-    return wav, torch.tensor(offs, dtype=torch.int64, device=device), torch.tensor(lens, dtype=torch.int32, device=device)
-
-
-class TaskClipArena:
+class TaskClipArena(_ClipStore):
     """iTHOR counterpart of ClipArena: the `words[loc][obj][act]` lists of loadFSCData_ai2thor
     (Envs/audioLoader.py:61-98) in one int16 device buffer, plus the per-task tables of the two synonym
     draws of getAudioFromTask (Envs/audioLoader.py:223-232) for the device sampler.  Task order is the
@@ -125,7 +137,7 @@ class TaskClipArena:
                     self.nclips[t, li, oi], self.clip_base[t, li, oi] = n, base[key]
                     self.resolved[(t, li, oi)] = key
         self.n_clips = cur
-        self.wav, self.clip_off, self.clip_len = _pack_clips([words[k[0]][k[1]][k[2]] for k in self.lists], device)
+        self._pack([words[k[0]][k[1]][k[2]] for k in self.lists], device)
         self.dataset_names = [[config.soundSource['dataset']]]
 
 

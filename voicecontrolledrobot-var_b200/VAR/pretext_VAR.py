@@ -33,13 +33,19 @@ class VAR_Pretext(Pretext):
             return multistep_lr(base_lr, ep, self.config.pretextLRDecayEpoch, self.config.pretextLRDecayGamma)
         return base_lr
 
-    def train_epoch(self, eng, data_generator, lr, world=1, rank=0):
-        """One pass over the generator; returns the per-step device loss scalars."""
+    def train_epoch(self, eng, data_generator, lr, world=1, rank=0, max_steps=None, on_step=None):
+        """One pass over the generator (at most `max_steps` steps); returns the per-step device loss
+        scalars.  `data_generator`: a DeviceTripletLoader, an iterator of its raw batches
+        (`loader.stream()`), or any iterable of the reference's host tuples (image, sound_positive,
+        sound_negative, gt).  `on_step(loss)` runs after each step's launches (e.g. to read the loss)."""
         cfg = self.config
         losses = []
         if isinstance(data_generator, DeviceTripletLoader):
             data_generator.rank, data_generator.world_size = rank, world
             batches = ((img, snd, gB) for img, snd, _, gB, _ in data_generator.raw_batches())
+        elif getattr(data_generator, "gi_code", None) is not None and \
+                data_generator.gi_code.co_name in ("stream", "raw_batches", "_resident_batches", "_streaming_batches"):
+            batches = ((img, snd, gB) for img, snd, _, gB, _ in data_generator)
         else:
             def host_batches():
                 for image, sp, sn, _ in data_generator:
@@ -65,6 +71,10 @@ class VAR_Pretext(Pretext):
                 dist.all_reduce(loss)
             eng.adam_step(lr, weight_decay=cfg.pretextAdamL2)
             losses.append(loss)
+            if on_step is not None:
+                on_step(loss)
+            if max_steps is not None and len(losses) >= max_steps:
+                break
         return losses
 
     def trainRepresentation(self, epoch, lr, start_ep=0, plot=False):

@@ -17,6 +17,8 @@ getAudioFromTask leaves mfcc_from=None -- the python_speech_features-flavoured M
 import glob
 import os
 import pickle
+import queue
+import threading
 
 import numpy as np
 import torch
@@ -207,23 +209,52 @@ class VARFineTuneDataset(VARDataset):
         return image, item['sound_positive'], item['sound_negative'], int(item['ground_truth'])
 
 
+class _Slot:
+    """One in-flight batch of the streaming loader: pinned host staging + device staging."""
+
+    def __init__(self, bs, max_clip, device):
+        self.h_img = torch.empty(bs, 3, 96, 96, dtype=torch.uint8).pin_memory()
+        self.h_wav = torch.empty(2 * bs * (max_clip + 1), dtype=torch.int16).pin_memory()
+        self.h_meta = torch.empty(2, 2 * bs, dtype=torch.int64).pin_memory()
+        self.d_img = torch.empty(bs, 3, 96, 96, dtype=torch.uint8, device=device)
+        self.d_wav = torch.empty(2 * bs * (max_clip + 1), dtype=torch.int16, device=device)
+        self.d_meta = torch.empty(2, 2 * bs, dtype=torch.int64, device=device)
+        self.free = threading.Event()
+        self.free.set()
+        self.consumed = None  # CUDA event: the compute stream is done reading this slot
+
+
 class DeviceTripletLoader:
     """Iterable replacing `DataLoader(ConcatDataset, batch_size, shuffle=True, num_workers=0)` for
-    VARDataset records: device-resident images / labels / clips, batches assembled by
-    var_sampler_batch[_tasks] + var_mfcc_fwd.  Yields the reference tuples; `raw_batches()` yields the
-    uint8 / [2B, F, 40] form the fused trainer consumes (rank-sliced under data parallelism).
+    VARDataset records; batches are assembled by var_sampler_batch[_tasks] + var_mfcc_fwd.  Yields the
+    reference tuples; `raw_batches()` yields the uint8 / [2B, F, 40] form the fused trainer consumes
+    (rank-sliced under data parallelism).  Two residency modes:
+
+    * resident=True (default): uint8 frames, labels and the int16 clip arena live in HBM (a B200 holds
+      180 GB: 6 M frames); the sampler and the MFCC of batch k+1 run on a side stream under step k.
+    * resident=False: frames and clips stay in pinned host memory (datasets beyond HBM).  A prefetch
+      thread -- the counterpart of the reference's DataLoader workers -- draws batch k+1's indices on a
+      side stream, gathers its frames / clips into pinned staging and uploads them while the GPU runs
+      step k; only the MFCC runs on the compute stream.
 
     seed=None (default) continues torch's global CPU generator from its state at construction, as the
     reference's DataLoader does; an int starts a fresh `torch.manual_seed(seed)` stream."""
 
     def __init__(self, images_u8, gt, stored_sn, audio, arena, config, batch_size, shuffle=True, drop_last=False,
-                 seed=None, device=None, rank=0, world_size=1):
+                 seed=None, device=None, rank=0, world_size=1, resident=True):
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.config, self.audio, self.arena = config, audio, arena
         self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
         self.rank, self.world_size = rank, world_size
-        self.images = torch.as_tensor(images_u8, dtype=torch.uint8).to(self.device).contiguous()
-        self.n_items = self.images.shape[0]
+        self.resident = bool(resident)
+        images_u8 = torch.as_tensor(images_u8, dtype=torch.uint8).contiguous()
+        self.n_items = images_u8.shape[0]
+        if self.resident:
+            self.images = images_u8.to(self.device)
+        else:
+            self.images_host = images_u8.pin_memory()
+            self._clip_off_host = arena.clip_off.cpu().numpy()
+            self.h2d_bytes = 0  # bytes uploaded by the batches yielded so far
         # one STFT parameter set per loader: the reference picks it per drawn dataset
         # (audioLoader.py:183); mixing NSynth/UrbanSound (1024-point) with the 512-point sets in
         # ONE intent table would need two plans per batch and is rejected here.
@@ -239,36 +270,178 @@ class DeviceTripletLoader:
         self.sampler = DeviceTripletSampler(config.taskNum, None if ithor else arena.dataset_sizes, gt, stored_sn, seed,
                                             self.device, arena.clip_off, arena.clip_len,
                                             task_tables=arena if ithor else None)
+        # the sampler state is only ever touched on this stream (seeded above on the current one)
+        self._ls = torch.cuda.Stream(self.device)
+        self._ls.wait_stream(torch.cuda.current_stream(self.device))
+        self._slots = None
 
     def __len__(self):
         n = self.n_items // self.batch_size
         return n if (self.drop_last or self.n_items % self.batch_size == 0) else n + 1
 
+    # ------------------------------------------------------------------ batch assembly
+    def _epoch_perm(self):
+        with torch.cuda.stream(self._ls):
+            if self.shuffle:
+                return self.sampler.begin_epoch().clone()
+            return torch.arange(self.n_items, dtype=torch.int32, device=self.device)
+
+    def _batch_starts(self):
+        n, bs = self.n_items, self.batch_size
+        return [s for s in range(0, n, bs) if not (self.drop_last and n - s < bs)]
+
+    def _draw(self, perm, s):
+        """Sampler launch for the batch starting at permutation position s (on the loader stream)."""
+        items = perm[s:s + self.batch_size]
+        B = int(items.numel())
+        rec = self.sampler.sample(items)  # every rank draws the GLOBAL batch: identical streams
+        lo, hi = (B * self.rank) // self.world_size, (B * (self.rank + 1)) // self.world_size
+        return rec, B, lo, hi
+
+    def _resident_batches(self):
+        """Batch k+1's sampler + MFCC launches are issued on the loader stream before batch k is handed
+        out, so they run under step k instead of on its critical path."""
+        cs = torch.cuda.current_stream(self.device)
+        n_fft, win, hop = self.audio.stft_params(self.param)
+        F = self.config.sound_dim[1]
+        wav = self.arena.wav  # first use uploads the arena on the compute stream
+        self._ls.wait_stream(cs)
+        perm = self._epoch_perm()
+
+        def issue(s):
+            with torch.cuda.stream(self._ls):
+                rec, B, lo, hi = self._draw(perm, s)
+                if hi == lo:
+                    out = (None, None, rec["gt"][lo:hi], B, rec)
+                else:
+                    off = torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]])
+                    ln = torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]])
+                    sounds = mfcc_device(wav, off, ln, self.audio.fs, n_fft, win, hop, F, flavour=self.flavour)
+                    out = (self.images[rec["item"][lo:hi].long()], sounds, rec["gt"][lo:hi], B, rec)
+                ev = torch.cuda.Event()
+                ev.record(self._ls)
+            return out, ev
+
+        starts = self._batch_starts()
+        nxt = issue(starts[0]) if starts else None
+        for k in range(len(starts)):
+            out, ev = nxt
+            nxt = issue(starts[k + 1]) if k + 1 < len(starts) else None
+            cs.wait_event(ev)
+            for t in out[:3] + tuple(out[4].values()):
+                if torch.is_tensor(t):
+                    t.record_stream(cs)  # allocated on the loader stream, consumed on the compute stream
+            yield out
+
+    def _producer(self, q, stop, perm, starts, max_clip):
+        def put(x):
+            while not stop.is_set():
+                try:
+                    q.put(x, timeout=0.05)
+                    return True
+                except queue.Full:
+                    pass
+            return False
+        try:
+            torch.cuda.set_device(self.device)
+            wav_host = self.arena.wav_host
+            for k, s in enumerate(starts):
+                slot = self._slots[k % len(self._slots)]
+                while not slot.free.wait(0.05):
+                    if stop.is_set():
+                        return
+                slot.free.clear()
+                with torch.cuda.stream(self._ls):
+                    rec, B, lo, hi = self._draw(perm, s)
+                    b = hi - lo
+                    if b:
+                        meta = torch.stack([torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]]),
+                                            torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]]).long()])
+                        slot.h_meta[:, :2 * b].copy_(meta, non_blocking=True)
+                        h_items = rec["item"][lo:hi].long().cpu()   # synchronises the loader stream only
+                gt = rec["gt"][lo:hi]
+                if not b:
+                    if not put((slot, 0, B, gt, rec, None, 0)):
+                        return
+                    continue
+                torch.index_select(self.images_host, 0, h_items, out=slot.h_img[:b])
+                off = slot.h_meta[0, :2 * b].numpy()
+                ln = slot.h_meta[1, :2 * b].numpy()
+                h_wav, cur = slot.h_wav.numpy(), 0
+                src = wav_host.numpy()
+                for j in range(2 * b):           # ragged gather into the staging arena (4-byte aligned)
+                    o, n = int(off[j]), int(ln[j])
+                    if o < 0:
+                        continue
+                    h_wav[cur:cur + n] = src[o:o + n]
+                    off[j] = cur
+                    cur += n + (n & 1)
+                with torch.cuda.stream(self._ls):
+                    if slot.consumed is not None:
+                        self._ls.wait_event(slot.consumed)   # the previous tenant of this slot was read on cs
+                    slot.d_img[:b].copy_(slot.h_img[:b], non_blocking=True)
+                    slot.d_wav[:cur].copy_(slot.h_wav[:cur], non_blocking=True)
+                    slot.d_meta[:, :2 * b].copy_(slot.h_meta[:, :2 * b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._ls)
+                if not put((slot, b, B, gt, rec, ev, b * 3 * 96 * 96 + cur * 2 + 2 * 2 * b * 8)):
+                    return
+            put(None)
+        except BaseException as e:  # noqa: BLE001 -- re-raised in the consumer
+            put(e)
+
+    def _streaming_batches(self):
+        cs = torch.cuda.current_stream(self.device)
+        n_fft, win, hop = self.audio.stft_params(self.param)
+        F = self.config.sound_dim[1]
+        max_clip = int(self.arena.clip_len.max()) if self.arena.clip_len.numel() else 0
+        if self._slots is None or self._slots[0].h_wav.numel() < 2 * self.batch_size * (max_clip + 1):
+            self._slots = [_Slot(self.batch_size, max_clip, self.device) for _ in range(3)]
+        for sl in self._slots:
+            sl.free.set()
+        perm = self._epoch_perm()
+        q, stop = queue.Queue(maxsize=2), threading.Event()
+        th = threading.Thread(target=self._producer, args=(q, stop, perm, self._batch_starts(), max_clip), daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                slot, b, B, gt, rec, ev, nbytes = item
+                if not b:
+                    slot.free.set()
+                    yield None, None, gt, B, rec
+                    continue
+                cs.wait_event(ev)
+                for t in [gt] + list(rec.values()):
+                    if torch.is_tensor(t):
+                        t.record_stream(cs)
+                sounds = mfcc_device(slot.d_wav, slot.d_meta[0, :2 * b], slot.d_meta[1, :2 * b].int(), self.audio.fs,
+                                     n_fft, win, hop, F, flavour=self.flavour)
+                self.h2d_bytes += nbytes
+                yield slot.d_img[:b], sounds, gt, B, rec
+                # the consumer has launched its step on cs: mark the slot reusable once that work is done
+                slot.consumed = torch.cuda.Event()
+                slot.consumed.record(cs)
+                slot.free.set()
+        finally:
+            stop.set()
+            for sl in self._slots:
+                sl.free.set()
+            th.join(timeout=5.0)
+
     def raw_batches(self):
         """-> (uint8 images [b, 3, 96, 96], sounds [2b, F, 40], gt [b], global batch B, sampler record) with
         b = this rank's slice of the global batch (may be 0 on a ragged tail: images/sounds are then None)."""
-        n, bs = self.n_items, self.batch_size
-        if self.shuffle:
-            perm = self.sampler.begin_epoch()
-        else:
-            perm = torch.arange(n, dtype=torch.int32, device=self.device)
-        n_fft, win, hop = self.audio.stft_params(self.param)
-        F = self.config.sound_dim[1]
-        for s in range(0, n, bs):
-            items = perm[s:s + bs]
-            B = int(items.numel())
-            if B < bs and self.drop_last:
-                break
-            rec = self.sampler.sample(items)  # every rank draws the GLOBAL batch: identical streams
-            lo, hi = (B * self.rank) // self.world_size, (B * (self.rank + 1)) // self.world_size
-            if hi == lo:
-                yield None, None, rec["gt"][lo:hi], B, rec
-                continue
-            idx = rec["item"][lo:hi].long()
-            off = torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]])
-            ln = torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]])
-            sounds = mfcc_device(self.arena.wav, off, ln, self.audio.fs, n_fft, win, hop, F, flavour=self.flavour)
-            yield self.images[idx], sounds, rec["gt"][lo:hi], B, rec
+        return self._resident_batches() if self.resident else self._streaming_batches()
+
+    def stream(self):
+        """Raw batches across epoch boundaries, endlessly (for step-counted training / benchmarking)."""
+        while True:
+            yield from self.raw_batches()
 
     def __iter__(self):
         for img_u8, sounds, gt, _, _ in self.raw_batches():
@@ -310,7 +483,10 @@ def loadEnvData(data_dir, config, batch_size, shuffle, num_workers, drop_last, l
         if any(has_sn) and not all(has_sn):
             raise ValueError("records mix stored and drawn sound_negative_id")
         stored = [int(p['sound_negative_id']) for p in records] if all(has_sn) else None
+        # config.pretextDataResident (optional, default True): keep frames + clips in HBM, or stream them from
+        # pinned host memory every step
         generator = DeviceTripletLoader(images, gt, stored, audio, audio.build_arena(), config, batch_size,
-                                        shuffle=shuffle, drop_last=drop_last)
+                                        shuffle=shuffle, drop_last=drop_last,
+                                        resident=getattr(config, "pretextDataResident", True))
     print("The number of pairs for each object in the dataset is:", num)
     return generator, final_dataset
