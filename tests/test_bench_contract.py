@@ -39,3 +39,33 @@ def test_b200_arm_has_no_cpu_fallback():
     r = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-reward", timeout=120)
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_bench_dataset_is_in_the_reference_formats(tmp_path):
+    """bench.py writes its synthetic triplets the way the reference stores them (pickled records + FSC csv /
+    GoogleCommand folders) and the audioLoader mirror reads them back through its reference-named loaders."""
+    import pickle
+    from importlib import import_module
+    sys.path.insert(0, ROOT)
+    import bench
+    al = import_module("voicecontrolledrobot-var_b200.Envs.audioLoader")
+    for name in ("ithor_b256", "kuka_b64"):
+        wl = dict(bench.WORKLOADS[name], items=40, clips_per_list=3)
+        root = str(tmp_path / name)
+        bench.write_dataset(root, wl, name)
+        cfg = bench.make_config(name, wl, root)
+        a = al.audioLoader(cfg)
+        a.loadData()
+        assert a.fs == 16000
+        if wl["net"] == "ithor":
+            assert cfg.name == "AI2ThorConfig" and cfg.taskNum == 4
+            lists = {(l, o, x): len(a.words[l][o][x]) for l in a.words for o in a.words[l] for x in a.words[l][o]}
+            assert len(lists) == 6 and set(lists.values()) == {3}
+        else:
+            assert cfg.name == "ArmConfig"
+            assert [len(a.words[i]["GoogleCommand"]) for i in range(4)] == [3, 3, 3, 3]
+        recs = []
+        for f in sorted(os.listdir(os.path.join(root, "data", "train"))):
+            recs += pickle.load(open(os.path.join(root, "data", "train", f), "rb"))
+        assert len(recs) == 40 and recs[0]["image"].shape == (3, 96, 96) and recs[0]["image"].dtype.name == "uint8"
+        assert set(recs[0]) == {"image", "ground_truth"} and all(0 <= r["ground_truth"] <= 4 for r in recs)
