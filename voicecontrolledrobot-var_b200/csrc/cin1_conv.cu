@@ -377,11 +377,7 @@ int cin1_conv_fwd(const Cin1Args& a, cudaStream_t st) {
   CUtensorMap tw;
   int rc = get_tmap_2d(a.w, kCout, kKpad, kKpad, kCout, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
-    configured = true;
-  }
+  VAR_ENSURE_SMEM(cin1_fwd_kernel, kSmemFwd);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   LaunchScope sc(T_GEMM_SCALAR, 2.0 * a.N * a.P * kQ * kCout * (double)kTaps, st);
   cin1_fwd_kernel<<<grid, kThreads, kSmemFwd, st>>>(tw, a, tiles, tpi);
@@ -395,11 +391,7 @@ int cin1_conv_wgrad(const Cin1Args& a, cudaStream_t st) {
   CUtensorMap tdy;
   int rc = get_tmap_2d(a.dy, a.N * a.P * kQ, kCout, kCout, 32, mn_cfg().tma_swizzle, &tdy);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWgrad));
-    configured = true;
-  }
+  VAR_ENSURE_SMEM(cin1_wgrad_kernel, kSmemWgrad);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   LaunchScope sc(T_WGRAD, 2.0 * a.N * a.P * kQ * kCout * (double)kTaps, st);
   cin1_wgrad_kernel<<<grid, kThreads, kSmemWgrad, st>>>(tdy, a, tiles, tpi, mn_cfg().lbo, mn_cfg().sbo,

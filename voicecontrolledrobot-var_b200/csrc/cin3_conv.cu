@@ -388,12 +388,8 @@ int cin3_conv_fwd(const Cin3Args& a, cudaStream_t st) {
   CUtensorMap tw;
   int rc = get_tmap_2d(a.w, kCout, 32, 32, kCout, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin3_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin3_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
-    configured = true;
-  }
+  VAR_ENSURE_SMEM(cin3_fwd_kernel<1>, kSmemFwd);
+  VAR_ENSURE_SMEM(cin3_fwd_kernel<2>, kSmemFwd);
   const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
   LaunchScope sc(T_GEMM_SCALAR, 2.0 * a.N * a.P * a.Q * kCout * (double)kTaps, st);
   if (a.stride == 1) cin3_fwd_kernel<1><<<grid, kThreads, kSmemFwd, st>>>(tw, a, ge, tiles);
@@ -409,12 +405,8 @@ int cin3_conv_wgrad(const Cin3Args& a, cudaStream_t st) {
   CUtensorMap tdy;
   int rc = get_tmap_2d(a.dy, a.N * a.P * a.Q, kCout, kCout, 32, mn_cfg().tma_swizzle, &tdy);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin3_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWgrad));
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(cin3_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWgrad));
-    configured = true;
-  }
+  VAR_ENSURE_SMEM(cin3_wgrad_kernel<1>, kSmemWgrad);
+  VAR_ENSURE_SMEM(cin3_wgrad_kernel<2>, kSmemWgrad);
   const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
   LaunchScope sc(T_WGRAD, 2.0 * a.N * a.P * a.Q * kCout * (double)kTaps, st);
   if (a.stride == 1) cin3_wgrad_kernel<1><<<grid, kThreads, kSmemWgrad, st>>>(tdy, a, ge, tiles, mn_cfg().sbo, mn_cfg().type);

@@ -22,6 +22,10 @@
   } while (0)
 
 void var_set_last_error(const char* msg, const char* file, int line);
+// Raises a kernel's dynamic shared memory limit to at least `bytes` on the CURRENT device (remembered
+// per (kernel, device), so repeated calls cost a hash lookup).  Returns a cudaError_t.
+cudaError_t var_ensure_dyn_smem(const void* kernel, size_t bytes);
+#define VAR_ENSURE_SMEM(kernel, bytes) VAR_CUDA_CHECK(var_ensure_dyn_smem((const void*)(kernel), (size_t)(bytes)))
 
 namespace var {
 

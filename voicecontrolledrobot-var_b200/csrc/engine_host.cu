@@ -20,6 +20,25 @@ void var_set_last_error(const char* msg, const char* file, int line) {
 }
 extern "C" const char* var_last_error(void) { return g_last_error; }
 
+cudaError_t var_ensure_dyn_smem(const void* kernel, size_t bytes) {
+  struct Key { const void* f; int dev; bool operator==(const Key& o) const { return f == o.f && dev == o.dev; } };
+  struct Hash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.f) * 31u + (size_t)k.dev; } };
+  static std::unordered_map<Key, size_t, Hash> done;
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = done[Key{kernel, dev}];
+  if (bytes <= cur) return cudaSuccess;
+  if (bytes > 48 * 1024 || cur > 0) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+  }
+  cur = bytes;
+  return cudaSuccess;
+}
+
 namespace var {
 
 // ---------------------------------------------------------------------------
@@ -254,12 +273,7 @@ static int launch_gemm_t(const CUtensorMap& t0, const CUtensorMap& t1, const CUt
   size_t smem = gemm_smem_bytes(p.bn, p.stages);
   if (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8)
     smem += (size_t)p.g[0].C * p.sc_nh * p.sc_wpad * 4 + 16;  // staged input patch
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<GMODE, EPI>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  VAR_ENSURE_SMEM((tc_gemm_kernel<GMODE, EPI>), smem);
   {
     double flops = 0;
     for (unsigned z = 0; z < grid.z; ++z)
@@ -314,12 +328,7 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
     p.epi_coalesce = 1;
     smem += 4 * 4352;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_persist_kernel<GMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = smem;
-  }
+  VAR_ENSURE_SMEM(tc_gemm_persist_kernel<GMODE>, smem);
   const long long total = (long long)m_tiles * n_tiles;
   const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
   int grid = kNumSMs * per_sm;
@@ -365,12 +374,7 @@ static int launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t st) {
   size_t smem = wgrad_smem_bytes(p.cout, p.stages);
   if (GMODE == G_SCALAR_F32 || GMODE == G_SCALAR_U8)
     smem += (size_t)p.g.C * p.sc_nh * p.sc_wpad * 4 + 16;  // staged input patch
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<GMODE>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  VAR_ENSURE_SMEM(tc_wgrad_kernel<GMODE>, smem);
   {
     LaunchScope sc(T_WGRAD, 2.0 * p.g.M * (double)p.cout * p.g.K, st);
     tc_wgrad_kernel<GMODE><<<grid, 160, smem, st>>>(p);
@@ -686,14 +690,9 @@ bool gru_persist_enabled() {  // VAR_GRU_PERSIST=0 falls back to one launch per 
 template <int BWD>
 static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3 grid, cudaStream_t st) {
   const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + gru_scr_bytes(BWD) + 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_persist_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = smem;
-  }
-  static int max_ctas = -1;
-  if (max_ctas < 0) {
+  VAR_ENSURE_SMEM(gru_persist_kernel<BWD>, smem);
+  int max_ctas = 0;
+  {  // per call and per device: one process may drive several GPUs
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -800,37 +799,54 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
   p.bn = 64; p.num_kb = (3 * p.Hd / 32) / 2; p.kps = 2; p.stages = 3;
   if (p.num_kb % p.kps) return VAR_ERR_UNSUPPORTED;
   const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + 2 * gru_scr_bytes(1) + 32;
-  static bool configured = false;
-  if (!configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_ksplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  // (cudaFuncSetAttribute is per device: set it every call -- it is a cheap host-side call)
+  VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_ksplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(2, p.Hd / 64, nrt * 2);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  // Cluster attribute only: the cooperative attribute on top of it makes the launch unprofilable
-  // (ncu aborts the application with LaunchFailed).  Co-residency -- needed for the spin waits --
-  // is checked against cudaOccupancyMaxActiveClusters instead; kernels of the other stream never
-  // wait on this one, so CTAs that start late only delay their peers.
-  cudaLaunchAttribute at[1];
+  // Cluster + cooperative attributes: the kernel spin-waits on peer CTAs, so the driver must guarantee
+  // that the whole grid is co-resident (the image branch runs concurrently on another stream).  ncu
+  // cannot replay a cooperative cluster launch (it aborts the application with LaunchFailed), so
+  // VAR_GRU_NO_COOP=1 drops the cooperative attribute for profiling runs only; co-residency is then
+  // merely checked against cudaOccupancyMaxActiveClusters.  All caches are per device.
+  constexpr int kMaxDev = 64;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return VAR_ERR_UNSUPPORTED;
+  static int no_coop = -1;
+  if (no_coop < 0) no_coop = env_int("VAR_GRU_NO_COOP", 0);
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;  // the occupancy query below takes the cluster shape only
+  static int max_clusters[kMaxDev];
+  static bool have_max[kMaxDev], refused[kMaxDev], coop_refused[kMaxDev];
+  if (!have_max[dev]) {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, gru_bwd_ksplit_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
-    max_clusters = n;
+    max_clusters[dev] = n;
+    have_max[dev] = true;
   }
-  static bool refused = false;  // a launch was rejected once (e.g. under a profiler that cannot replay it)
-  if (refused || (long long)max_clusters * 2 < (long long)grid.x * grid.y * grid.z) return VAR_ERR_UNSUPPORTED;
+  // refused: a launch was rejected once on this device (e.g. under a profiler that cannot replay it)
+  if (refused[dev] || (long long)max_clusters[dev] * 2 < (long long)grid.x * grid.y * grid.z) return VAR_ERR_UNSUPPORTED;
   VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * nrt * 2, st));
   void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
   LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
+  if (!no_coop && !coop_refused[dev]) {
+    cfg.numAttrs = 2;
+    if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args) == cudaSuccess) return VAR_OK;
+    (void)cudaGetLastError();  // not sticky
+    coop_refused[dev] = true;
+    static bool said = false;
+    if (!said) { fprintf(stderr, "[var] cooperative cluster launch of gru_bwd_ksplit_kernel refused; using the occupancy check\n"); said = true; }
+    cfg.numAttrs = 1;
+  }
   if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args) != cudaSuccess) {
     (void)cudaGetLastError();  // not sticky: fall back to the one-CTA-per-tile kernel from now on
-    refused = true;
+    refused[dev] = true;
     return VAR_ERR_UNSUPPORTED;
   }
   return VAR_OK;
@@ -1041,12 +1057,7 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
   p.pix_per_cta = ppc;
   p.cout = slab;
   const size_t smem = wgrad_smem_bytes(slab, p.stages * p.kps);
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = smem;
-  }
+  VAR_ENSURE_SMEM(tc_wgrad_tma_kernel<0>, smem);
   // all slabs of output channels in one launch (grid.z): one slab alone is ktiles * splits CTAs and
   // would leave a third of the SMs idle for wide layers (GRU: 6 slabs of 96 CTAs)
   dim3 grid(ktiles, splits, nslab);

@@ -312,12 +312,9 @@ int first_conv_wgrad(FirstConvArgs a, int u8, cudaStream_t st) {
   const size_t smem = (size_t)3 * ((a.rows - 1) * a.stride + 3) * (a.W + 2) * 4;
   int grid = 4 * kNumSMs;
   if (grid > items) grid = items;
-  static bool configured = false;
-  if (!configured) {  // static reduction buffer (29.6 KB) + patch can pass the 48 KB default
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(first_conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(first_conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
+  // static reduction buffer (29.6 KB) + patch can pass the 48 KB default
+  VAR_ENSURE_SMEM(first_conv_wgrad_kernel<true>, 64 * 1024);
+  VAR_ENSURE_SMEM(first_conv_wgrad_kernel<false>, 64 * 1024);
   LaunchScope sc(T_WGRAD, 2.0 * a.N * a.P * a.Q * kCout * (double)kK, st);
   if (tile4_ok(a)) {
     const int wp = pitch4(a);

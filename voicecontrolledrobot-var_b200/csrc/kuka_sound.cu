@@ -124,12 +124,7 @@ __global__ void __launch_bounds__(kThreads, 2) kuka_sound_fwd_kernel(KukaSoundAr
 int kuka_sound_fwd(const KukaSoundArgs& a, int N, cudaStream_t st) {
   if (N <= 0) return VAR_OK;
   const size_t smem = (size_t)(kF * kMelW + kK1 * kC + 3 * kK2 * kC + (kP1 + kP2 + kP3 + kP4) * kC) * 4;
-  static bool configured = false;
-  if (!configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(kuka_sound_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = true;
-  }
+  VAR_ENSURE_SMEM(kuka_sound_fwd_kernel, smem);
   LaunchScope sc(T_MISC, 2.0 * N * 447872.0, st);
   kuka_sound_fwd_kernel<<<N, kThreads, smem, st>>>(a);
   VAR_CUDA_CHECK(cudaGetLastError());

@@ -558,19 +558,11 @@ int mfcc_fwd(const MfccPlan* p, const int16_t* wav, const long long* offsets, co
   LaunchScope sc(T_MFCC, 0, st);
   if (p->n_fft == 512) {
     const size_t smem = mfcc_smem_bytes<512>(p->hop, p->t.maxcnt);
-    static bool cfg = false;
-    if (!cfg) {
-      VAR_CUDA_CHECK(cudaFuncSetAttribute(mfcc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cfg = true;
-    }
+    VAR_ENSURE_SMEM(mfcc_kernel<512>, smem);  // (maxcnt differs between the two filterbank flavours)
     mfcc_kernel<512><<<grid, kMfccThreads, smem, st>>>(a);
   } else {
     const size_t smem = mfcc_smem_bytes<1024>(p->hop, p->t.maxcnt);
-    static size_t cfg = 0;
-    if (smem > cfg) {
-      VAR_CUDA_CHECK(cudaFuncSetAttribute(mfcc_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cfg = smem;
-    }
+    VAR_ENSURE_SMEM(mfcc_kernel<1024>, smem);
     mfcc_kernel<1024><<<grid, kMfccThreads, smem, st>>>(a);
   }
   VAR_CUDA_CHECK(cudaGetLastError());

@@ -294,12 +294,7 @@ int sampler_set_state(uint32_t* state, const uint32_t* host_words, int pos, cuda
 int sampler_epoch(uint32_t* state, int n, int* perm, cudaStream_t st) {
   if (n <= 0) return VAR_ERR_ARG;
   const size_t smem = n <= 65536 ? (size_t)n * 2 + 16 : 0;
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(sampler_epoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = smem;
-  }
+  VAR_ENSURE_SMEM(sampler_epoch_kernel, smem);
   LaunchScope sc(T_SAMPLER, 0, st);
   sampler_epoch_kernel<<<1, 256, smem, st>>>(state, n, perm);
   VAR_CUDA_CHECK(cudaGetLastError());
@@ -312,12 +307,7 @@ int sampler_batch(const SamplerArgs& a_in, cudaStream_t st) {
   const int dpi = a.nds2 ? 7 : 5, cap = a.nds2 ? 4096 : 8192;  // keeps the draw window under the smem limit
   a.chunk = a.B < cap ? a.B : cap;
   const size_t smem = (size_t)(MT_N + dpi * a.chunk + MT_N) * 4 + (size_t)a.chunk * 4 + 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    VAR_CUDA_CHECK(cudaFuncSetAttribute(sampler_batch_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  VAR_ENSURE_SMEM(sampler_batch_kernel, smem);
   LaunchScope sc(T_SAMPLER, 0, st);
   sampler_batch_kernel<<<1, 256, smem, st>>>(a);
   VAR_CUDA_CHECK(cudaGetLastError());
