@@ -112,6 +112,15 @@ int var_net_raw_dims(void* net, int* img_raw, int* snd_raw);
  * high-priority side stream so the branches overlap); used by bench.py for uncontended per-kernel timings. */
 int var_net_set_overlap(void* net, int on);
 
+/* Data-parallel gradient buckets (no reference counterpart: the reference is single-GPU).  Bucket 0 is
+ * the contiguous range of the flat gradient buffer that holds every recurrent-layer gradient (rnn.*, iTHOR
+ * net only: 77 % of the gradient bytes); it is final half way through the backward pass.
+ * var_net_set_bucket_event registers a caller-owned cudaEvent_t (null = none) that the backward pass
+ * records at that point, on the stream that produced the gradients, so the caller's all-reduce of the
+ * range can run under the rest of the backward pass.  VAR_ERR_UNSUPPORTED for nets without the bucket. */
+int var_net_grad_bucket(void* net, int bucket, int64_t* offset_floats, int64_t* count_floats);
+int var_net_set_bucket_event(void* net, int bucket, void* cuda_event);
+
 /* VARPretextNet.forward (models/pretext/pretext_base.py:10-42) for a batch.
  *   d_images : [n_images, 3, 96, 96] NCHW; image_kind 0 = uint8 (scaled by 1/255 in the first
  *              conv's loader, dataset.py:67-68 / vec_pretext_normalize.py:85), 1 = fp32.

@@ -137,7 +137,7 @@ class RL_VAR(RLBase):
                 goal_area_count = infos[0]['goal_area_count']
                 goal_area_count_list.append(goal_area_count)
                 results.append(int(goal_area_count >= cfg.success_threshold))
-                eval_episode_rewards.append(float(eval_env_rewards))
+                eval_episode_rewards.append(float(np.asarray(eval_env_rewards).reshape(-1)[0]))
                 eval_env_rewards = 0.
         if not cfg.render:
             import pandas as pd

@@ -60,14 +60,18 @@ class VAR_Pretext(Pretext):
             batches = host_batches()
         for img, snd, global_b in batches:
             eng.zero_grad()
-            if img is None or img.shape[0] == 0:
+            stepped = not (img is None or img.shape[0] == 0)
+            if not stepped:
                 # ragged tail batch smaller than the world size: this rank has no triplet, but it must
                 # still take part in both collectives and in the (identical) Adam step
                 loss = torch.zeros((), dtype=torch.float32, device=self.device)
             else:
                 loss = eng.triplet_step(img, snd, margin=cfg.tripletMargin, loss_denominator=global_b)
             if world > 1:
-                dist.all_reduce(eng.grads)
+                if hasattr(eng, "allreduce_grads"):
+                    eng.allreduce_grads(stepped)   # bucketed: the recurrent-layer range overlaps the backward pass
+                else:
+                    dist.all_reduce(eng.grads)
                 dist.all_reduce(loss)
             eng.adam_step(lr, weight_decay=cfg.pretextAdamL2)
             losses.append(loss)

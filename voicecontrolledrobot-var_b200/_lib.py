@@ -53,6 +53,8 @@ PROTOTYPES = {
     "var_net_refresh_mma": (_i, [_p, _p]),
     "var_net_workspace_bytes": (_i64, [_p, _i, _i, _i]),
     "var_net_set_overlap": (_i, [_p, _i]),
+    "var_net_grad_bucket": (_i, [_p, _i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "var_net_set_bucket_event": (_i, [_p, _i, _p]),
     "var_net_raw_dims": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
     "var_net_forward": (_i, [_p, _p, _i, _i, _p, _i, _p, _i64, _i, _p, _p, _p, _p, _p]),
     "var_net_backward": (_i, [_p, _p, _p, _p, _i64, _p]),

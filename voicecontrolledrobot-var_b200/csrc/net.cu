@@ -99,6 +99,11 @@ struct Net {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;
+  // Data-parallel overlap: the recurrent-layer gradients (rnn.*: 77 % of the iTHOR gradient bytes, one
+  // contiguous range of the flat buffer) are complete half way through the backward pass.  The caller
+  // may hand in an event that is recorded at that point (on whichever stream produced them), so its
+  // all-reduce of that range runs under the remaining conv backward kernels.
+  cudaEvent_t ev_rnn_grads = nullptr;  // not owned
 
   ~Net() {
     if (side) cudaStreamDestroy(side);
@@ -556,15 +561,18 @@ struct Net {
       }
       if (rc) return rc;
     }
+    ConvShape cih{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
     for (int d = 0; d < 2; ++d) {
       // dW_hh += dgh^T h_prev ; db_hh += colsum(dgh)      (rows: step-major)
       ConvShape chh{(int)BT, 1, 1, kGruH, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
       rc = conv_wgrad(chh, g.h_r[d], SRC_NHWC_F32, nullptr, dgh[d], gr(t_gru[d][1]), gr(t_gru[d][3]), st);
       if (rc) return rc;
       // dW_ih += dgi^T x ; db_ih += colsum(dgi)           (rows: batch-major)
-      ConvShape cih{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
       rc = conv_wgrad(cih, g.x, SRC_NHWC_F32, nullptr, dgi[d], gr(t_gru[d][0]), gr(t_gru[d][2]), st);
       if (rc) return rc;
+    }
+    if (ev_rnn_grads) VAR_CUDA_CHECK(cudaEventRecord(ev_rnn_grads, st));  // every rnn.* gradient is final
+    for (int d = 0; d < 2; ++d) {
       // dX = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd, ReLU mask of the conv output
       rc = conv_dgrad(cih, dgi[d], wr(t_gru[d][0]), d == 0 ? dx0 : dx, d == 0 ? nullptr : g.x,
                       d == 0 ? nullptr : dx0, d == 0 ? 0 : 1, st);
@@ -704,6 +712,22 @@ int var_net_refresh_mma(void* net, void* stream) {
   Net* n = NET(net);
   if (!n->P || !n->PR) return VAR_ERR_ARG;
   return var::round_copy(n->P, n->PR, n->nparams, ST(stream));
+}
+int var_net_grad_bucket(void* net, int bucket, int64_t* offset, int64_t* count) {
+  Net* n = NET(net);
+  if (!offset || !count) return VAR_ERR_ARG;
+  if (bucket != 0 || !n->has_gru) return VAR_ERR_UNSUPPORTED;
+  const auto& first = n->tensors[n->t_gru[0][0]];
+  const auto& last = n->tensors[n->t_gru[1][3]];
+  *offset = first.off;
+  *count = last.off + last.packed - first.off;
+  return VAR_OK;
+}
+int var_net_set_bucket_event(void* net, int bucket, void* cuda_event) {
+  Net* n = NET(net);
+  if (bucket != 0 || !n->has_gru) return VAR_ERR_UNSUPPORTED;
+  n->ev_rnn_grads = reinterpret_cast<cudaEvent_t>(cuda_event);
+  return VAR_OK;
 }
 int var_net_set_overlap(void* net, int on) {
   NET(net)->overlap = on != 0;

@@ -46,10 +46,13 @@ class VarEngine:
         self._ws = None
         self._ws_need = {}
         self._reward_graphs = {}
+        self._bucket = None
 
     def __del__(self):
         try:
             if getattr(self, "_net", None):
+                if getattr(self, "_bucket", None):
+                    lib.var_net_set_bucket_event(self._net, 0, None)
                 lib.var_net_destroy(self._net)
                 self._net = None
         except Exception:
@@ -181,6 +184,39 @@ class VarEngine:
                                  ptr(goal_feat_cached), ptr(env_reward), N, ptr(ws), ws.numel(), ptr(img_feat),
                                  ptr(goal_feat), ptr(dot), ptr(rew), stream_ptr()), "var_net_reward")
         return img_feat, goal_feat, dot, rew
+
+    # ------------------------------------------------------------------- data parallel
+    def allreduce_grads(self, stepped=True):
+        """Sum the flat gradient buffer over the ranks (the one collective of a training step).  For the
+        iTHOR net the recurrent-layer gradients (rnn.*, 77 % of the bytes, one contiguous range) are final
+        half way through the backward pass: the library records an event there, and that range is reduced
+        on a side stream under the remaining conv backward kernels; the rest follows on the compute
+        stream.  `stepped=False` (this rank ran no triplet_step since zero_grad) reduces everything in order."""
+        import torch.distributed as dist
+        if not stepped or not self._bucket_setup():
+            dist.all_reduce(self.grads)
+            return
+        off, cnt, ev, comm = self._bucket
+        comm.wait_event(ev)  # recorded by the backward pass of the last triplet_step
+        with torch.cuda.stream(comm):
+            work = dist.all_reduce(self.grads[off:off + cnt], async_op=True)
+        if off > 0:
+            dist.all_reduce(self.grads[:off])
+        if off + cnt < self.nparams:
+            dist.all_reduce(self.grads[off + cnt:])
+        work.wait()  # the compute stream waits for the side-stream reduction
+
+    def _bucket_setup(self):
+        if self._bucket is None:
+            off, cnt = C.c_int64(), C.c_int64()
+            if lib.var_net_grad_bucket(self._net, 0, C.byref(off), C.byref(cnt)) != 0:
+                self._bucket = False
+            else:
+                ev = torch.cuda.Event()
+                ev.record()  # creates the underlying cudaEvent_t
+                check(lib.var_net_set_bucket_event(self._net, 0, ev.cuda_event), "var_net_set_bucket_event")
+                self._bucket = (off.value, cnt.value, ev, torch.cuda.Stream(self.device))
+        return bool(self._bucket)
 
     def reset_optimizer(self):
         """Forget the Adam moments and the bias-correction step count (a fresh torch.optim.Adam)."""
