@@ -375,7 +375,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
-        return
+        return None
 
     # ---- rank 0 only, outside any process group: per-kernel profile, peaks, baselines ---------
     # branches serialised for this pass: with the two-stream overlap on, the events around a small
@@ -451,7 +451,7 @@ def run_b200(args):
         "model_tflops": value * FLOP_PER_TRIPLET[net] / 1e12, "tf32_peak_tflops": tf32_peak,
         "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "reward": reward,
     }
-    print(json.dumps(out))
+    return json.dumps(out)
 
 
 def bench_reward(vb, trainer, cfg, net, wl, dev, rank, world, dist):
@@ -650,7 +650,7 @@ def run_reference(args):
     does not travel to the GPU box) on the workload's FULL per-GPU batch, all host threads."""
     rank, world, _ = dist_env()
     if rank != 0:
-        return
+        return None
     wl = WORKLOADS[args.workload]
     net = wl["net"]
     B = wl["batch"] if wl["batch"] else min(wl["global_batch"], 1024)
@@ -666,7 +666,7 @@ def run_reference(args):
     v = B / dt
     sample = (f"each step = the workload's batch ({B} triplets: {2 * B} clips through the numpy MFCC, fp32 torch-CPU "
               f"fwd/bwd, Adam) on {os.cpu_count()} host threads; {steps} timed steps after {warm} warm-up")
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": "VAR train triplets/sec", "value": v, "unit": "triplets/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
@@ -674,12 +674,16 @@ def run_reference(args):
                                         "global_batch": B, "per_gpu_batch": B},
         "cpu_baseline": {"value": v, "unit": "triplets/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 if __name__ == "__main__":
+    import contextlib
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    _stdout = sys.stdout
+    # the reference-shaped API prints progress ("Sound Loaded", class histogram ...): keep stdout for the ONE JSON line
+    with contextlib.redirect_stdout(sys.stderr):
+        line = run_reference(a) if a.impl == "reference" else run_b200(a)
+    if line is not None:
+        _stdout.write(line + "\n")
+        _stdout.flush()
