@@ -198,6 +198,8 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if self.idx is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -335,9 +337,11 @@ def run_b200(args):
     loader = build_loader(True)
     batches = loader.stream()
     warm = max(args.warmup, 3)
-    trainer.train_epoch(eng, batches, lr, world, rank, max_steps=warm)
-    clocks = ClockSampler(local)
+    # clocks are sampled on rank 0's GPU only, and the sampler is started BEFORE the warm-up steps: the
+    # start-up of nvidia-smi (NVML initialisation takes the driver lock) must not fall into the timed region
+    clocks = ClockSampler(local if rank == 0 else None)
     clocks.start()
+    trainer.train_epoch(eng, batches, lr, world, rank, max_steps=warm)
     l0 = lib.var_launch_count()
     total_ms = timed(lambda: trainer.train_epoch(eng, batches, lr, world, rank, max_steps=args.steps))
     launches = lib.var_launch_count() - l0

@@ -83,6 +83,73 @@ int round_copy(const float* src, float* dst, long long n, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// 16-bit operand helpers (the f16 conv region):
+//  * cvt_f16: fp32 -> f16 copy (weights; n % 4 == 0)
+//  * grad_scale_prepare + cvt_f16_scaled: the gradient entering the region is stored as f16 times a
+//    power-of-two scale chosen on the device from its largest magnitude (so that the largest element
+//    sits at ~2^12 of f16's 65504 range and ~2^-36 of that magnitude is still representable); the
+//    region's kernels undo the scale where gradients leave it (weight gradients, the fp32 dX).
+//    scale[0] = S, scale[1] = 1/S.
+// ---------------------------------------------------------------------------
+__global__ void cvt_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+  }
+}
+int cvt_f16(const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n & 3) return VAR_ERR_ARG;
+  LaunchScope sc(T_MISC, 0, st);
+  cvt_f16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+__global__ void amax_kernel(const float4* __restrict__ src, long long n4, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));  // non-negative floats order like uints
+}
+__global__ void cvt_f16_scaled_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4,
+                                      const unsigned int* __restrict__ amax_bits, float* __restrict__ scale) {
+  // S = 2^(12 - ceil(log2(amax))): exact power of two, identical in every thread
+  const float amax = __uint_as_float(*amax_bits);
+  float S = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) {
+    int e;
+    frexpf(amax, &e);           // amax = f * 2^e, f in [0.5, 1)
+    e = 12 - e;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    S = ldexpf(1.f, e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = S; scale[1] = 1.f / S; }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_uint2(pack_f16x2(v.x * S, v.y * S), pack_f16x2(v.z * S, v.w * S));
+  }
+}
+int grad_to_f16_scaled(const float* src, void* dst, long long n, float* scale, unsigned int* amax_bits, cudaStream_t st) {
+  if (n & 3) return VAR_ERR_ARG;
+  VAR_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, sizeof(unsigned int), st));
+  {
+    LaunchScope sc(T_MISC, 0, st);
+    amax_kernel<<<grid_for(n / 4, 256, 4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), n / 4, amax_bits);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  {
+    LaunchScope sc(T_MISC, 0, st);
+    cvt_f16_scaled_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src),
+                                                                  reinterpret_cast<uint2*>(dst), n / 4, amax_bits, scale);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// ---------------------------------------------------------------------------
 // 2x2/2 max pooling, NHWC, C % 4 == 0 (nn.MaxPool2d(2, 2) of
 // models/pretext/ai2thor_pretext_model.py:9-11).
 // ---------------------------------------------------------------------------

@@ -10,6 +10,10 @@ int unpack_weight(const float* packed, float* ref, int O, int I, int R, int S, i
                   cudaStream_t st);
 int round_copy(const float* src, float* dst, long long n, cudaStream_t st);
 
+// 16-bit operand region helpers (aux_kernels.cu)
+int cvt_f16(const float* src, void* dst, long long n, cudaStream_t st);
+int grad_to_f16_scaled(const float* src, void* dst, long long n, float* scale, unsigned int* amax_bits, cudaStream_t st);
+
 int maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st);
 int maxpool_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C,
                 cudaStream_t st);

@@ -194,6 +194,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A * B, 16-bit inputs (f16 / bf16 per the instruction descriptor), f32 accumulate, K = 16.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread retire.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -245,6 +255,28 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n, int a_mn_major, in
          | ((uint32_t)b_mn_major << 16)  // b_major
          | ((uint32_t)(n >> 3) << 17)    // N
          | ((uint32_t)(128 >> 4) << 24); // M = 128
+}
+
+// Instruction descriptor for kind::f16 (a_fmt / b_fmt: 0 = f16, 1 = bf16), f32 accumulate, M=128.
+__host__ __device__ constexpr uint32_t make_idesc_h16(int n, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// fp32 -> packed 16-bit pairs (round to nearest even)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_bits_to_f32(uint16_t h) {
+  float f;
+  asm("{\n\t.reg .b16 t;\n\tmov.b16 t, %1;\n\tcvt.f32.f16 %0, t;\n\t}" : "=f"(f) : "h"(h));
+  return f;
 }
 
 // Byte offset of 16-byte chunk `chunk` (0..7) in row `row` of a 128B-swizzled

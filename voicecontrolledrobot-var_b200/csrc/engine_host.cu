@@ -115,9 +115,10 @@ struct TmapKey {
   const void* ptr;
   int rows, cols, box_rows, swz;
   long long pitch;
+  int esize;
   bool operator==(const TmapKey& o) const {
     return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows &&
-           swz == o.swz && pitch == o.pitch;
+           swz == o.swz && pitch == o.pitch && esize == o.esize;
   }
 };
 struct TmapHash {
@@ -128,15 +129,22 @@ struct TmapHash {
     h = h * 1315423911u + (size_t)k.box_rows;
     h = h * 1315423911u + (size_t)k.swz;
     h = h * 1315423911u + (size_t)k.pitch;
+    h = h * 1315423911u + (size_t)k.esize;
     return h;
   }
 };
 
 int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_rows, int swizzle,
                 CUtensorMap* out) {
+  return get_tmap_2d_e(ptr, 4, rows, cols, pitch, box_rows, swizzle, out);
+}
+
+// esize = 4 (fp32 / tf32) or 2 (f16 / bf16): the box is always 128 bytes wide (32 or 64 elements).
+int get_tmap_2d_e(const void* ptr, int esize, int rows, int cols, long long pitch, int box_rows, int swizzle,
+                  CUtensorMap* out) {
   static std::unordered_map<TmapKey, CUtensorMap, TmapHash> cache;
   static std::mutex mu;
-  TmapKey key{ptr, rows, cols, box_rows, swizzle, pitch};
+  TmapKey key{ptr, rows, cols, box_rows, swizzle, pitch, esize};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -150,16 +158,18 @@ int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_r
     var_set_last_error("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
     return VAR_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((pitch * 4) & 15)) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((pitch * esize) & 15) || (esize != 4 && esize != 2)) {
     var_set_last_error("tensor map needs 16-byte aligned base and pitch", __FILE__, __LINE__);
     return VAR_ERR_ARG;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)pitch * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)pitch * (cuuint64_t)esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUtensorMap m;
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box,
+  // 16-bit payloads are moved as opaque 16-bit words (f16 and bf16 alike)
+  CUresult r = fn(&m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                  const_cast<void*>(ptr), gdim, gstr, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -222,19 +232,26 @@ static EncodeIm2colFn encode_im2col_fn() {
 // [low, extent-1+up] with `stride`; each load covers `pixels` base pixels x 32 channels.
 int get_tmap_im2col(const float* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w,
                     int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out) {
+  return get_tmap_im2col_e(ptr, 4, N, H, W, C, low_w, low_h, up_w, up_h, stride_w, stride_h, pixels, swizzle, out);
+}
+
+int get_tmap_im2col_e(const void* ptr, int esize, int N, int H, int W, int C, int low_w, int low_h, int up_w,
+                      int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out) {
   EncodeIm2colFn fn = encode_im2col_fn();
   if (!fn) {
     var_set_last_error("cuTensorMapEncodeIm2col entry point unavailable", __FILE__, __LINE__);
     return VAR_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (C & 3)) return VAR_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((C * esize) & 15) || (esize != 4 && esize != 2)) return VAR_ERR_ARG;
+  const cuuint64_t es = (cuuint64_t)esize;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
   int lower[2] = {low_w, low_h};
   int upper[2] = {up_w, up_h};
   cuuint32_t estr[4] = {1u, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1u};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), gdim, gstr, lower,
-                  upper, 32u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4,
+                  const_cast<void*>(ptr), gdim, gstr, lower,
+                  upper, (cuuint32_t)(128 / esize), (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

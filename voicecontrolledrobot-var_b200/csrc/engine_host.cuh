@@ -15,6 +15,11 @@ MnCfg& mn_cfg();  // process-wide (selftest may override to probe the hardware)
 // `pitch` elements; box = {32 cols, box_rows}.  Cached by value of all args.
 int get_tmap_2d(const float* ptr, int rows, int cols, long long pitch, int box_rows, int swizzle,
                 CUtensorMap* out);
+// esize-aware forms (esize 4: fp32 boxes of 32 elements; esize 2: f16 / bf16 boxes of 64 elements)
+int get_tmap_2d_e(const void* ptr, int esize, int rows, int cols, long long pitch, int box_rows, int swizzle,
+                  CUtensorMap* out);
+int get_tmap_im2col_e(const void* ptr, int esize, int N, int H, int W, int C, int low_w, int low_h, int up_w,
+                      int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out);
 int get_tmap_im2col(const float* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w,
                     int up_h, int stride_w, int stride_h, int pixels, int swizzle, CUtensorMap* out);
 // 3-D fp32 tensor map over a dense [d2][d1][d0] array, box {b0, b1, 1}, no swizzle (not cached).

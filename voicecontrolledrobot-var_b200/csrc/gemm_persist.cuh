@@ -19,7 +19,12 @@
 
 namespace var {
 
-template <int GMODE>
+// H16: operands are 16-bit (f16 activations / weights, bf16 gradients; kind::f16 MMAs with K = 16): a
+// k-block is still one 128-byte row per pixel / weight row, i.e. 64 elements instead of 32 -- half the
+// shared-memory fill per MAC, which is what bounds the N = 64 convs.  MN-major B
+// boxes are {64 n, 64 k} (8 KB) in the plain 128B swizzle (16-byte granules).  The epilogue can store
+// f16 / bf16 (e.out_kind) and read an f16 ReLU mask (e.mask_kind); no addsrc / coalescing path.
+template <int GMODE, bool H16 = false>
 __global__ void __launch_bounds__(192)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA,
                        const __grid_constant__ GemmParams p, int m_tiles, int n_tiles) {
@@ -67,7 +72,8 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
   const int total = m_tiles * n_tiles;
   if (warp == 5) {
     // ===================== TMA producer =====================
-    const int nb_boxes = p.b_mn_major ? (bn >> 5) : p.nbox;
+    constexpr int KSH = H16 ? 6 : 5;  // log2(elements per 128-byte k-block row)
+    const int nb_boxes = p.b_mn_major ? (bn >> KSH) : p.nbox;
     const bool multi = nb_boxes >= 3;
     if (lane == 0 || (multi && lane <= 3 && lane - 1 < nb_boxes)) {
       int st = 0, ph = 0;
@@ -95,25 +101,26 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
             const int it = it0 + sub;
             const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
             const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
-            const int c0 = GMODE == G_TMA_IM2COL ? (cb << 5) : (it << 5);
+            const int c0 = GMODE == G_TMA_IM2COL ? (cb << KSH) : (it << KSH);
             if (lane == 0) {
               if constexpr (GMODE == G_TMA_IM2COL)
                 tma_load_im2col_4d(dstA, &tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
               else
-                tma_load_2d(dstA, &tmA, full_bar(st), it * 32, m0);
+                tma_load_2d(dstA, &tmA, full_bar(st), it << KSH, m0);
             }
             if (!p.b_mn_major) {
               for (int b = 0; b < p.nbox; ++b)
                 if (lane == (multi ? 1 + (b % 3) : 0))
-                  tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it * 32,
+                  tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it << KSH,
                               p.boxbase[b] + ntile * p.box_rows);
             } else {
               const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
-              const int k0 = cb << 5;
-              for (int gidx = 0; gidx < (bn >> 5); ++gidx)
+              const int k0 = cb << KSH;
+              // one box = {128 bytes of n, one k-block of k rows}: 4 KB (tf32: 32 x 32) or 8 KB (16-bit: 64 x 64)
+              for (int gidx = 0; gidx < (bn >> KSH); ++gidx)
                 if (lane == (multi ? 1 + (gidx % 3) : 0))
-                  tma_load_2d(dstB + (uint32_t)gidx * 4096u, &tmB, full_bar(st),
-                              rs * p.cin_total + ntile * bn + gidx * 32, k0);
+                  tma_load_2d(dstB + (uint32_t)gidx * (H16 ? 8192u : 4096u), &tmB, full_bar(st),
+                              rs * p.cin_total + ntile * bn + (gidx << KSH), k0);
             }
             if (++cb == period) { cb = 0; ++tap; }
           }
@@ -123,11 +130,15 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_tf32(bn, 0, p.b_mn_major);
+    const uint32_t idesc = H16 ? make_idesc_h16(bn, p.a_fmt, p.b_fmt, 0, p.b_mn_major) : make_idesc_tf32(bn, 0, p.b_mn_major);
     const uint64_t adesc0 = make_smem_desc(sA, 16u, 1024u);
-    const uint64_t bdesc0 = p.b_mn_major ? make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
+    // MN-major B: tf32 = 32-byte-granule swizzle (mn_cfg), 16-bit = plain 128B swizzle with 8-k-row atoms
+    // (SBO 1024) and 8 KB between 64-wide n groups (LBO)
+    const uint64_t bdesc0 = p.b_mn_major ? (H16 ? make_smem_desc(sB, 8192u, 1024u, 2)
+                                                : make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type))
                                          : make_smem_desc(sB, 16u, 1024u);
-    const int bstep = p.b_mn_major ? 64 : 2;  // 1024 B (8 k-rows, MN-major) or 32 B (8 columns, K-major) per MMA
+    // start-address step per MMA (>> 4): K-major 32 B; MN-major 8 k-rows (tf32, 1024 B) / 16 k-rows (16-bit, 2048 B)
+    const int bstep = p.b_mn_major ? (H16 ? 128 : 64) : 2;
     int st = 0, ph = 0, i = 0;
     if (lane == 0)  // one thread runs the whole issue loop (no warp-wide spin / re-convergence per stage)
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
@@ -148,9 +159,14 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
             const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA + (uint32_t)sub * kTileABytes) >> 4);
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB + (uint32_t)sub * tileB_bytes) >> 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              umma_tf32(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc,
-                        (uint32_t)((kb0 | sub | j) != 0));
+            for (int j = 0; j < 4; ++j) {
+              if constexpr (H16)
+                umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc,
+                         (uint32_t)((kb0 | sub | j) != 0));
+              else
+                umma_tf32(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc,
+                          (uint32_t)((kb0 | sub | j) != 0));
+            }
           }
           umma_commit(empty_bar(st));
           if (kb0 + kps >= num_kb) umma_commit(tfull_bar(acc));
@@ -227,6 +243,79 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
             }
           }
           __syncwarp();
+        }
+      } else if (H16 && (e.out_kind != 0 || e.mask_kind != 0)) {
+        // 16-bit storage: a thread owns 32 consecutive columns of its row = 64 bytes = four 16-byte stores
+        for (int c = 0; c < bn; c += 32) {
+          float v[32];
+          tmem_ld32(trow + (uint32_t)c, v);
+          tmem_ld_wait();
+          const int col0 = ntile * bn + c;
+          if (m < g.M && col0 < e.ncols) {
+            if (e.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(e.bias + col0 + j);
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+            if (e.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (e.mask) {
+              if (e.mask_kind == 1) {
+                const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.mask) + orow * e.ldm + col0);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const uint4 w4 = mk[q4];
+                  const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    // f16 > 0  <=>  sign bit clear and magnitude bits non-zero
+                    const uint32_t lo = ww[u] & 0xFFFFu, hi = ww[u] >> 16;
+                    if (!(lo != 0u && lo < 0x8000u)) v[q4 * 8 + u * 2] = 0.f;
+                    if (!(hi != 0u && hi < 0x8000u)) v[q4 * 8 + u * 2 + 1] = 0.f;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 k4 = *reinterpret_cast<const float4*>(e.mask + orow * e.ldm + col0 + j);
+                  if (!(k4.x > 0.f)) v[j] = 0.f;
+                  if (!(k4.y > 0.f)) v[j + 1] = 0.f;
+                  if (!(k4.z > 0.f)) v[j + 2] = 0.f;
+                  if (!(k4.w > 0.f)) v[j + 3] = 0.f;
+                }
+              }
+            }
+            if (e.out_kind == 0) {
+              float* o = e.out + orow * e.ldo + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (e.round_out) {
+                  r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+                  r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+                }
+                *reinterpret_cast<float4*>(o + j) = r4;
+              }
+            } else {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + orow * e.ldo + col0);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                uint4 w4;
+                if (e.out_kind == 1) {
+                  w4.x = pack_f16x2(v[q4 * 8], v[q4 * 8 + 1]); w4.y = pack_f16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+                  w4.z = pack_f16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); w4.w = pack_f16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+                } else {
+                  w4.x = pack_bf16x2(v[q4 * 8], v[q4 * 8 + 1]); w4.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+                  w4.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]); w4.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+                }
+                o[q4] = w4;
+              }
+            }
+          }
         }
       } else
       for (int c = 0; c < bn; c += 32) {

@@ -17,19 +17,6 @@
 
 using namespace var;
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// a_fmt / b_fmt: 0 = f16, 1 = bf16
-__host__ __device__ constexpr uint32_t make_idesc_h16(int n, int a_fmt, int b_fmt, int a_mn, int b_mn) {
-  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
 constexpr int M = 128, N = 64, K = 64;
 
 // A: logical [M][K], B: logical [N][K] (both "K-major" logical indexing); *_mn selects the smem image.
@@ -99,14 +86,19 @@ static uint16_t enc(float x, int fmt) {
   return *reinterpret_cast<uint16_t*>(&b);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int only = argc > 1 ? atoi(argv[1]) : -1;  // one case per process: a faulting MMA poisons the context
   struct Case { const char* name; int a_fmt, b_fmt, a_mn, b_mn; };
   const Case cases[] = {{"A f16 K / B f16 K", 0, 0, 0, 0}, {"A f16 K / B bf16 K (mixed)", 0, 1, 0, 0},
                         {"A bf16 K / B f16 MN (dgrad)", 1, 0, 0, 1}, {"A f16 MN / B bf16 MN (wgrad)", 0, 1, 1, 1},
-                        {"A bf16 K / B bf16 K", 1, 1, 0, 0}};
+                        {"A bf16 K / B bf16 K", 1, 1, 0, 0}, {"A f16 K / B f16 MN (dgrad)", 0, 0, 0, 1},
+                        {"A f16 MN / B f16 MN (wgrad)", 0, 0, 1, 1}, {"A bf16 MN / B bf16 MN", 1, 1, 1, 1}};
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
   int fails = 0;
+  int ci = -1;
   for (const Case& c : cases) {
+    ++ci;
+    if (only >= 0 && ci != only) continue;
     std::vector<float> a(M * K), b(N * K);
     std::vector<uint16_t> ha(M * K), hb(N * K);
     uint32_t s = 7;

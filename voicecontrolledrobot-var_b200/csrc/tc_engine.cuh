@@ -69,6 +69,9 @@ struct EpiParams {
   int relu;
   int round_out;         // store tf32-rounded values
   RowMap map;
+  // 16-bit engine (gemm_persist.cuh, H16): storage type of `out` (0 fp32, 1 f16, 2 bf16; ldo in elements)
+  // and of the ReLU mask source (0 fp32, 1 f16)
+  int out_kind, mask_kind;
 };
 
 // GRU cell epilogue (forward): columns of the tile are [r | z | n] blocks of
@@ -127,6 +130,7 @@ struct GemmParams {
   int sc_nh, sc_wpad;          // staged rows / padded row width
   int epi_coalesce;            // persistent kernel: transpose the accumulator through smem (512 B per store instr.)
   int kps;                     // persistent kernel: k-blocks per pipeline stage (1 or 2)
+  int a_fmt, b_fmt;            // 16-bit engine: operand formats of the kind::f16 MMA (0 f16, 1 bf16)
 };
 
 constexpr int kTileM = 128;

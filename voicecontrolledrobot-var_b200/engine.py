@@ -192,8 +192,9 @@ class VarEngine:
         half way through the backward pass: the library records an event there, and that range is reduced
         on a side stream under the remaining conv backward kernels; the rest follows on the compute
         stream.  `stepped=False` (this rank ran no triplet_step since zero_grad) reduces everything in order."""
+        import os
         import torch.distributed as dist
-        if not stepped or not self._bucket_setup():
+        if not stepped or os.environ.get("VAR_DP_BUCKET", "1") == "0" or not self._bucket_setup():
             dist.all_reduce(self.grads)
             return
         off, cnt, ev, comm = self._bucket
