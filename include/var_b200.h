@@ -194,6 +194,25 @@ int var_conv2d_dgrad(const float* d_dy, const float* d_w_packed, float* d_dx, co
 int var_conv2d_wgrad(const void* d_x, int src_kind, const int64_t* strides, float scale,
                      const float* d_dy, float* d_dw_packed, float* d_db, int N, int H, int W, int Cin,
                      int Cout, int R, int S, int sh, int sw, int ph, int pw, void* stream);
+/* 16-bit operand forms of the same three conv passes (Cin % 64 == 0, Cout % 64 == 0, not 1x1): activations
+ * and packed weights stored as IEEE f16 (the same 10-bit mantissa as tf32 at half the bytes per MAC --
+ * what bounds the N = 64 convs), tcgen05.mma kind::f16, fp32 accumulation.  Gradients travel through the
+ * region as f16 times a power-of-two scale picked on the device from the largest incoming magnitude
+ * (var_grad_to_f16_scaled: d_scale[0] = S, d_scale[1] = 1/S); kernels multiply by d_out_scale /
+ * d_inv_scale where a gradient leaves the region.  out_kind: 0 fp32, 1 f16.  mask_kind: 0 fp32, 1 f16.
+ * var_cvt_f16: packed fp32 weights (or any fp32 array, n % 4 == 0) -> f16 copy. */
+int var_cvt_f16(const float* d_src, void* d_dst, int64_t n, void* stream);
+int var_grad_to_f16_scaled(const float* d_src, void* d_dst, int64_t n, float* d_scale, uint32_t* d_amax_scratch,
+                           void* stream);
+int var_conv2d_fwd_h16(const void* d_x_f16, int N, int H, int W, int Cin, int Cout, int R, int S, int sh, int sw,
+                       int ph, int pw, const void* d_w_f16_packed, const float* d_bias, void* d_y, int out_kind,
+                       int relu, int round_out, void* stream);
+int var_conv2d_dgrad_h16(const void* d_dy_f16, const void* d_w_f16_packed, void* d_dx, int out_kind,
+                         const void* d_mask, int mask_kind, const float* d_out_scale, int N, int H, int W, int Cin,
+                         int Cout, int R, int S, int sh, int sw, int ph, int pw, int round_out, void* stream);
+int var_conv2d_wgrad_h16(const void* d_x_f16, const void* d_dy_f16, float* d_dw_packed, float* d_db,
+                         const float* d_inv_scale, int N, int H, int W, int Cin, int Cout, int R, int S, int sh,
+                         int sw, int ph, int pw, void* stream);
 int var_maxpool2x2_fwd(const float* d_x, float* d_y, int N, int H, int W, int C, void* stream);
 int var_maxpool2x2_bwd(const float* d_x, const float* d_dy, float* d_dx, int N, int H, int W, int C,
                        void* stream);

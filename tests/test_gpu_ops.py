@@ -221,3 +221,83 @@ def test_fused_triplet_kernel_vs_torch(vb, B, Ki, Ks):
     assert rel_to_max(dW_s.cpu().numpy(), Ws.grad.numpy()) < 1e-4
     assert rel_to_max(db_i[:D].cpu().numpy(), bi.grad.numpy()) < 1e-4
     assert rel_to_max(db_s[:D].cpu().numpy(), bs.grad.numpy()) < 1e-4
+
+
+H16_CASES = [  # N, H, W, Cin, Cout, R, S, sh, sw, ph, pw   (Cin, Cout multiples of 64)
+    (1, 60, 20, 64, 64, 11, 5, 2, 2, 5, 5),    # thor.snd.conv2 geometry (K = 3520: free 64-row group -> fused bias grad)
+    (70, 60, 20, 64, 64, 11, 5, 2, 2, 5, 5),   # same, many tiles per resident CTA
+    (2, 31, 13, 64, 64, 7, 3, 2, 2, 1, 1),     # thor.snd.conv3 geometry, odd extents (K = 1344)
+    (5, 12, 12, 64, 64, 3, 3, 2, 2, 1, 1),     # K = 576 = 4.5 k tiles
+    (3, 12, 12, 64, 128, 3, 3, 1, 1, 1, 1),    # thor.img.conv5-like, stride 1, N = 128
+    (3, 6, 6, 128, 128, 3, 3, 2, 2, 1, 1),     # two 64-channel chunks per tap; K = 1152 = 9 tiles (separate column sum)
+]
+
+
+@pytest.mark.parametrize("case", H16_CASES)
+def test_conv_h16_fwd_dgrad_wgrad_vs_torch(vb, case):
+    """The 16-bit operand region: f16 activations / weights / scaled f16 gradients through kind::f16 MMAs.
+    Operands are pre-rounded to f16 (products exact in fp32), so only the summation order differs."""
+    lib = vb._lib.lib
+    N, H, W, Cin, Cout, R, S, sh, sw, ph, pw = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    h16 = lambda t: t.half().float()
+    x = h16(torch.randn(N, Cin, H, W, generator=g)).requires_grad_(True)
+    w = h16(torch.randn(Cout, Cin, R, S, generator=g) / (R * S * Cin) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, generator=g)
+    y_ref = F.relu(F.conv2d(x, w, b, stride=(sh, sw), padding=(ph, pw)))
+    P, Q = y_ref.shape[2], y_ref.shape[3]
+    # incoming gradient: small magnitudes (like 1/B-scaled losses) so the dynamic scale matters
+    dy32 = torch.randn(y_ref.shape, generator=g) * 3e-6 * (y_ref > 0)
+    x_h = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV).half()
+    wp32, kpad = _pack(lib, w.detach())
+    w_h = torch.empty(Cout, kpad, dtype=torch.half, device=DEV)
+    assert lib.var_cvt_f16(wp32.data_ptr(), w_h.data_ptr(), Cout * kpad, None) == 0
+    bd = b.to(DEV)
+    # forward, f16 output and fp32 (tf32-rounded) output
+    y_h = torch.empty(N, P, Q, Cout, dtype=torch.half, device=DEV)
+    rc = lib.var_conv2d_fwd_h16(x_h.data_ptr(), N, H, W, Cin, Cout, R, S, sh, sw, ph, pw, w_h.data_ptr(), bd.data_ptr(),
+                                y_h.data_ptr(), 1, 1, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    y32 = torch.empty(N, P, Q, Cout, device=DEV)
+    rc = lib.var_conv2d_fwd_h16(x_h.data_ptr(), N, H, W, Cin, Cout, R, S, sh, sw, ph, pw, w_h.data_ptr(), bd.data_ptr(),
+                                y32.data_ptr(), 0, 1, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    ref_nhwc = y_ref.detach().permute(0, 2, 3, 1)
+    assert rel_to_max(y32.cpu().numpy(), ref_nhwc.numpy()) < 1e-5
+    assert rel_to_max(y_h.float().cpu().numpy(), ref_nhwc.numpy()) < 1e-3   # f16 storage: 2^-11 relative
+    # gradient entering the region: device-chosen power-of-two scale
+    dy_nhwc = dy32.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dy_h = torch.empty(N, P, Q, Cout, dtype=torch.half, device=DEV)
+    scale = torch.zeros(2, device=DEV)
+    amax = torch.zeros(1, dtype=torch.int32, device=DEV)
+    assert lib.var_grad_to_f16_scaled(dy_nhwc.data_ptr(), dy_h.data_ptr(), dy_nhwc.numel(), scale.data_ptr(),
+                                      amax.data_ptr(), None) == 0
+    S_, inv = scale.cpu().tolist()
+    assert S_ * inv == 1.0 and np.log2(S_) == round(np.log2(S_))
+    assert 2048 <= float(dy_nhwc.abs().max()) * S_ <= 4096
+    dy_exact = (dy_h.float() / S_).cpu()                       # what the kernels actually multiply
+    y_ref.backward(dy_exact.permute(0, 3, 1, 2))
+    # dgrad: f16 mask (previous activation), fp32 output unscaled; and f16 output (still scaled)
+    mask = (torch.rand(N, H, W, Cin, generator=g) > 0.3).to(DEV)
+    mask_h = (mask.half() * 0.37)
+    dx = torch.full((N, H, W, Cin), float("nan"), device=DEV)
+    rc = lib.var_conv2d_dgrad_h16(dy_h.data_ptr(), w_h.data_ptr(), dx.data_ptr(), 0, mask_h.data_ptr(), 1,
+                                  scale[1:].data_ptr(), N, H, W, Cin, Cout, R, S, sh, sw, ph, pw, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    dx_ref = x.grad.permute(0, 2, 3, 1) * mask.cpu()
+    assert rel_to_max(dx.cpu().numpy(), dx_ref.numpy()) < 1e-5
+    dx_h = torch.zeros(N, H, W, Cin, dtype=torch.half, device=DEV)
+    rc = lib.var_conv2d_dgrad_h16(dy_h.data_ptr(), w_h.data_ptr(), dx_h.data_ptr(), 1, mask_h.data_ptr(), 1, None, N, H,
+                                  W, Cin, Cout, R, S, sh, sw, ph, pw, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    assert rel_to_max((dx_h.float() / S_).cpu().numpy(), dx_ref.numpy()) < 1e-3
+    # wgrad (+ bias gradient), unscaled by inv
+    dw = torch.zeros(Cout, kpad, device=DEV)
+    db = torch.zeros(Cout, device=DEV)
+    rc = lib.var_conv2d_wgrad_h16(x_h.data_ptr(), dy_h.data_ptr(), dw.data_ptr(), db.data_ptr(), scale[1:].data_ptr(), N,
+                                  H, W, Cin, Cout, R, S, sh, sw, ph, pw, None)
+    assert rc == 0, vb._lib.last_error()
+    dw_ref = torch.empty(Cout, Cin, R, S, device=DEV)
+    assert lib.var_unpack_weight(dw.data_ptr(), dw_ref.data_ptr(), Cout, Cin, R, S, kpad, None) == 0
+    assert rel_to_max(dw_ref.cpu().numpy(), w.grad.numpy()) < 2e-5
+    assert rel_to_max(db.cpu().numpy(), dy_exact.sum(dim=(0, 1, 2)).numpy()) < 2e-5

@@ -67,6 +67,11 @@ PROTOTYPES = {
     "var_conv2d_fwd": (_i, [_p, _i, _p, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p]),
     "var_conv2d_dgrad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "var_conv2d_wgrad": (_i, [_p, _i, _p, _f, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "var_cvt_f16": (_i, [_p, _p, _i64, _p]),
+    "var_grad_to_f16_scaled": (_i, [_p, _p, _i64, _p, _p, _p]),
+    "var_conv2d_fwd_h16": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p]),
+    "var_conv2d_dgrad_h16": (_i, [_p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "var_conv2d_wgrad_h16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "var_maxpool2x2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "var_maxpool2x2_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "var_launch_count": (C.c_longlong, []),

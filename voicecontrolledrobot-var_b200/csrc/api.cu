@@ -144,6 +144,31 @@ int var_conv2d_wgrad(const void* x, int src_kind, const int64_t* strides, float 
   const SrcLayout sl = make_layout(strides, scale);
   return conv_wgrad(cs, x, src_kind, &sl, dy, dw, db, ST(stream));
 }
+int var_cvt_f16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst) return VAR_ERR_ARG;
+  return cvt_f16(src, dst, n, ST(stream));
+}
+int var_grad_to_f16_scaled(const float* src, void* dst, int64_t n, float* scale, uint32_t* amax_scratch, void* stream) {
+  if (!src || !dst || !scale || !amax_scratch) return VAR_ERR_ARG;
+  return grad_to_f16_scaled(src, dst, n, scale, amax_scratch, ST(stream));
+}
+int var_conv2d_fwd_h16(const void* x, int N, int H, int W, int Cin, int Cout, int R, int S, int sh, int sw, int ph,
+                       int pw, const void* w, const float* bias, void* y, int out_kind, int relu, int round_out,
+                       void* stream) {
+  const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
+  return conv_fwd_h16(cs, x, w, bias, y, out_kind, relu, round_out, ST(stream));
+}
+int var_conv2d_dgrad_h16(const void* dy, const void* w, void* dx, int out_kind, const void* mask, int mask_kind,
+                         const float* out_scale, int N, int H, int W, int Cin, int Cout, int R, int S, int sh, int sw,
+                         int ph, int pw, int round_out, void* stream) {
+  const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
+  return conv_dgrad_h16(cs, dy, w, dx, out_kind, mask, mask_kind, out_scale, round_out, ST(stream));
+}
+int var_conv2d_wgrad_h16(const void* x, const void* dy, float* dw, float* db, const float* inv_scale, int N, int H,
+                         int W, int Cin, int Cout, int R, int S, int sh, int sw, int ph, int pw, void* stream) {
+  const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
+  return conv_wgrad_h16(cs, x, dy, dw, db, inv_scale, nullptr, ST(stream));
+}
 int var_maxpool2x2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   return maxpool_fwd(x, y, N, H, W, C, ST(stream));
 }

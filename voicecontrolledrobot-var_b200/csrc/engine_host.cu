@@ -6,6 +6,7 @@
 #include "gemm_persist.cuh"
 #include "gru_persist.cuh"
 #include "gru_ksplit.cuh"
+#include "h16_engine.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -325,7 +326,7 @@ static bool gemm_persist_enabled() {  // VAR_GEMM_PERSIST=0 keeps one CTA per ti
   return on == 1;
 }
 
-template <int GMODE>
+template <int GMODE, bool H16 = false>
 static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, const GemmParams& p_in, int m_tiles,
                                  int n_tiles, cudaStream_t st) {
   GemmParams p = p_in;
@@ -341,18 +342,18 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
   static int coal = -1;
   if (coal < 0) { const char* e = getenv("VAR_EPI_COALESCE"); coal = (e && e[0] == '0') ? 0 : 1; }
   const long long stream_clk = (long long)p.num_kb * (kTileABytes + p.bn * 128) / 50;
-  if (coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
+  if (!H16 && coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
     p.epi_coalesce = 1;
     smem += 4 * 4352;
   }
-  VAR_ENSURE_SMEM(tc_gemm_persist_kernel<GMODE>, smem);
+  VAR_ENSURE_SMEM((tc_gemm_persist_kernel<GMODE, H16>), smem);
   const long long total = (long long)m_tiles * n_tiles;
   const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
   int grid = kNumSMs * per_sm;
   if (grid > total) grid = (int)total;
   const double flops = 2.0 * p.g[0].M * (double)p.e[0].ncols * p.g[0].K;
   LaunchScope sc(p.b_mn_major ? T_GEMM_DGRAD : T_GEMM_FWD, flops, st);
-  tc_gemm_persist_kernel<GMODE><<<grid, 192, smem, st>>>(tb, ta, p, m_tiles, n_tiles);
+  tc_gemm_persist_kernel<GMODE, H16><<<grid, 192, smem, st>>>(tb, ta, p, m_tiles, n_tiles);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
@@ -1173,6 +1174,185 @@ int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout
     if (rc) return rc;
   }
   if (db) return colsum(dy, M, cs.Cout, cs.Cout, db, st);
+  return VAR_OK;
+}
+
+// ===========================================================================
+// 16-bit operand region (f16 activations / weights / scaled gradients; kind::f16 MMAs).  Used for convs
+// with Cin % 64 == 0 whose N = 32 / 64 tiles are bound by the shared-memory fill per MAC in tf32.
+// ===========================================================================
+static void fill_fwd_taps(GemmParams& p, const ConvShape& cs) {
+  p.ntaps = cs.R * cs.S;
+  p.base_w = -cs.pw; p.base_h = -cs.ph; p.step_w = cs.sw; p.step_h = cs.sh;
+  for (int r = 0; r < cs.R; ++r)
+    for (int s_ = 0; s_ < cs.S; ++s_) {
+      const int t = r * cs.S + s_;
+      p.tap_w[t] = (uint8_t)s_; p.tap_h[t] = (uint8_t)r; p.tap_id[t] = (uint8_t)t;
+    }
+}
+
+bool conv_h16_ok(const ConvShape& cs) {
+  static int on = -1;
+  if (on < 0) on = env_int("VAR_H16", 1);
+  return on && gather_mode() == 1 && cs.Cin % 64 == 0 && cs.Cout % 64 == 0 && cs.Cout <= 256 && cs.R * cs.S <= kMaxTaps &&
+         cs.R >= cs.sh && cs.S >= cs.sw && !is_linear(cs);
+}
+
+// y = act(conv(x, w) + b): x f16 NHWC, w f16 packed [Cout][kpad] (same indexing as the tf32 copy, K % 64 == 0),
+// y stored as fp32 (out_kind 0, optionally tf32-rounded) or f16 (out_kind 1).
+int conv_fwd_h16(const ConvShape& cs, const void* x, const void* w, const float* bias, void* y, int out_kind, int relu,
+                 int round_out, cudaStream_t st) {
+  prof_note("fwd16 N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (!conv_h16_ok(cs)) return VAR_ERR_UNSUPPORTED;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  GatherGeom& g = p.g[0];
+  g.src = x; g.M = cs.N * cs.P * cs.Q; g.P = cs.P; g.Q = cs.Q; g.H = cs.H; g.W = cs.W; g.C = cs.Cin;
+  g.R = cs.R; g.S = cs.S; g.sh = cs.sh; g.sw = cs.sw; g.ph = cs.ph; g.pw = cs.pw;
+  g.K = cs.R * cs.S * cs.Cin; g.scale = 1.f;
+  const int kpad = round_up32(g.K);
+  p.bn = cs.Cout;
+  p.nbox = 1; p.box_rows = p.bn; p.boxbase[0] = 0;
+  p.num_kb = g.K / 64; p.cpb = cs.Cin / 64;
+  pick_pipeline(p.bn, &p.stages, &p.lookahead);
+  fill_fwd_taps(p, cs);
+  EpiParams& e = p.e[0];
+  e.out = reinterpret_cast<float*>(y); e.ldo = cs.Cout; e.bias = bias; e.ncols = cs.Cout; e.relu = relu;
+  e.round_out = round_out; e.out_kind = out_kind;
+  CUtensorMap tm, ta;
+  int rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, p.bn, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm);
+  if (rc) return rc;
+  rc = get_tmap_im2col_e(x, 2, cs.N, cs.H, cs.W, cs.Cin, -cs.pw, -cs.ph, cs.pw - (cs.S - 1), cs.ph - (cs.R - 1), cs.sw,
+                         cs.sh, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+  if (rc) return rc;
+  return launch_gemm_persist_t<G_TMA_IM2COL, true>(tm, ta, p, (g.M + 127) / 128, 1, st);
+}
+
+// dx = conv_transpose(dy, w) [* out_scale] [* (mask > 0)]: dy f16 (scaled), w f16 packed (read transposed, MN-major),
+// dx stored fp32 (out_kind 0) or f16 (1); mask = forward activation of the previous layer (mask_kind 0 fp32, 1 f16).
+int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx, int out_kind, const void* mask,
+                   int mask_kind, const float* out_scale, int round_out, cudaStream_t st) {
+  prof_note("dgrad16 N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (!conv_h16_ok(cs)) return VAR_ERR_UNSUPPORTED;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int kfwd = cs.R * cs.S * cs.Cin, kpad = round_up32(kfwd);
+  p.bn = cs.Cin;
+  p.b_mn_major = 1;
+  p.kb_per_rs = cs.Cout / 64; p.cpb = cs.Cout / 64;
+  p.cin_total = cs.Cin;
+  pick_pipeline(p.bn, &p.stages, &p.lookahead);
+  p.step_w = 1; p.step_h = 1;
+  EpiParams& e0 = p.e[0];
+  e0.out = reinterpret_cast<float*>(dx); e0.ldo = cs.Cin; e0.ncols = cs.Cin;
+  e0.mask = reinterpret_cast<const float*>(mask); e0.ldm = cs.Cin; e0.mask_kind = mask_kind;
+  e0.round_out = round_out; e0.out_kind = out_kind; e0.out_scale = out_scale;
+  CUtensorMap tm, ta;
+  int rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm);
+  if (rc) return rc;
+  for (int hp = 0; hp < cs.sh; ++hp)
+    for (int wp = 0; wp < cs.sw; ++wp) {
+      const int H2 = (cs.H - hp + cs.sh - 1) / cs.sh, W2 = (cs.W - wp + cs.sw - 1) / cs.sw;
+      if (H2 <= 0 || W2 <= 0) continue;
+      const int r0 = (hp + cs.ph) % cs.sh, s0 = (wp + cs.pw) % cs.sw;
+      const int J = (cs.R - r0 + cs.sh - 1) / cs.sh, I = (cs.S - s0 + cs.sw - 1) / cs.sw;
+      const int a_h = (hp + cs.ph - r0) / cs.sh, a_w = (wp + cs.pw - s0) / cs.sw;
+      GemmParams q = p;
+      q.base_h = a_h - (J - 1); q.base_w = a_w - (I - 1);
+      q.ntaps = J * I;
+      for (int j = 0; j < J; ++j)
+        for (int i = 0; i < I; ++i) {
+          const int t = j * I + i;
+          q.tap_h[t] = (uint8_t)(J - 1 - j); q.tap_w[t] = (uint8_t)(I - 1 - i);
+          q.tap_id[t] = (uint8_t)((r0 + cs.sh * j) * cs.S + (s0 + cs.sw * i));
+        }
+      q.num_kb = q.ntaps * q.cpb;
+      GatherGeom& g = q.g[0];
+      g.src = dy; g.M = cs.N * H2 * W2; g.P = H2; g.Q = W2;
+      g.H = cs.P; g.W = cs.Q; g.C = cs.Cout; g.R = cs.R; g.S = cs.S;
+      g.sh = cs.sh; g.sw = cs.sw; g.ph = cs.ph; g.pw = cs.pw;
+      g.K = q.num_kb * 64; g.scale = 1.f;
+      EpiParams& e = q.e[0];
+      if (cs.sh > 1 || cs.sw > 1) {
+        e.map.on = 1; e.map.P2 = H2; e.map.Q2 = W2; e.map.H = cs.H; e.map.W = cs.W;
+        e.map.sh = cs.sh; e.map.sw = cs.sw; e.map.oh = hp; e.map.ow = wp;
+      }
+      rc = get_tmap_im2col_e(dy, 2, cs.N, cs.P, cs.Q, cs.Cout, q.base_w, q.base_h, W2 - cs.Q + q.base_w,
+                             H2 - cs.P + q.base_h, 1, 1, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+      if (rc) return rc;
+      rc = launch_gemm_persist_t<G_TMA_IM2COL, true>(tm, ta, q, (g.M + 127) / 128, cs.Cin / q.bn, st);
+      if (rc) return rc;
+    }
+  return VAR_OK;
+}
+
+// Fallback bias gradient for f16 dY when the weight-gradient kernel has no free row group: db += inv * colsum(dy).
+__global__ void __launch_bounds__(256)
+colsum_f16_kernel(const uint16_t* __restrict__ dy, long long M, int C, float* __restrict__ db,
+                  const float* __restrict__ inv_scale, int rows_per_cta) {
+  const float inv = inv_scale ? __ldg(inv_scale) : 1.f;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(r0 + (long long)rows_per_cta, M);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += f16_bits_to_f32(dy[r * C + c]);
+    atomicAdd(db + c, acc * inv);
+  }
+}
+
+// dw[Cout][kpad] += inv_scale * im2col(x)^T dy ; db[Cout] += inv_scale * colsum(dy): x f16 NHWC, dy f16 (scaled).
+// The bias gradient comes out of the same kernel when the last k tile has a free 64-row group (K % 128 == 64);
+// otherwise *db_done = 0 and the caller must produce it.
+int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw, float* db, const float* inv_scale,
+                   int* db_done, cudaStream_t st) {
+  prof_note("wgrad16 N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (!conv_h16_ok(cs)) return VAR_ERR_UNSUPPORTED;
+  WgradH16Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = cs.N * cs.P * cs.Q;
+  p.K = cs.R * cs.S * cs.Cin;
+  p.kpad = round_up32(p.K);
+  p.cout = cs.Cout;
+  p.dw = dw; p.inv_scale = inv_scale;
+  p.kps = env_int("VAR_WGRAD16_KPS", 2);
+  p.stages = env_int("VAR_WGRAD16_STAGES", 4);
+  p.P = cs.P; p.Q = cs.Q; p.cpb = cs.Cin / 64;
+  p.base_w = -cs.pw; p.base_h = -cs.ph; p.step_w = cs.sw; p.step_h = cs.sh;
+  for (int r = 0; r < cs.R; ++r)
+    for (int s_ = 0; s_ < cs.S; ++s_) { p.tap_w[r * cs.S + s_] = (uint8_t)s_; p.tap_h[r * cs.S + s_] = (uint8_t)r; }
+  const int ktiles = (p.K + 127) / 128;
+  p.ones_ktile = (p.K % 128 == 64) ? ktiles - 1 : -1;
+  p.db = (db && p.ones_ktile >= 0) ? db : nullptr;
+  if (db_done) *db_done = p.db != nullptr;
+  CUtensorMap tx, tdy;
+  int rc = get_tmap_im2col_e(x, 2, cs.N, cs.H, cs.W, cs.Cin, -cs.pw, -cs.ph, cs.pw - (cs.S - 1), cs.ph - (cs.R - 1), cs.sw,
+                             cs.sh, 32, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tx);
+  if (rc) return rc;
+  rc = get_tmap_2d_e(dy, 2, p.M, cs.Cout, cs.Cout, 32, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tdy);
+  if (rc) return rc;
+  const size_t smem = wgrad_h16_smem_bytes(cs.Cout, p.stages, p.kps);
+  const int per_sm = smem * 3 + 6144 <= 227 * 1024 ? 3 : (smem * 2 + 4096 <= 227 * 1024 ? 2 : 1);
+  int splits = (2 * per_sm * kNumSMs) / ktiles;
+  if (splits < 1) splits = 1;
+  int ppc = (p.M + splits - 1) / splits;
+  ppc = ((ppc + 32 * p.kps - 1) / (32 * p.kps)) * (32 * p.kps);
+  if (ppc < 256) ppc = 256;
+  splits = (p.M + ppc - 1) / ppc;
+  p.pix_per_cta = ppc;
+  VAR_ENSURE_SMEM(tc_wgrad_h16_kernel, smem);
+  dim3 grid(ktiles, splits, 1);
+  {
+    LaunchScope sc(T_WGRAD, 2.0 * p.M * (double)cs.Cout * p.K, st);
+    tc_wgrad_h16_kernel<<<grid, 160, smem, st>>>(tx, tdy, p);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  if (db && !p.db) {  // no free row group in the last k tile: separate (slow, rarely needed) column sum
+    const int rp = 512;
+    LaunchScope sc(T_COLSUM, 0, st);
+    colsum_f16_kernel<<<(unsigned)((p.M + rp - 1) / rp), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(dy), p.M, cs.Cout, db,
+                                                                       inv_scale, rp);
+    VAR_CUDA_CHECK(cudaGetLastError());
+    if (db_done) *db_done = 1;
+  }
   return VAR_OK;
 }
 

@@ -70,4 +70,13 @@ int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStr
 int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl,
                const float* dy, float* dw, float* db, cudaStream_t st);
 
+// ---- 16-bit operand region (f16 NHWC activations, f16 packed weights, f16 scaled gradients) ----
+bool conv_h16_ok(const ConvShape& cs);
+int conv_fwd_h16(const ConvShape& cs, const void* x, const void* w, const float* bias, void* y, int out_kind, int relu,
+                 int round_out, cudaStream_t st);
+int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx, int out_kind, const void* mask,
+                   int mask_kind, const float* out_scale, int round_out, cudaStream_t st);
+int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw, float* db, const float* inv_scale,
+                   int* db_done, cudaStream_t st);
+
 }  // namespace var

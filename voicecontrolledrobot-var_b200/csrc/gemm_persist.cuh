@@ -244,14 +244,19 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
           }
           __syncwarp();
         }
-      } else if (H16 && (e.out_kind != 0 || e.mask_kind != 0)) {
+      } else if (H16 && (e.out_kind != 0 || e.mask_kind != 0 || e.out_scale != nullptr)) {
         // 16-bit storage: a thread owns 32 consecutive columns of its row = 64 bytes = four 16-byte stores
+        const float osc = e.out_scale ? __ldg(e.out_scale) : 1.f;
         for (int c = 0; c < bn; c += 32) {
           float v[32];
           tmem_ld32(trow + (uint32_t)c, v);
           tmem_ld_wait();
           const int col0 = ntile * bn + c;
           if (m < g.M && col0 < e.ncols) {
+            if (e.out_scale) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= osc;
+            }
             if (e.bias) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {

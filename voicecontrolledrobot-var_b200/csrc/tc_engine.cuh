@@ -72,6 +72,8 @@ struct EpiParams {
   // 16-bit engine (gemm_persist.cuh, H16): storage type of `out` (0 fp32, 1 f16, 2 bf16; ldo in elements)
   // and of the ReLU mask source (0 fp32, 1 f16)
   int out_kind, mask_kind;
+  const float* out_scale;  // device scalar multiplied into the result before mask / store (nullptr = 1): undoes the
+                           // f16 gradient scale where a gradient leaves the 16-bit region
 };
 
 // GRU cell epilogue (forward): columns of the tile are [r | z | n] blocks of
