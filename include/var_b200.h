@@ -100,6 +100,7 @@ int var_net_num_tensors(void* net);
 /* name: state_dict key; shape[4]/ndim: reference shape; offset/packed: location in the flat buffer */
 int var_net_tensor_info(void* net, int index, char* name, int name_cap, int* ndim, int* shape,
                         int64_t* offset, int64_t* packed_floats);
+/* (also allocates the net's own device scratch: f16 copies of the weights of the 16-bit conv region, 0.6 MB) */
 int var_net_bind(void* net, float* d_params, float* d_params_mma, float* d_grads);
 /* reference layout (contiguous fp32, device) -> packed master + tf32 copy */
 int var_net_load_tensor(void* net, int index, const float* d_src, void* stream);

@@ -207,7 +207,9 @@ cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int t
         const int chunk = lane & 15, rsub = lane >> 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.bias) b4 = __ldg(reinterpret_cast<const float4*>(a.bias + chunk * 4));
-        float* out = a.y + ((long long)(tp.n * a.P + tp.p0) * kQ + wq * 32) * kCout + chunk * 4;
+        const long long obase = ((long long)(tp.n * a.P + tp.p0) * kQ + wq * 32) * kCout + chunk * 4;
+        float* out = a.y + obase;
+        uint16_t* out_h = reinterpret_cast<uint16_t*>(a.y) + obase;
 #pragma unroll
         for (int i2 = 0; i2 < 16; ++i2) {
           const int row = i2 * 2 + rsub;           // row within the warp's 32
@@ -219,6 +221,11 @@ cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int t
             if (a.relu) {
               r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
               r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+            }
+            if (a.out_f16) {  // 16 lanes x 8 bytes = one 128-byte pixel row per half warp
+              *reinterpret_cast<uint2*>(out_h + (long long)row * kCout) =
+                  make_uint2(pack_f16x2(r4.x, r4.y), pack_f16x2(r4.z, r4.w));
+              continue;
             }
             if (a.round_out) {
               r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);

@@ -9,8 +9,8 @@ struct Cin1Args {
   int N, H, P;         // P = output rows (Q = 20)
   const float* w;      // fwd: packed tf32 weights [64][128], k = r*11 + s
   const float* bias;   // fwd: [64] fp32 (nullable)
-  float* y;            // fwd: [N, P, 20, 64]
-  int relu, round_out;
+  float* y;            // fwd: [N, P, 20, 64] fp32, or IEEE f16 when out_f16 != 0 (the 16-bit conv region reads it)
+  int relu, round_out, out_f16;
   const float* dy;     // wgrad: [N, P, 20, 64] (tf32-rounded values)
   float* dw;           // wgrad: packed [64][128] (+=)
   float* db;           // wgrad: [64] (+=, nullable)

@@ -458,8 +458,12 @@ static int gmode_of(int src_kind) {
 }
 
 int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
-             const float* bias, float* y, int relu, int round_out, cudaStream_t st) {
+             const float* bias, float* y, int relu, int round_out, cudaStream_t st, int out_kind) {
   prof_note("fwd N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
+  if (out_kind != 0 && !(src_kind == SRC_STRIDED_F32 && sl &&
+                         cin1_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, sl->sN,
+                                         sl->sH, sl->sW, sl->scale, x)))
+    return VAR_ERR_UNSUPPORTED;
   if (src_kind == SRC_STRIDED_U8 && sl &&
       cin3_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, cs.P, cs.Q, sl->sN, sl->sH,
                       sl->sW, sl->sC, x)) {
@@ -484,7 +488,7 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
     Cin1Args a;
     memset(&a, 0, sizeof(a));
     a.x = reinterpret_cast<const float*>(x); a.N = cs.N; a.H = cs.H; a.P = cs.P;
-    a.w = w; a.bias = bias; a.y = y; a.relu = relu; a.round_out = round_out;
+    a.w = w; a.bias = bias; a.y = y; a.relu = relu; a.round_out = round_out; a.out_f16 = out_kind == 1;
     return cin1_conv_fwd(a, st);
   }
   GemmParams p;

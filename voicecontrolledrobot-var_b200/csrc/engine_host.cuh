@@ -43,8 +43,9 @@ struct SrcLayout {       // element strides for strided sources
 inline int round_up32(int k) { return (k + 31) & ~31; }
 
 // y[N,P,Q,Cout] = act(conv(x, w) + b).  w packed [Cout, Kpad], k = (r*S+s)*Cin + c.
+// out_kind 1 stores y as IEEE f16 (only the first-layer kernel feeding the 16-bit region supports it).
 int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
-             const float* bias, float* y, int relu, int round_out, cudaStream_t st);
+             const float* bias, float* y, int relu, int round_out, cudaStream_t st, int out_kind = 0);
 
 // dx[N,H,W,Cin] = conv_transpose(dy, w) [* (mask > 0)] ; mask = forward output of the
 // previous layer (ReLU backward fused), may be null.

@@ -35,6 +35,10 @@ struct Layer {
   int H, W, Cin, Cout, R, S, sh, sw, ph, pw, P, Q;
   int relu, round_out, mask_in;
   int tw, tb;  // tensor indices of weight / bias
+  // 16-bit operand region: h16 = this conv runs kind::f16 MMAs on f16 input / weights (w16 = f16 copy of the
+  // packed weights, refreshed from the fp32 master at every forward); out_h16 = its output is stored as f16
+  int h16, out_h16;
+  void* w16;
   // run state
   const void* in;
   int in_kind;
@@ -104,8 +108,15 @@ struct Net {
   // may hand in an event that is recorded at that point (on whichever stream produced them), so its
   // all-reduce of that range runs under the remaining conv backward kernels.
   cudaEvent_t ev_rnn_grads = nullptr;  // not owned
+  float* h16_scale = nullptr;          // device: {S, 1/S} of the gradient entering the 16-bit region
+  unsigned int* h16_amax = nullptr;
 
   ~Net() {
+    for (auto* L : {&img_trunk, &img_head, &snd_trunk, &snd_head})
+      for (Layer& l : *L)
+        if (l.w16) cudaFree(l.w16);
+    if (h16_scale) cudaFree(h16_scale);
+    if (h16_amax) cudaFree(h16_amax);
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -249,6 +260,17 @@ struct Net {
       add_conv(snd_trunk, "cnn.2", 300, 20, 64, 64, 11, 5, 2, 2, 5, 5, 1, 1, 1);
       add_conv(snd_trunk, "cnn.4", 150, 13, 64, 64, 7, 3, 2, 2, 1, 1, 1, 1, 1);
       if (snd_trunk.back().P != kGruT || snd_trunk.back().Q != 7) return VAR_ERR_UNSUPPORTED;
+      {  // cnn.2 / cnn.4 (Cin = Cout = 64: bound by the operand bytes per MAC in tf32) run in the 16-bit region;
+        // cnn.0 feeds them f16 activations, cnn.4 hands tf32-rounded fp32 to the GRU input projection
+        Layer& c0 = snd_trunk[0]; Layer& c2 = snd_trunk[1]; Layer& c4 = snd_trunk[2];
+        const ConvShape s2{1, c2.H, c2.W, c2.Cin, c2.Cout, c2.R, c2.S, c2.sh, c2.sw, c2.ph, c2.pw, c2.P, c2.Q};
+        const ConvShape s4{1, c4.H, c4.W, c4.Cin, c4.Cout, c4.R, c4.S, c4.sh, c4.sw, c4.ph, c4.pw, c4.P, c4.Q};
+        if (conv_h16_ok(s2) && conv_h16_ok(s4)) {
+          c0.out_h16 = 1;
+          c2.h16 = 1; c2.out_h16 = 1;
+          c4.h16 = 1;
+        }
+      }
       snd_raw_dim = 2 * kGruH;
       add_linear(img_head, "imgTriplet.0", 128, 3, 3, 128, 1, 0, 1);
       add_tail("imgTriplet.2", 128, &t_tail_img_w, &t_tail_img_b);
@@ -259,6 +281,23 @@ struct Net {
     } else {
       return VAR_ERR_UNSUPPORTED;
     }
+    return VAR_OK;
+  }
+
+  // Device-side scratch of the 16-bit region (f16 weight copies: 0.6 MB for the iTHOR net; gradient scale).
+  // Called from var_net_bind, the first call that is given device memory (var_net_create also runs on
+  // hosts without a GPU, for plan inspection).
+  int alloc_h16() {
+    for (auto* L : {&img_trunk, &img_head, &snd_trunk, &snd_head})
+      for (Layer& l : *L)
+        if (l.h16 && !l.w16) {
+          const TensorDesc& t = tensors[l.tw];
+          VAR_CUDA_CHECK(cudaMalloc(&l.w16, (size_t)t.O * t.kpad * 2));
+          if (!h16_scale) {
+            VAR_CUDA_CHECK(cudaMalloc(&h16_scale, 2 * sizeof(float)));
+            VAR_CUDA_CHECK(cudaMalloc(&h16_amax, sizeof(unsigned int)));
+          }
+        }
     return VAR_OK;
   }
 
@@ -275,13 +314,21 @@ struct Net {
     for (size_t i = 0; i < L.size(); ++i) {
       Layer& l = L[i];
       l.in = cur; l.in_kind = kind_; l.in_sl = sl; l.N = N;
-      l.out = ar.alloc((long long)N * l.P * l.Q * l.Cout);
+      const long long out_elems = (long long)N * l.P * l.Q * l.Cout;
+      l.out = ar.alloc(l.out_h16 ? (out_elems + 1) / 2 : out_elems);
       if (ar.base) {
         if (ar.overflow) return VAR_ERR_WORKSPACE;
         int rc;
         if (l.type == LT_CONV) {
           ConvShape cs{N, l.H, l.W, l.Cin, l.Cout, l.R, l.S, l.sh, l.sw, l.ph, l.pw, l.P, l.Q};
-          rc = conv_fwd(cs, cur, kind_, &sl, wr(l.tw), wm(l.tb), l.out, l.relu, l.round_out, st);
+          if (l.h16) {
+            const TensorDesc& t = tensors[l.tw];
+            rc = cvt_f16(wm(l.tw), l.w16, (long long)t.O * t.kpad, st);  // weights may have moved (Adam, load)
+            if (rc) return rc;
+            rc = conv_fwd_h16(cs, cur, l.w16, wm(l.tb), l.out, l.out_h16, l.relu, l.round_out, st);
+          } else {
+            rc = conv_fwd(cs, cur, kind_, &sl, wr(l.tw), wm(l.tb), l.out, l.relu, l.round_out, st, l.out_h16);
+          }
         } else {
           rc = maxpool_fwd(reinterpret_cast<const float*>(cur), l.out, N, l.H, l.W, l.Cin, st);
         }
@@ -453,10 +500,39 @@ struct Net {
   // branch input, which needs no gradient).
   int run_layers_bwd(std::vector<Layer>& L, float* dY, Arena& ar, cudaStream_t st, float** dx_out) {
     float* dy = dY;
+    bool dy_h16 = false;  // dy is f16 times the region's gradient scale (produced by an h16 dgrad below)
     for (int i = (int)L.size() - 1; i >= 0; --i) {
       Layer& l = L[i];
       const int N = l.N;
       const bool need_dx = l.in_kind == SRC_NHWC_F32;
+      if (l.type == LT_CONV && l.h16) {
+        // ---- 16-bit region: f16 activations (l.in), f16 weights, f16 scaled gradients
+        const long long dy_elems = (long long)N * l.P * l.Q * l.Cout, dx_elems = (long long)N * l.H * l.W * l.Cin;
+        const bool prev_h16 = i > 0 && L[i - 1].type == LT_CONV && L[i - 1].h16;
+        float* dy16 = dy_h16 ? dy : ar.alloc((dy_elems + 1) / 2);
+        float* dx = need_dx ? ar.alloc(prev_h16 ? (dx_elems + 1) / 2 : dx_elems) : nullptr;
+        if (ar.base) {
+          if (ar.overflow) return VAR_ERR_WORKSPACE;
+          ConvShape cs{N, l.H, l.W, l.Cin, l.Cout, l.R, l.S, l.sh, l.sw, l.ph, l.pw, l.P, l.Q};
+          int rc = VAR_OK;
+          if (!dy_h16) {  // gradient enters the region: pick the power-of-two scale from its largest magnitude
+            rc = grad_to_f16_scaled(dy, dy16, dy_elems, h16_scale, h16_amax, st);
+            if (rc) return rc;
+          }
+          rc = conv_wgrad_h16(cs, l.in, dy16, gr(l.tw), gr(l.tb), h16_scale + 1, nullptr, st);
+          if (rc) return rc;
+          if (need_dx) {
+            // towards another h16 layer the gradient stays f16 and scaled; leaving the region it is
+            // unscaled and stored as tf32-rounded fp32
+            rc = conv_dgrad_h16(cs, dy16, l.w16, dx, prev_h16 ? 1 : 0, l.mask_in ? l.in : nullptr, 1,
+                                prev_h16 ? nullptr : h16_scale + 1, 1, st);
+            if (rc) return rc;
+          }
+        }
+        dy = dx;
+        dy_h16 = prev_h16;
+        continue;
+      }
       float* dx = need_dx ? ar.alloc((long long)N * l.H * l.W * l.Cin) : nullptr;
       if (ar.base) {
         if (ar.overflow) return VAR_ERR_WORKSPACE;
@@ -692,7 +768,7 @@ int var_net_tensor_info(void* net, int index, char* name, int name_cap, int* ndi
 int var_net_bind(void* net, float* p, float* pr, float* g) {
   Net* n = NET(net);
   n->P = p; n->PR = pr; n->G = g;
-  return VAR_OK;
+  return n->alloc_h16();
 }
 int var_net_load_tensor(void* net, int index, const float* src, void* stream) {
   Net* n = NET(net);
