@@ -1317,8 +1317,9 @@ int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw
   p.kpad = round_up32(p.K);
   p.cout = cs.Cout;
   p.dw = dw; p.inv_scale = inv_scale;
-  p.kps = env_int("VAR_WGRAD16_KPS", 2);
+  p.pb = env_int("VAR_WGRAD16_PB", 128);      // pixels per TMA box / pipeline stage
   p.stages = env_int("VAR_WGRAD16_STAGES", 4);
+  if (p.pb < 16 || p.pb > 256 || p.pb % 16) return VAR_ERR_ARG;
   p.P = cs.P; p.Q = cs.Q; p.cpb = cs.Cin / 64;
   p.base_w = -cs.pw; p.base_h = -cs.ph; p.step_w = cs.sw; p.step_h = cs.sh;
   for (int r = 0; r < cs.R; ++r)
@@ -1329,17 +1330,19 @@ int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw
   if (db_done) *db_done = p.db != nullptr;
   CUtensorMap tx, tdy;
   int rc = get_tmap_im2col_e(x, 2, cs.N, cs.H, cs.W, cs.Cin, -cs.pw, -cs.ph, cs.pw - (cs.S - 1), cs.ph - (cs.R - 1), cs.sw,
-                             cs.sh, 32, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tx);
+                             cs.sh, p.pb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tx);
   if (rc) return rc;
-  rc = get_tmap_2d_e(dy, 2, p.M, cs.Cout, cs.Cout, 32, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tdy);
+  rc = get_tmap_2d_e(dy, 2, p.M, cs.Cout, cs.Cout, p.pb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tdy);
   if (rc) return rc;
-  const size_t smem = wgrad_h16_smem_bytes(cs.Cout, p.stages, p.kps);
+  size_t smem = wgrad_h16_smem_bytes(cs.Cout, p.stages, p.pb);
+  while (smem > 227 * 1024 - 2048 && p.stages > 2) { --p.stages; smem = wgrad_h16_smem_bytes(cs.Cout, p.stages, p.pb); }
   const int per_sm = smem * 3 + 6144 <= 227 * 1024 ? 3 : (smem * 2 + 4096 <= 227 * 1024 ? 2 : 1);
-  int splits = (2 * per_sm * kNumSMs) / ktiles;
+  // one wave of resident CTAs (waves == 2 for small layers would only add partial-sum atomics)
+  int splits = (per_sm * kNumSMs) / ktiles;
   if (splits < 1) splits = 1;
   int ppc = (p.M + splits - 1) / splits;
-  ppc = ((ppc + 32 * p.kps - 1) / (32 * p.kps)) * (32 * p.kps);
-  if (ppc < 256) ppc = 256;
+  ppc = ((ppc + p.pb - 1) / p.pb) * p.pb;
+  if (ppc < 2 * p.pb) ppc = 2 * p.pb;
   splits = (p.M + ppc - 1) / ppc;
   p.pix_per_cta = ppc;
   VAR_ENSURE_SMEM(tc_wgrad_h16_kernel, smem);

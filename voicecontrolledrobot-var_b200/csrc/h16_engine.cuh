@@ -1,9 +1,11 @@
 // 16-bit-operand weight gradient for the f16 conv region (see gemm_persist.cuh, H16, for the forward /
 // dgrad side): dW[o, k] += sum_pix X[pix@tap, c] * dY[pix, o] with X (f16 NHWC activations) and dY (f16,
 // scaled by the region's power-of-two gradient scale) both MN-major operands of kind::f16 MMAs
-// (M = 128 k-rows = two taps x 64 channels, N = Cout, K = 16 pixels per instruction).  Per 32-pixel
-// block a CTA moves 2 x 4 KB of X^T (im2col-mode TMA, 64 channels x 32 pixels) + 4 KB of dY per 64
-// output channels -- half the bytes of the tf32 kernel (tc_wgrad_tma_kernel) for the same MACs.
+// (M = 128 k-rows = two taps x 64 channels, N = Cout, K = 16 pixels per instruction).  A pipeline stage
+// is one block of p.pb (32 ... 128) pixels: two im2col-mode TMA boxes of X^T (64 channels x pb pixels,
+// one per tap group) + one box of dY per 64 output channels -- half the bytes of the tf32 kernel
+// (tc_wgrad_tma_kernel) for the same MACs, and with 128-pixel boxes a quarter of its TMA instructions
+// (32-pixel boxes reached only ~10 TB/s of L2 -> smem fill; the forward kernel's 16 KB boxes reach 18).
 // Bias gradient: when K is not a multiple of 128 the last k tile has an unused 64-row group; it is
 // filled with ones once, so row K of the accumulator is colsum(dY) -- no separate column-sum pass.
 #pragma once
@@ -16,16 +18,16 @@ struct WgradH16Params {
   float* dw;
   float* db;                 // nullable; only written when ones_ktile >= 0
   const float* inv_scale;    // device scalar: results are multiplied by it (nullptr = 1)
-  int pix_per_cta;           // multiple of 32 * kps
-  int stages, kps;
+  int pix_per_cta;           // multiple of pb
+  int stages, pb;            // pipeline stages; pixels per stage (multiple of 16, <= 256 by the TMA box limit)
   int ones_ktile;            // k tile whose second 64-row group is free (-1: none)
   int P, Q, cpb;             // output extents; 64-channel chunks per tap
   int base_w, base_h, step_w, step_h;
   uint8_t tap_w[kMaxTaps], tap_h[kMaxTaps];
 };
 
-__host__ __device__ inline size_t wgrad_h16_smem_bytes(int cout, int stages, int kps) {
-  return (size_t)stages * kps * (8192 + (size_t)(cout / 64) * 4096) + 1024 + 256;
+__host__ __device__ inline size_t wgrad_h16_smem_bytes(int cout, int stages, int pb) {
+  return (size_t)stages * (size_t)pb * 128 * (2 + (size_t)(cout / 64)) + 1024 + 256;
 }
 
 __global__ void __launch_bounds__(160)
@@ -33,11 +35,10 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const __grid_constant__ WgradH16Params p) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int stages = p.stages, kps = p.kps;
+  const int stages = p.stages, pb = p.pb;
   const int bgroups = p.cout >> 6;
-  const uint32_t tileA_bytes = 2u * 4096u;
-  const uint32_t tileB_bytes = (uint32_t)bgroups * 4096u;
-  const uint32_t stageA = (uint32_t)kps * tileA_bytes, stageB = (uint32_t)kps * tileB_bytes;
+  const uint32_t grp = (uint32_t)pb * 128u;  // bytes of one 64-wide MN group of a stage
+  const uint32_t stageA = 2u * grp, stageB = (uint32_t)bgroups * grp;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
   const uint32_t sB = base + (uint32_t)stages * stageA;
@@ -50,7 +51,7 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int ktile = blockIdx.x;
   const int pix0 = blockIdx.y * p.pix_per_cta;
   const int pix1 = min(pix0 + p.pix_per_cta, p.M);
-  const int num_kb = ((pix1 - pix0 + 31) / 32 + kps - 1) / kps;
+  const int num_kb = (pix1 - pix0 + pb - 1) / pb;
   const int kgroups = min(2, (p.K - ktile * 128 + 63) / 64);
   const bool ones = p.db != nullptr && ktile == p.ones_ktile && kgroups == 1;
 
@@ -66,9 +67,9 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
   if (ones) {
     // second 64-row group of every X^T block := 1.0 (f16 0x3C00); TMA never writes it in this k tile
-    for (uint32_t blk = 0; blk < (uint32_t)(stages * kps); ++blk)
-      for (uint32_t i = tid; i < 4096u / 16u; i += 160u)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + blk * tileA_bytes + 4096u + i * 16u), "r"(0x3C003C00u) : "memory");
+    for (uint32_t blk = 0; blk < (uint32_t)stages; ++blk)
+      for (uint32_t i = tid; i < grp / 16u; i += 160u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + blk * stageA + grp + i * 16u), "r"(0x3C003C00u) : "memory");
     fence_proxy_async_smem();
   }
   const uint32_t ncols = (uint32_t)tmem_cols_for(p.cout);
@@ -95,19 +96,19 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int it = 0; it < num_kb; ++it) {
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
           if (warp == 0)
-            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kps * ((uint32_t)kgroups * 4096u + tileB_bytes));
-          for (int sub = 0; sub < kps; ++sub) {
-            const int m = pix0 + (it * kps + sub) * 32;
-            const uint32_t dA = sA + (uint32_t)st * stageA + (uint32_t)sub * tileA_bytes;
-            const uint32_t dB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
+            mbar_arrive_expect_tx(full_bar(st), (uint32_t)kgroups * grp + stageB);
+          {
+            const int m = pix0 + it * pb;
+            const uint32_t dA = sA + (uint32_t)st * stageA;
+            const uint32_t dB = sB + (uint32_t)st * stageB;
             if (gq < kgroups)
-              tma_load_im2col_4d(dA + (uint32_t)gq * 4096u, &tmX, full_bar(st), c0, qq * p.step_w + p.base_w,
+              tma_load_im2col_4d(dA + (uint32_t)gq * grp, &tmX, full_bar(st), c0, qq * p.step_w + p.base_w,
                                  pp * p.step_h + p.base_h, n, p.tap_w[tap], p.tap_h[tap]);
-            qq += 32;
+            qq += pb;
             while (qq >= p.Q) { qq -= p.Q; ++pp; }
             while (pp >= p.P) { pp -= p.P; ++n; }
             for (int bg = warp; bg < bgroups; bg += 4)
-              tma_load_2d(dB + (uint32_t)bg * 4096u, &tmDY, full_bar(st), bg * 64, m);
+              tma_load_2d(dB + (uint32_t)bg * grp, &tmDY, full_bar(st), bg * 64, m);
           }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
@@ -134,20 +135,18 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       tc_fence_before();
     } else {
       const uint32_t idesc = make_idesc_h16(p.cout, 0, 0, 1, 1);
-      // MN-major, plain 128B swizzle: 8-pixel atoms 1024 B apart (SBO), 64-wide MN groups 4096 B apart (LBO)
-      const uint64_t adesc0 = make_smem_desc(sA, 4096u, 1024u, 2), bdesc0 = make_smem_desc(sB, 4096u, 1024u, 2);
+      // MN-major, plain 128B swizzle: 8-pixel atoms 1024 B apart (SBO), 64-wide MN groups one group apart (LBO)
+      const uint64_t adesc0 = make_smem_desc(sA, grp, 1024u, 2), bdesc0 = make_smem_desc(sB, grp, 1024u, 2);
+      const int nmma = pb >> 4;  // 16 pixels (2048 B) per MMA
       int st = 0, ph = 0;
       if (lane == 0)
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        for (int sub = 0; sub < kps; ++sub) {
-          const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA + (uint32_t)sub * tileA_bytes) >> 4);
-          const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB + (uint32_t)sub * tileB_bytes) >> 4);
-#pragma unroll
-          for (int j = 0; j < 2; ++j)  // 16 pixels (2048 B) per MMA
-            umma_f16(tmem_base, ad0 + (uint64_t)(j * 128), bd0 + (uint64_t)(j * 128), idesc, (uint32_t)((kb | sub | j) != 0));
-        }
+        const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA) >> 4);
+        const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB) >> 4);
+        for (int j = 0; j < nmma; ++j)
+          umma_f16(tmem_base, ad0 + (uint64_t)(j * 128), bd0 + (uint64_t)(j * 128), idesc, (uint32_t)((kb | j) != 0));
         umma_commit(empty_bar(st));
         if (kb == num_kb - 1) umma_commit(tfull_bar);
         if (++st == stages) { st = 0; ph ^= 1; }
