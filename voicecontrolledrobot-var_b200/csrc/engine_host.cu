@@ -1317,7 +1317,7 @@ int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw
   p.kpad = round_up32(p.K);
   p.cout = cs.Cout;
   p.dw = dw; p.inv_scale = inv_scale;
-  p.pb = env_int("VAR_WGRAD16_PB", 128);      // pixels per TMA box / pipeline stage
+  p.pb = env_int("VAR_WGRAD16_PB", 64);       // pixels per TMA box / pipeline stage (64 x 4 stages: 2 CTAs per SM, measured best)
   p.stages = env_int("VAR_WGRAD16_STAGES", 4);
   if (p.pb < 16 || p.pb > 256 || p.pb % 16) return VAR_ERR_ARG;
   p.P = cs.P; p.Q = cs.Q; p.cpb = cs.Cin / 64;
