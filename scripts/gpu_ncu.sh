@@ -1,18 +1,26 @@
 #!/bin/bash
-# ncu evidence for profiles/: launch list of a short bench run + a small full capture of the
-# GEMM kernels.  Keeps gpurun_out/ well under the 64 MiB pull limit.
+# ncu evidence for profiles/ (usage: bash scripts/gpu_ncu.sh): launch list of a short bench run, then
+# `--set full` captures of every weight-gradient launch of ONE step (the bench line's roofline family),
+# of the recurrent kernels and of a few persistent conv GEMMs.  VAR_GRU_NO_COOP=1: ncu cannot replay the
+# cooperative cluster launch of the BPTT kernel.
 mkdir -p gpurun_out
+export VAR_GRU_NO_COOP=1
 CMD="python scripts/profile_step.py"
-SKIP=${SKIP:-1100}
-COUNT=${COUNT:-8}
-KRE=${KRE:-tc_gemm|tc_wgrad}
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+$CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "== launch list exit $?"
-$CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s $SKIP -c $COUNT -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
-echo "== full capture exit $?"
-ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2> /dev/null
-ls -la gpurun_out/
-sz=$(stat -c %s gpurun_out/prof.ncu-rep 2>/dev/null || echo 0)
-if [ "$sz" -gt 45000000 ]; then echo "dropping oversized report ($sz bytes)"; rm -f gpurun_out/prof.ncu-rep; fi
+# 3 warm-up steps x 16 weight-gradient launches are skipped: launches 48..63 are the measured step
+ncu --set full --clock-control none --import-source on -k regex:"wgrad" -s 48 -c 16 -f -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu_full_wgrad.log 2>&1
+echo "== wgrad capture exit $?"
+ncu -i gpurun_out/prof_wgrad.ncu-rep --page raw --csv > gpurun_out/prof_wgrad_raw.csv 2> /dev/null
+ncu --set full --clock-control none --import-source on -k regex:"gru_|mfcc" -s 9 -c 3 -f -o gpurun_out/prof_gru $CMD > gpurun_out/ncu_full_gru.log 2>&1
+echo "== gru/mfcc capture exit $?"
+ncu -i gpurun_out/prof_gru.ncu-rep --page raw --csv > gpurun_out/prof_gru_raw.csv 2> /dev/null
+ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_persist" -s 84 -c 28 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1
+echo "== gemm capture exit $?"
+ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/prof_gemm_raw.csv 2> /dev/null
+for f in prof_wgrad prof_gru prof_gemm; do
+  sz=$(stat -c %s gpurun_out/$f.ncu-rep 2>/dev/null || echo 0)
+  if [ "$sz" -gt 14000000 ]; then echo "dropping oversized report $f ($sz bytes)"; rm -f gpurun_out/$f.ncu-rep; fi
+done
+ls -la gpurun_out/ | grep -E "prof_|launches"
