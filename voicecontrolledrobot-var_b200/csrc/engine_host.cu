@@ -709,16 +709,16 @@ bool gru_persist_enabled() {  // VAR_GRU_PERSIST=0 falls back to one launch per 
   return on == 1;
 }
 
-template <int BWD>
+template <int BWD, bool H16 = false>
 static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3 grid, cudaStream_t st) {
   const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + gru_scr_bytes(BWD) + 16;
-  VAR_ENSURE_SMEM(gru_persist_kernel<BWD>, smem);
+  VAR_ENSURE_SMEM((gru_persist_kernel<BWD, H16>), smem);
   int max_ctas = 0;
   {  // per call and per device: one process may drive several GPUs
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_persist_kernel<BWD>, kGruThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_persist_kernel<BWD, H16>, kGruThreads, smem);
     max_ctas = per_sm * sms;
   }
   if ((long long)grid.x * grid.y * grid.z > max_ctas) return VAR_ERR_UNSUPPORTED;  // not co-resident
@@ -743,7 +743,7 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
   if (cluster > 1 && grid.y % cluster == 0) {
     static bool np_set = false;
     if (!np_set) {
-      cudaFuncSetAttribute(gru_persist_kernel<BWD>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(gru_persist_kernel<BWD, H16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       np_set = true;
     }
     cudaLaunchConfig_t cfg;
@@ -756,9 +756,9 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, gru_persist_kernel<BWD>, &cfg) == cudaSuccess &&
+    if (cudaOccupancyMaxActiveClusters(&nclusters, gru_persist_kernel<BWD, H16>, &cfg) == cudaSuccess &&
         (long long)nclusters * cluster >= (long long)grid.x * grid.y * grid.z) {
-      cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gru_persist_kernel<BWD>, args);
+      cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gru_persist_kernel<BWD, H16>, args);
       if (e == cudaSuccess) launched = true;
       else (void)cudaGetLastError();
     } else {
@@ -768,7 +768,7 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
     if (!said) { fprintf(stderr, "[var] gru cluster %d: max active clusters %d, launched=%d\n", cluster, nclusters, (int)launched); said = true; }
   }
   if (!launched)
-    VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD>, grid, dim3(kGruThreads, 1, 1), args, smem, st));
+    VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD, H16>, grid, dim3(kGruThreads, 1, 1), args, smem, st));
   if (trace_on) {
     std::vector<long long> h(8 * 128);
     VAR_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -788,15 +788,24 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
 // All T forward steps of both directions in one cooperative launch (gru_persist.cuh).
 // h_r: [(T+1), B, H] with slot 0 zeroed; h32[d][0] zeroed.  Returns VAR_ERR_UNSUPPORTED when the
 // grid cannot be co-resident (caller falls back to per-step launches).
+bool gru_h16_enabled() {  // VAR_GRU_H16=0 keeps tf32 operands in the recurrent kernels
+  static int on = -1;
+  if (on < 0) on = env_int("VAR_GRU_H16", 1) && env_int("VAR_H16", 1);
+  return on == 1;
+}
+
 int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long ldx, const float* const whh[2],
                     const float* const bhh[2], float* const h32[2][2], float* const h_r[2],
-                    float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st) {
+                    float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st,
+                    const void* const whh16[2], void* const h_h[2]) {
   if (!gru_persist_enabled() || gather_mode() != 1 || Hd % 64) return VAR_ERR_UNSUPPORTED;
-  prof_note("gru_persist_fwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
+  const bool h16 = gru_h16_enabled() && whh16 && h_h && whh16[0] && h_h[0];
+  prof_note(h16 ? "gru_persist_fwd16 M%d H%d T%d %d%d" : "gru_persist_fwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
   GruPersistParams p;
   memset(&p, 0, sizeof(p));
   const int jb = 32;
-  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / 32; p.stages = env_int("VAR_GRU_STAGES_FWD", 2);
+  const int ke = h16 ? 64 : 32;
+  p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / ke; p.stages = env_int("VAR_GRU_STAGES_FWD", 2);
   p.kps = env_int("VAR_GRU_KPS_FWD", 2);
   p.a_split = env_int("VAR_GRU_ASPLIT", 0);
   p.counters = counters; p.ldx = ldx;
@@ -805,24 +814,35 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
     p.xproj[d] = xproj[d]; p.bhh[d] = bhh[d];
     p.h32[d][0] = h32[d][0]; p.h32[d][1] = h32[d][1];
     p.h_r[d] = h_r[d]; p.gates[d] = gates[d]; p.hn_save[d] = hn_save[d];
-    int rc = get_tmap_2d(whh[d], 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[d]);
-    if (rc) return rc;
-    rc = get_tmap_2d(h_r[d], (T + 1) * B, Hd, Hd, p.a_split ? 32 : 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    int rc;
+    if (h16) {
+      p.h_h[d] = reinterpret_cast<uint16_t*>(h_h[d]);
+      rc = get_tmap_2d_e(whh16[d], 2, 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[d]);
+      if (rc) return rc;
+      rc = get_tmap_2d_e(h_h[d], 2, (T + 1) * B, Hd, Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    } else {
+      rc = get_tmap_2d(whh[d], 3 * Hd, Hd, Hd, jb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[d]);
+      if (rc) return rc;
+      rc = get_tmap_2d(h_r[d], (T + 1) * B, Hd, Hd, p.a_split ? 32 : 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
+    }
     if (rc) return rc;
   }
+  if (h16) p.a_split = 0;
   dim3 grid((B + 127) / 128, Hd / jb, 2);
   p.arrivals = (int)grid.y;
+  if (h16) return launch_gru_persist<0, true>(tm, p, grid, st);
   return launch_gru_persist<0>(tm, p, grid, st);
 }
 
 // K-split variant of the BPTT kernel (gru_ksplit.cuh): 2-CTA clusters, each CTA streams half of the
 // reduction dimension.  Returns VAR_ERR_UNSUPPORTED when the clusters cannot all be resident.
+template <bool H16>
 static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, int nrt, cudaStream_t st) {
-  p.bn = 64; p.num_kb = (3 * p.Hd / 32) / 2; p.kps = 2; p.stages = 3;
+  p.bn = 64; p.num_kb = (3 * p.Hd / (H16 ? 64 : 32)) / 2; p.kps = 2; p.stages = 3;
   if (p.num_kb % p.kps) return VAR_ERR_UNSUPPORTED;
   const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + 2 * gru_scr_bytes(1) + 32;
   // (cudaFuncSetAttribute is per device: set it every call -- it is a cheap host-side call)
-  VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_ksplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_ksplit_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(2, p.Hd / 64, nrt * 2);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -848,7 +868,7 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
   static bool have_max[kMaxDev], refused[kMaxDev], coop_refused[kMaxDev];
   if (!have_max[dev]) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gru_bwd_ksplit_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, gru_bwd_ksplit_kernel<H16>, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     max_clusters[dev] = n;
     have_max[dev] = true;
   }
@@ -859,14 +879,14 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
   LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
   if (!no_coop && !coop_refused[dev]) {
     cfg.numAttrs = 2;
-    if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args) == cudaSuccess) return VAR_OK;
+    if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel<H16>, args) == cudaSuccess) return VAR_OK;
     (void)cudaGetLastError();  // not sticky
     coop_refused[dev] = true;
     static bool said = false;
-    if (!said) { fprintf(stderr, "[var] cooperative cluster launch of gru_bwd_ksplit_kernel refused; using the occupancy check\n"); said = true; }
+    if (!said) { fprintf(stderr, "[var] cooperative cluster launch of gru_bwd_ksplit_kernel<H16> refused; using the occupancy check\n"); said = true; }
     cfg.numAttrs = 1;
   }
-  if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel, args) != cudaSuccess) {
+  if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel<H16>, args) != cudaSuccess) {
     (void)cudaGetLastError();  // not sticky: fall back to the one-CTA-per-tile kernel from now on
     refused[dev] = true;
     return VAR_ERR_UNSUPPORTED;
@@ -878,8 +898,11 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
 // the cell backward of the last step (gru_cell_bwd).
 int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float* const gates[2],
                     const float* const hn_save[2], const float* const h_r[2], float* const dgh[2],
-                    float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st) {
+                    float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st,
+                    const GruBwdExtra* ex) {
   if (!gru_persist_enabled() || gather_mode() != 1 || Hd % 32) return VAR_ERR_UNSUPPORTED;
+  const bool h16 = ex && gru_h16_enabled() && ex->whh16[0] && ex->dgh_h[0] && ex->gscale[0] && Hd % 64 == 0 &&
+                   env_int("VAR_GRU_KSPLIT", 1);
   prof_note("gru_persist_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
   GruPersistParams p;
   memset(&p, 0, sizeof(p));
@@ -897,13 +920,33 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
     rc = get_tmap_2d(dgh[d], T * B, 3 * Hd, 3 * Hd, p.a_split ? 32 : 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm[2 + d]);
     if (rc) return rc;
   }
+  if (ex) {
+    for (int d = 0; d < 2; ++d) { p.db_ih[d] = ex->db_ih[d]; p.db_hh[d] = ex->db_hh[d]; }
+    if (ex->bias_done) *ex->bias_done = 0;
+  }
+  if (h16) {
+    CUtensorMap th[4];
+    int rc = VAR_OK;
+    for (int d = 0; d < 2 && !rc; ++d) {
+      p.dgh_h[d] = reinterpret_cast<uint16_t*>(ex->dgh_h[d]); p.gscale[d] = ex->gscale[d];
+      rc = get_tmap_2d_e(ex->whh16[d], 2, 3 * Hd, Hd, Hd, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &th[d]);
+      if (!rc) rc = get_tmap_2d_e(ex->dgh_h[d], 2, T * B, 3 * Hd, 3 * Hd, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &th[2 + d]);
+    }
+    if (rc) return rc;
+    prof_note("gru_ksplit_bwd16 M%d H%d T%d %d%d", B, Hd, T, 0, 0);
+    rc = launch_gru_bwd_ksplit<true>(th, p, (B + 127) / 128, st);
+    if (rc == VAR_OK && ex->bias_done) *ex->bias_done = ex->db_ih[0] != nullptr;
+    if (rc != VAR_ERR_UNSUPPORTED) return rc;
+  }
   if (env_int("VAR_GRU_KSPLIT", 1) && Hd % 64 == 0 && !p.a_split) {
     prof_note("gru_ksplit_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
-    const int rc = launch_gru_bwd_ksplit(tm, p, (B + 127) / 128, st);
+    const int rc = launch_gru_bwd_ksplit<false>(tm, p, (B + 127) / 128, st);
+    if (rc == VAR_OK && ex && ex->bias_done) *ex->bias_done = ex->db_ih[0] != nullptr;
     if (rc != VAR_ERR_UNSUPPORTED) return rc;
     p.bn = 32; p.num_kb = 3 * Hd / 32;
     p.stages = env_int("VAR_GRU_STAGES_BWD", 3); p.kps = env_int("VAR_GRU_KPS_BWD", 2);
   }
+  for (int d = 0; d < 2; ++d) { p.db_ih[d] = nullptr; p.db_hh[d] = nullptr; }  // fallback kernel: caller sums the columns
   dim3 grid((B + 127) / 128, Hd / p.bn, 2);
   p.arrivals = (int)grid.y;
   return launch_gru_persist<1>(tm, p, grid, st);
@@ -1037,7 +1080,8 @@ int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStr
   return VAR_OK;
 }
 
-static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, float* dw, cudaStream_t st) {
+static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, float* dw, float* db, int* db_done,
+                          cudaStream_t st) {
   WgradTmaParams p;
   memset(&p, 0, sizeof(p));
   p.M = cs.N * cs.P * cs.Q;
@@ -1067,6 +1111,10 @@ static int conv_wgrad_tma(const ConvShape& cs, const float* x, const float* dy, 
   const int slab = pick_bn(cs.Cout);
   if (slab == 0 || slab % 32) return VAR_ERR_UNSUPPORTED;
   const int nslab = cs.Cout / slab;
+  // bias gradient from an all-ones row group when the last k tile has a free one (VAR_WGRAD_ONES=0: column-sum pass)
+  p.ones_ktile = (p.K % 128 != 0 && env_int("VAR_WGRAD_ONES", 1)) ? ktiles - 1 : -1;
+  p.db = (db && p.ones_ktile >= 0) ? db : nullptr;
+  *db_done = p.db != nullptr;
   // 2 CTAs fit per SM: size the pixel split so the grid is a whole number of 296-CTA waves
   // (a 616-CTA grid runs three waves for 2.08 waves of work)
   const int per_split = ktiles * nslab;
@@ -1126,9 +1174,10 @@ int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout
   }
   if (src_kind == SRC_NHWC_F32 && gather_mode() == 1 && cs.Cin % 32 == 0 && cs.Cout % 32 == 0 &&
       cs.R * cs.S <= kMaxTaps) {
-    const int rc = conv_wgrad_tma(cs, reinterpret_cast<const float*>(x), dy, dw, st);
+    int db_done = 0;
+    const int rc = conv_wgrad_tma(cs, reinterpret_cast<const float*>(x), dy, dw, db, &db_done, st);
     if (rc) return rc;
-    if (db) return colsum(dy, (long long)cs.N * cs.P * cs.Q, cs.Cout, cs.Cout, db, st);
+    if (db && !db_done) return colsum(dy, (long long)cs.N * cs.P * cs.Q, cs.Cout, cs.Cout, db, st);
     return VAR_OK;
   }
   WgradParams p;

@@ -59,12 +59,25 @@ int gru_step_fwd(int ndir, int B, int Hd, const float* const hprev_r[2], const f
                  const GruEpiParams q[2], cudaStream_t st);
 int gru_step_bwd(int ndir, int B, int Hd, const float* const dgh[2], const float* const whh[2],
                  const GruBwdEpiParams q[2], cudaStream_t st);
+// whh16 / h_h (nullable): f16 copies of W_hh and a [(T+1), B, H] f16 hidden-state buffer (slot 0 zeroed) -> the
+// recurrent GEMM runs on 16-bit operands (half the per-step operand stream).
 int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long ldx, const float* const whh[2],
                     const float* const bhh[2], float* const h32[2][2], float* const h_r[2],
-                    float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st);
+                    float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st,
+                    const void* const whh16[2] = nullptr, void* const h_h[2] = nullptr);
+struct GruBwdExtra {
+  const void* whh16[2];    // f16 W_hh copies
+  void* dgh_h[2];          // [T][B, 3H] f16 scaled gate gradients; slot T-1 filled by the caller (grad_to_f16_scaled)
+  const float* gscale[2];  // device {S, 1/S} per direction
+  float* db_ih[2];         // bias gradients accumulated inside the BPTT kernel (nullable)
+  float* db_hh[2];
+  int* bias_done;          // out: 1 when the kernel produced the bias gradients (else the caller sums columns)
+};
 int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float* const gates[2],
                     const float* const hn_save[2], const float* const h_r[2], float* const dgh[2],
-                    float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st);
+                    float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st,
+                    const GruBwdExtra* ex = nullptr);
+bool gru_h16_enabled();
 int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st);
 
 // dw[Cout, Kpad] += im2col(x)^T dy ; db[Cout] += colsum(dy) (db may be null).

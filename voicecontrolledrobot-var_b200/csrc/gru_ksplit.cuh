@@ -29,6 +29,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // grid = (2 = k half / cluster rank, hidden tiles of 64, row tiles * 2 directions), cluster (2,1,1),
 // block = kGruThreads.  p.bn = 64, p.num_kb = k-blocks per CTA and step (24), p.kps | p.num_kb.
+// H16: dgh (A) and W_hh (B, read transposed) are f16; dgh_h carries the gradients times the power-of-two
+// scale gscale[z][0], the epilogue multiplies the partial sums by 1/S.  A k-block is 64 columns of dgh.
+template <bool H16>
 __global__ void __launch_bounds__(kGruThreads, 1)
 gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                       const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -82,9 +85,14 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
   const int nsteps = T - 1;
   const int kb_base = rank * num_kb;
   const int quarter = warp & 3, sub = warp >> 2;
-  const uint32_t idesc = make_idesc_tf32(bn, 0, 1);
+  constexpr int KE = H16 ? 64 : 32;  // dgh columns per k-block
+  const uint32_t idesc = H16 ? make_idesc_h16(bn, 0, 0, 0, 1) : make_idesc_tf32(bn, 0, 1);
   const uint64_t adesc0 = make_smem_desc(sA, 16u, 1024u);
-  const uint64_t bdesc0 = make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type);
+  const uint64_t bdesc0 = H16 ? make_smem_desc(sB, 8192u, 1024u, 2)
+                              : make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type);
+  float gS = 1.f, gInv = 1.f;
+  if constexpr (H16) { gS = __ldg(p.gscale[z]); gInv = __ldg(p.gscale[z] + 1); }
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of dr, dz, dn, dn*r over this thread's rows and all steps
   int mst = 0, mph = 0;  // MMA ring position (warp 4)
   int st = 0, ph = 0;    // producer ring position (warp 0 lane 0)
   constexpr int RB = 8;
@@ -137,9 +145,13 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
             const int kb = kb_base + kb0 + sb;
             const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sb * kTileABytes;
             const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sb * tileB_bytes;
-            tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
-            tma_load_2d(dstB, tmB, full_bar(st), ntile * 64, kb * 32);
-            tma_load_2d(dstB + 4096u, tmB, full_bar(st), ntile * 64 + 32, kb * 32);
+            tma_load_2d(dstA, tmA, full_bar(st), kb * KE, arow);
+            if constexpr (H16) {
+              tma_load_2d(dstB, tmB, full_bar(st), ntile * 64, kb * KE);  // one {64 n, 64 k} box
+            } else {
+              tma_load_2d(dstB, tmB, full_bar(st), ntile * 64, kb * 32);
+              tma_load_2d(dstB + 4096u, tmB, full_bar(st), ntile * 64 + 32, kb * 32);
+            }
           }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
@@ -155,9 +167,14 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
             const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)mst * stageA + (uint32_t)sb * kTileABytes) >> 4);
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)mst * stageB + (uint32_t)sb * tileB_bytes) >> 4);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              umma_tf32(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * 64), idesc,
-                        (uint32_t)((kb0 | sb | jj) != 0));
+            for (int jj = 0; jj < 4; ++jj) {
+              if constexpr (H16)
+                umma_f16(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * 128), idesc,
+                         (uint32_t)((kb0 | sb | jj) != 0));
+              else
+                umma_tf32(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * 64), idesc,
+                          (uint32_t)((kb0 | sb | jj) != 0));
+            }
           }
           umma_commit(empty_bar(mst));
           if (kb0 + kps >= num_kb) umma_commit(tfull_bar);
@@ -190,12 +207,26 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
       float* dgi = p.dgi[z] + (long long)t * 3 * Hd;
       const long long ldgi = (long long)T * 3 * Hd;
       float* dgh = p.dgh[z] + (long long)sp * B * 3 * Hd;
+      if (it_s == 0 && p.db_ih[z]) {
+        // the cell backward of the LAST step ran in gru_cell_bwd: fold its gate gradients into the bias sums
+        const float* gl = p.dgh[z] + (long long)s * B * 3 * Hd;
+        const float* gil = p.dgi[z] + (long long)(z == 0 ? s : T - 1 - s) * 3 * Hd;
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int mr = mrow0 + u;
+          if (mr < B) {
+            const float* gh = gl + (long long)mr * 3 * Hd + j;
+            bsum[0] += gh[0]; bsum[1] += gh[Hd]; bsum[3] += gh[2 * Hd];
+            bsum[2] += gil[(long long)mr * ldgi + 2 * Hd + j];
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const int rr = sub * RB + u, mr = mrow0 + u;
         if (mr < B) {
           const long long hoff = (long long)mr * Hd + j;
-          const float dh = scr[rr * 33 + lane] + xch[rr * 33 + lane] + in0[u];
+          const float dh = (scr[rr * 33 + lane] + xch[rr * 33 + lane]) * gInv + in0[u];
           const float r_ = in1[u], z_ = in2[u], n_ = in3[u];
           const float dnn = dh * (1.f - z_);
           const float dzz = dh * (in5[u] - n_);
@@ -206,7 +237,13 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
           float* gi = dgi + (long long)mr * ldgi + j;
           gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
           float* gh = dgh + (long long)mr * 3 * Hd + j;
-          gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = round_tf32(dnp * r_);
+          const float dnr = round_tf32(dnp * r_);
+          gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
+          if constexpr (H16) {
+            uint16_t* ghh = p.dgh_h[z] + (long long)sp * B * 3 * Hd + (long long)mr * 3 * Hd + j;
+            ghh[0] = f16_sat_bits(dr * gS); ghh[Hd] = f16_sat_bits(dz * gS); ghh[2 * Hd] = f16_sat_bits(dnr * gS);
+          }
+          bsum[0] += dr; bsum[1] += dz; bsum[2] += dn; bsum[3] += dnr;
           dhd_out[hoff] = dh * z_;
         }
       }
@@ -218,6 +255,10 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
       __threadfence();
       atomicAdd(counter, 1u);
     }
+  }
+  if (p.db_ih[z]) {  // bias gradients: b_ih gets (dr, dz, dn), b_hh gets (dr, dz, dn * r)
+    atomicAdd(p.db_ih[z] + j, bsum[0]); atomicAdd(p.db_ih[z] + Hd + j, bsum[1]); atomicAdd(p.db_ih[z] + 2 * Hd + j, bsum[2]);
+    atomicAdd(p.db_hh[z] + j, bsum[0]); atomicAdd(p.db_hh[z] + Hd + j, bsum[1]); atomicAdd(p.db_hh[z] + 2 * Hd + j, bsum[3]);
   }
   tc_fence_before();
   cluster_sync_all();  // nobody leaves while the partner could still address its shared memory

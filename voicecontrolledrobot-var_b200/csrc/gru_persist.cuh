@@ -45,6 +45,13 @@ struct GruPersistParams {
   float* dgi[2];          // [B, T, 3H] batch-major
   float* dhd[2][2];       // dh * z ping-pong [B, H]
   long long* trace;       // optional [steps][8] clock64 samples of CTA (0,0,0) (VAR_GRU_TRACE=1)
+  // 16-bit operand variants (H16): the recurrent GEMM operands are f16 copies -- half the per-step operand
+  // stream that bounds both kernels -- while the cell state, gates and every saved tensor stay fp32.
+  uint16_t* h_h[2];         // fwd: [(T+1), B, H] f16 hidden states (slot 0 = zeros): A operand
+  uint16_t* dgh_h[2];       // bwd: [T][B, 3H] f16 gate gradients times gscale[z][0]: A operand
+  const float* gscale[2];   // bwd: device {S, 1/S} per direction (power of two, from the last step's gradient)
+  float* db_ih[2];          // bwd: bias gradients accumulated in the epilogue (+=, nullable): colsum(dgi) / colsum(dgh)
+  float* db_hh[2];
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -74,7 +81,15 @@ __device__ __forceinline__ void quarter_sync(int q) {
   asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
 }
 
-template <int BWD>
+// f32 -> f16 with saturation to +-65504 instead of overflow to inf
+__device__ __forceinline__ uint16_t f16_sat_bits(float x) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  uint16_t h;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+
+template <int BWD, bool H16 = false>
 __global__ void __launch_bounds__(kGruThreads, 1)
 gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                    const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -128,7 +143,9 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
   {
     const int quarter = warp & 3;
     const int sub = warp >> 2;
-    const uint32_t idesc = make_idesc_tf32(bn, 0, BWD ? 1 : 0);
+    static_assert(!(BWD && H16), "the 16-bit BPTT kernel is gru_bwd_ksplit_kernel<true>");
+    constexpr int KE = H16 ? 64 : 32;  // elements per 128-byte k-block row
+    const uint32_t idesc = H16 ? make_idesc_h16(bn, 0, 0, 0, 0) : make_idesc_tf32(bn, 0, BWD ? 1 : 0);
     const uint64_t adesc0 = make_smem_desc(sA, 16u, 1024u);
     const uint64_t bdesc0 = BWD ? make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type)
                                 : make_smem_desc(sB, 16u, 1024u);
@@ -207,12 +224,12 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
               const int kb = kb0 + sub;
               const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
               const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
-              if (p.a_split) tma_load_2d(dstA + (uint32_t)warp * 4096u, tmA, full_bar(st), kb * 32, arow + warp * 32);
-              else if (warp == 0) tma_load_2d(dstA, tmA, full_bar(st), kb * 32, arow);
+              if (p.a_split) tma_load_2d(dstA + (uint32_t)warp * 4096u, tmA, full_bar(st), kb * KE, arow + warp * 32);
+              else if (warp == 0) tma_load_2d(dstA, tmA, full_bar(st), kb * KE, arow);
               if constexpr (!BWD) {
                 for (int b = 0; b < 3; ++b)
                   if (warp == 1 + b)
-                    tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * 32, b * Hd + ntile * jb);
+                    tma_load_2d(dstB + (uint32_t)(b * jb) * 128u, tmB, full_bar(st), kb * KE, b * Hd + ntile * jb);
               } else {
                 for (int gidx = 0; gidx < (bn >> 5); ++gidx)
                   if (warp == ((multi || p.a_split) ? 1 + (gidx % 3) : 0))
@@ -247,9 +264,14 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
               const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)mst * stageA + (uint32_t)sub * kTileABytes) >> 4);
               const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)mst * stageB + (uint32_t)sub * tileB_bytes) >> 4);
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                umma_tf32(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * (BWD ? 64 : 2)), idesc,
-                          (uint32_t)((kb0 | sub | jj) != 0));
+              for (int jj = 0; jj < 4; ++jj) {
+                if constexpr (H16)
+                  umma_f16(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * 2), idesc,
+                           (uint32_t)((kb0 | sub | jj) != 0));
+                else
+                  umma_tf32(tmem_base, ad0 + (uint64_t)(jj * 2), bd0 + (uint64_t)(jj * (BWD ? 64 : 2)), idesc,
+                            (uint32_t)((kb0 | sub | jj) != 0));
+              }
             }
             umma_commit(empty_bar(mst));
             if (kb0 + kps >= num_kb) umma_commit(tfull_bar);
@@ -279,6 +301,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
             const long long ho = (long long)mr * Hd + j;
             hnew[ho] = h_;
             hnew_r[ho] = round_tf32(h_);
+            if constexpr (H16) p.h_h[z][(long long)(s + 1) * B * Hd + ho] = f16_sat_bits(h_);  // |h| < 1
             if (gates) {
               float* gs = gates + (long long)mr * 3 * Hd + j;
               gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;

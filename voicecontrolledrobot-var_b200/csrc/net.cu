@@ -75,6 +75,7 @@ struct GruState {
   float* out;           // [B, 1024]
   float* out_r;
   unsigned int* counters;  // [row tiles * 2] persistent-kernel group barriers
+  void* h_h[2];         // [T+1][B, 512] f16 hidden states: A operand of the 16-bit recurrent GEMM (nullptr: tf32)
 };
 
 }  // namespace
@@ -110,6 +111,9 @@ struct Net {
   cudaEvent_t ev_rnn_grads = nullptr;  // not owned
   float* h16_scale = nullptr;          // device: {S, 1/S} of the gradient entering the 16-bit region
   unsigned int* h16_amax = nullptr;
+  void* whh16[2] = {nullptr, nullptr}; // f16 copies of W_hh (both recurrent kernels), refreshed every forward
+  float* gru_scale = nullptr;          // device: [2 directions][S, 1/S] of the BPTT gate gradients
+  unsigned int* gru_amax = nullptr;    // [2]
 
   ~Net() {
     for (auto* L : {&img_trunk, &img_head, &snd_trunk, &snd_head})
@@ -117,6 +121,9 @@ struct Net {
         if (l.w16) cudaFree(l.w16);
     if (h16_scale) cudaFree(h16_scale);
     if (h16_amax) cudaFree(h16_amax);
+    for (int d = 0; d < 2; ++d) if (whh16[d]) cudaFree(whh16[d]);
+    if (gru_scale) cudaFree(gru_scale);
+    if (gru_amax) cudaFree(gru_amax);
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -298,6 +305,11 @@ struct Net {
             VAR_CUDA_CHECK(cudaMalloc(&h16_amax, sizeof(unsigned int)));
           }
         }
+    if (has_gru && gru_h16_enabled() && !whh16[0]) {
+      for (int d = 0; d < 2; ++d) VAR_CUDA_CHECK(cudaMalloc(&whh16[d], (size_t)3 * kGruH * kGruH * 2));
+      VAR_CUDA_CHECK(cudaMalloc(&gru_scale, 4 * sizeof(float)));
+      VAR_CUDA_CHECK(cudaMalloc(&gru_amax, 2 * sizeof(unsigned int)));
+    }
     return VAR_OK;
   }
 
@@ -350,6 +362,7 @@ struct Net {
       g.gates[d] = train ? ar.alloc(BT * 3 * kGruH) : nullptr;
       g.hn_save[d] = train ? ar.alloc(BT * kGruH) : nullptr;
       g.h_r[d] = ar.alloc((long long)(kGruT + 1) * B * kGruH);
+      g.h_h[d] = (gru_h16_enabled() && (whh16[0] || !ar.base)) ? ar.alloc(((long long)(kGruT + 1) * B * kGruH + 1) / 2) : nullptr;
       g.h32[d][0] = ar.alloc((long long)B * kGruH);
       g.h32[d][1] = ar.alloc((long long)B * kGruH);
     }
@@ -366,6 +379,11 @@ struct Net {
       if (rc) return rc;
       VAR_CUDA_CHECK(cudaMemsetAsync(g.h_r[d], 0, (size_t)B * kGruH * 4, st));
       VAR_CUDA_CHECK(cudaMemsetAsync(g.h32[d][0], 0, (size_t)B * kGruH * 4, st));
+      if (g.h_h[d]) {
+        VAR_CUDA_CHECK(cudaMemsetAsync(g.h_h[d], 0, (size_t)B * kGruH * 2, st));
+        rc = cvt_f16(wm(t_gru[d][1]), whh16[d], (long long)3 * kGruH * kGruH, st);  // weights may have moved
+        if (rc) return rc;
+      }
     }
     const long long slot = (long long)B * kGruH;
     {  // all 73 steps in one cooperative launch when the grid fits the device
@@ -376,8 +394,10 @@ struct Net {
       float* hr[2] = {g.h_r[0], g.h_r[1]};
       float* gt[2] = {g.gates[0], g.gates[1]};
       float* hs[2] = {g.hn_save[0], g.hn_save[1]};
+      const void* w16[2] = {whh16[0], whh16[1]};
+      void* hh[2] = {g.h_h[0], g.h_h[1]};
       const int rc = gru_persist_fwd(B, kGruH, kGruT, xp, (long long)kGruT * 3 * kGruH, whh, bhh, h32, hr, gt, hs,
-                                     g.counters, st);
+                                     g.counters, st, g.h_h[0] ? w16 : nullptr, g.h_h[0] ? hh : nullptr);
       if (rc == VAR_OK)
         return concat2(g.h32[0][kGruT & 1], g.h32[1][kGruT & 1], g.out, g.out_r, B, kGruH, st);
       if (rc != VAR_ERR_UNSUPPORTED) return rc;
@@ -570,6 +590,9 @@ struct Net {
     }
     float* dx0 = ar.alloc(BT * kGruI);
     float* dx = ar.alloc(BT * kGruI);
+    const bool h16 = gru_h16_enabled() && (whh16[0] || !ar.base);
+    void* dgh_h[2] = {nullptr, nullptr};
+    if (h16) for (int d = 0; d < 2; ++d) dgh_h[d] = ar.alloc((BT * 3 * kGruH + 1) / 2);
     if (!ar.base) { *dx_out = nullptr; return VAR_OK; }
     if (ar.overflow) return VAR_ERR_WORKSPACE;
     int rc = split2(d_out, dh[0][0], dh[1][0], B, kGruH, st);
@@ -594,6 +617,21 @@ struct Net {
     // steps T-1 .. 1: recurrence GEMM with the cell backward of the previous step fused in
     float* dhd_pp[2][2] = {{dhd[0], dh[0][1]}, {dhd[1], dh[1][1]}};
     bool persistent_done = false;
+    int bias_done = 0;  // the BPTT kernel also produced db_ih / db_hh
+    GruBwdExtra ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.bias_done = &bias_done;
+    for (int d = 0; d < 2; ++d) {
+      ex.db_ih[d] = gr(t_gru[d][2]); ex.db_hh[d] = gr(t_gru[d][3]);
+      if (h16) {
+        // the gate gradients of the last step enter the 16-bit recurrence: scale from their largest magnitude
+        const long long lo = (long long)(kGruT - 1) * B * 3 * kGruH;
+        rc = grad_to_f16_scaled(dgh[d] + lo, reinterpret_cast<uint16_t*>(dgh_h[d]) + lo, (long long)B * 3 * kGruH,
+                                gru_scale + 2 * d, gru_amax + d, st);
+        if (rc) return rc;
+        ex.whh16[d] = whh16[d]; ex.dgh_h[d] = dgh_h[d]; ex.gscale[d] = gru_scale + 2 * d;
+      }
+    }
     {
       const float* whh[2] = {wr(t_gru[0][1]), wr(t_gru[1][1])};
       const float* gt[2] = {g.gates[0], g.gates[1]};
@@ -601,7 +639,7 @@ struct Net {
       const float* hr[2] = {g.h_r[0], g.h_r[1]};
       float* dgh2[2] = {dgh[0], dgh[1]};
       float* dgi2[2] = {dgi[0], dgi[1]};
-      rc = gru_persist_bwd(B, kGruH, kGruT, whh, gt, hs, hr, dgh2, dgi2, dhd_pp, g.counters, st);
+      rc = gru_persist_bwd(B, kGruH, kGruT, whh, gt, hs, hr, dgh2, dgi2, dhd_pp, g.counters, st, &ex);
       if (rc == VAR_OK) persistent_done = true;
       else if (rc != VAR_ERR_UNSUPPORTED) return rc;
     }
@@ -641,10 +679,11 @@ struct Net {
     for (int d = 0; d < 2; ++d) {
       // dW_hh += dgh^T h_prev ; db_hh += colsum(dgh)      (rows: step-major)
       ConvShape chh{(int)BT, 1, 1, kGruH, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
-      rc = conv_wgrad(chh, g.h_r[d], SRC_NHWC_F32, nullptr, dgh[d], gr(t_gru[d][1]), gr(t_gru[d][3]), st);
+      // (bias gradients: accumulated inside the BPTT kernel when it ran; else column sums here)
+      rc = conv_wgrad(chh, g.h_r[d], SRC_NHWC_F32, nullptr, dgh[d], gr(t_gru[d][1]), bias_done ? nullptr : gr(t_gru[d][3]), st);
       if (rc) return rc;
       // dW_ih += dgi^T x ; db_ih += colsum(dgi)           (rows: batch-major)
-      rc = conv_wgrad(cih, g.x, SRC_NHWC_F32, nullptr, dgi[d], gr(t_gru[d][0]), gr(t_gru[d][2]), st);
+      rc = conv_wgrad(cih, g.x, SRC_NHWC_F32, nullptr, dgi[d], gr(t_gru[d][0]), bias_done ? nullptr : gr(t_gru[d][2]), st);
       if (rc) return rc;
     }
     if (ev_rnn_grads) VAR_CUDA_CHECK(cudaEventRecord(ev_rnn_grads, st));  // every rnn.* gradient is final

@@ -871,6 +871,10 @@ struct WgradTmaParams {
   int P, Q;           // output extents: pixel m -> (n, p, q)
   int cpb, base_w, base_h, step_w, step_h;
   uint8_t tap_w[kMaxTaps], tap_h[kMaxTaps];
+  // bias gradient without a column-sum pass: when K % 128 != 0 the last k tile has unused 32-row groups; the
+  // first of them is filled with ones once, so accumulator row K is colsum(dY) (db += it; nullptr = off)
+  float* db;
+  int ones_ktile;
 };
 
 template <int kVariant>
@@ -917,6 +921,15 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int pix1 = min(pix0 + p.pix_per_cta, p.M);
   const int num_kb = ((pix1 - pix0 + 31) / 32 + kps - 1) / kps;  // pipeline stages of kps pixel blocks
   const int kgroups = min(4, (p.K - ktile * 128 + 31) / 32);  // valid 32-row groups of this k tile
+  const bool ones = p.db != nullptr && ktile == p.ones_ktile && kgroups < 4 && blockIdx.z * p.cout < 1 << 30;
+  if (ones) {  // group `kgroups` of every X^T block := 1.0f (TMA never writes it in this k tile)
+    for (uint32_t blk = 0; blk < (uint32_t)(stages * kps); ++blk)
+      for (uint32_t i = tid; i < 4096u / 16u; i += 160u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + blk * tileA_bytes + (uint32_t)kgroups * 4096u + i * 16u),
+                     "r"(0x3F800000u) : "memory");
+    fence_proxy_async_smem();
+    __syncthreads();
+  }
 
   if (num_kb > 0) {
     if (warp < 4) {
@@ -984,6 +997,9 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (k < p.K) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(dw_slab + (long long)(c + j) * p.kpad + k, v[j]);
+        } else if (ones && k == p.K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(p.db + (long long)blockIdx.z * p.cout + c + j, v[j]);
         }
       }
       tc_fence_before();
