@@ -721,65 +721,40 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_persist_kernel<BWD, H16>, kGruThreads, smem);
     max_ctas = per_sm * sms;
   }
-  if ((long long)grid.x * grid.y * grid.z > max_ctas) return VAR_ERR_UNSUPPORTED;  // not co-resident
-  VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * grid.x * grid.z, st));
-  void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
+  // Batches whose grid cannot be co-resident run as consecutive launches over chunks of row tiles (rows are
+  // independent; every chunk uses the same kernel, so results do not depend on the batch size).
+  const int nrt = (int)grid.x;
+  const int chunk = max_ctas / (int)(grid.y * grid.z);
+  if (chunk < 1) return VAR_ERR_UNSUPPORTED;
   const int nsteps = BWD ? p.T - 1 : p.T;
-  LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)(p.bn * grid.y) * (p.num_kb * 32.0) * grid.z * nsteps, st);
   static int trace_on = -1;
   if (trace_on < 0) { const char* e = getenv("VAR_GRU_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
   static long long* d_trace = nullptr;
-  if (trace_on) {  // debugging aid: per-step clock64 samples of CTA (0,0,0), dumped after a sync
-    if (!d_trace) VAR_CUDA_CHECK(cudaMalloc(&d_trace, sizeof(long long) * 8 * 128));
-    VAR_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 128, st));
-    p.trace = d_trace;
-  }
-  // Optional placement experiment: launch the 16 CTAs of a (row tile, direction) group as one
-  // thread-block cluster so that they share a GPC (VAR_GRU_CLUSTER=8|16); the kernel itself uses no
-  // cluster feature.
-  static int cluster = -1;
-  if (cluster < 0) cluster = env_int("VAR_GRU_CLUSTER", 0);
-  bool launched = false;
-  if (cluster > 1 && grid.y % cluster == 0) {
-    static bool np_set = false;
-    if (!np_set) {
-      cudaFuncSetAttribute(gru_persist_kernel<BWD, H16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      np_set = true;
+  for (int rt0 = 0; rt0 < nrt; rt0 += chunk) {
+    p.rt0 = rt0;
+    grid.x = (unsigned)(nrt - rt0 < chunk ? nrt - rt0 : chunk);
+    VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * grid.x * grid.z, st));
+    void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
+    const int rows = (int)grid.x * 128 < p.B - rt0 * 128 ? (int)grid.x * 128 : p.B - rt0 * 128;
+    LaunchScope sc(T_GRU_STEP, 2.0 * rows * (double)(p.bn * grid.y) * (p.num_kb * (H16 ? 64.0 : 32.0)) * grid.z * nsteps, st);
+    if (trace_on) {  // debugging aid: per-step clock64 samples of CTA (0,0,0), dumped after a sync
+      if (!d_trace) VAR_CUDA_CHECK(cudaMalloc(&d_trace, sizeof(long long) * 8 * 128));
+      VAR_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 128, st));
+      p.trace = d_trace;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cluster; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeCooperative;
-    at[1].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, gru_persist_kernel<BWD, H16>, &cfg) == cudaSuccess &&
-        (long long)nclusters * cluster >= (long long)grid.x * grid.y * grid.z) {
-      cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gru_persist_kernel<BWD, H16>, args);
-      if (e == cudaSuccess) launched = true;
-      else (void)cudaGetLastError();
-    } else {
-      (void)cudaGetLastError();
-    }
-    static bool said = false;
-    if (!said) { fprintf(stderr, "[var] gru cluster %d: max active clusters %d, launched=%d\n", cluster, nclusters, (int)launched); said = true; }
-  }
-  if (!launched)
     VAR_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persist_kernel<BWD, H16>, grid, dim3(kGruThreads, 1, 1), args, smem, st));
-  if (trace_on) {
-    std::vector<long long> h(8 * 128);
-    VAR_CUDA_CHECK(cudaStreamSynchronize(st));
-    VAR_CUDA_CHECK(cudaMemcpy(h.data(), d_trace, sizeof(long long) * 8 * 128, cudaMemcpyDeviceToHost));
-    FILE* f = fopen(BWD ? "gpurun_out/gru_trace_bwd.csv" : "gpurun_out/gru_trace_fwd.csv", "w");
-    if (f) {
-      fprintf(f, "step,start,acquired,issued,tfull,epi_done,released\n");
-      for (int i = 0; i < nsteps && i < 128; ++i)
-        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld\n", i, h[i * 8] - h[0], h[i * 8 + 1] - h[0], h[i * 8 + 2] - h[0],
-                h[i * 8 + 3] - h[0], h[i * 8 + 4] - h[0], h[i * 8 + 5] - h[0]);
-      fclose(f);
+    if (trace_on) {
+      std::vector<long long> h(8 * 128);
+      VAR_CUDA_CHECK(cudaStreamSynchronize(st));
+      VAR_CUDA_CHECK(cudaMemcpy(h.data(), d_trace, sizeof(long long) * 8 * 128, cudaMemcpyDeviceToHost));
+      FILE* f = fopen(BWD ? "gpurun_out/gru_trace_bwd.csv" : "gpurun_out/gru_trace_fwd.csv", "w");
+      if (f) {
+        fprintf(f, "step,start,acquired,issued,tfull,epi_done,released\n");
+        for (int i = 0; i < nsteps && i < 128; ++i)
+          fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld,%lld\n", i, h[i * 8] - h[0], h[i * 8 + 1] - h[0], h[i * 8 + 2] - h[0],
+                  h[i * 8 + 3] - h[0], h[i * 8 + 4] - h[0], h[i * 8 + 5] - h[0]);
+        fclose(f);
+      }
     }
   }
   return VAR_OK;
@@ -843,7 +818,7 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
   const size_t smem = gemm_smem_bytes(p.bn, p.stages * p.kps) + 2 * gru_scr_bytes(1) + 32;
   // (cudaFuncSetAttribute is per device: set it every call -- it is a cheap host-side call)
   VAR_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_ksplit_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(2, p.Hd / 64, nrt * 2);
+  dim3 grid(2, p.Hd / 64, 2);  // .z = row tiles of the chunk * 2 directions, set below
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(kGruThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -80,7 +80,7 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
   cluster_sync_all();  // the partner's shared memory exists before anybody writes into it
 
-  const int m0 = rt * kTileM;
+  const int m0 = (p.rt0 + rt) * kTileM;
   unsigned int* counter = p.counters + (z * (int)(gridDim.z >> 1) + rt);
   const int nsteps = T - 1;
   const int kb_base = rank * num_kb;

@@ -27,6 +27,7 @@ struct GruPersistParams {
   int kps;            // k-blocks (32 columns) per pipeline stage: 1 or 2
   int a_split;        // 1: the A tile arrives as four 32-row boxes issued by four threads
   int arrivals;       // CTA arrivals per group per step = gridDim.y
+  int rt0;            // first 128-row tile of this launch (batches beyond the co-resident grid run in row chunks)
   unsigned int* counters;  // [gridDim.x * gridDim.z], zero before launch
   int mn_lbo, mn_sbo, mn_type;
   // forward
@@ -132,7 +133,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
-  const int m0 = blockIdx.x * kTileM;
+  const int m0 = (p.rt0 + (int)blockIdx.x) * kTileM;
   const int ntile = blockIdx.y;
   unsigned int* counter = p.counters + (blockIdx.z * gridDim.x + blockIdx.x);
   const int nsteps = BWD ? T - 1 : T;
