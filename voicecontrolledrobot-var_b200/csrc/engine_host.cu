@@ -725,6 +725,8 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
   // independent; every chunk uses the same kernel, so results do not depend on the batch size).
   const int nrt = (int)grid.x;
   const int chunk = max_ctas / (int)(grid.y * grid.z);
+  if (env_int("VAR_DEBUG", 0))
+    fprintf(stderr, "[var] gru_persist<%d,%d>: B %d nrt %d max_ctas %d chunk %d\n", BWD, (int)H16, p.B, nrt, max_ctas, chunk);
   if (chunk < 1) return VAR_ERR_UNSUPPORTED;
   const int nsteps = BWD ? p.T - 1 : p.T;
   static int trace_on = -1;
@@ -848,23 +850,40 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
     have_max[dev] = true;
   }
   // refused: a launch was rejected once on this device (e.g. under a profiler that cannot replay it)
-  if (refused[dev] || (long long)max_clusters[dev] * 2 < (long long)grid.x * grid.y * grid.z) return VAR_ERR_UNSUPPORTED;
-  VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * nrt * 2, st));
-  void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
-  LaunchScope sc(T_GRU_STEP, 2.0 * p.B * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
-  if (!no_coop && !coop_refused[dev]) {
-    cfg.numAttrs = 2;
-    if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel<H16>, args) == cudaSuccess) return VAR_OK;
-    (void)cudaGetLastError();  // not sticky
-    coop_refused[dev] = true;
-    static bool said = false;
-    if (!said) { fprintf(stderr, "[var] cooperative cluster launch of gru_bwd_ksplit_kernel<H16> refused; using the occupancy check\n"); said = true; }
-    cfg.numAttrs = 1;
-  }
-  if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel<H16>, args) != cudaSuccess) {
-    (void)cudaGetLastError();  // not sticky: fall back to the one-CTA-per-tile kernel from now on
-    refused[dev] = true;
-    return VAR_ERR_UNSUPPORTED;
+  const int chunk = max_clusters[dev] / (int)(grid.y * 2);  // row tiles whose clusters are co-resident
+  if (env_int("VAR_DEBUG", 0))
+    fprintf(stderr, "[var] gru_bwd_ksplit<%d>: B %d nrt %d max_clusters %d chunk %d refused %d coop_refused %d\n", (int)H16, p.B,
+            nrt, max_clusters[dev], chunk, (int)refused[dev], (int)coop_refused[dev]);
+  if (refused[dev] || chunk < 1) return VAR_ERR_UNSUPPORTED;
+  for (int rt0 = 0; rt0 < nrt; rt0 += chunk) {  // larger batches: consecutive launches over row-tile chunks
+    const int n = nrt - rt0 < chunk ? nrt - rt0 : chunk;
+    p.rt0 = rt0;
+    grid.z = (unsigned)(n * 2);
+    cfg.gridDim = grid;
+    VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * n * 2, st));
+    void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
+    const int rows = n * 128 < p.B - rt0 * 128 ? n * 128 : p.B - rt0 * 128;
+    LaunchScope sc(T_GRU_STEP, 2.0 * rows * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
+    bool done = false;
+    if (!no_coop && !coop_refused[dev]) {
+      cfg.numAttrs = 2;
+      if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel<H16>, args) == cudaSuccess) done = true;
+      else {
+        (void)cudaGetLastError();  // not sticky
+        coop_refused[dev] = true;
+        static bool said = false;
+        if (!said) { fprintf(stderr, "[var] cooperative cluster launch of the K-split BPTT kernel refused; using the occupancy check\n"); said = true; }
+      }
+    }
+    if (!done) {
+      cfg.numAttrs = 1;
+      if (cudaLaunchKernelExC(&cfg, (const void*)gru_bwd_ksplit_kernel<H16>, args) != cudaSuccess) {
+        (void)cudaGetLastError();  // not sticky: fall back to the one-CTA-per-tile kernel from now on
+        refused[dev] = true;
+        if (rt0 > 0) { var_set_last_error("BPTT chunk launch refused after earlier chunks ran", __FILE__, __LINE__); return VAR_ERR_CUDA; }
+        return VAR_ERR_UNSUPPORTED;
+      }
+    }
   }
   return VAR_OK;
 }
