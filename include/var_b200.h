@@ -84,6 +84,15 @@ int var_sampler_batch_tasks(uint32_t* d_state, int B, int task_num, const int32_
  * DataLoader / __getitem__ draw from (dataset.py:76, :157-162). */
 int var_sampler_set_state(uint32_t* d_state, const uint32_t* host_words, int pos, void* stream);
 
+/* Host-side staging helpers of the streaming triplet loader (datasets kept in pinned HOST memory, the
+ * counterpart of the reference's DataLoader workers, dataset.py:157-162): gather the rows (uint8 frames) /
+ * clips (int16, packed back to back and 4-byte aligned; offset < 0 = empty class) a batch draws into a
+ * pinned staging buffer with `nthreads` memcpy threads.  Host pointers only; no device work.
+ * var_host_gather_clips returns the number of int16 written (or a negative VAR_ERR_*). */
+int var_host_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int n, void* dst, int nthreads);
+int64_t var_host_gather_clips(const int16_t* arena, const int64_t* offsets, const int64_t* lengths, int n, int16_t* dst,
+                              int64_t* new_offsets, int nthreads);
+
 /* ------------------------------------------------------------------------------------
  * Encoders.  A net object holds the layer plan of one VARPretextNet
  *   kind 0: models/pretext/arm_pretext_model.py:37-59   (Kuka)

@@ -94,3 +94,23 @@ def test_engine_refuses_to_run_without_cuda(vb):
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         vb.VarEngine(vb.KUKA, 100, 3)
+
+
+def test_host_gather_helpers(vb):
+    """Host-side staging helpers of the streaming loader (no device access): row gather and ragged clip packing."""
+    import torch
+    lib = vb._lib.lib
+    src = torch.arange(10 * 6, dtype=torch.uint8).reshape(10, 6)
+    idx = torch.tensor([3, 0, 9, 9], dtype=torch.int64)
+    dst = torch.zeros(4, 6, dtype=torch.uint8)
+    assert lib.var_host_gather_rows(src.data_ptr(), 6, idx.data_ptr(), 4, dst.data_ptr(), 2) == 0
+    assert torch.equal(dst, src[idx])
+    arena = torch.arange(100, dtype=torch.int16)
+    off = torch.tensor([10, -1, 40, 3], dtype=torch.int64)
+    ln = torch.tensor([5, 0, 4, 7], dtype=torch.int64)
+    out = torch.zeros(64, dtype=torch.int16)
+    new_off = torch.zeros(4, dtype=torch.int64)
+    n = lib.var_host_gather_clips(arena.data_ptr(), off.data_ptr(), ln.data_ptr(), 4, out.data_ptr(), new_off.data_ptr(), 3)
+    assert n == 18 and new_off.tolist() == [0, -1, 6, 10]      # clips packed back to back, 4-byte aligned
+    assert out[0:5].tolist() == [10, 11, 12, 13, 14] and out[6:10].tolist() == [40, 41, 42, 43]
+    assert out[10:17].tolist() == list(range(3, 10))

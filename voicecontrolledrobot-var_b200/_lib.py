@@ -41,6 +41,8 @@ PROTOTYPES = {
     "var_sampler_batch_tasks": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p]),
     "var_sampler_set_state": (_i, [_p, _p, _i, _p]),
+    "var_host_gather_rows": (_i, [_p, _i64, _p, _i, _p, _i]),
+    "var_host_gather_clips": (_i64, [_p, _p, _p, _i, _p, _p, _i]),
     "var_net_create": (_i, [_i, _i, _i, C.POINTER(_p)]),
     "var_net_destroy": (_i, [_p]),
     "var_net_param_floats": (_i64, [_p]),

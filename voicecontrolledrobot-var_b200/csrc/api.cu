@@ -1,6 +1,9 @@
 // extern "C" surface of libvar_b200.so that is not tied to a net object
 // (include/var_b200.h).  Thin argument marshalling only.
 #include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
 
 #include "../../include/var_b200.h"
 #include "aux_kernels.cuh"
@@ -100,6 +103,42 @@ int var_sampler_batch_tasks(uint32_t* state, int B, int task_num, const int32_t*
 int var_sampler_set_state(uint32_t* state, const uint32_t* host_words, int pos, void* stream) {
   if (!state || !host_words || pos < 0 || pos > 624) return VAR_ERR_ARG;
   return sampler_set_state(state, host_words, pos, ST(stream));
+}
+
+// ---- host-side staging helpers of the streaming triplet loader (plain memcpy work, no device access) ----
+static void run_parallel(int n, int nthreads, const std::function<void(int, int)>& fn) {
+  if (nthreads <= 1 || n < 2 * nthreads) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  const int per = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    const int lo = t * per, hi = lo + per < n ? lo + per : n;
+    if (lo < hi) th.emplace_back(fn, lo, hi);
+  }
+  for (auto& x : th) x.join();
+}
+int var_host_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int n, void* dst, int nthreads) {
+  if (!src || !idx || !dst || row_bytes <= 0 || n < 0) return VAR_ERR_ARG;
+  const char* s_ = reinterpret_cast<const char*>(src);
+  char* d_ = reinterpret_cast<char*>(dst);
+  run_parallel(n, nthreads, [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i) memcpy(d_ + (int64_t)i * row_bytes, s_ + idx[i] * row_bytes, (size_t)row_bytes);
+  });
+  return VAR_OK;
+}
+int64_t var_host_gather_clips(const int16_t* arena, const int64_t* offsets, const int64_t* lengths, int n, int16_t* dst,
+                              int64_t* new_offsets, int nthreads) {
+  if (!arena || !offsets || !lengths || !dst || !new_offsets || n < 0) return VAR_ERR_ARG;
+  int64_t cur = 0;
+  for (int i = 0; i < n; ++i) {  // destination offsets: clips packed back to back, 4-byte aligned
+    if (offsets[i] < 0) { new_offsets[i] = -1; continue; }
+    new_offsets[i] = cur;
+    cur += lengths[i] + (lengths[i] & 1);
+  }
+  run_parallel(n, nthreads, [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i)
+      if (offsets[i] >= 0) memcpy(dst + new_offsets[i], arena + offsets[i], (size_t)lengths[i] * 2);
+  });
+  return cur;
 }
 
 int var_adam_step(float* p, const float* g, float* m, float* v, float* p_mma, int64_t n, float lr,

@@ -364,18 +364,15 @@ class DeviceTripletLoader:
                     if not put((slot, 0, B, gt, rec, None, 0)):
                         return
                     continue
-                torch.index_select(self.images_host, 0, h_items, out=slot.h_img[:b])
-                off = slot.h_meta[0, :2 * b].numpy()
-                ln = slot.h_meta[1, :2 * b].numpy()
-                h_wav, cur = slot.h_wav.numpy(), 0
-                src = wav_host.numpy()
-                for j in range(2 * b):           # ragged gather into the staging arena (4-byte aligned)
-                    o, n = int(off[j]), int(ln[j])
-                    if o < 0:
-                        continue
-                    h_wav[cur:cur + n] = src[o:o + n]
-                    off[j] = cur
-                    cur += n + (n & 1)
+                # gather into pinned staging with the library's memcpy threads (ctypes releases the GIL: the
+                # main thread keeps launching kernels meanwhile)
+                check(lib.var_host_gather_rows(self.images_host.data_ptr(), 3 * 96 * 96, h_items.data_ptr(), b,
+                                               slot.h_img.data_ptr(), 4), "var_host_gather_rows")
+                new_off = torch.empty(2 * b, dtype=torch.int64)
+                cur = int(lib.var_host_gather_clips(wav_host.data_ptr(), slot.h_meta[0].data_ptr(), slot.h_meta[1].data_ptr(),
+                                                    2 * b, slot.h_wav.data_ptr(), new_off.data_ptr(), 4))
+                check(cur, "var_host_gather_clips")
+                slot.h_meta[0, :2 * b] = new_off
                 with torch.cuda.stream(self._ls):
                     if slot.consumed is not None:
                         self._ls.wait_event(slot.consumed)   # the previous tenant of this slot was read on cs
