@@ -395,38 +395,41 @@ def run_b200(args):
     step_kernel_ms = sum(v[0] for v in prof.values()) / prof_steps
     hbm, bf16_burst, bf16_sus, src = measured_peaks()
     tf32_peak = measure_tf32_peak(dev)
-    kernels = {}
-    for tag, (ms, fl, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        kernels[tag] = {"ms_per_step": round(ms / prof_steps, 4), "launches_per_step": cnt / prof_steps,
-                        "share": round(ms / prof_steps / step_kernel_ms, 4)}
-        if fl > 0:
-            kernels[tag]["tflops"] = round(fl / (ms * 1e-3) / 1e12, 2)
-    ttag, (tms, tfl, tcnt) = max(prof.items(), key=lambda kv: kv[1][0])
+    h16_flags = lib.var_h16_flags()
+    # tensor peak a family is compared with: the kind::f16 kernels against MEASURED_PEAKS.json's bf16 figure (the
+    # sustained one: they are timed inside a long step), the tf32 kernels against cuBLAS tf32 measured in this run
+    f16_fams = {"gemm_fwd16", "gemm_dgrad16", "wgrad16"} | ({"gru_step"} if (h16_flags & 2 and net == "ithor") else set())
     clips_per_step = 2 * local_b
     bytes_per_clip = wl["clip"] * 2 + wl["F"] * 160  # int16 in + [F, 40] f32 out
     mfcc_bytes = clips_per_step * bytes_per_clip
-    traffic = ncu_traffic(args.workload, ttag)
-    if tfl > 0:
-        roof = {"kernel": ttag, "bound": "tensor", "achieved": tfl / (tms * 1e-3) / 1e12, "peak": tf32_peak,
-                "unit": "TFLOP/s", "peak_source": "cuBLAS tf32 8192^3 measured in this run "
-                f"(MEASURED_PEAKS bf16 burst {bf16_burst} TF/s, {src})",
-                "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
-                "flops_per_launch": tfl / tcnt, "avg_launch_ms": tms / tcnt}
+    kernels, rooflines = {}, {}
+    for tag, (ms, fl, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        kernels[tag] = {"ms_per_step": round(ms / prof_steps, 4), "launches_per_step": cnt / prof_steps,
+                        "share": round(ms / prof_steps / step_kernel_ms, 4)}
+        traffic = ncu_traffic(args.workload, tag)
+        if fl > 0:
+            tfs = fl / (ms * 1e-3) / 1e12
+            kernels[tag]["tflops"] = round(tfs, 2)
+            peak, psrc = ((bf16_sus, f"MEASURED_PEAKS.json bf16 sustained ({src}); f16 operands, kind::f16") if tag in f16_fams
+                          else (tf32_peak, "cuBLAS tf32 8192^3 measured in this run (no tf32 entry in MEASURED_PEAKS.json)"))
+            rooflines[tag] = {"kernel": tag, "bound": "tensor", "achieved": tfs, "peak": peak, "unit": "TFLOP/s",
+                              "frac": tfs / peak, "peak_source": psrc, "flops_per_launch": fl / cnt,
+                              "avg_launch_ms": ms / cnt, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                              "traffic_detail": traffic}
+    ttag = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    if ttag in rooflines:
+        roof = rooflines[ttag]
     else:
+        tms, _, tcnt = prof[ttag]
         nbytes = mfcc_bytes * prof_steps if ttag == "mfcc" else None
+        tr = ncu_traffic(args.workload, ttag)
         roof = {"kernel": ttag, "bound": "hbm", "achieved": (nbytes / (tms * 1e-3) / 1e9) if nbytes else None,
-                "peak": hbm, "unit": "GB/s", "peak_source": src,
-                "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
-                "avg_launch_ms": tms / tcnt}
-    roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["achieved"] else None
-    m = prof.get("mfcc")
-    mfcc_roof = None
-    if m:
-        gbs = mfcc_bytes * prof_steps / (m[0] * 1e-3) / 1e9
-        mt = ncu_traffic(args.workload, "mfcc")
-        mfcc_roof = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                     "bytes_per_clip": bytes_per_clip, "avg_launch_ms": m[0] / m[2], "peak_source": src,
-                     "traffic": mt["dram_bytes_per_launch"] if mt else None}
+                "peak": hbm, "unit": "GB/s", "peak_source": src, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                "traffic_detail": tr, "avg_launch_ms": tms / tcnt}
+        roof["frac"] = (roof["achieved"] / roof["peak"]) if roof["achieved"] else None
+    # the MFCC front-end timed ALONE (inside a step it runs on the loader's side stream under the previous step's
+    # kernels, so its in-step events measure contention, not the kernel)
+    mfcc_roof = mfcc_alone(ds, loader, wl, clips_per_step, bytes_per_clip, hbm, src, args.workload)
     cpu = torch_gpu = None
     if world == 1:
         if not args.no_torch_baseline and net in ("ithor", "kuka") and args.workload in ("ithor_b256", "kuka_b64"):
@@ -438,7 +441,9 @@ def run_b200(args):
     out = {
         "metric": "VAR train triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "tf32 tensor-core MMA, fp32 accumulate/state",
+        "scaling": wl["scaling"], "vs_baseline": None,
+        "dtype": ("f16 (sound convs, GRU recurrences) + tf32 tensor-core MMA operands, fp32 accumulate / state / master weights"
+                  if net == "ithor" and (h16_flags & 1) else "tf32 tensor-core MMA, fp32 accumulate/state"),
         "data": "synthetic (seeded uint8 frames + int16 16 kHz clips written to disk in the reference's formats), "
                 "random-init weights",
         "config": {"workload": args.workload, "description": wl["desc"], "net": net, "config_name": cfg.name,
@@ -448,7 +453,7 @@ def run_b200(args):
                    "api": "loadEnvData -> VAR_Pretext.train_epoch", "parallelism": f"dp{world}",
                    "l2": "no flush: one step streams >1 GB of activations (>> 126 MB L2) and draws fresh images/clips"},
         "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
-        "clocks": clk, "roofline": roof, "mfcc_roofline": mfcc_roof, "kernels": kernels,
+        "clocks": clk, "roofline": roof, "rooflines": rooflines, "mfcc_roofline": mfcc_roof, "kernels": kernels,
         "kernels_note": "per-family CUDA-event times of 3 extra steps with the image/sound stream overlap OFF "
                         f"(serial kernel sum {step_kernel_ms:.2f} ms/step vs {ms_per_step:.2f} ms/step measured "
                         "with overlap ON); at N > 1 taken on rank 0 after the process group is destroyed",
@@ -456,6 +461,32 @@ def run_b200(args):
         "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "reward": reward,
     }
     return json.dumps(out)
+
+
+def mfcc_alone(ds, loader, wl, clips, bytes_per_clip, hbm, src, workload):
+    """The fused MFCC kernel on one step's worth of drawn clips, nothing else running: CUDA events over 20 launches."""
+    al = __import__("importlib").import_module(f"{PKG}.Envs.audioLoader")
+    arena, dev = loader.arena, loader.device
+    n = int(arena.clip_off.numel())
+    idx = torch.randint(0, n, (clips,), device=dev)
+    off, ln = arena.clip_off[idx].contiguous(), arena.clip_len[idx].contiguous()
+    n_fft, win, hop = loader.audio.stft_params(loader.param)
+    out = torch.empty(clips, wl["F"], 40, device=dev)
+    run = lambda: al.mfcc_device(arena.wav, off, ln, loader.audio.fs, n_fft, win, hop, wl["F"], flavour=loader.flavour, out=out)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(20):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    gbs = clips * bytes_per_clip / (ms * 1e-3) / 1e9
+    tr = ncu_traffic(workload, "mfcc")
+    return {"bound": "hbm (target) / fp32 issue (actual, DESIGN.md section 7)", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+            "frac": gbs / hbm, "bytes_per_clip": bytes_per_clip, "clips": clips, "avg_launch_ms": ms, "peak_source": src,
+            "timed": "alone, 20 launches, CUDA events", "traffic": tr["dram_bytes_per_launch"] if tr else None}
 
 
 def bench_reward(vb, trainer, cfg, net, wl, dev, rank, world, dist):
@@ -475,6 +506,8 @@ def bench_reward(vb, trainer, cfg, net, wl, dev, rank, world, dist):
     fresh_every = 50 if net == "ithor" else 1   # iTHOR sends inf after an episode's first step (RLEnvMaxSteps 50)
     extra = "occupancy" if net == "ithor" else "robot_pose"
     res = {"sharding": f"envs split by index over {world} rank(s), no collective",
+           "e2e": "VecPretextNormalize.step_wait(): numpy observations -> H2D -> captured-graph query -> one D2H -> the reference's "
+                  "host post-processing (float64 image / 255, return normalisation); e2e_device_protocol: step_wait_device()",
            "goal_sound": "cached except every 50th step" if net == "ithor" else "re-encoded every step"}
 
     def max_over_ranks(x):
@@ -542,8 +575,24 @@ def bench_reward(vb, trainer, cfg, net, wl, dev, rank, world, dist):
         for _ in range(iters):
             w.step_wait()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / iters)
+        # the device-resident protocol (step_wait_device: numpy observations in, reward / embeddings / policy inputs
+        # stay on the device, return normalisation on the device; one D2H of the [N] rewards to close the step)
+        wd = vpn.VecPretextNormalize(Venv(), ob=False, ret=True, gamma=0.99, config=cfg,
+                                     pretextObj=types.SimpleNamespace(pretextModel=model))
+        wd.reset()
+        for _ in range(3):
+            wd.step_wait_device()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            _, r_dev, _, _ = wd.step_wait_device()
+            r_dev.cpu()
+        dev_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / iters)
         res[str(N)] = {"queries_per_s": N / (ms * 1e-3), "ms": ms, "envs_per_rank": n,
                        "e2e_queries_per_s": N / (e2e_ms * 1e-3), "e2e_ms": e2e_ms,
+                       "e2e_device_protocol_queries_per_s": N / (dev_ms * 1e-3), "e2e_device_protocol_ms": dev_ms,
                        "tflops": N / (ms * 1e-3) * FLOP_PER_QUERY[net] / 1e12}
     model.train()
     return res

@@ -239,12 +239,15 @@ int var_triplet_fwd_bwd(const float* d_h_img, const float* d_h_pos, const float*
  * per-kernel-family CUDA-event profiler (events recorded on the launching stream).
  * var_prof_end fills arrays of var_prof_num_tags() entries: total ms, algorithmic FLOPs of
  * the GEMM families, launch count.  Tag order: gemm_fwd, gemm_dgrad, gemm_scalar, gru_step,
- * wgrad, colsum, mfcc, tail, pool, adam, gru_cell_bwd, sampler, misc.
+ * wgrad, colsum, mfcc, tail, pool, adam, gru_cell_bwd, sampler, misc, gemm_fwd16, gemm_dgrad16, wgrad16
+ * (the last three: the kind::f16 conv kernels).  var_h16_flags: bit 0 = 16-bit conv region on, bit 1 = the
+ * recurrent kernels use f16 operands (decides which tensor peak a family is compared with).
  * ---------------------------------------------------------------------------------- */
 long long var_launch_count(void);
 int var_prof_begin(void);
 int var_prof_end(double* ms, double* flops, long long* count, int ntags);
 int var_prof_num_tags(void);
+int var_h16_flags(void);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "var_prof_begin": (_i, []),
     "var_prof_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), _i]),
     "var_prof_num_tags": (_i, []),
+    "var_h16_flags": (_i, []),
     "var_triplet_fwd_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p,
                                  _p, _p, _p, _p, _p]),
 }
@@ -91,7 +92,7 @@ for _name, (_res, _args) in PROTOTYPES.items():
 
 
 PROF_TAGS = ["gemm_fwd", "gemm_dgrad", "gemm_scalar", "gru_step", "wgrad", "colsum", "mfcc", "tail", "pool", "adam",
-             "gru_cell_bwd", "sampler", "misc"]
+             "gru_cell_bwd", "sampler", "misc", "gemm_fwd16", "gemm_dgrad16", "wgrad16"]
 
 
 def prof_end():

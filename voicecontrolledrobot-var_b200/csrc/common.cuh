@@ -36,7 +36,9 @@ constexpr int kNumSMs = 148;
 // brackets the launch with CUDA events on the launching stream.
 enum LaunchTag : int {
   T_GEMM_FWD = 0, T_GEMM_DGRAD, T_GEMM_SCALAR, T_GRU_STEP, T_WGRAD, T_COLSUM, T_MFCC, T_TAIL,
-  T_POOL, T_ADAM, T_GRU_CELL_BWD, T_SAMPLER, T_MISC, T_NUM_TAGS
+  T_POOL, T_ADAM, T_GRU_CELL_BWD, T_SAMPLER, T_MISC,
+  T_GEMM_FWD16, T_GEMM_DGRAD16, T_WGRAD16,  // the 16-bit operand (kind::f16) conv kernels
+  T_NUM_TAGS
 };
 struct LaunchScope {
   LaunchScope(int tag, double flops, cudaStream_t st);

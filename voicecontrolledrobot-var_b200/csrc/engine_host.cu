@@ -352,7 +352,7 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
   int grid = kNumSMs * per_sm;
   if (grid > total) grid = (int)total;
   const double flops = 2.0 * p.g[0].M * (double)p.e[0].ncols * p.g[0].K;
-  LaunchScope sc(p.b_mn_major ? T_GEMM_DGRAD : T_GEMM_FWD, flops, st);
+  LaunchScope sc(H16 ? (p.b_mn_major ? T_GEMM_DGRAD16 : T_GEMM_FWD16) : (p.b_mn_major ? T_GEMM_DGRAD : T_GEMM_FWD), flops, st);
   tc_gemm_persist_kernel<GMODE, H16><<<grid, 192, smem, st>>>(tb, ta, p, m_tiles, n_tiles);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -1391,7 +1391,7 @@ int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw
   VAR_ENSURE_SMEM(tc_wgrad_h16_kernel, smem);
   dim3 grid(ktiles, splits, 1);
   {
-    LaunchScope sc(T_WGRAD, 2.0 * p.M * (double)cs.Cout * p.K, st);
+    LaunchScope sc(T_WGRAD16, 2.0 * p.M * (double)cs.Cout * p.K, st);
     tc_wgrad_h16_kernel<<<grid, 160, smem, st>>>(tx, tdy, p);
   }
   VAR_CUDA_CHECK(cudaGetLastError());
@@ -1439,6 +1439,11 @@ int var_prof_end(double* ms, double* flops, long long* count, int ntags) {
   return VAR_OK;
 }
 int var_prof_num_tags(void) { return var::T_NUM_TAGS; }
+// bit 0: the 16-bit conv region is enabled, bit 1: the recurrent kernels run f16 operands
+int var_h16_flags(void) {
+  var::ConvShape probe{1, 8, 8, 64, 64, 3, 3, 1, 1, 1, 1, 8, 8};
+  return (var::conv_h16_ok(probe) ? 1 : 0) | (var::gru_h16_enabled() ? 2 : 0);
+}
 // Like var_prof_end but writes one CSV line per launch (tag, ms, flops, note) to `path`.
 int var_prof_dump(const char* path) {
   auto& p = var::prof();

@@ -366,11 +366,12 @@ class DeviceTripletLoader:
                     continue
                 # gather into pinned staging with the library's memcpy threads (ctypes releases the GIL: the
                 # main thread keeps launching kernels meanwhile)
+                nth = max(1, min(4, (os.cpu_count() or 4) // max(1, self.world_size)))  # ranks share the host cores
                 check(lib.var_host_gather_rows(self.images_host.data_ptr(), 3 * 96 * 96, h_items.data_ptr(), b,
-                                               slot.h_img.data_ptr(), 4), "var_host_gather_rows")
+                                               slot.h_img.data_ptr(), nth), "var_host_gather_rows")
                 new_off = torch.empty(2 * b, dtype=torch.int64)
                 cur = int(lib.var_host_gather_clips(wav_host.data_ptr(), slot.h_meta[0].data_ptr(), slot.h_meta[1].data_ptr(),
-                                                    2 * b, slot.h_wav.data_ptr(), new_off.data_ptr(), 4))
+                                                    2 * b, slot.h_wav.data_ptr(), new_off.data_ptr(), nth))
                 check(cur, "var_host_gather_clips")
                 slot.h_meta[0, :2 * b] = new_off
                 with torch.cuda.stream(self._ls):
