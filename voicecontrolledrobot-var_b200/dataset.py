@@ -115,17 +115,26 @@ class DeviceTripletSampler:
         check(lib.var_sampler_epoch(ptr(self.state), self.n_items, ptr(self.perm), stream_ptr()), "var_sampler_epoch")
         return self.perm
 
-    def sample(self, items):
-        """items: int32 device tensor of dataset indices (a slice of the epoch permutation)."""
-        B = int(items.numel())
+    def alloc_outputs(self, B):
+        """Output buffers of one `sample()` call for batches of up to B items (reusable across calls)."""
         dev = self.device
-        out = {"item": torch.empty(B, dtype=torch.int32, device=dev),
-               "gt": torch.empty(B, dtype=torch.int32, device=dev),
-               "sn": torch.empty(B, dtype=torch.int32, device=dev),
-               "rec": torch.empty(B, 6, dtype=torch.int32, device=dev),
-               "off": torch.empty(2 * B, dtype=torch.int64, device=dev),
-               "len": torch.empty(2 * B, dtype=torch.int32, device=dev)}
-        scratch = torch.empty(B, dtype=torch.int32, device=dev)
+        return {"item": torch.empty(B, dtype=torch.int32, device=dev),
+                "gt": torch.empty(B, dtype=torch.int32, device=dev),
+                "sn": torch.empty(B, dtype=torch.int32, device=dev),
+                "rec": torch.empty(B, 6, dtype=torch.int32, device=dev),
+                "off": torch.empty(2 * B, dtype=torch.int64, device=dev),
+                "len": torch.empty(2 * B, dtype=torch.int32, device=dev),
+                "_scratch": torch.empty(B, dtype=torch.int32, device=dev)}
+
+    def sample(self, items, buffers=None):
+        """items: int32 device tensor of dataset indices (a slice of the epoch permutation).  `buffers`: the
+        result of alloc_outputs() to write into (views of the first B entries are returned)."""
+        B = int(items.numel())
+        if buffers is None:
+            buffers = self.alloc_outputs(B)
+        out = {"item": buffers["item"][:B], "gt": buffers["gt"][:B], "sn": buffers["sn"][:B], "rec": buffers["rec"][:B],
+               "off": buffers["off"][:2 * B], "len": buffers["len"][:2 * B]}
+        scratch = buffers["_scratch"][:B]
         items = items.contiguous()
         tail = (ptr(self.clip_off), ptr(self.clip_len), ptr(scratch), ptr(out["item"]), ptr(out["gt"]), ptr(out["sn"]),
                 ptr(out["rec"]), ptr(out["off"]), ptr(out["len"]), stream_ptr())
@@ -222,6 +231,7 @@ class _Slot:
         self.free = threading.Event()
         self.free.set()
         self.consumed = None  # CUDA event: the compute stream is done reading this slot
+        self.buf = None       # sampler output buffers of this slot (allocated on first use)
 
 
 class DeviceTripletLoader:
@@ -290,48 +300,66 @@ class DeviceTripletLoader:
         n, bs = self.n_items, self.batch_size
         return [s for s in range(0, n, bs) if not (self.drop_last and n - s < bs)]
 
-    def _draw(self, perm, s):
+    def _draw(self, perm, s, buffers=None):
         """Sampler launch for the batch starting at permutation position s (on the loader stream)."""
         items = perm[s:s + self.batch_size]
         B = int(items.numel())
-        rec = self.sampler.sample(items)  # every rank draws the GLOBAL batch: identical streams
+        rec = self.sampler.sample(items, buffers)  # every rank draws the GLOBAL batch: identical streams
         lo, hi = (B * self.rank) // self.world_size, (B * (self.rank + 1)) // self.world_size
         return rec, B, lo, hi
 
     def _resident_batches(self):
-        """Batch k+1's sampler + MFCC launches are issued on the loader stream before batch k is handed
-        out, so they run under step k instead of on its critical path."""
+        """Batch k+1's sampler + gather + MFCC launches are issued on the loader stream before batch k is handed
+        out, so they run under step k instead of on its critical path.  Every batch writes into one of three
+        preallocated slots (no allocation on the loader stream: a cross-stream free would stall the caching
+        allocator until the consumer's work has drained)."""
         cs = torch.cuda.current_stream(self.device)
         n_fft, win, hop = self.audio.stft_params(self.param)
         F = self.config.sound_dim[1]
         wav = self.arena.wav  # first use uploads the arena on the compute stream
+        bs = self.batch_size
+        bmax = (bs + self.world_size - 1) // self.world_size + 1
+        if getattr(self, "_rslots", None) is None or self._rslots[0]["img"].shape[0] < bmax:
+            dev = self.device
+            self._rslots = [dict(buf=self.sampler.alloc_outputs(bs), img=torch.empty(bmax, 3, 96, 96, dtype=torch.uint8, device=dev),
+                                 snd=torch.empty(2 * bmax, F, 40, dtype=torch.float32, device=dev),
+                                 idx=torch.empty(bmax, dtype=torch.int64, device=dev),
+                                 off=torch.empty(2 * bmax, dtype=torch.int64, device=dev),
+                                 ln=torch.empty(2 * bmax, dtype=torch.int32, device=dev), consumed=None) for _ in range(3)]
         self._ls.wait_stream(cs)
         perm = self._epoch_perm()
 
-        def issue(s):
+        def issue(k, s):
+            slot = self._rslots[k % 3]
             with torch.cuda.stream(self._ls):
-                rec, B, lo, hi = self._draw(perm, s)
-                if hi == lo:
+                if slot["consumed"] is not None:
+                    self._ls.wait_event(slot["consumed"])  # the slot's previous batch has been read on cs
+                rec, B, lo, hi = self._draw(perm, s, slot["buf"])
+                b = hi - lo
+                if b == 0:
                     out = (None, None, rec["gt"][lo:hi], B, rec)
                 else:
-                    off = torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]])
-                    ln = torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]])
-                    sounds = mfcc_device(wav, off, ln, self.audio.fs, n_fft, win, hop, F, flavour=self.flavour)
-                    out = (self.images[rec["item"][lo:hi].long()], sounds, rec["gt"][lo:hi], B, rec)
+                    torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]], out=slot["off"][:2 * b])
+                    torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]], out=slot["ln"][:2 * b])
+                    slot["idx"][:b].copy_(rec["item"][lo:hi])
+                    torch.index_select(self.images, 0, slot["idx"][:b], out=slot["img"][:b])
+                    mfcc_device(wav, slot["off"][:2 * b], slot["ln"][:2 * b], self.audio.fs, n_fft, win, hop, F,
+                                flavour=self.flavour, out=slot["snd"][:2 * b])
+                    out = (slot["img"][:b], slot["snd"][:2 * b], rec["gt"][lo:hi], B, rec)
                 ev = torch.cuda.Event()
                 ev.record(self._ls)
-            return out, ev
+            return out, ev, slot
 
         starts = self._batch_starts()
-        nxt = issue(starts[0]) if starts else None
+        nxt = issue(0, starts[0]) if starts else None
         for k in range(len(starts)):
-            out, ev = nxt
-            nxt = issue(starts[k + 1]) if k + 1 < len(starts) else None
+            out, ev, slot = nxt
+            nxt = issue(k + 1, starts[k + 1]) if k + 1 < len(starts) else None
             cs.wait_event(ev)
-            for t in out[:3] + tuple(out[4].values()):
-                if torch.is_tensor(t):
-                    t.record_stream(cs)  # allocated on the loader stream, consumed on the compute stream
             yield out
+            # the consumer has launched its step on cs: the slot may be refilled once that work is done
+            slot["consumed"] = torch.cuda.Event()
+            slot["consumed"].record(cs)
 
     def _producer(self, q, stop, perm, starts, max_clip):
         def put(x):
@@ -352,7 +380,11 @@ class DeviceTripletLoader:
                         return
                 slot.free.clear()
                 with torch.cuda.stream(self._ls):
-                    rec, B, lo, hi = self._draw(perm, s)
+                    if slot.consumed is not None:
+                        self._ls.wait_event(slot.consumed)   # the previous tenant of this slot was read on cs
+                    if slot.buf is None:
+                        slot.buf = self.sampler.alloc_outputs(self.batch_size)
+                    rec, B, lo, hi = self._draw(perm, s, slot.buf)
                     b = hi - lo
                     if b:
                         meta = torch.stack([torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]]),
@@ -375,8 +407,6 @@ class DeviceTripletLoader:
                 check(cur, "var_host_gather_clips")
                 slot.h_meta[0, :2 * b] = new_off
                 with torch.cuda.stream(self._ls):
-                    if slot.consumed is not None:
-                        self._ls.wait_event(slot.consumed)   # the previous tenant of this slot was read on cs
                     slot.d_img[:b].copy_(slot.h_img[:b], non_blocking=True)
                     slot.d_wav[:cur].copy_(slot.h_wav[:cur], non_blocking=True)
                     slot.d_meta[:, :2 * b].copy_(slot.h_meta[:, :2 * b], non_blocking=True)
@@ -410,13 +440,10 @@ class DeviceTripletLoader:
                     raise item
                 slot, b, B, gt, rec, ev, nbytes = item
                 if not b:
-                    slot.free.set()
                     yield None, None, gt, B, rec
+                    slot.free.set()
                     continue
                 cs.wait_event(ev)
-                for t in [gt] + list(rec.values()):
-                    if torch.is_tensor(t):
-                        t.record_stream(cs)
                 sounds = mfcc_device(slot.d_wav, slot.d_meta[0, :2 * b], slot.d_meta[1, :2 * b].int(), self.audio.fs,
                                      n_fft, win, hop, F, flavour=self.flavour)
                 self.h2d_bytes += nbytes
