@@ -784,7 +784,7 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
   const int ke = h16 ? 64 : 32;
   p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / ke; p.stages = env_int("VAR_GRU_STAGES_FWD", 2);
   p.kps = env_int("VAR_GRU_KPS_FWD", 2);
-  p.a_split = env_int("VAR_GRU_ASPLIT", 0);
+  p.a_split = 0;  // (the split-A-box experiment is retired: its extra issuers read h without acquiring the group counter)
   p.counters = counters; p.ldx = ldx;
   CUtensorMap tm[4];
   for (int d = 0; d < 2; ++d) {
@@ -902,7 +902,7 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
   memset(&p, 0, sizeof(p));
   p.B = B; p.Hd = Hd; p.T = T; p.bn = 32; p.num_kb = 3 * Hd / 32; p.stages = env_int("VAR_GRU_STAGES_BWD", 3);
   p.kps = env_int("VAR_GRU_KPS_BWD", 2);
-  p.a_split = env_int("VAR_GRU_ASPLIT", 0);
+  p.a_split = 0;  // (the split-A-box experiment is retired: its extra issuers read h without acquiring the group counter)
   p.counters = counters;
   p.mn_lbo = mn_cfg().lbo; p.mn_sbo = mn_cfg().sbo; p.mn_type = mn_cfg().type;
   CUtensorMap tm[4];
