@@ -92,17 +92,12 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
                               : make_smem_desc(sB, (uint32_t)p.mn_lbo, (uint32_t)p.mn_sbo, (uint32_t)p.mn_type);
   float gS = 1.f, gInv = 1.f;
   if constexpr (H16) { gS = __ldg(p.gscale[z]); gInv = __ldg(p.gscale[z] + 1); }
-  // lane = (row r4 of a group of four, four consecutive hidden units c4): float4 global accesses, four
-  // 128-byte rows per warp instruction (a quarter of the memory instructions of lane = hidden unit)
-  const int r4 = lane >> 3, c4 = lane & 7;
-  float bsum[4][4];  // [unit][dr, dz, dn, dn*r]: column sums over this thread's rows and all steps
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { bsum[k][0] = 0.f; bsum[k][1] = 0.f; bsum[k][2] = 0.f; bsum[k][3] = 0.f; }
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of dr, dz, dn, dn*r over this thread's rows and all steps
   int mst = 0, mph = 0;  // MMA ring position (warp 4)
   int st = 0, ph = 0;    // producer ring position (warp 0 lane 0)
   constexpr int RB = 8;
   const int mrow0 = m0 + quarter * 32 + sub * RB;
-  const int j = ntile * 64 + rank * 32 + c4 * 4;  // first of this lane's four hidden units
+  const int j = ntile * 64 + rank * 32 + lane;  // hidden unit of this lane
   float* scr = scr_base + quarter * kQuarterFloats;
   const float* xch = xch_base + quarter * kQuarterFloats;
   const uint32_t xch_remote = mapa_shared(xch_u32 + (uint32_t)quarter * kQuarterFloats * 4u, (uint32_t)(rank ^ 1));
@@ -112,26 +107,25 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
   for (int it_s = 0; it_s < nsteps; ++it_s) {
     const int s = T - 1 - it_s;  // slot whose dgh is the A operand
     // ---- cell inputs of step s-1, in flight during the operand stream
-    float4 in0[2], in1[2], in2[2], in3[2], in4[2], in5[2];
+    float in0[RB], in1[RB], in2[RB], in3[RB], in4[RB], in5[RB];
     {
       const int sp = s - 1;
       const float* dhd_in = p.dhd[z][it_s & 1];  // written by this very thread last step
       const float* __restrict__ gates = p.gates_c[z] + (long long)sp * B * 3 * Hd;
       const float* __restrict__ hn_save = p.hn_save_c[z] + (long long)sp * B * Hd;
       const float* __restrict__ hprev = p.h_r_c[z] + (long long)sp * B * Hd;
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int mr = mrow0 + r4 + 4 * u;
+      for (int u = 0; u < RB; ++u) {
+        const int mr = mrow0 + u;
         const bool ok = mr < B;
         const long long hoff = (long long)(ok ? mr : 0) * Hd + j;
         const float* gt = gates + (long long)(ok ? mr : 0) * 3 * Hd + j;
-        in0[u] = ok ? *reinterpret_cast<const float4*>(dhd_in + hoff) : zero4;
-        in1[u] = ok ? __ldg(reinterpret_cast<const float4*>(gt)) : zero4;
-        in2[u] = ok ? __ldg(reinterpret_cast<const float4*>(gt + Hd)) : zero4;
-        in3[u] = ok ? __ldg(reinterpret_cast<const float4*>(gt + 2 * Hd)) : zero4;
-        in4[u] = ok ? __ldg(reinterpret_cast<const float4*>(hn_save + hoff)) : zero4;
-        in5[u] = ok ? __ldg(reinterpret_cast<const float4*>(hprev + hoff)) : zero4;
+        in0[u] = ok ? dhd_in[hoff] : 0.f;
+        in1[u] = ok ? __ldg(gt) : 0.f;
+        in2[u] = ok ? __ldg(gt + Hd) : 0.f;
+        in3[u] = ok ? __ldg(gt + 2 * Hd) : 0.f;
+        in4[u] = ok ? __ldg(hn_save + hoff) : 0.f;
+        in5[u] = ok ? __ldg(hprev + hoff) : 0.f;
       }
     }
     if (warp == 0) {
@@ -218,63 +212,39 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
         const float* gl = p.dgh[z] + (long long)s * B * 3 * Hd;
         const float* gil = p.dgi[z] + (long long)(z == 0 ? s : T - 1 - s) * 3 * Hd;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int mr = mrow0 + r4 + 4 * u;
+        for (int u = 0; u < RB; ++u) {
+          const int mr = mrow0 + u;
           if (mr < B) {
             const float* gh = gl + (long long)mr * 3 * Hd + j;
-            const float4 a = *reinterpret_cast<const float4*>(gh), b = *reinterpret_cast<const float4*>(gh + Hd),
-                         c = *reinterpret_cast<const float4*>(gh + 2 * Hd),
-                         d = *reinterpret_cast<const float4*>(gil + (long long)mr * ldgi + 2 * Hd + j);
-            bsum[0][0] += a.x; bsum[1][0] += a.y; bsum[2][0] += a.z; bsum[3][0] += a.w;
-            bsum[0][1] += b.x; bsum[1][1] += b.y; bsum[2][1] += b.z; bsum[3][1] += b.w;
-            bsum[0][3] += c.x; bsum[1][3] += c.y; bsum[2][3] += c.z; bsum[3][3] += c.w;
-            bsum[0][2] += d.x; bsum[1][2] += d.y; bsum[2][2] += d.z; bsum[3][2] += d.w;
+            bsum[0] += gh[0]; bsum[1] += gh[Hd]; bsum[3] += gh[2 * Hd];
+            bsum[2] += gil[(long long)mr * ldgi + 2 * Hd + j];
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int rr = sub * RB + r4 + 4 * u, mr = mrow0 + r4 + 4 * u;
+      for (int u = 0; u < RB; ++u) {
+        const int rr = sub * RB + u, mr = mrow0 + u;
         if (mr < B) {
           const long long hoff = (long long)mr * Hd + j;
-          const float din[4] = {in0[u].x, in0[u].y, in0[u].z, in0[u].w}, rv[4] = {in1[u].x, in1[u].y, in1[u].z, in1[u].w};
-          const float zv[4] = {in2[u].x, in2[u].y, in2[u].z, in2[u].w}, nv[4] = {in3[u].x, in3[u].y, in3[u].z, in3[u].w};
-          const float hnv[4] = {in4[u].x, in4[u].y, in4[u].z, in4[u].w}, hpv[4] = {in5[u].x, in5[u].y, in5[u].z, in5[u].w};
-          float dr[4], dz[4], dn[4], dnr[4], dout[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // scratch rows are 33 floats apart: (row + 4 * c4 + k) mod 32 is distinct over the warp
-            const float dh = (scr[rr * 33 + c4 * 4 + k] + xch[rr * 33 + c4 * 4 + k]) * gInv + din[k];
-            const float r_ = rv[k], z_ = zv[k], n_ = nv[k];
-            const float dnn = dh * (1.f - z_);
-            const float dzz = dh * (hpv[k] - n_);
-            const float dnp = dnn * (1.f - n_ * n_);
-            const float dzp = dzz * z_ * (1.f - z_);
-            const float drp = dnp * hnv[k] * r_ * (1.f - r_);
-            dr[k] = round_tf32(drp); dz[k] = round_tf32(dzp); dn[k] = round_tf32(dnp);
-            dnr[k] = round_tf32(dnp * r_);
-            dout[k] = dh * z_;
-            bsum[k][0] += dr[k]; bsum[k][1] += dz[k]; bsum[k][2] += dn[k]; bsum[k][3] += dnr[k];
-          }
+          const float dh = (scr[rr * 33 + lane] + xch[rr * 33 + lane]) * gInv + in0[u];
+          const float r_ = in1[u], z_ = in2[u], n_ = in3[u];
+          const float dnn = dh * (1.f - z_);
+          const float dzz = dh * (in5[u] - n_);
+          const float dnp = dnn * (1.f - n_ * n_);
+          const float dzp = dzz * z_ * (1.f - z_);
+          const float drp = dnp * in4[u] * r_ * (1.f - r_);
+          const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
           float* gi = dgi + (long long)mr * ldgi + j;
-          *reinterpret_cast<float4*>(gi) = make_float4(dr[0], dr[1], dr[2], dr[3]);
-          *reinterpret_cast<float4*>(gi + Hd) = make_float4(dz[0], dz[1], dz[2], dz[3]);
-          *reinterpret_cast<float4*>(gi + 2 * Hd) = make_float4(dn[0], dn[1], dn[2], dn[3]);
+          gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
           float* gh = dgh + (long long)mr * 3 * Hd + j;
-          *reinterpret_cast<float4*>(gh) = make_float4(dr[0], dr[1], dr[2], dr[3]);
-          *reinterpret_cast<float4*>(gh + Hd) = make_float4(dz[0], dz[1], dz[2], dz[3]);
-          *reinterpret_cast<float4*>(gh + 2 * Hd) = make_float4(dnr[0], dnr[1], dnr[2], dnr[3]);
+          const float dnr = round_tf32(dnp * r_);
+          gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
           if constexpr (H16) {
             uint16_t* ghh = p.dgh_h[z] + (long long)sp * B * 3 * Hd + (long long)mr * 3 * Hd + j;
-            auto pk = [&](const float* v) {
-              return make_uint2((uint32_t)f16_sat_bits(v[0] * gS) | ((uint32_t)f16_sat_bits(v[1] * gS) << 16),
-                                (uint32_t)f16_sat_bits(v[2] * gS) | ((uint32_t)f16_sat_bits(v[3] * gS) << 16));
-            };
-            *reinterpret_cast<uint2*>(ghh) = pk(dr);
-            *reinterpret_cast<uint2*>(ghh + Hd) = pk(dz);
-            *reinterpret_cast<uint2*>(ghh + 2 * Hd) = pk(dnr);
+            ghh[0] = f16_sat_bits(dr * gS); ghh[Hd] = f16_sat_bits(dz * gS); ghh[2 * Hd] = f16_sat_bits(dnr * gS);
           }
-          *reinterpret_cast<float4*>(dhd_out + hoff) = make_float4(dout[0], dout[1], dout[2], dout[3]);
+          bsum[0] += dr; bsum[1] += dz; bsum[2] += dn; bsum[3] += dnr;
+          dhd_out[hoff] = dh * z_;
         }
       }
     }
@@ -287,13 +257,8 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
     }
   }
   if (p.db_ih[z]) {  // bias gradients: b_ih gets (dr, dz, dn), b_hh gets (dr, dz, dn * r)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      atomicAdd(p.db_ih[z] + j + k, bsum[k][0]); atomicAdd(p.db_ih[z] + Hd + j + k, bsum[k][1]);
-      atomicAdd(p.db_ih[z] + 2 * Hd + j + k, bsum[k][2]);
-      atomicAdd(p.db_hh[z] + j + k, bsum[k][0]); atomicAdd(p.db_hh[z] + Hd + j + k, bsum[k][1]);
-      atomicAdd(p.db_hh[z] + 2 * Hd + j + k, bsum[k][3]);
-    }
+    atomicAdd(p.db_ih[z] + j, bsum[0]); atomicAdd(p.db_ih[z] + Hd + j, bsum[1]); atomicAdd(p.db_ih[z] + 2 * Hd + j, bsum[2]);
+    atomicAdd(p.db_hh[z] + j, bsum[0]); atomicAdd(p.db_hh[z] + Hd + j, bsum[1]); atomicAdd(p.db_hh[z] + 2 * Hd + j, bsum[3]);
   }
   tc_fence_before();
   cluster_sync_all();  // nobody leaves while the partner could still address its shared memory

@@ -159,38 +159,28 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
     int st = 0, ph = 0;  // producer ring position (kept by every issuing lane)
     const bool issuer = warp < 4 && lane == 0 && (p.a_split || warp == 0 || (multi && warp - 1 < nb_boxes));
     const bool tracer = p.trace && tid == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    float br = 0.f, bz = 0.f, bq = 0.f;
+    if constexpr (!BWD) { br = __ldg(p.bhh[z] + j); bz = __ldg(p.bhh[z] + Hd + j); bq = __ldg(p.bhh[z] + 2 * Hd + j); }
     // ---------------------------------------- cell inputs of a step: issued at the top of the step
     // (after the previous release: a fence behind outstanding loads would wait for them) so the
     // loads fly during the wait for peers, the operand stream and the MMAs
     float in0[RB], in1[RB], in2[RB], in3[RB], in4[RB], in5[RB];
-    float4 x0[2], x1[2], x2[2], hp4[2];                  // forward: vectorised cell inputs (see prefetch)
-    const int r4 = lane >> 3, c4 = lane & 7;
-    const int j4 = ntile * jb + c4 * 4;                  // first of this lane's four hidden units (forward)
-    float4 br4 = make_float4(0.f, 0.f, 0.f, 0.f), bz4 = br4, bq4 = br4;
-    if constexpr (!BWD) {
-      br4 = __ldg(reinterpret_cast<const float4*>(p.bhh[z] + j4));
-      bz4 = __ldg(reinterpret_cast<const float4*>(p.bhh[z] + Hd + j4));
-      bq4 = __ldg(reinterpret_cast<const float4*>(p.bhh[z] + 2 * Hd + j4));
-    }
     auto prefetch = [&](int it) {
       const int s = BWD ? T - 1 - it : it;
       if constexpr (!BWD) {
-        // lane = (row r4 of a group of four, four consecutive hidden units c4): every global access of the
-        // warp is four 128-byte rows per instruction (float4 per thread) -- a quarter of the memory
-        // instructions of the lane = hidden-unit mapping
         const int t = z == 0 ? s : T - 1 - s;
         const float* __restrict__ xproj = p.xproj[z] + (long long)t * 3 * Hd;
         const float* hprev = p.h32[z][s & 1];  // rows of this warp: written by this very thread last step
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int mr = mrow0 + r4 + 4 * u;
+        for (int u = 0; u < RB; ++u) {
+          const int mr = mrow0 + u;
           const bool ok = mr < B;
-          const float* xp = xproj + (long long)(ok ? mr : 0) * p.ldx + j4;
-          const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          x0[u] = ok ? __ldg(reinterpret_cast<const float4*>(xp)) : zero4;
-          x1[u] = ok ? __ldg(reinterpret_cast<const float4*>(xp + Hd)) : zero4;
-          x2[u] = ok ? __ldg(reinterpret_cast<const float4*>(xp + 2 * Hd)) : zero4;
-          hp4[u] = ok ? *reinterpret_cast<const float4*>(hprev + (long long)mr * Hd + j4) : zero4;
+          const float* xp = xproj + (long long)(ok ? mr : 0) * p.ldx;
+          in0[u] = ok ? __ldg(xp + j) : 0.f;
+          in1[u] = ok ? __ldg(xp + Hd + j) : 0.f;
+          in2[u] = ok ? __ldg(xp + 2 * Hd + j) : 0.f;
+          in3[u] = ok ? hprev[(long long)mr * Hd + j] : 0.f;
+          in4[u] = 0.f; in5[u] = 0.f;
         }
       } else {
         const int sp = s - 1;
@@ -299,38 +289,24 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         float* gates = p.gates[z] ? p.gates[z] + (long long)s * B * 3 * Hd : nullptr;
         float* hn_save = p.hn_save[z] ? p.hn_save[z] + (long long)s * B * Hd : nullptr;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int rr = sub * RB + r4 + 4 * u, mr = mrow0 + r4 + 4 * u;
+        for (int u = 0; u < RB; ++u) {
+          const int rr = sub * RB + u, mr = mrow0 + u;
           if (mr < B) {
-            const float xr[4] = {x0[u].x, x0[u].y, x0[u].z, x0[u].w}, xz[4] = {x1[u].x, x1[u].y, x1[u].z, x1[u].w};
-            const float xn[4] = {x2[u].x, x2[u].y, x2[u].z, x2[u].w}, hpv[4] = {hp4[u].x, hp4[u].y, hp4[u].z, hp4[u].w};
-            const float brv[4] = {br4.x, br4.y, br4.z, br4.w}, bzv[4] = {bz4.x, bz4.y, bz4.z, bz4.w};
-            const float bqv[4] = {bq4.x, bq4.y, bq4.z, bq4.w};
-            float h_[4], r_[4], z_[4], n_[4], hnv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // scratch rows are 33 floats apart: (row + 4 * c4 + k) mod 32 is distinct over the warp
-              const float vr = scr[(0 * 32 + rr) * 33 + c4 * 4 + k], vz = scr[(1 * 32 + rr) * 33 + c4 * 4 + k],
-                          vn = scr[(2 * 32 + rr) * 33 + c4 * 4 + k];
-              r_[k] = sigmoidf_(xr[k] + vr + brv[k]);
-              z_[k] = sigmoidf_(xz[k] + vz + bzv[k]);
-              hnv[k] = vn + bqv[k];
-              n_[k] = tanhf(xn[k] + r_[k] * hnv[k]);
-              h_[k] = (1.f - z_[k]) * n_[k] + z_[k] * hpv[k];
-            }
-            const long long ho = (long long)mr * Hd + j4;
-            *reinterpret_cast<float4*>(hnew + ho) = make_float4(h_[0], h_[1], h_[2], h_[3]);
-            *reinterpret_cast<float4*>(hnew_r + ho) =
-                make_float4(round_tf32(h_[0]), round_tf32(h_[1]), round_tf32(h_[2]), round_tf32(h_[3]));
-            if constexpr (H16)  // |h| < 1
-              *reinterpret_cast<uint2*>(p.h_h[z] + (long long)(s + 1) * B * Hd + ho) =
-                  make_uint2(pack_f16x2(h_[0], h_[1]), pack_f16x2(h_[2], h_[3]));
+            const float vr = scr[(0 * 32 + rr) * 33 + lane], vz = scr[(1 * 32 + rr) * 33 + lane],
+                        vn = scr[(2 * 32 + rr) * 33 + lane];
+            const float r_ = sigmoidf_(in0[u] + vr + br);
+            const float z_ = sigmoidf_(in1[u] + vz + bz);
+            const float hnv = vn + bq;
+            const float n_ = tanhf(in2[u] + r_ * hnv);
+            const float h_ = (1.f - z_) * n_ + z_ * in3[u];
+            const long long ho = (long long)mr * Hd + j;
+            hnew[ho] = h_;
+            hnew_r[ho] = round_tf32(h_);
+            if constexpr (H16) p.h_h[z][(long long)(s + 1) * B * Hd + ho] = f16_sat_bits(h_);  // |h| < 1
             if (gates) {
-              float* gs = gates + (long long)mr * 3 * Hd + j4;
-              *reinterpret_cast<float4*>(gs) = make_float4(r_[0], r_[1], r_[2], r_[3]);
-              *reinterpret_cast<float4*>(gs + Hd) = make_float4(z_[0], z_[1], z_[2], z_[3]);
-              *reinterpret_cast<float4*>(gs + 2 * Hd) = make_float4(n_[0], n_[1], n_[2], n_[3]);
-              *reinterpret_cast<float4*>(hn_save + ho) = make_float4(hnv[0], hnv[1], hnv[2], hnv[3]);
+              float* gs = gates + (long long)mr * 3 * Hd + j;
+              gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
+              hn_save[ho] = hnv;
             }
           }
         }
