@@ -221,27 +221,30 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
           }
         }
       }
-      // Critical before the release: only the next step's A operand (dgh of slot s-1: f16 scaled copy, or the
-      // fp32 tensor itself on the tf32 path).  dh is stashed in the scratch plane; dgi / dgh fp32 / dh*z and the
-      // bias sums follow AFTER the release, while the CTA would otherwise wait for its peers.
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const int rr = sub * RB + u, mr = mrow0 + u;
         if (mr < B) {
+          const long long hoff = (long long)mr * Hd + j;
           const float dh = (scr[rr * 33 + lane] + xch[rr * 33 + lane]) * gInv + in0[u];
           const float r_ = in1[u], z_ = in2[u], n_ = in3[u];
-          const float dnp = dh * (1.f - z_) * (1.f - n_ * n_);
-          const float dzp = dh * (in5[u] - n_) * z_ * (1.f - z_);
+          const float dnn = dh * (1.f - z_);
+          const float dzz = dh * (in5[u] - n_);
+          const float dnp = dnn * (1.f - n_ * n_);
+          const float dzp = dzz * z_ * (1.f - z_);
           const float drp = dnp * in4[u] * r_ * (1.f - r_);
-          const float dr = round_tf32(drp), dz = round_tf32(dzp), dnr = round_tf32(dnp * r_);
+          const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
+          float* gi = dgi + (long long)mr * ldgi + j;
+          gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
+          float* gh = dgh + (long long)mr * 3 * Hd + j;
+          const float dnr = round_tf32(dnp * r_);
+          gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
           if constexpr (H16) {
             uint16_t* ghh = p.dgh_h[z] + (long long)sp * B * 3 * Hd + (long long)mr * 3 * Hd + j;
             ghh[0] = f16_sat_bits(dr * gS); ghh[Hd] = f16_sat_bits(dz * gS); ghh[2 * Hd] = f16_sat_bits(dnr * gS);
-          } else {
-            float* gh = dgh + (long long)mr * 3 * Hd + j;
-            gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
           }
-          scr[rr * 33 + lane] = dh;  // own entry: re-read below by this very thread
+          bsum[0] += dr; bsum[1] += dz; bsum[2] += dn; bsum[3] += dnr;
+          dhd_out[hoff] = dh * z_;
         }
       }
     }
@@ -251,36 +254,6 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
     if (tid == 0) {
       __threadfence();
       atomicAdd(counter, 1u);
-    }
-    {  // ---- deferred stores of this step (recomputed from the stashed dh and the cell inputs still in registers)
-      const int sp = s - 1;
-      const int t = z == 0 ? sp : T - 1 - sp;
-      float* dhd_out = p.dhd[z][(it_s + 1) & 1];
-      float* dgi = p.dgi[z] + (long long)t * 3 * Hd;
-      const long long ldgi = (long long)T * 3 * Hd;
-      float* dgh = p.dgh[z] + (long long)sp * B * 3 * Hd;
-#pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        const int rr = sub * RB + u, mr = mrow0 + u;
-        if (mr < B) {
-          const long long hoff = (long long)mr * Hd + j;
-          const float dh = scr[rr * 33 + lane];
-          const float r_ = in1[u], z_ = in2[u], n_ = in3[u];
-          const float dnp = dh * (1.f - z_) * (1.f - n_ * n_);
-          const float dzp = dh * (in5[u] - n_) * z_ * (1.f - z_);
-          const float drp = dnp * in4[u] * r_ * (1.f - r_);
-          const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp), dnr = round_tf32(dnp * r_);
-          float* gi = dgi + (long long)mr * ldgi + j;
-          gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
-          if constexpr (H16) {
-            float* gh = dgh + (long long)mr * 3 * Hd + j;
-            gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
-          }
-          bsum[0] += dr; bsum[1] += dz; bsum[2] += dn; bsum[3] += dnr;
-          dhd_out[hoff] = dh * z_;
-        }
-      }
-      quarter_sync(quarter);  // the quarter's TMEM warp refills the scratch plane only after its helpers have read it
     }
   }
   if (p.db_ih[z]) {  // bias gradients: b_ih gets (dr, dz, dn), b_hh gets (dr, dz, dn * r)

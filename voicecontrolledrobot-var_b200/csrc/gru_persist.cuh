@@ -76,9 +76,7 @@ __device__ __forceinline__ void fence_proxy_async_all() {
 // the 19.9 us per forward step.)
 constexpr int kGruThreads = 512;
 constexpr int kGruEpiWarps = 16;
-// per quarter: backward one 32 x 33 plane (partial sums); forward five planes (r | z | n accumulators, reused
-// as the stash of the cell outputs whose stores are deferred behind the release, + W_hn h + b_hn, + h)
-__host__ __device__ inline size_t gru_scr_bytes(int bwd) { return (size_t)4 * (bwd ? 32 * 33 : 5 * 32 * 33) * 4; }
+__host__ __device__ inline size_t gru_scr_bytes(int bwd) { return (size_t)4 * (bwd ? 32 * 33 : 3 * 32 * 33) * 4; }
 
 __device__ __forceinline__ void quarter_sync(int q) {
   asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
@@ -156,7 +154,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
     constexpr int RB = 8;                         // rows per epilogue warp
     const int mrow0 = m0 + quarter * 32 + sub * RB;
     const int j = ntile * jb + lane;
-    float* scr = scr_base + quarter * (BWD ? 32 * 33 : 5 * 32 * 33);
+    float* scr = scr_base + quarter * (BWD ? 32 * 33 : 3 * 32 * 33);
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int st = 0, ph = 0;  // producer ring position (kept by every issuing lane)
     const bool issuer = warp < 4 && lane == 0 && (p.a_split || warp == 0 || (multi && warp - 1 < nb_boxes));
@@ -286,11 +284,10 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
       quarter_sync(quarter);
       // --------------------------------------------------------------- cell maths, 8 rows
       if constexpr (!BWD) {
-        // Only the next step's A operand (the f16 / tf32-rounded h) has to be visible to the peers before the
-        // release; everything saved for the backward pass is stashed in the scratch planes and stored AFTER
-        // the release, while the CTA would otherwise wait for its peers (the release fence drains every
-        // outstanding store of the CTA: 7 stores per element cost ~1.5 us per step on the critical path).
+        float* hnew = p.h32[z][(s + 1) & 1];
         float* hnew_r = p.h_r[z] + (long long)(s + 1) * B * Hd;
+        float* gates = p.gates[z] ? p.gates[z] + (long long)s * B * 3 * Hd : nullptr;
+        float* hn_save = p.hn_save[z] ? p.hn_save[z] + (long long)s * B * Hd : nullptr;
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           const int rr = sub * RB + u, mr = mrow0 + u;
@@ -303,11 +300,14 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
             const float n_ = tanhf(in2[u] + r_ * hnv);
             const float h_ = (1.f - z_) * n_ + z_ * in3[u];
             const long long ho = (long long)mr * Hd + j;
+            hnew[ho] = h_;
+            hnew_r[ho] = round_tf32(h_);
             if constexpr (H16) p.h_h[z][(long long)(s + 1) * B * Hd + ho] = f16_sat_bits(h_);  // |h| < 1
-            else hnew_r[ho] = round_tf32(h_);
-            scr[(0 * 32 + rr) * 33 + lane] = r_; scr[(1 * 32 + rr) * 33 + lane] = z_;
-            scr[(2 * 32 + rr) * 33 + lane] = n_; scr[(3 * 32 + rr) * 33 + lane] = hnv;
-            scr[(4 * 32 + rr) * 33 + lane] = h_;
+            if (gates) {
+              float* gs = gates + (long long)mr * 3 * Hd + j;
+              gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
+              hn_save[ho] = hnv;
+            }
           }
         }
       } else {
@@ -351,30 +351,6 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         atomicAdd(counter, 1u);
       }
       if (tracer) p.trace[it_s * 8 + 5] = clock64();
-      if constexpr (!BWD) {
-        // deferred stores of this step (own stash entries only): fp32 state, rounded copy, saved gates
-        float* hnew = p.h32[z][(s + 1) & 1];
-        float* hnew_r = p.h_r[z] + (long long)(s + 1) * B * Hd;
-        float* gates = p.gates[z] ? p.gates[z] + (long long)s * B * 3 * Hd : nullptr;
-        float* hn_save = p.hn_save[z] ? p.hn_save[z] + (long long)s * B * Hd : nullptr;
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int rr = sub * RB + u, mr = mrow0 + u;
-          if (mr < B) {
-            const float r_ = scr[(0 * 32 + rr) * 33 + lane], z_ = scr[(1 * 32 + rr) * 33 + lane],
-                        n_ = scr[(2 * 32 + rr) * 33 + lane], h_ = scr[(4 * 32 + rr) * 33 + lane];
-            const long long ho = (long long)mr * Hd + j;
-            hnew[ho] = h_;
-            if constexpr (H16) hnew_r[ho] = round_tf32(h_);
-            if (gates) {
-              float* gs = gates + (long long)mr * 3 * Hd + j;
-              gs[0] = r_; gs[Hd] = z_; gs[2 * Hd] = n_;
-              hn_save[ho] = scr[(3 * 32 + rr) * 33 + lane];
-            }
-          }
-        }
-        quarter_sync(quarter);  // the quarter's TMEM warp refills the planes only after its helpers have read them
-      }
     }
   }
   tc_fence_before();
