@@ -584,60 +584,6 @@ static int fill_dgrad(GemmParams& p, int z, const ConvShape& cs, const float* dy
   return VAR_OK;
 }
 
-// The stride-parity classes of a dgrad are independent sub-GEMMs writing disjoint pixels.  Launched back
-// to back on one stream every class pays its own tail (the persistent grid drains before the next class
-// starts); on sibling streams the block scheduler back-fills the SMs a finishing class frees with CTAs of
-// the next one.  Pool: 3 high-priority non-blocking streams + events per device (VAR_DGRAD_STREAMS=0: off).
-struct ClassStreams {
-  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
-  bool ok = false;
-};
-static ClassStreams* class_streams() {
-  static int on = -1;
-  if (on < 0) on = env_int("VAR_DGRAD_STREAMS", 1);
-  if (!on) return nullptr;
-  static ClassStreams pool[64];
-  static std::mutex mu;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(mu);
-  ClassStreams& c = pool[dev];
-  if (!c.ok) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    bool good = cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 3 && good; ++i)
-      good = cudaStreamCreateWithPriority(&c.s[i], cudaStreamNonBlocking, hi) == cudaSuccess &&
-             cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!good) { (void)cudaGetLastError(); return nullptr; }
-    c.ok = true;
-  }
-  return &c;
-}
-// RAII: stream for class `idx` (0 = the caller's stream), joined back into `st` on destruction.
-struct ClassFork {
-  ClassStreams* cs;
-  cudaStream_t st;
-  int used = 0;
-  ClassFork(cudaStream_t st_, int nclasses) : cs(nclasses > 1 ? class_streams() : nullptr), st(st_) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cs && (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) cs = nullptr;
-    if (cs) cudaEventRecord(cs->fork, st);
-  }
-  cudaStream_t stream(int idx) {
-    if (!cs || idx == 0) return st;
-    const int i = (idx - 1) % 3;
-    if (!(used & (1 << i))) { cudaStreamWaitEvent(cs->s[i], cs->fork, 0); used |= 1 << i; }
-    return cs->s[i];
-  }
-  ~ClassFork() {
-    if (!cs) return;
-    for (int i = 0; i < 3; ++i)
-      if (used & (1 << i)) { cudaEventRecord(cs->join[i], cs->s[i]); cudaStreamWaitEvent(st, cs->join[i], 0); }
-  }
-};
-
 static bool is_linear(const ConvShape& cs) {
   return cs.R == 1 && cs.S == 1 && cs.sh == 1 && cs.sw == 1 && cs.ph == 0 && cs.pw == 0;
 }
@@ -669,8 +615,6 @@ int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, 
   if (cs.R < cs.sh || cs.S < cs.sw) return VAR_ERR_UNSUPPORTED;
   p.cpb = cs.Cout / 32;
   p.step_w = 1; p.step_h = 1;
-  ClassFork fork(st, cs.sh * cs.sw);
-  int cls = 0;
   for (int hp = 0; hp < cs.sh; ++hp)
     for (int wp = 0; wp < cs.sw; ++wp) {
       const int H2 = (cs.H - hp + cs.sh - 1) / cs.sh, W2 = (cs.W - wp + cs.sw - 1) / cs.sw;
@@ -700,7 +644,7 @@ int conv_dgrad(const ConvShape& cs, const float* dy, const float* w, float* dx, 
                            H2 - cs.P + q.base_h, 1, 1, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
       if (rc) return rc;
       dim3 grid((g.M + 127) / 128, cs.Cin / q.bn, 1);
-      rc = launch_gemm(G_TMA_IM2COL, EPI_STD, tm, tm, ta, ta, q, grid, fork.stream(cls++));
+      rc = launch_gemm(G_TMA_IM2COL, EPI_STD, tm, tm, ta, ta, q, grid, st);
       if (rc) return rc;
     }
   return VAR_OK;
@@ -1353,8 +1297,6 @@ int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx,
   CUtensorMap tm, ta;
   int rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tm);
   if (rc) return rc;
-  ClassFork fork(st, cs.sh * cs.sw);
-  int cls = 0;
   for (int hp = 0; hp < cs.sh; ++hp)
     for (int wp = 0; wp < cs.sw; ++wp) {
       const int H2 = (cs.H - hp + cs.sh - 1) / cs.sh, W2 = (cs.W - wp + cs.sw - 1) / cs.sw;
@@ -1385,7 +1327,7 @@ int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx,
       rc = get_tmap_im2col_e(dy, 2, cs.N, cs.P, cs.Q, cs.Cout, q.base_w, q.base_h, W2 - cs.Q + q.base_w,
                              H2 - cs.P + q.base_h, 1, 1, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
       if (rc) return rc;
-      rc = launch_gemm_persist_t<G_TMA_IM2COL, true>(tm, ta, q, (g.M + 127) / 128, cs.Cin / q.bn, fork.stream(cls++));
+      rc = launch_gemm_persist_t<G_TMA_IM2COL, true>(tm, ta, q, (g.M + 127) / 128, cs.Cin / q.bn, st);
       if (rc) return rc;
     }
   return VAR_OK;
