@@ -149,6 +149,103 @@ int grad_to_f16_scaled(const float* src, void* dst, long long n, float* scale, u
   return VAR_OK;
 }
 
+// Last BPTT step -> 16-bit recurrence / input-projection operands with ONE gradient scale for both directions:
+// amax over the dgi slices (|dgi| >= |dgh| element-wise: dgh_n = dgi_n * r), then dgh[d] ([rows, cols] dense) and the
+// dgi[d] slices ([rows] x cols, row pitches ldgi / ldgi_h) are stored as f16 * S.
+__global__ void amax_rows_kernel(const float* __restrict__ s0, const float* __restrict__ s1, int rows, int cols4,
+                                 long long ld, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  const long long total = 2LL * rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols4);
+    const long long r = i / cols4;
+    const float* src = r < rows ? s0 : s1;
+    const float4 v = *reinterpret_cast<const float4*>(src + (r < rows ? r : r - rows) * ld + 4 * c);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+struct GruLastArgs {
+  const float* dgh[2]; uint16_t* dgh_h[2];
+  const float* dgi[2]; uint16_t* dgi_h[2];
+  long long ldgi, ldgi_h;
+  int rows, cols4;
+};
+__global__ void gru_last_cvt_kernel(const GruLastArgs a, const unsigned int* __restrict__ amax_bits,
+                                    float* __restrict__ scale) {
+  const float amax = __uint_as_float(*amax_bits);
+  float S = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) {
+    int e;
+    frexpf(amax, &e);
+    e = 12 - e;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    S = ldexpf(1.f, e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = S; scale[1] = 1.f / S; }
+  const long long per = (long long)a.rows * a.cols4, total = 4 * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int which = (int)(i / per);      // 0, 1: dgh of direction 0, 1; 2, 3: dgi
+    const long long rem = i - which * per;
+    const int c = (int)(rem % a.cols4);
+    const long long r = rem / a.cols4;
+    const int d = which & 1;
+    const float* src = which < 2 ? a.dgh[d] + r * (4LL * a.cols4) : a.dgi[d] + r * a.ldgi;
+    uint16_t* dst = which < 2 ? a.dgh_h[d] + r * (4LL * a.cols4) : a.dgi_h[d] + r * a.ldgi_h;
+    const float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+    *reinterpret_cast<uint2*>(dst + 4 * c) = make_uint2(pack_f16x2(v.x * S, v.y * S), pack_f16x2(v.z * S, v.w * S));
+  }
+}
+int gru_last_to_f16(const float* const dgh[2], void* const dgh_h[2], const float* const dgi[2], long long ldgi,
+                    void* const dgi_h[2], long long ldgi_h, int rows, int cols, float* scale, unsigned int* amax_bits,
+                    cudaStream_t st) {
+  if (cols & 3) return VAR_ERR_ARG;
+  VAR_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, sizeof(unsigned int), st));
+  {
+    LaunchScope sc(T_MISC, 0, st);
+    amax_rows_kernel<<<grid_for(2LL * rows * (cols / 4), 256, 4), 256, 0, st>>>(dgi[0], dgi[1], rows, cols / 4, ldgi, amax_bits);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  GruLastArgs a;
+  for (int d = 0; d < 2; ++d) {
+    a.dgh[d] = dgh[d]; a.dgh_h[d] = reinterpret_cast<uint16_t*>(dgh_h[d]);
+    a.dgi[d] = dgi[d]; a.dgi_h[d] = reinterpret_cast<uint16_t*>(dgi_h[d]);
+  }
+  a.ldgi = ldgi; a.ldgi_h = ldgi_h; a.rows = rows; a.cols4 = cols / 4;
+  {
+    LaunchScope sc(T_MISC, 0, st);
+    gru_last_cvt_kernel<<<grid_for(4LL * rows * (cols / 4), 256), 256, 0, st>>>(a, amax_bits, scale);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// dst[c][col0 + r] = f16(src[r][c]): fp32 [R, C] -> f16 [C, dst_ld] (transposed, at column offset col0);
+// 32 x 32 tiles through shared memory
+__global__ void cvt_f16_transpose_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int R, int C,
+                                         long long dst_ld, int col0) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[(long long)c * dst_ld + col0 + r] = (uint16_t)(pack_f16x2(tile[threadIdx.x][i], 0.f) & 0xFFFFu);
+  }
+}
+int cvt_f16_transpose(const float* src, void* dst, int R, int C, long long dst_ld, int dst_col0, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  LaunchScope sc(T_MISC, 0, st);
+  cvt_f16_transpose_kernel<<<grid, block, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), R, C, dst_ld, dst_col0);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
 // ---------------------------------------------------------------------------
 // 2x2/2 max pooling, NHWC, C % 4 == 0 (nn.MaxPool2d(2, 2) of
 // models/pretext/ai2thor_pretext_model.py:9-11).

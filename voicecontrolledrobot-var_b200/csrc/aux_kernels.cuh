@@ -13,6 +13,13 @@ int round_copy(const float* src, float* dst, long long n, cudaStream_t st);
 // 16-bit operand region helpers (aux_kernels.cu)
 int cvt_f16(const float* src, void* dst, long long n, cudaStream_t st);
 int grad_to_f16_scaled(const float* src, void* dst, long long n, float* scale, unsigned int* amax_bits, cudaStream_t st);
+// last BPTT step: one gradient scale for both directions (amax over the dgi slices), dgh[d] ([rows, cols] dense) and
+// the dgi[d] slices (row pitches ldgi -> ldgi_h) stored as f16 * S
+int gru_last_to_f16(const float* const dgh[2], void* const dgh_h[2], const float* const dgi[2], long long ldgi,
+                    void* const dgi_h[2], long long ldgi_h, int rows, int cols, float* scale, unsigned int* amax_bits,
+                    cudaStream_t st);
+// dst[c][col0 + r] = f16(src[r][c]) (fp32 [R, C] -> f16 rows of pitch dst_ld)
+int cvt_f16_transpose(const float* src, void* dst, int R, int C, long long dst_ld, int dst_col0, cudaStream_t st);
 
 int maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st);
 int maxpool_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C,

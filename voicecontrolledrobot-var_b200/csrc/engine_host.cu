@@ -342,7 +342,8 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
   static int coal = -1;
   if (coal < 0) { const char* e = getenv("VAR_EPI_COALESCE"); coal = (e && e[0] == '0') ? 0 : 1; }
   const long long stream_clk = (long long)p.num_kb * (kTileABytes + p.bn * 128) / 50;
-  if (!H16 && coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
+  const bool plain_f32_epi = !H16 || (p.e[0].out_kind == 0 && p.e[0].mask_kind == 0 && p.e[0].out_scale == nullptr);
+  if (plain_f32_epi && coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
     p.epi_coalesce = 1;
     smem += 4 * 4352;
   }
@@ -352,7 +353,8 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
   int grid = kNumSMs * per_sm;
   if (grid > total) grid = (int)total;
   const double flops = 2.0 * p.g[0].M * (double)p.e[0].ncols * p.g[0].K;
-  LaunchScope sc(H16 ? (p.b_mn_major ? T_GEMM_DGRAD16 : T_GEMM_FWD16) : (p.b_mn_major ? T_GEMM_DGRAD : T_GEMM_FWD), flops, st);
+  const bool is_dgrad = p.b_mn_major || p.prof_dgrad;
+  LaunchScope sc(H16 ? (is_dgrad ? T_GEMM_DGRAD16 : T_GEMM_FWD16) : (is_dgrad ? T_GEMM_DGRAD : T_GEMM_FWD), flops, st);
   tc_gemm_persist_kernel<GMODE, H16><<<grid, 192, smem, st>>>(tb, ta, p, m_tiles, n_tiles);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -765,6 +767,11 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
 // All T forward steps of both directions in one cooperative launch (gru_persist.cuh).
 // h_r: [(T+1), B, H] with slot 0 zeroed; h32[d][0] zeroed.  Returns VAR_ERR_UNSUPPORTED when the
 // grid cannot be co-resident (caller falls back to per-step launches).
+bool gru_x16_enabled() {  // VAR_GRU_X16=0 keeps the tf32 GEMMs for the GRU input projection and its backward
+  static int on = -1;
+  if (on < 0) on = env_int("VAR_GRU_X16", 1);
+  return on && gru_h16_enabled() && gather_mode() == 1;
+}
 bool gru_h16_enabled() {  // VAR_GRU_H16=0 keeps tf32 operands in the recurrent kernels
   static int on = -1;
   if (on < 0) on = env_int("VAR_GRU_H16", 1) && env_int("VAR_H16", 1);
@@ -774,7 +781,7 @@ bool gru_h16_enabled() {  // VAR_GRU_H16=0 keeps tf32 operands in the recurrent 
 int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long ldx, const float* const whh[2],
                     const float* const bhh[2], float* const h32[2][2], float* const h_r[2],
                     float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st,
-                    const void* const whh16[2], void* const h_h[2]) {
+                    const void* const whh16[2], void* const h_h[2], long long x_tstride) {
   if (!gru_persist_enabled() || gather_mode() != 1 || Hd % 64) return VAR_ERR_UNSUPPORTED;
   const bool h16 = gru_h16_enabled() && whh16 && h_h && whh16[0] && h_h[0];
   prof_note(h16 ? "gru_persist_fwd16 M%d H%d T%d %d%d" : "gru_persist_fwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
@@ -785,7 +792,7 @@ int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long
   p.B = B; p.Hd = Hd; p.T = T; p.bn = 3 * jb; p.num_kb = Hd / ke; p.stages = env_int("VAR_GRU_STAGES_FWD", 2);
   p.kps = env_int("VAR_GRU_KPS_FWD", 2);
   p.a_split = 0;  // (the split-A-box experiment is retired: its extra issuers read h without acquiring the group counter)
-  p.counters = counters; p.ldx = ldx;
+  p.counters = counters; p.ldx = ldx; p.xts = x_tstride ? x_tstride : 3LL * Hd;
   CUtensorMap tm[4];
   for (int d = 0; d < 2; ++d) {
     p.xproj[d] = xproj[d]; p.bhh[d] = bhh[d];
@@ -917,6 +924,7 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
   if (ex) {
     for (int d = 0; d < 2; ++d) { p.db_ih[d] = ex->db_ih[d]; p.db_hh[d] = ex->db_hh[d]; }
     if (ex->bias_done) *ex->bias_done = 0;
+    if (ex->dgi_h_done) *ex->dgi_h_done = 0;
   }
   if (h16) {
     CUtensorMap th[4];
@@ -928,9 +936,15 @@ int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float
     }
     if (rc) return rc;
     prof_note("gru_ksplit_bwd16 M%d H%d T%d %d%d", B, Hd, T, 0, 0);
+    if (ex->dgi_h[0]) {
+      for (int d = 0; d < 2; ++d) p.dgi_h[d] = reinterpret_cast<uint16_t*>(ex->dgi_h[d]);
+      p.dgi_h_ld = ex->dgi_h_ld; p.dgi_h_ts = ex->dgi_h_ts; p.skip_f32 = 1;
+    }
     rc = launch_gru_bwd_ksplit<true>(th, p, (B + 127) / 128, st);
     if (rc == VAR_OK && ex->bias_done) *ex->bias_done = ex->db_ih[0] != nullptr;
+    if (rc == VAR_OK && ex->dgi_h_done) *ex->dgi_h_done = ex->dgi_h[0] != nullptr;
     if (rc != VAR_ERR_UNSUPPORTED) return rc;
+    p.dgi_h[0] = p.dgi_h[1] = nullptr; p.skip_f32 = 0;
   }
   if (env_int("VAR_GRU_KSPLIT", 1) && Hd % 64 == 0 && !p.a_split) {
     prof_note("gru_ksplit_bwd M%d H%d T%d %d%d", B, Hd, T, 0, 0);
@@ -1403,6 +1417,79 @@ int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw
     VAR_CUDA_CHECK(cudaGetLastError());
     if (db_done) *db_done = 1;
   }
+  return VAR_OK;
+}
+
+// ---- plain [M, K] x [N, K]^T GEMMs on f16 operands (GRU input projection and its backward) ----
+// out[M, N] (fp32, row pitch ldo) = A (f16, [M, K], pitch lda) x W^T (f16, [N, K] K-major) (+ bias) (* *out_scale)
+// (* (mask > 0)); K % 64 == 0, N split into column tiles of the largest divisor <= 256 that is a multiple of 32.
+int linear_h16(int M, int K, int N, const void* a, long long lda, const void* w, const float* bias, float* out,
+               long long ldo, const void* mask, int mask_kind, long long ldm, const float* out_scale, int round_out,
+               int is_dgrad, cudaStream_t st) {
+  prof_note(is_dgrad ? "lin_dgrad16 M%d K%d N%d %d%d" : "lin_fwd16 M%d K%d N%d %d%d", M, K, N, 0, 0);
+  if (!env_int("VAR_H16", 1) || gather_mode() != 1 || K % 64 || M <= 0) return VAR_ERR_UNSUPPORTED;
+  const int bn = pick_bn(N);
+  if (bn == 0 || bn % 32) return VAR_ERR_UNSUPPORTED;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.g[0].M = M; p.g[0].K = K; p.g[0].scale = 1.f;
+  p.bn = bn; p.nbox = 1; p.box_rows = bn; p.boxbase[0] = 0;
+  p.num_kb = K / 64;
+  p.prof_dgrad = is_dgrad;
+  pick_pipeline(bn, &p.stages, &p.lookahead);
+  EpiParams& e = p.e[0];
+  e.out = out; e.ldo = ldo; e.bias = bias; e.ncols = N; e.round_out = round_out;
+  e.mask = reinterpret_cast<const float*>(mask); e.ldm = ldm; e.mask_kind = mask_kind; e.out_scale = out_scale;
+  CUtensorMap tb, ta;
+  int rc = get_tmap_2d_e(w, 2, N, K, K, bn, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tb);
+  if (rc) return rc;
+  rc = get_tmap_2d_e(a, 2, M, K, lda, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
+  if (rc) return rc;
+  return launch_gemm_persist_t<G_TMA_TILED, true>(tb, ta, p, (M + 127) / 128, N / bn, st);
+}
+
+// dw[N][kpad] += *inv_scale * X^T dY over M rows: X f16 [M, K] (pitch ldx), dY f16 [M, N] (pitch ldy, scaled);
+// output columns are processed in slabs of <= 256 (grid.z), K in tiles of 128 (grid.x), rows split over grid.y.
+int linear_wgrad_h16(int M, int K, int N, const void* x, long long ldx, const void* dy, long long ldy, float* dw,
+                     int kpad, const float* inv_scale, cudaStream_t st) {
+  prof_note("lin_wgrad16 M%d K%d N%d %d%d", M, K, N, 0, 0);
+  if (!env_int("VAR_H16", 1) || gather_mode() != 1 || K % 64 || M <= 0) return VAR_ERR_UNSUPPORTED;
+  const int slab = N <= 256 ? N : 256;
+  if (N % slab || slab % 64) return VAR_ERR_UNSUPPORTED;
+  WgradH16Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.K = K; p.kpad = kpad; p.cout = slab;
+  p.dw = dw; p.inv_scale = inv_scale;
+  p.pb = env_int("VAR_WGRAD16_PB", 64);
+  p.stages = env_int("VAR_WGRAD16_STAGES", 4);
+  if (p.pb < 16 || p.pb > 256 || p.pb % 16) return VAR_ERR_ARG;
+  p.a_tiled = 1;
+  p.P = 1; p.Q = 1; p.cpb = K / 64;
+  p.ones_ktile = -1;
+  const int ktiles = (K + 127) / 128, nslab = N / slab;
+  CUtensorMap tx, tdy;
+  int rc = get_tmap_2d_e(x, 2, M, K, ldx, p.pb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tx);
+  if (rc) return rc;
+  rc = get_tmap_2d_e(dy, 2, M, N, ldy, p.pb, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tdy);
+  if (rc) return rc;
+  size_t smem = wgrad_h16_smem_bytes(slab, p.stages, p.pb);
+  while (smem > 227 * 1024 - 2048 && p.stages > 2) { --p.stages; smem = wgrad_h16_smem_bytes(slab, p.stages, p.pb); }
+  if (smem > 227 * 1024 - 2048) return VAR_ERR_UNSUPPORTED;
+  const int per_sm = smem * 3 + 6144 <= 227 * 1024 ? 3 : (smem * 2 + 4096 <= 227 * 1024 ? 2 : 1);
+  int splits = (per_sm * kNumSMs) / (ktiles * nslab);
+  if (splits < 1) splits = 1;
+  int ppc = (M + splits - 1) / splits;
+  ppc = ((ppc + p.pb - 1) / p.pb) * p.pb;
+  if (ppc < 2 * p.pb) ppc = 2 * p.pb;
+  splits = (M + ppc - 1) / ppc;
+  p.pix_per_cta = ppc;
+  VAR_ENSURE_SMEM(tc_wgrad_h16_kernel, smem);
+  dim3 grid(ktiles, splits, nslab);
+  {
+    LaunchScope sc(T_WGRAD16, 2.0 * M * (double)N * K, st);
+    tc_wgrad_h16_kernel<<<grid, 160, smem, st>>>(tx, tdy, p);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }
 

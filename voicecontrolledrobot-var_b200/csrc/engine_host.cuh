@@ -64,7 +64,7 @@ int gru_step_bwd(int ndir, int B, int Hd, const float* const dgh[2], const float
 int gru_persist_fwd(int B, int Hd, int T, const float* const xproj[2], long long ldx, const float* const whh[2],
                     const float* const bhh[2], float* const h32[2][2], float* const h_r[2],
                     float* const gates[2], float* const hn_save[2], unsigned int* counters, cudaStream_t st,
-                    const void* const whh16[2] = nullptr, void* const h_h[2] = nullptr);
+                    const void* const whh16[2] = nullptr, void* const h_h[2] = nullptr, long long x_tstride = 0);
 struct GruBwdExtra {
   const void* whh16[2];    // f16 W_hh copies
   void* dgh_h[2];          // [T][B, 3H] f16 scaled gate gradients; slot T-1 filled by the caller (grad_to_f16_scaled)
@@ -72,12 +72,18 @@ struct GruBwdExtra {
   float* db_ih[2];         // bias gradients accumulated inside the BPTT kernel (nullable)
   float* db_hh[2];
   int* bias_done;          // out: 1 when the kernel produced the bias gradients (else the caller sums columns)
+  // 16-bit input projection: scaled f16 dgi, element (b, t, c) at b * dgi_h_ld + t * dgi_h_ts + c (nullable); when the
+  // kernel wrote it (*dgi_h_done = 1) the fp32 dgi / dgh of steps < T-1 were NOT stored
+  void* dgi_h[2];
+  long long dgi_h_ld, dgi_h_ts;
+  int* dgi_h_done;
 };
 int gru_persist_bwd(int B, int Hd, int T, const float* const whh[2], const float* const gates[2],
                     const float* const hn_save[2], const float* const h_r[2], float* const dgh[2],
                     float* const dgi[2], float* const dhd[2][2], unsigned int* counters, cudaStream_t st,
                     const GruBwdExtra* ex = nullptr);
 bool gru_h16_enabled();
+bool gru_x16_enabled();
 int colsum(const float* dy, long long M, long long ld, int C, float* db, cudaStream_t st);
 
 // dw[Cout, Kpad] += im2col(x)^T dy ; db[Cout] += colsum(dy) (db may be null).
@@ -92,5 +98,10 @@ int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx,
                    int mask_kind, const float* out_scale, int round_out, cudaStream_t st);
 int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw, float* db, const float* inv_scale,
                    int* db_done, cudaStream_t st);
+int linear_h16(int M, int K, int N, const void* a, long long lda, const void* w, const float* bias, float* out,
+               long long ldo, const void* mask, int mask_kind, long long ldm, const float* out_scale, int round_out,
+               int is_dgrad, cudaStream_t st);
+int linear_wgrad_h16(int M, int K, int N, const void* x, long long ldx, const void* dy, long long ldy, float* dw,
+                     int kpad, const float* inv_scale, cudaStream_t st);
 
 }  // namespace var

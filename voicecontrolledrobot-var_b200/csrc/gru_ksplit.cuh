@@ -234,14 +234,21 @@ gru_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_con
           const float dzp = dzz * z_ * (1.f - z_);
           const float drp = dnp * in4[u] * r_ * (1.f - r_);
           const float dr = round_tf32(drp), dz = round_tf32(dzp), dn = round_tf32(dnp);
-          float* gi = dgi + (long long)mr * ldgi + j;
-          gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
-          float* gh = dgh + (long long)mr * 3 * Hd + j;
           const float dnr = round_tf32(dnp * r_);
-          gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
+          if (!p.skip_f32) {
+            float* gi = dgi + (long long)mr * ldgi + j;
+            gi[0] = dr; gi[Hd] = dz; gi[2 * Hd] = dn;
+            float* gh = dgh + (long long)mr * 3 * Hd + j;
+            gh[0] = dr; gh[Hd] = dz; gh[2 * Hd] = dnr;
+          }
           if constexpr (H16) {
             uint16_t* ghh = p.dgh_h[z] + (long long)sp * B * 3 * Hd + (long long)mr * 3 * Hd + j;
-            ghh[0] = f16_sat_bits(dr * gS); ghh[Hd] = f16_sat_bits(dz * gS); ghh[2 * Hd] = f16_sat_bits(dnr * gS);
+            const uint16_t hr = f16_sat_bits(dr * gS), hz = f16_sat_bits(dz * gS);
+            ghh[0] = hr; ghh[Hd] = hz; ghh[2 * Hd] = f16_sat_bits(dnr * gS);
+            if (p.dgi_h[z]) {
+              uint16_t* gih = p.dgi_h[z] + (long long)mr * p.dgi_h_ld + (long long)t * p.dgi_h_ts + j;
+              gih[0] = hr; gih[Hd] = hz; gih[2 * Hd] = f16_sat_bits(dn * gS);
+            }
           }
           bsum[0] += dr; bsum[1] += dz; bsum[2] += dn; bsum[3] += dnr;
           dhd_out[hoff] = dh * z_;

@@ -31,8 +31,8 @@ struct GruPersistParams {
   unsigned int* counters;  // [gridDim.x * gridDim.z], zero before launch
   int mn_lbo, mn_sbo, mn_type;
   // forward
-  const float* xproj[2];  // [B, T, 3H] incl. b_ih
-  long long ldx;
+  const float* xproj[2];  // [B, T, 3H] incl. b_ih: element (b, t, c) at b * ldx + t * xts + c
+  long long ldx, xts;
   const float* bhh[2];
   float* h32[2][2];       // fp32 hidden state ping-pong [B, H]
   float* h_r[2];          // [(T+1), B, H] tf32-rounded hidden states (slot 0 = zeros): A operand
@@ -53,6 +53,12 @@ struct GruPersistParams {
   const float* gscale[2];   // bwd: device {S, 1/S} per direction (power of two, from the last step's gradient)
   float* db_ih[2];          // bwd: bias gradients accumulated in the epilogue (+=, nullable): colsum(dgi) / colsum(dgh)
   float* db_hh[2];
+  // bwd, 16-bit input projection: scaled f16 copy of dgi, element (b, t, c) at b * dgi_h_ld + t * dgi_h_ts + c
+  // (both directions interleaved in one [B*T, 6H] matrix); skip_f32 drops the fp32 dgi / dgh stores (their only
+  // readers are then the f16 weight-gradient / dgrad GEMMs)
+  uint16_t* dgi_h[2];
+  long long dgi_h_ld, dgi_h_ts;
+  int skip_f32;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -169,7 +175,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
       const int s = BWD ? T - 1 - it : it;
       if constexpr (!BWD) {
         const int t = z == 0 ? s : T - 1 - s;
-        const float* __restrict__ xproj = p.xproj[z] + (long long)t * 3 * Hd;
+        const float* __restrict__ xproj = p.xproj[z] + (long long)t * p.xts;
         const float* hprev = p.h32[z][s & 1];  // rows of this warp: written by this very thread last step
 #pragma unroll
         for (int u = 0; u < RB; ++u) {

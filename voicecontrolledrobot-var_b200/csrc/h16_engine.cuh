@@ -14,7 +14,9 @@
 namespace var {
 
 struct WgradH16Params {
-  int M, K, cout, kpad;      // kpad: row pitch (floats) of the fp32 gradient dw[cout][kpad]
+  int M, K, cout, kpad;      // cout: output channels of ONE CTA (slab blockIdx.z covers channels [z * cout, (z+1) * cout));
+                             // kpad: row pitch (floats) of the fp32 gradient dw[.][kpad]
+  int a_tiled;               // 1: X is a plain [M, K] matrix (2-D tensor map, box {64 channels, pb rows}), not im2col
   float* dw;
   float* db;                 // nullable; only written when ones_ktile >= 0
   const float* inv_scale;    // device scalar: results are multiplied by it (nullptr = 1)
@@ -49,6 +51,7 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const uint32_t tslot = tfull_bar + 8u;
 
   const int ktile = blockIdx.x;
+  const int col0 = blockIdx.z * p.cout;  // first output channel of this CTA's slab
   const int pix0 = blockIdx.y * p.pix_per_cta;
   const int pix1 = min(pix0 + p.pix_per_cta, p.M);
   const int num_kb = (pix1 - pix0 + pb - 1) / pb;
@@ -101,14 +104,20 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const int m = pix0 + it * pb;
             const uint32_t dA = sA + (uint32_t)st * stageA;
             const uint32_t dB = sB + (uint32_t)st * stageB;
-            if (gq < kgroups)
-              tma_load_im2col_4d(dA + (uint32_t)gq * grp, &tmX, full_bar(st), c0, qq * p.step_w + p.base_w,
-                                 pp * p.step_h + p.base_h, n, p.tap_w[tap], p.tap_h[tap]);
-            qq += pb;
-            while (qq >= p.Q) { qq -= p.Q; ++pp; }
-            while (pp >= p.P) { pp -= p.P; ++n; }
+            if (gq < kgroups) {
+              if (p.a_tiled)
+                tma_load_2d(dA + (uint32_t)gq * grp, &tmX, full_bar(st), kbg << 6, m);
+              else
+                tma_load_im2col_4d(dA + (uint32_t)gq * grp, &tmX, full_bar(st), c0, qq * p.step_w + p.base_w,
+                                   pp * p.step_h + p.base_h, n, p.tap_w[tap], p.tap_h[tap]);
+            }
+            if (!p.a_tiled) {
+              qq += pb;
+              while (qq >= p.Q) { qq -= p.Q; ++pp; }
+              while (pp >= p.P) { pp -= p.P; ++n; }
+            }
             for (int bg = warp; bg < bgroups; bg += 4)
-              tma_load_2d(dB + (uint32_t)bg * grp, &tmDY, full_bar(st), bg * 64, m);
+              tma_load_2d(dB + (uint32_t)bg * grp, &tmDY, full_bar(st), col0 + bg * 64, m);
           }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
@@ -126,10 +135,10 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_ld_wait();
         if (k < p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + (long long)(c + j) * p.kpad + k, v[j] * inv);
+          for (int j = 0; j < 32; ++j) atomicAdd(p.dw + (long long)(col0 + c + j) * p.kpad + k, v[j] * inv);
         } else if (ones && k == p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(p.db + c + j, v[j] * inv);
+          for (int j = 0; j < 32; ++j) atomicAdd(p.db + col0 + c + j, v[j] * inv);
         }
       }
       tc_fence_before();

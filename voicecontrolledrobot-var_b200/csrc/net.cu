@@ -76,6 +76,9 @@ struct GruState {
   float* out_r;
   unsigned int* counters;  // [row tiles * 2] persistent-kernel group barriers
   void* h_h[2];         // [T+1][B, 512] f16 hidden states: A operand of the 16-bit recurrent GEMM (nullptr: tf32)
+  void* x16;            // [B*T, 448] f16 copy of x: A operand of the 16-bit input projection (nullptr: tf32)
+  long long ldx, xts;   // xproj element (b, t, c) at b * ldx + t * xts + c
+  bool x16_on;          // the forward pass took the 16-bit input projection
 };
 
 }  // namespace
@@ -114,6 +117,12 @@ struct Net {
   void* whh16[2] = {nullptr, nullptr}; // f16 copies of W_hh (both recurrent kernels), refreshed every forward
   float* gru_scale = nullptr;          // device: [2 directions][S, 1/S] of the BPTT gate gradients
   unsigned int* gru_amax = nullptr;    // [2]
+  // 16-bit input projection (x W_ih^T for both directions as ONE [B*T, 448] x [448, 3072] GEMM, its weight gradients
+  // and dX = dgi W_ih as ONE GEMM over K = 3072): f16 W_ih of both directions stacked [3072][448], the same matrix
+  // transposed [448][3072] (B operand of the dX GEMM), b_ih of both directions [3072]
+  void* wih16 = nullptr;
+  void* wih16_t = nullptr;
+  float* bih_cat = nullptr;
 
   ~Net() {
     for (auto* L : {&img_trunk, &img_head, &snd_trunk, &snd_head})
@@ -124,6 +133,9 @@ struct Net {
     for (int d = 0; d < 2; ++d) if (whh16[d]) cudaFree(whh16[d]);
     if (gru_scale) cudaFree(gru_scale);
     if (gru_amax) cudaFree(gru_amax);
+    if (wih16) cudaFree(wih16);
+    if (wih16_t) cudaFree(wih16_t);
+    if (bih_cat) cudaFree(bih_cat);
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -310,6 +322,11 @@ struct Net {
       VAR_CUDA_CHECK(cudaMalloc(&gru_scale, 4 * sizeof(float)));
       VAR_CUDA_CHECK(cudaMalloc(&gru_amax, 2 * sizeof(unsigned int)));
     }
+    if (has_gru && gru_x16_enabled() && !wih16) {
+      VAR_CUDA_CHECK(cudaMalloc(&wih16, (size_t)6 * kGruH * kGruI * 2));
+      VAR_CUDA_CHECK(cudaMalloc(&wih16_t, (size_t)6 * kGruH * kGruI * 2));
+      VAR_CUDA_CHECK(cudaMalloc(&bih_cat, (size_t)6 * kGruH * sizeof(float)));
+    }
     return VAR_OK;
   }
 
@@ -357,8 +374,15 @@ struct Net {
     GruState& g = gru;
     g.B = B; g.x = x;
     const long long BT = (long long)B * kGruT;
+    // 16-bit input projection: both directions in one [B*T, 6H] matrix (direction d at column d * 3H)
+    const bool x16 = gru_x16_enabled() && (wih16 || !ar.base);
+    float* xproj_all = ar.alloc(BT * 6 * kGruH);
+    g.x16 = x16 ? ar.alloc((BT * kGruI + 1) / 2) : nullptr;
+    g.x16_on = x16;
+    g.ldx = x16 ? (long long)kGruT * 6 * kGruH : (long long)kGruT * 3 * kGruH;
+    g.xts = x16 ? 6LL * kGruH : 3LL * kGruH;
     for (int d = 0; d < 2; ++d) {
-      g.xproj[d] = ar.alloc(BT * 3 * kGruH);
+      g.xproj[d] = x16 ? xproj_all + (long long)d * 3 * kGruH : xproj_all + (long long)d * BT * 3 * kGruH;
       g.gates[d] = train ? ar.alloc(BT * 3 * kGruH) : nullptr;
       g.hn_save[d] = train ? ar.alloc(BT * kGruH) : nullptr;
       g.h_r[d] = ar.alloc((long long)(kGruT + 1) * B * kGruH);
@@ -371,12 +395,27 @@ struct Net {
     g.counters = reinterpret_cast<unsigned int*>(ar.alloc(256));
     if (!ar.base) return VAR_OK;
     if (ar.overflow) return VAR_ERR_WORKSPACE;
-    for (int d = 0; d < 2; ++d) {
-      // x-projection for all steps: [B*T, 448] x W_ih^T + b_ih
-      ConvShape cs{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
-      int rc = conv_fwd(cs, x, SRC_NHWC_F32, nullptr, wr(t_gru[d][0]), wm(t_gru[d][2]), g.xproj[d], 0,
-                        0, st);
+    if (x16) {
+      // x-projection of both directions for all steps as one f16 GEMM: [B*T, 448] x [448, 6H] + (b_ih_fwd | b_ih_bwd)
+      int rc = cvt_f16(x, g.x16, BT * kGruI, st);
+      for (int d = 0; d < 2 && !rc; ++d) {
+        rc = cvt_f16(wm(t_gru[d][0]), reinterpret_cast<uint16_t*>(wih16) + (size_t)d * 3 * kGruH * kGruI,
+                     (long long)3 * kGruH * kGruI, st);  // weights may have moved
+        if (!rc && cudaMemcpyAsync(bih_cat + (size_t)d * 3 * kGruH, wm(t_gru[d][2]), (size_t)3 * kGruH * 4,
+                                   cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = VAR_ERR_CUDA;
+      }
+      if (!rc) rc = linear_h16((int)BT, kGruI, 6 * kGruH, g.x16, kGruI, wih16, bih_cat, xproj_all, 6LL * kGruH, nullptr, 0,
+                               0, nullptr, 0, 0, st);
       if (rc) return rc;
+    }
+    for (int d = 0; d < 2; ++d) {
+      int rc = VAR_OK;
+      if (!x16) {
+        // x-projection for all steps: [B*T, 448] x W_ih^T + b_ih
+        ConvShape cs{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
+        rc = conv_fwd(cs, x, SRC_NHWC_F32, nullptr, wr(t_gru[d][0]), wm(t_gru[d][2]), g.xproj[d], 0, 0, st);
+        if (rc) return rc;
+      }
       VAR_CUDA_CHECK(cudaMemsetAsync(g.h_r[d], 0, (size_t)B * kGruH * 4, st));
       VAR_CUDA_CHECK(cudaMemsetAsync(g.h32[d][0], 0, (size_t)B * kGruH * 4, st));
       if (g.h_h[d]) {
@@ -396,8 +435,8 @@ struct Net {
       float* hs[2] = {g.hn_save[0], g.hn_save[1]};
       const void* w16[2] = {whh16[0], whh16[1]};
       void* hh[2] = {g.h_h[0], g.h_h[1]};
-      const int rc = gru_persist_fwd(B, kGruH, kGruT, xp, (long long)kGruT * 3 * kGruH, whh, bhh, h32, hr, gt, hs,
-                                     g.counters, st, g.h_h[0] ? w16 : nullptr, g.h_h[0] ? hh : nullptr);
+      const int rc = gru_persist_fwd(B, kGruH, kGruT, xp, g.ldx, whh, bhh, h32, hr, gt, hs,
+                                     g.counters, st, g.h_h[0] ? w16 : nullptr, g.h_h[0] ? hh : nullptr, g.xts);
       if (rc == VAR_OK)
         return concat2(g.h32[0][kGruT & 1], g.h32[1][kGruT & 1], g.out, g.out_r, B, kGruH, st);
       if (rc != VAR_ERR_UNSUPPORTED) return rc;
@@ -413,8 +452,8 @@ struct Net {
         hp[d] = g.h_r[d] + cur_slot * slot;
         whh[d] = wr(t_gru[d][1]);
         memset(&q[d], 0, sizeof(GruEpiParams));
-        q[d].xproj = g.xproj[d] + (long long)t * 3 * kGruH;
-        q[d].ldx = (long long)kGruT * 3 * kGruH;
+        q[d].xproj = g.xproj[d] + (long long)t * g.xts;
+        q[d].ldx = g.ldx;
         q[d].bhh = wm(t_gru[d][3]);
         q[d].hprev = g.h32[d][s & 1];
         q[d].hnew = g.h32[d][(s + 1) & 1];
@@ -593,6 +632,14 @@ struct Net {
     const bool h16 = gru_h16_enabled() && (whh16[0] || !ar.base);
     void* dgh_h[2] = {nullptr, nullptr};
     if (h16) for (int d = 0; d < 2; ++d) dgh_h[d] = ar.alloc((BT * 3 * kGruH + 1) / 2);
+    // 16-bit input projection backward: scaled f16 dgi of both directions in one [B*T, 6H] matrix
+    const bool x16 = h16 && g.x16_on && (wih16 || !ar.base);
+    void* dgi_h[2] = {nullptr, nullptr};
+    if (x16) {
+      dgi_h[0] = ar.alloc(BT * 3 * kGruH);  // (B*T * 6H halves)
+      dgi_h[1] = ar.base ? reinterpret_cast<uint16_t*>(dgi_h[0]) + 3 * kGruH : nullptr;
+    }
+    const long long ldgi_h = (long long)kGruT * 6 * kGruH, tsgi_h = 6LL * kGruH;
     if (!ar.base) { *dx_out = nullptr; return VAR_OK; }
     if (ar.overflow) return VAR_ERR_WORKSPACE;
     int rc = split2(d_out, dh[0][0], dh[1][0], B, kGruH, st);
@@ -621,15 +668,32 @@ struct Net {
     GruBwdExtra ex;
     memset(&ex, 0, sizeof(ex));
     ex.bias_done = &bias_done;
+    int dgi_h_done = 0;  // the BPTT kernel wrote the scaled f16 dgi (and skipped the fp32 dgi / dgh stores)
+    ex.dgi_h_done = &dgi_h_done;
+    if (x16) {
+      // one gradient scale for both directions (their dgi are the K dimension of ONE dX GEMM), chosen from the last
+      // step's gate gradients; that step's dgh / dgi slices are converted here, the BPTT kernel writes the rest
+      const long long lo = (long long)(kGruT - 1) * B * 3 * kGruH;
+      const float* gh[2] = {dgh[0] + lo, dgh[1] + lo};
+      void* ghh[2] = {reinterpret_cast<uint16_t*>(dgh_h[0]) + lo, reinterpret_cast<uint16_t*>(dgh_h[1]) + lo};
+      const float* gi[2] = {dgi[0] + (long long)slot_t(0, kGruT - 1) * 3 * kGruH, dgi[1] + (long long)slot_t(1, kGruT - 1) * 3 * kGruH};
+      void* gih[2] = {reinterpret_cast<uint16_t*>(dgi_h[0]) + (long long)slot_t(0, kGruT - 1) * tsgi_h,
+                      reinterpret_cast<uint16_t*>(dgi_h[1]) + (long long)slot_t(1, kGruT - 1) * tsgi_h};
+      rc = gru_last_to_f16(gh, ghh, gi, (long long)kGruT * 3 * kGruH, gih, ldgi_h, B, 3 * kGruH, gru_scale, gru_amax, st);
+      if (rc) return rc;
+    }
     for (int d = 0; d < 2; ++d) {
       ex.db_ih[d] = gr(t_gru[d][2]); ex.db_hh[d] = gr(t_gru[d][3]);
       if (h16) {
-        // the gate gradients of the last step enter the 16-bit recurrence: scale from their largest magnitude
-        const long long lo = (long long)(kGruT - 1) * B * 3 * kGruH;
-        rc = grad_to_f16_scaled(dgh[d] + lo, reinterpret_cast<uint16_t*>(dgh_h[d]) + lo, (long long)B * 3 * kGruH,
-                                gru_scale + 2 * d, gru_amax + d, st);
-        if (rc) return rc;
-        ex.whh16[d] = whh16[d]; ex.dgh_h[d] = dgh_h[d]; ex.gscale[d] = gru_scale + 2 * d;
+        if (!x16) {
+          // the gate gradients of the last step enter the 16-bit recurrence: scale from their largest magnitude
+          const long long lo = (long long)(kGruT - 1) * B * 3 * kGruH;
+          rc = grad_to_f16_scaled(dgh[d] + lo, reinterpret_cast<uint16_t*>(dgh_h[d]) + lo, (long long)B * 3 * kGruH,
+                                  gru_scale + 2 * d, gru_amax + d, st);
+          if (rc) return rc;
+        }
+        ex.whh16[d] = whh16[d]; ex.dgh_h[d] = dgh_h[d]; ex.gscale[d] = x16 ? gru_scale : gru_scale + 2 * d;
+        if (x16) { ex.dgi_h[d] = dgi_h[d]; ex.dgi_h_ld = ldgi_h; ex.dgi_h_ts = tsgi_h; }
       }
     }
     {
@@ -674,6 +738,30 @@ struct Net {
         rc = gru_cell_bwd(a[0], a[1], 2, B, kGruH, st);
       }
       if (rc) return rc;
+    }
+    if (dgi_h_done) {
+      // every gate gradient exists as scaled f16: weight gradients and dX on 16-bit operands
+      for (int d = 0; d < 2; ++d) {
+        // dW_hh += dgh^T h_prev (rows step-major; h_h slots 0 .. T-1 are the previous states)
+        rc = linear_wgrad_h16((int)BT, kGruH, 3 * kGruH, g.h_h[d], kGruH, dgh_h[d], 3 * kGruH, gr(t_gru[d][1]), kGruH,
+                              gru_scale + 1, st);
+        if (rc) return rc;
+        // dW_ih += dgi^T x (rows batch-major; direction d = columns d * 3H of the [B*T, 6H] matrix)
+        rc = linear_wgrad_h16((int)BT, kGruI, 3 * kGruH, g.x16, kGruI, dgi_h[d], 6 * kGruH, gr(t_gru[d][0]), kGruI,
+                              gru_scale + 1, st);
+        if (rc) return rc;
+      }
+      if (ev_rnn_grads) VAR_CUDA_CHECK(cudaEventRecord(ev_rnn_grads, st));  // every rnn.* gradient is final
+      // dX = [dgi_fwd | dgi_bwd] [W_ih_fwd ; W_ih_bwd] / S, ReLU mask of the conv output: one GEMM over K = 6H
+      for (int d = 0; d < 2; ++d) {
+        rc = cvt_f16_transpose(wm(t_gru[d][0]), wih16_t, 3 * kGruH, kGruI, 6LL * kGruH, d * 3 * kGruH, st);
+        if (rc) return rc;
+      }
+      rc = linear_h16((int)BT, 6 * kGruH, kGruI, dgi_h[0], 6LL * kGruH, wih16_t, nullptr, dx, kGruI, g.x, 0, kGruI,
+                      gru_scale + 1, 1, 1, st);
+      if (rc) return rc;
+      *dx_out = dx;
+      return VAR_OK;
     }
     ConvShape cih{(int)BT, 1, 1, kGruI, 3 * kGruH, 1, 1, 1, 1, 0, 0, 1, 1};
     for (int d = 0; d < 2; ++d) {

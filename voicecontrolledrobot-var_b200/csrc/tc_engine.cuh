@@ -133,6 +133,7 @@ struct GemmParams {
   int epi_coalesce;            // persistent kernel: transpose the accumulator through smem (512 B per store instr.)
   int kps;                     // persistent kernel: k-blocks per pipeline stage (1 or 2)
   int a_fmt, b_fmt;            // 16-bit engine: operand formats of the kind::f16 MMA (0 f16, 1 bf16)
+  int prof_dgrad;              // profiler tag only: count this K-major-B GEMM with the dgrad family
 };
 
 constexpr int kTileM = 128;
