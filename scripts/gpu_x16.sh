@@ -2,8 +2,8 @@
 # A/B of the 16-bit GRU input projection: GPU parity suite, then the headline bench with and without it.
 mkdir -p gpurun_out
 timeout -s KILL 1200 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "== pytest exit $?"; tail -n 12 gpurun_out/pytest_gpu.log
-for v in 1 0; do
-  VAR_GRU_X16=$v timeout -s KILL 600 python bench.py --workload ithor_b256 --steps 20 --warmup 5 --no-cpu-baseline --no-torch-baseline --no-reward > gpurun_out/bench_x16_$v.json 2> gpurun_out/bench_x16_$v.err
+for v in 1 0; do export VAR_EPI_TMA=$v
+  timeout -s KILL 600 python bench.py --workload ithor_b256 --steps 20 --warmup 5 --no-cpu-baseline --no-torch-baseline --no-reward > gpurun_out/bench_x16_$v.json 2> gpurun_out/bench_x16_$v.err
   echo "== x16=$v exit $?"; python - <<E
 import json
 try:

@@ -281,6 +281,22 @@ __device__ __forceinline__ float f16_bits_to_f32(uint16_t h) {
   return f;
 }
 
+// TMA store of one 2-D box from shared memory (bulk async group; the box is clipped at the tensor bounds)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src_smem),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {  // at most N groups still READING their shared source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Byte offset of 16-byte chunk `chunk` (0..7) in row `row` of a 128B-swizzled
 // tile whose rows are 128 bytes and whose base is 1024-byte aligned.
 __device__ __forceinline__ uint32_t swz128(uint32_t row, uint32_t chunk) {

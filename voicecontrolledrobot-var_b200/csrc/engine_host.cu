@@ -342,8 +342,24 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
   static int coal = -1;
   if (coal < 0) { const char* e = getenv("VAR_EPI_COALESCE"); coal = (e && e[0] == '0') ? 0 : 1; }
   const long long stream_clk = (long long)p.num_kb * (kTileABytes + p.bn * 128) / 50;
-  const bool plain_f32_epi = !H16 || (p.e[0].out_kind == 0 && p.e[0].mask_kind == 0 && p.e[0].out_scale == nullptr);
-  if (plain_f32_epi && coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
+  const EpiParams& e0 = p.e[0];
+  const bool plain_f32_epi = !H16 || (e0.out_kind == 0 && e0.mask_kind == 0 && e0.out_scale == nullptr);
+  CUtensorMap tc = tb;
+  static int epi_tma = -1;
+  if (epi_tma < 0) epi_tma = env_int("VAR_EPI_TMA", 1);
+  if (plain_f32_epi && coal && epi_tma && smem * 2 + 4096 > 227 * 1024 && 64LL * p.bn > stream_clk && !e0.mask && !e0.addsrc &&
+      !e0.map.on && p.bn % 32 == 0 && e0.ncols % 32 == 0 && (e0.ldo % 4) == 0) {
+    // epilogue-bound wide tiles with a plain fp32 output: TMA-store epilogue (two 16 KB staging boxes); a shallower
+    // operand ring makes room for them (the main loop of these tiles is far from being the limiter)
+    p.kps = 1; p.stages = 3;
+    smem = gemm_smem_bytes(p.bn, p.stages) + 1024 + 2 * 16384;
+    if (smem <= 227 * 1024 &&
+        get_tmap_2d(e0.out, p.g[0].M, e0.ncols, e0.ldo, 128, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tc) == VAR_OK)
+      p.epi_tma = 1;
+    else { p = p_in; p.kps = env_int("VAR_GEMM_KPS", 2); if (p.kps < 1 || p.stages % p.kps) p.kps = 1; p.stages /= p.kps;
+           smem = gemm_smem_bytes(p.bn, p.stages * p.kps); }
+  }
+  if (!p.epi_tma && plain_f32_epi && coal && smem * 2 + 4096 > 227 * 1024 && smem + 4 * 4352 <= 227 * 1024 && 64LL * p.bn > stream_clk) {
     p.epi_coalesce = 1;
     smem += 4 * 4352;
   }
@@ -355,7 +371,7 @@ static int launch_gemm_persist_t(const CUtensorMap& tb, const CUtensorMap& ta, c
   const double flops = 2.0 * p.g[0].M * (double)p.e[0].ncols * p.g[0].K;
   const bool is_dgrad = p.b_mn_major || p.prof_dgrad;
   LaunchScope sc(H16 ? (is_dgrad ? T_GEMM_DGRAD16 : T_GEMM_FWD16) : (is_dgrad ? T_GEMM_DGRAD : T_GEMM_FWD), flops, st);
-  tc_gemm_persist_kernel<GMODE, H16><<<grid, 192, smem, st>>>(tb, ta, p, m_tiles, n_tiles);
+  tc_gemm_persist_kernel<GMODE, H16><<<grid, 192, smem, st>>>(tb, ta, tc, p, m_tiles, n_tiles);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }

@@ -27,7 +27,8 @@ namespace var {
 template <int GMODE, bool H16 = false>
 __global__ void __launch_bounds__(192)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA,
-                       const __grid_constant__ GemmParams p, int m_tiles, int n_tiles) {
+                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmParams p, int m_tiles,
+                       int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const GatherGeom& g = p.g[0];
   const EpiParams& e = p.e[0];
@@ -46,6 +47,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
   auto tempty_bar = [&](int a) { return bars + (uint32_t)(2 * stages + 2 + a) * 8u; };
   const uint32_t tslot = bars + (uint32_t)(2 * stages + 4) * 8u;
   const uint32_t stage_base = bars + 128u;  // epi_coalesce: 4 x (32 rows x 128 B + 32 row offsets)
+  const uint32_t tma_stage = (bars + 256u + 1023u) & ~1023u;  // epi_tma: two 128-row x 128-byte swizzled boxes
 
   const uint32_t acc_cols = (uint32_t)tmem_cols_for(bn);
   const int nacc = acc_cols * 2 <= 256 ? 2 : 1;  // 2 CTAs per SM share the 512 TMEM columns
@@ -179,6 +181,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
   } else {
     // ===================== epilogue warps 0-3 =====================
     int i = 0;
+    uint32_t nbox_out = 0;  // epi_tma: boxes stored so far (staging buffer = parity)
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
       const int ntile = tile % n_tiles, mtile = tile / n_tiles;
       const int acc = nacc == 2 ? (i & 1) : 0;
@@ -187,6 +190,48 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
       tc_fence_after();
       const int m = mtile * kTileM + warp * 32 + lane;
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(warp * 32) << 16);
+      if (p.epi_tma) {
+        // Plain fp32 tiles of wide, short-K GEMMs (the GRU input projection writes 460 MB): a thread owns a row after
+        // tcgen05.ld, so the four epilogue warps write each 128 x 32 chunk (+ bias / ReLU / rounding) into a
+        // 128B-swizzled shared box and ONE thread hands it to the TMA store engine -- full-line asynchronous writes,
+        // no per-row address arithmetic, two boxes in flight.
+        for (int c = 0; c < bn; c += 32, ++nbox_out) {
+          const uint32_t buf = tma_stage + (nbox_out & 1u) * 16384u;
+          if (tid == 0) bulk_wait_group_read<1>();  // the store issued two chunks ago has drained this buffer
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float v[32];
+          tmem_ld32(trow + (uint32_t)c, v);
+          tmem_ld_wait();
+          const int col0 = ntile * bn + c;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 r4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (e.bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+            }
+            if (e.relu) {
+              r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f);
+              r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
+            }
+            if (e.round_out) {
+              r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);
+              r4.z = round_tf32(r4.z); r4.w = round_tf32(r4.w);
+            }
+            st_shared_v4(buf + swz128((uint32_t)(warp * 32 + lane), (uint32_t)j), r4.x, r4.y, r4.z, r4.w);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == 0) {
+            tma_store_2d(&tmC, buf, col0, mtile * kTileM);
+            bulk_commit_group();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       long long orow = m;
       if (e.map.on) {
         const int pq2 = e.map.P2 * e.map.Q2;
@@ -364,6 +409,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
+  if (p.epi_tma && tid == 0) bulk_wait_group<0>();  // every output box has left shared memory and is written
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();

@@ -131,6 +131,7 @@ struct GemmParams {
   int sc_rpt, sc_tpi;          // output rows per tile, tiles per image
   int sc_nh, sc_wpad;          // staged rows / padded row width
   int epi_coalesce;            // persistent kernel: transpose the accumulator through smem (512 B per store instr.)
+  int epi_tma;                 // persistent kernel: plain fp32 output tiles leave through swizzled smem boxes + TMA stores
   int kps;                     // persistent kernel: k-blocks per pipeline stage (1 or 2)
   int a_fmt, b_fmt;            // 16-bit engine: operand formats of the kind::f16 MMA (0 f16, 1 bf16)
   int prof_dgrad;              // profiler tag only: count this K-major-B GEMM with the dgrad family
