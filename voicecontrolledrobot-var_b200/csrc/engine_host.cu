@@ -2,6 +2,7 @@
 #include "engine_host.cuh"
 #include "first_conv.cuh"
 #include "cin1_conv.cuh"
+#include "kuka_sound.cuh"
 #include "cin3_conv.cuh"
 #include "gemm_persist.cuh"
 #include "gru_persist.cuh"
@@ -1187,6 +1188,11 @@ int conv_wgrad(const ConvShape& cs, const void* x, int src_kind, const SrcLayout
     a.kpad = round_up32(27); a.dy = dy; a.dw = dw; a.db = db;
     return first_conv_wgrad(a, src_kind == SRC_STRIDED_U8, st);
   }
+  if (src_kind == SRC_STRIDED_F32 && sl && env_int("VAR_FULLW", 1) &&
+      fullw_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, cs.P, cs.Q, sl->sN, sl->sH,
+                       sl->sW, sl->scale, x))
+    return fullw_conv_wgrad(reinterpret_cast<const float*>(x), dy, dw, db, cs.N, cs.H, cs.W, cs.R, cs.sh, cs.P,
+                            round_up32(cs.R * cs.S * cs.Cin), st);
   if (src_kind == SRC_STRIDED_F32 && sl &&
       cin1_conv_match(cs.H, cs.W, cs.Cin, cs.Cout, cs.R, cs.S, cs.sh, cs.sw, cs.ph, cs.pw, sl->sN, sl->sH, sl->sW,
                       sl->scale, x)) {

@@ -131,4 +131,112 @@ int kuka_sound_fwd(const KukaSoundArgs& a, int N, cudaStream_t st) {
   return VAR_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Weight + bias gradient of a full-width first conv (Cin = 1, S == W, pad 0, Q == 1, Cout = 32): Kuka soundCNN.0,
+// models/pretext/arm_pretext_model.py (5 x 40 kernel over [N, 100, 40] MFCC maps, stride (2, 1)).
+// The im2col row of output pixel (n, p) is the CONTIGUOUS run x[n][p*sh .. p*sh + R - 1][0 .. W - 1] of K = R*W
+// floats, so dW[o][k] = sum_{n,p} dY[n,p,o] * x[n][p*sh*W + k] needs no gather at all.  The GEMM is tiny (10 GFLOP at
+// N = 16384) and HBM bound (x + dY = 360 MB); the generic first-layer tensor path spent 3.4 ms on it (per-tile set-up
+// for 48-row tiles).  Here: persistent CTAs, one clip per iteration double-buffered through cp.async, plain fp32 FMAs
+// with a 4 (k) x 8 (o) register tile per thread, partial sums kept in registers across ALL clips of the CTA and
+// reduced with one atomic per element at the end.
+// ---------------------------------------------------------------------------
+struct FullwArgs {
+  const float* x; const float* dy; float* dw; float* db;
+  int N, HW, K, P, step, kpad;  // HW floats per clip, K = R*W, step = sh*W
+};
+constexpr int kFwThreads = 256, kFwCout = 32;
+__global__ void __launch_bounds__(kFwThreads)
+fullw_wgrad_kernel(const FullwArgs a) {
+  extern __shared__ __align__(16) uint8_t fw_smem[];
+  const int tid = threadIdx.x;
+  const int xs_floats = (a.HW + 3) & ~3, ds_floats = a.P * kFwCout;
+  const int buf_floats = xs_floats + ds_floats;
+  float* bufs = reinterpret_cast<float*>(fw_smem);
+  const int groups = a.K >> 2;                 // 4-k groups; 4 * groups <= 224 compute threads
+  const bool compute = tid < 4 * groups;
+  const int og = compute ? tid / groups : 0, k4 = compute ? tid - og * groups : 0;
+  const bool biasthr = tid >= kFwThreads - kFwCout;
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  float bacc = 0.f;
+  auto load = [&](int n, int b) {
+    const uint32_t dst = smem_u32(bufs + (size_t)b * buf_floats);
+    const float* xg = a.x + (long long)n * a.HW;
+    const float* dg = a.dy + (long long)n * ds_floats;
+    for (int i = tid; i < a.HW / 4; i += kFwThreads) cp_async_16(dst + (uint32_t)i * 16u, xg + 4 * i, 16u);
+    for (int i = tid; i < ds_floats / 4; i += kFwThreads)
+      cp_async_16(dst + (uint32_t)(xs_floats + 4 * i) * 4u, dg + 4 * i, 16u);
+  };
+  int n = blockIdx.x, b = 0;
+  if (n < a.N) load(n, 0);
+  cp_async_commit();
+  for (; n < a.N; n += gridDim.x, b ^= 1) {
+    const int nn = n + gridDim.x;
+    if (nn < a.N) load(nn, b ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* xs = bufs + (size_t)b * buf_floats;
+    const float* ds = xs + xs_floats;
+    if (compute) {
+      const float* xp = xs + 4 * k4;
+      const float* dp = ds + 8 * og;
+#pragma unroll 4
+      for (int p = 0; p < a.P; ++p) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + p * a.step);
+        const float4 d0 = *reinterpret_cast<const float4*>(dp + p * kFwCout);
+        const float4 d1 = *reinterpret_cast<const float4*>(dp + p * kFwCout + 4);
+        const float xc[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float dj[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(xc[c], dj[j], acc[c][j]);
+      }
+    } else if (biasthr) {
+      const int o = tid - (kFwThreads - kFwCout);
+      for (int p = 0; p < a.P; ++p) bacc += ds[p * kFwCout + o];
+    }
+    __syncthreads();
+  }
+  if (compute) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(a.dw + (long long)(8 * og + j) * a.kpad + 4 * k4 + c, acc[c][j]);
+  } else if (biasthr && a.db) {
+    atomicAdd(a.db + tid - (kFwThreads - kFwCout), bacc);
+  }
+}
+
+bool fullw_conv_match(int H, int W, int Cin, int Cout, int R, int S, int sh, int sw, int ph, int pw, int P, int Q,
+                      long long sN, long long sH, long long sW, float scale, const void* x) {
+  const int K = R * W;
+  return Cin == 1 && Cout == kFwCout && S == W && sw == 1 && ph == 0 && pw == 0 && Q == 1 && P >= 1 && (K & 3) == 0 &&
+         K <= 224 && ((H * W) & 3) == 0 && ((sh * W) & 3) == 0 && sW == 1 && sH == W && sN == (long long)H * W &&
+         scale == 1.f && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+         (size_t)2 * (((H * W + 3) & ~3) + P * kFwCout) * 4 <= 200 * 1024;
+}
+
+int fullw_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int R, int sh, int P,
+                     int kpad, cudaStream_t st) {
+  if (N <= 0) return VAR_OK;
+  FullwArgs a;
+  a.x = x; a.dy = dy; a.dw = dw; a.db = db;
+  a.N = N; a.HW = H * W; a.K = R * W; a.P = P; a.step = sh * W; a.kpad = kpad;
+  const size_t smem = (size_t)2 * (((a.HW + 3) & ~3) + P * kFwCout) * 4;
+  VAR_ENSURE_SMEM(fullw_wgrad_kernel, smem);
+  int grid = kNumSMs * (smem * 4 + 4096 <= 227 * 1024 ? 4 : (smem * 2 + 2048 <= 227 * 1024 ? 2 : 1));
+  if (grid > N) grid = N;
+  LaunchScope sc(T_WGRAD, 2.0 * N * (double)P * a.K * kFwCout, st);
+  fullw_wgrad_kernel<<<grid, kFwThreads, smem, st>>>(a);
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
 }  // namespace var

@@ -13,4 +13,10 @@ struct KukaSoundArgs {
   float* hidden;                        // [N,128]   fp32, post-ReLU (input of the fused tail)
 };
 int kuka_sound_fwd(const KukaSoundArgs& a, int N, cudaStream_t st);
+// weight + bias gradient of a full-width first conv (Cin = 1, S == W, Q == 1, Cout = 32, contiguous fp32 input):
+// dw[32][kpad] += dY^T x-windows, db[32] += colsum(dY)
+bool fullw_conv_match(int H, int W, int Cin, int Cout, int R, int S, int sh, int sw, int ph, int pw, int P, int Q,
+                      long long sN, long long sH, long long sW, float scale, const void* x);
+int fullw_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int N, int H, int W, int R, int sh, int P,
+                     int kpad, cudaStream_t st);
 }  // namespace var
