@@ -25,7 +25,7 @@ namespace var {
 // boxes are {64 n, 64 k} (8 KB) in the plain 128B swizzle (16-byte granules).  The epilogue can store
 // f16 / bf16 (e.out_kind) and read an f16 ReLU mask (e.mask_kind); no addsrc / coalescing path.
 template <int GMODE, bool H16 = false>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(192, 2)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmParams p, int m_tiles,
                        int n_tiles) {
@@ -186,9 +186,55 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
       const int ntile = tile % n_tiles, mtile = tile / n_tiles;
       const int acc = nacc == 2 ? (i & 1) : 0;
       const int use = nacc == 2 ? (i >> 1) : i;
+      const int m = mtile * kTileM + warp * 32 + lane;
+      long long orow = m;
+      if (e.map.on) {
+        const int pq2 = e.map.P2 * e.map.Q2;
+        const int n_ = m / pq2, rem_ = m - n_ * pq2;
+        const int h2 = rem_ / e.map.Q2, w2 = rem_ - h2 * e.map.Q2;
+        orow = ((long long)n_ * e.map.H + h2 * e.map.sh + e.map.oh) * e.map.W + w2 * e.map.sw + e.map.ow;
+      }
+      // ReLU-backward mask of this thread's output row, fetched BEFORE waiting for the accumulator and packed to one
+      // bit per column: short-K dgrad tiles (1-4 k-blocks for stride-2 3x3 convs) are epilogue bound, and the mask
+      // read was a dependent global round trip between tcgen05.ld and the store.
+      uint32_t mbits[8];
+      const bool mask_pre = e.mask != nullptr && !p.epi_coalesce && bn <= 256;
+      if (mask_pre) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          mbits[q] = 0xFFFFFFFFu;
+          const int col0 = ntile * bn + q * 32;
+          if (q * 32 < bn && m < g.M && col0 < e.ncols) {
+            uint32_t bits = 0u;
+            if (H16 && e.mask_kind == 1) {
+              const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.mask) + orow * e.ldm + col0);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint4 w4 = __ldg(mk + q4);
+                const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  // f16 > 0  <=>  sign bit clear and magnitude bits non-zero
+                  const uint32_t lo = ww[u] & 0xFFFFu, hi = ww[u] >> 16;
+                  bits |= (uint32_t)(lo != 0u && lo < 0x8000u) << (q4 * 8 + u * 2);
+                  bits |= (uint32_t)(hi != 0u && hi < 0x8000u) << (q4 * 8 + u * 2 + 1);
+                }
+              }
+            } else {
+              const float4* mk = reinterpret_cast<const float4*>(e.mask + orow * e.ldm + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 k4 = __ldg(mk + j);
+                bits |= (uint32_t)(k4.x > 0.f) << (4 * j) | (uint32_t)(k4.y > 0.f) << (4 * j + 1) |
+                        (uint32_t)(k4.z > 0.f) << (4 * j + 2) | (uint32_t)(k4.w > 0.f) << (4 * j + 3);
+              }
+            }
+            mbits[q] = bits;
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), (uint32_t)(use & 1));
       tc_fence_after();
-      const int m = mtile * kTileM + warp * 32 + lane;
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(warp * 32) << 16);
       if (p.epi_tma) {
         // Plain fp32 tiles of wide, short-K GEMMs (the GRU input projection writes 460 MB): a thread owns a row after
@@ -231,13 +277,6 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         continue;
-      }
-      long long orow = m;
-      if (e.map.on) {
-        const int pq2 = e.map.P2 * e.map.Q2;
-        const int n_ = m / pq2, rem_ = m - n_ * pq2;
-        const int h2 = rem_ / e.map.Q2, w2 = rem_ - h2 * e.map.Q2;
-        orow = ((long long)n_ * e.map.H + h2 * e.map.sh + e.map.oh) * e.map.W + w2 * e.map.sw + e.map.ow;
       }
       if (p.epi_coalesce) {
         // thread = row after tcgen05.ld; a direct store would touch 32 different 128-byte lines per
@@ -314,30 +353,10 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (e.mask) {
-              if (e.mask_kind == 1) {
-                const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.mask) + orow * e.ldm + col0);
+              const uint32_t bits = mbits[c >> 5];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const uint4 w4 = mk[q4];
-                  const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    // f16 > 0  <=>  sign bit clear and magnitude bits non-zero
-                    const uint32_t lo = ww[u] & 0xFFFFu, hi = ww[u] >> 16;
-                    if (!(lo != 0u && lo < 0x8000u)) v[q4 * 8 + u * 2] = 0.f;
-                    if (!(hi != 0u && hi < 0x8000u)) v[q4 * 8 + u * 2 + 1] = 0.f;
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 k4 = *reinterpret_cast<const float4*>(e.mask + orow * e.ldm + col0 + j);
-                  if (!(k4.x > 0.f)) v[j] = 0.f;
-                  if (!(k4.y > 0.f)) v[j + 1] = 0.f;
-                  if (!(k4.z > 0.f)) v[j + 2] = 0.f;
-                  if (!(k4.w > 0.f)) v[j + 3] = 0.f;
-                }
-              }
+              for (int j = 0; j < 32; ++j)
+                if (!((bits >> j) & 1u)) v[j] = 0.f;
             }
             if (e.out_kind == 0) {
               float* o = e.out + orow * e.ldo + col0;
@@ -391,9 +410,9 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
               r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f);
             }
             if (e.mask) {
-              const float4 k4 = *reinterpret_cast<const float4*>(e.mask + orow * e.ldm + col0 + j);
-              r4.x = k4.x > 0.f ? r4.x : 0.f; r4.y = k4.y > 0.f ? r4.y : 0.f;
-              r4.z = k4.z > 0.f ? r4.z : 0.f; r4.w = k4.w > 0.f ? r4.w : 0.f;
+              const uint32_t bits = mbits[c >> 5] >> j;
+              r4.x = (bits & 1u) ? r4.x : 0.f; r4.y = (bits & 2u) ? r4.y : 0.f;
+              r4.z = (bits & 4u) ? r4.z : 0.f; r4.w = (bits & 8u) ? r4.w : 0.f;
             }
             if (e.round_out) {
               r4.x = round_tf32(r4.x); r4.y = round_tf32(r4.y);

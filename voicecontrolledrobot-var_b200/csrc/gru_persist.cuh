@@ -303,7 +303,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
             const float r_ = sigmoidf_(in0[u] + vr + br);
             const float z_ = sigmoidf_(in1[u] + vz + bz);
             const float hnv = vn + bq;
-            const float n_ = tanhf(in2[u] + r_ * hnv);
+            const float n_ = tanhf_(in2[u] + r_ * hnv);
             const float h_ = (1.f - z_) * n_ + z_ * in3[u];
             const long long ho = (long long)mr * Hd + j;
             hnew[ho] = h_;

@@ -49,23 +49,27 @@ __device__ __forceinline__ void store_rounded(const float* __restrict__ s, float
 }
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 2) kuka_sound_fwd_kernel(KukaSoundArgs a) {
+// Persistent CTAs: the transposed conv weights (62 KB) are staged ONCE per CTA, clips stream through a cp.async
+// double buffer (restaging the weights per clip cost more than the clip's arithmetic).
+__global__ void __launch_bounds__(kThreads, 2) kuka_sound_fwd_kernel(KukaSoundArgs a, int N) {
   extern __shared__ __align__(16) float sm[];
-  float* sx = sm;                       // [100*40]
-  float* w1t = sx + kF * kMelW;         // [200][32]
+  float* sx0 = sm;                      // 2 x [100*40]
+  float* w1t = sx0 + 2 * kF * kMelW;    // [200][32]
   float* w2t = w1t + kK1 * kC;          // 3 x [96][32]
   float* a1 = w2t + 3 * kK2 * kC;       // [48*32]
   float* a2 = a1 + kP1 * kC;            // [23*32]
   float* a3 = a2 + kP2 * kC;            // [11*32]
   float* a4 = a3 + kP3 * kC;            // [5*32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.x;
-
-  // stage the clip (128-bit loads) and the transposed conv weights
-  {
-    const float4* src = reinterpret_cast<const float4*>(a.x + (long long)n * kF * kMelW);
-    float4* dst = reinterpret_cast<float4*>(sx);
-    for (int i = tid; i < kF * kMelW / 4; i += kThreads) dst[i] = src[i];
+  auto load_clip = [&](int n, int b) {
+    const float* src = a.x + (long long)n * kF * kMelW;
+    const uint32_t dst = smem_u32(sx0 + b * kF * kMelW);
+    for (int i = tid; i < kF * kMelW / 4; i += kThreads) cp_async_16(dst + (uint32_t)i * 16u, src + 4 * i, 16u);
+  };
+  int n = blockIdx.x, buf = 0;
+  if (n < N) load_clip(n, 0);
+  cp_async_commit();
+  {  // transposed conv weights
     for (int i = tid; i < kK1 * kC; i += kThreads) {
       const int c = i / kK1, k = i - c * kK1;  // coalesced read of packed [32][224]
       w1t[k * kC + c] = a.w1[c * kK1Pad + k];
@@ -78,55 +82,68 @@ __global__ void __launch_bounds__(kThreads, 2) kuka_sound_fwd_kernel(KukaSoundAr
       }
     }
   }
-  __syncthreads();
+  const float b1 = a.b1[lane];
+  for (; n < N; n += gridDim.x, buf ^= 1) {
+    cp_async_wait<0>();
+    __syncthreads();  // clip n landed; every read of the activation buffers by the previous clip is done
+    if (n + (int)gridDim.x < N) load_clip(n + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    const float* sx = sx0 + buf * kF * kMelW;
 
-  // conv1: out[p][c] = relu(b + sum_{k<200} x[2p*40 + k] * w1t[k][c])   (5x40 window is contiguous)
-  {
-    constexpr int J = kP1 / 8;  // 6 rows per warp
-    float acc[J];
-    const float b = a.b1[lane];
+    // conv1: out[p][c] = relu(b + sum_{k<200} x[2p*40 + k] * w1t[k][c])   (5x40 window is contiguous);
+    // lane = c, 6 rows per warp, x read as broadcast 128-bit loads (10 shared loads per 24 FMAs)
+    {
+      constexpr int J = kP1 / 8;
+      float acc[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) acc[j] = b;
-#pragma unroll 4
-    for (int k = 0; k < kK1; ++k) {
-      const float w = w1t[k * kC + lane];
+      for (int j = 0; j < J; ++j) acc[j] = b1;
+#pragma unroll 2
+      for (int k = 0; k < kK1; k += 4) {
+        const float w0 = w1t[k * kC + lane], w1 = w1t[(k + 1) * kC + lane], w2 = w1t[(k + 2) * kC + lane],
+                    w3 = w1t[(k + 3) * kC + lane];
 #pragma unroll
-      for (int j = 0; j < J; ++j) acc[j] = fmaf(sx[(2 * (warp + 8 * j)) * kMelW + k], w, acc[j]);
+        for (int j = 0; j < J; ++j) {
+          const float4 xv = *reinterpret_cast<const float4*>(sx + (2 * (warp + 8 * j)) * kMelW + k);
+          acc[j] = fmaf(xv.x, w0, acc[j]); acc[j] = fmaf(xv.y, w1, acc[j]);
+          acc[j] = fmaf(xv.z, w2, acc[j]); acc[j] = fmaf(xv.w, w3, acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) a1[(warp + 8 * j) * kC + lane] = fmaxf(acc[j], 0.f);
     }
-#pragma unroll
-    for (int j = 0; j < J; ++j) a1[(warp + 8 * j) * kC + lane] = fmaxf(acc[j], 0.f);
-  }
-  __syncthreads();
-  conv3x1<kP1, kP2>(a1, w2t, a.b2, a2, warp, lane);
-  __syncthreads();
-  conv3x1<kP2, kP3>(a2, w2t + kK2 * kC, a.b3, a3, warp, lane);
-  __syncthreads();
-  conv3x1<kP3, kP4>(a3, w2t + 2 * kK2 * kC, a.b4, a4, warp, lane);
-  __syncthreads();
+    __syncthreads();
+    conv3x1<kP1, kP2>(a1, w2t, a.b2, a2, warp, lane);
+    __syncthreads();
+    conv3x1<kP2, kP3>(a2, w2t + kK2 * kC, a.b3, a3, warp, lane);
+    __syncthreads();
+    conv3x1<kP3, kP4>(a3, w2t + 2 * kK2 * kC, a.b4, a4, warp, lane);
+    __syncthreads();
 
-  store_rounded(a1, a.act1 ? a.act1 + (long long)n * kP1 * kC : nullptr, kP1 * kC);
-  store_rounded(a2, a.act2 ? a.act2 + (long long)n * kP2 * kC : nullptr, kP2 * kC);
-  store_rounded(a3, a.act3 ? a.act3 + (long long)n * kP3 * kC : nullptr, kP3 * kC);
-  store_rounded(a4, a.act4 + (long long)n * kP4 * kC, kP4 * kC);
+    store_rounded(a1, a.act1 ? a.act1 + (long long)n * kP1 * kC : nullptr, kP1 * kC);
+    store_rounded(a2, a.act2 ? a.act2 + (long long)n * kP2 * kC : nullptr, kP2 * kC);
+    store_rounded(a3, a.act3 ? a.act3 + (long long)n * kP3 * kC : nullptr, kP3 * kC);
+    store_rounded(a4, a.act4 + (long long)n * kP4 * kC, kP4 * kC);
 
-  // Linear 160 -> 128 + ReLU: 16 outputs per warp, lanes split k (weights stream from L2)
-  for (int o = warp * 16; o < warp * 16 + 16; ++o) {
-    const float* w = a.wl + (long long)o * kFlat;
-    float acc = 0.f;
+    // Linear 160 -> 128 + ReLU: 16 outputs per warp, lanes split k (weights stream from L1 / L2)
+    for (int o = warp * 16; o < warp * 16 + 16; ++o) {
+      const float* w = a.wl + (long long)o * kFlat;
+      float acc = 0.f;
 #pragma unroll
-    for (int u = 0; u < kFlat / 32; ++u) acc = fmaf(a4[lane + 32 * u], w[lane + 32 * u], acc);
+      for (int u = 0; u < kFlat / 32; ++u) acc = fmaf(a4[lane + 32 * u], w[lane + 32 * u], acc);
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) a.hidden[(long long)n * kHid + o] = fmaxf(acc + a.bl[o], 0.f);
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) a.hidden[(long long)n * kHid + o] = fmaxf(acc + a.bl[o], 0.f);
+    }
   }
 }
 
 int kuka_sound_fwd(const KukaSoundArgs& a, int N, cudaStream_t st) {
   if (N <= 0) return VAR_OK;
-  const size_t smem = (size_t)(kF * kMelW + kK1 * kC + 3 * kK2 * kC + (kP1 + kP2 + kP3 + kP4) * kC) * 4;
+  const size_t smem = (size_t)(2 * kF * kMelW + kK1 * kC + 3 * kK2 * kC + (kP1 + kP2 + kP3 + kP4) * kC) * 4;
   VAR_ENSURE_SMEM(kuka_sound_fwd_kernel, smem);
+  const int grid = N < 2 * kNumSMs ? N : 2 * kNumSMs;
   LaunchScope sc(T_MISC, 2.0 * N * 447872.0, st);
-  kuka_sound_fwd_kernel<<<N, kThreads, smem, st>>>(a);
+  kuka_sound_fwd_kernel<<<grid, kThreads, smem, st>>>(a, N);
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
 }

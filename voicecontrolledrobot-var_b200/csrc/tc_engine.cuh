@@ -212,7 +212,11 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
   }
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// Gate non-linearities of the GRU epilogues: the cell maths of a step is issue bound (128 rows x 32 units x 3 gates per
+// CTA and step), so both go through ex2.approx + rcp.approx (absolute error ~1e-7, two orders below the operand
+// rounding) instead of the IEEE division / libm tanhf sequences.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // ---------------------------------------------------------------------------
 // Main GEMM kernel.  grid = (M tiles, N tiles, instances<=2), block = 160.
@@ -517,7 +521,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
               const float r_ = sigmoidf_(xr[u] + vr + br);
               const float z_ = sigmoidf_(xz[u] + vz + bz);
               const float hnv = vn + bq;
-              const float n_ = tanhf(xn[u] + r_ * hnv);
+              const float n_ = tanhf_(xn[u] + r_ * hnv);
               const float h_ = (1.f - z_) * n_ + z_ * hp[u];
               q.hnew[(long long)mr * Hd + j] = h_;
               if (q.hnew_r) q.hnew_r[(long long)mr * Hd + j] = round_tf32(h_);
