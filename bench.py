@@ -398,7 +398,7 @@ def run_b200(args):
     h16_flags = lib.var_h16_flags()
     # tensor peak a family is compared with: the kind::f16 kernels against MEASURED_PEAKS.json's bf16 figure (the
     # sustained one: they are timed inside a long step), the tf32 kernels against cuBLAS tf32 measured in this run
-    f16_fams = {"gemm_fwd16", "gemm_dgrad16", "wgrad16"} | ({"gru_step"} if (h16_flags & 2 and net == "ithor") else set())
+    f16_fams = {"gemm_fwd16", "gemm_dgrad16", "wgrad16"} | ({"gru_step", "gru_bwd"} if (h16_flags & 2 and net == "ithor") else set())
     clips_per_step = 2 * local_b
     bytes_per_clip = wl["clip"] * 2 + wl["F"] * 160  # int16 in + [F, 40] f32 out
     mfcc_bytes = clips_per_step * bytes_per_clip
@@ -416,6 +416,10 @@ def run_b200(args):
                               "frac": tfs / peak, "peak_source": psrc, "flops_per_launch": fl / cnt,
                               "avg_launch_ms": ms / cnt, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                               "traffic_detail": traffic}
+            if tag in ("gru_step", "gru_bwd"):
+                rooflines[tag]["note"] = ("sequential recurrence: one persistent launch runs 73 (72) dependent time steps, each bounded by a "
+                                          "cross-CTA release/acquire round trip + the gate maths (>= 9 us per step measured, DESIGN section 7), "
+                                          "not by the tensor pipe")
     ttag = max(prof.items(), key=lambda kv: kv[1][0])[0]
     if ttag in rooflines:
         roof = rooflines[ttag]

@@ -13,7 +13,7 @@ echo "== launch list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:"wgrad" -s 48 -c 16 -f -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu_full_wgrad.log 2>&1
 echo "== wgrad capture exit $?"
 ncu -i gpurun_out/prof_wgrad.ncu-rep --page raw --csv > gpurun_out/prof_wgrad_raw.csv 2> /dev/null
-ncu --set full --clock-control none --import-source on -k regex:"gru_|mfcc" -s 9 -c 3 -f -o gpurun_out/prof_gru $CMD > gpurun_out/ncu_full_gru.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gru_persist|gru_bwd_ksplit|mfcc" -s 9 -c 3 -f -o gpurun_out/prof_gru $CMD > gpurun_out/ncu_full_gru.log 2>&1
 echo "== gru/mfcc capture exit $?"
 ncu -i gpurun_out/prof_gru.ncu-rep --page raw --csv > gpurun_out/prof_gru_raw.csv 2> /dev/null
 ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_persist" -s 84 -c 28 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1

@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU evidence: DP test, iTHOR weak-scaling line (with sharded reward queries), Kuka global-batch-8192 lines at N=8 and N=4.
 mkdir -p gpurun_out
-timeout -s KILL 600 python -m pytest tests/test_gpu_dist.py -m gpu -q > gpurun_out/pytest_dist.log 2>&1; echo "== dist pytest exit $?"; tail -n 3 gpurun_out/pytest_dist.log
+# (the 2-GPU data-parallel tests run on the 2-GPU box: scripts/gpu_multi.sh)
 run() {  # N workload extra-args
   timeout -s KILL 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29631 \
     bench.py --gpus $1 --steps 20 --warmup 5 --workload $2 $3 > gpurun_out/bench_$2_n$1.json 2> gpurun_out/bench_$2_n$1.err

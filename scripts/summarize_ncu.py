@@ -42,8 +42,14 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum"]
-FAMILY = {"wgrad": ("wgrad",), "gru_step": ("gru_persist", "gru_bwd_ksplit"), "mfcc": ("mfcc_kernel",),
-          "gemm_persist": ("tc_gemm_persist",)}
+# bench.py family tag -> (substrings that must ALL appear in the ncu kernel name)
+FAMILY = {"wgrad": (("tc_wgrad_tma",), ("cin1_wgrad",), ("cin3_wgrad",), ("tc_wgrad_kernel",), ("fullw_wgrad",)),
+          "wgrad16": (("tc_wgrad_h16",),),
+          "gru_step": (("gru_persist_kernel",),), "gru_bwd": (("gru_bwd_ksplit",),),
+          "mfcc": (("mfcc_kernel",),),
+          # the 16-bit forward and dgrad GEMMs are the same kernel template: one entry serves both tags
+          "gemm_fwd16": (("tc_gemm_persist", ", 1>"),), "gemm_dgrad16": (("tc_gemm_persist", ", 1>"),),
+          "gemm_fwd": (("tc_gemm_persist", ", 0>"),), "gemm_dgrad": (("tc_gemm_persist", ", 0>"),)}
 traffic = {}
 
 
@@ -66,7 +72,7 @@ for part in ("wgrad", "gru", "gemm"):
         for r in rows[2:]:
             w.writerow([r[idx[c]][:70] for c in cols])
     for fam, keys in FAMILY.items():
-        sel = [r for r in rows[2:] if any(k in r[idx["Kernel Name"]] for k in keys)]
+        sel = [r for r in rows[2:] if any(all(k in r[idx["Kernel Name"]] for k in alt) for alt in keys)]
         if not sel:
             continue
         rd = sum(to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) for r in sel)

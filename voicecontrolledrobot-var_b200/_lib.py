@@ -92,7 +92,7 @@ for _name, (_res, _args) in PROTOTYPES.items():
 
 
 PROF_TAGS = ["gemm_fwd", "gemm_dgrad", "gemm_scalar", "gru_step", "wgrad", "colsum", "mfcc", "tail", "pool", "adam",
-             "gru_cell_bwd", "sampler", "misc", "gemm_fwd16", "gemm_dgrad16", "wgrad16"]
+             "gru_cell_bwd", "sampler", "misc", "gemm_fwd16", "gemm_dgrad16", "wgrad16", "gru_bwd"]
 
 
 def prof_end():

@@ -38,6 +38,7 @@ enum LaunchTag : int {
   T_GEMM_FWD = 0, T_GEMM_DGRAD, T_GEMM_SCALAR, T_GRU_STEP, T_WGRAD, T_COLSUM, T_MFCC, T_TAIL,
   T_POOL, T_ADAM, T_GRU_CELL_BWD, T_SAMPLER, T_MISC,
   T_GEMM_FWD16, T_GEMM_DGRAD16, T_WGRAD16,  // the 16-bit operand (kind::f16) conv kernels
+  T_GRU_BWD,                                // the persistent BPTT kernels (T_GRU_STEP: forward + per-step fallbacks)
   T_NUM_TAGS
 };
 struct LaunchScope {

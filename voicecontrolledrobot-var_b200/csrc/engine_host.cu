@@ -757,7 +757,7 @@ static int launch_gru_persist(const CUtensorMap tm[4], GruPersistParams& p, dim3
     VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * grid.x * grid.z, st));
     void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
     const int rows = (int)grid.x * 128 < p.B - rt0 * 128 ? (int)grid.x * 128 : p.B - rt0 * 128;
-    LaunchScope sc(T_GRU_STEP, 2.0 * rows * (double)(p.bn * grid.y) * (p.num_kb * (H16 ? 64.0 : 32.0)) * grid.z * nsteps, st);
+    LaunchScope sc(BWD ? T_GRU_BWD : T_GRU_STEP, 2.0 * rows * (double)(p.bn * grid.y) * (p.num_kb * (H16 ? 64.0 : 32.0)) * grid.z * nsteps, st);
     if (trace_on) {  // debugging aid: per-step clock64 samples of CTA (0,0,0), dumped after a sync
       if (!d_trace) VAR_CUDA_CHECK(cudaMalloc(&d_trace, sizeof(long long) * 8 * 128));
       VAR_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 128, st));
@@ -887,7 +887,7 @@ static int launch_gru_bwd_ksplit(const CUtensorMap tm[4], GruPersistParams& p, i
     VAR_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, sizeof(unsigned int) * n * 2, st));
     void* args[] = {(void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3], (void*)&p};
     const int rows = n * 128 < p.B - rt0 * 128 ? n * 128 : p.B - rt0 * 128;
-    LaunchScope sc(T_GRU_STEP, 2.0 * rows * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
+    LaunchScope sc(T_GRU_BWD, 2.0 * rows * (double)p.Hd * (3.0 * p.Hd) * 2 * (p.T - 1), st);
     bool done = false;
     if (!no_coop && !coop_refused[dev]) {
       cfg.numAttrs = 2;
