@@ -10,4 +10,3 @@ run() {  # N workload extra-args
 run 8 ithor_b256 "--no-cpu-baseline --no-torch-baseline"
 run 8 kuka_dp8192 "--no-cpu-baseline --no-torch-baseline --no-reward"
 run 4 kuka_dp8192 "--no-cpu-baseline --no-torch-baseline --no-reward"
-run 4 ithor_b256 "--no-cpu-baseline --no-torch-baseline --no-reward"
