@@ -225,9 +225,12 @@ class _Slot:
         self.h_img = torch.empty(bs, 3, 96, 96, dtype=torch.uint8).pin_memory()
         self.h_wav = torch.empty(2 * bs * (max_clip + 1), dtype=torch.int16).pin_memory()
         self.h_meta = torch.empty(2, 2 * bs, dtype=torch.int64).pin_memory()
+        self.h_items = torch.empty(bs, dtype=torch.int64).pin_memory()
         self.d_img = torch.empty(bs, 3, 96, 96, dtype=torch.uint8, device=device)
         self.d_wav = torch.empty(2 * bs * (max_clip + 1), dtype=torch.int16, device=device)
         self.d_meta = torch.empty(2, 2 * bs, dtype=torch.int64, device=device)
+        self.d_len32 = torch.empty(2 * bs, dtype=torch.int32, device=device)
+        self.d_snd = None     # [2 * bs, F, 40] MFCC features of this slot (allocated on first use)
         self.free = threading.Event()
         self.free.set()
         self.consumed = None  # CUDA event: the compute stream is done reading this slot
@@ -244,8 +247,8 @@ class DeviceTripletLoader:
       180 GB: 6 M frames); the sampler and the MFCC of batch k+1 run on a side stream under step k.
     * resident=False: frames and clips stay in pinned host memory (datasets beyond HBM).  A prefetch
       thread -- the counterpart of the reference's DataLoader workers -- draws batch k+1's indices on a
-      side stream, gathers its frames / clips into pinned staging and uploads them while the GPU runs
-      step k; only the MFCC runs on the compute stream.
+      side stream, gathers its frames / clips into pinned staging, uploads them and runs their MFCC on that
+      stream while the GPU runs step k.
 
     seed=None (default) continues torch's global CPU generator from its state at construction, as the
     reference's DataLoader does; an int starts a fresh `torch.manual_seed(seed)` stream."""
@@ -281,7 +284,10 @@ class DeviceTripletLoader:
                                             self.device, arena.clip_off, arena.clip_len,
                                             task_tables=arena if ithor else None)
         # the sampler state is only ever touched on this stream (seeded above on the current one)
-        self._ls = torch.cuda.Stream(self.device)
+        # streaming mode: the producer thread WAITS for the sampler's indices, so the loader work (1-CTA sampler, uploads,
+        # MFCC) runs at high priority instead of queueing behind the step's persistent kernels; resident mode is fully
+        # asynchronous and keeps the default priority
+        self._ls = torch.cuda.Stream(self.device, priority=0 if resident else -1)
         self._ls.wait_stream(torch.cuda.current_stream(self.device))
         self._slots = None
 
@@ -361,7 +367,7 @@ class DeviceTripletLoader:
             slot["consumed"] = torch.cuda.Event()
             slot["consumed"].record(cs)
 
-    def _producer(self, q, stop, perm, starts, max_clip):
+    def _producer(self, q, stop, perm, starts, max_clip, mfcc_args):
         def put(x):
             while not stop.is_set():
                 try:
@@ -373,12 +379,23 @@ class DeviceTripletLoader:
         try:
             torch.cuda.set_device(self.device)
             wav_host = self.arena.wav_host
-            for k, s in enumerate(starts):
+            import time as _t
+            st_ = self.producer_stats = {"batches": 0, "wait_slot": 0.0, "draw_launch": 0.0, "draw_wait": 0.0, "gather": 0.0,
+                                         "upload": 0.0, "put": 0.0}
+            n_fft, win, hop, F = mfcc_args
+            nth = max(1, min(4, (os.cpu_count() or 4) // max(1, self.world_size)))  # ranks share the host cores
+
+            def launch_draw(k, s):
+                """Stage 1 of batch k (asynchronous): indices drawn on the loader stream, index / clip tables copied to
+                the slot's pinned buffers.  On a busy GPU the single-CTA sampler waits milliseconds for an SM, so it is
+                issued one batch ahead and its latency hides behind the host gather of the previous batch."""
+                t0 = _t.perf_counter()
                 slot = self._slots[k % len(self._slots)]
                 while not slot.free.wait(0.05):
                     if stop.is_set():
-                        return
+                        return None
                 slot.free.clear()
+                t1 = _t.perf_counter(); st_["wait_slot"] += t1 - t0
                 with torch.cuda.stream(self._ls):
                     if slot.consumed is not None:
                         self._ls.wait_event(slot.consumed)   # the previous tenant of this slot was read on cs
@@ -390,30 +407,58 @@ class DeviceTripletLoader:
                         meta = torch.stack([torch.cat([rec["off"][lo:hi], rec["off"][B + lo:B + hi]]),
                                             torch.cat([rec["len"][lo:hi], rec["len"][B + lo:B + hi]]).long()])
                         slot.h_meta[:, :2 * b].copy_(meta, non_blocking=True)
-                        h_items = rec["item"][lo:hi].long().cpu()   # synchronises the loader stream only
+                        slot.h_items[:b].copy_(rec["item"][lo:hi], non_blocking=True)
+                    drawn = torch.cuda.Event()
+                    drawn.record(self._ls)
+                st_["draw_launch"] += _t.perf_counter() - t1
+                return slot, rec, B, lo, hi, b, drawn
+
+            def finish(p):
+                """Stage 2: wait for the indices, gather frames / clips into pinned staging with the library's memcpy
+                threads (ctypes releases the GIL: the main thread keeps launching kernels meanwhile), upload, MFCC."""
+                slot, rec, B, lo, hi, b, drawn = p
+                t1 = _t.perf_counter()
+                drawn.synchronize()
                 gt = rec["gt"][lo:hi]
+                t2 = _t.perf_counter(); st_["draw_wait"] += t2 - t1
                 if not b:
-                    if not put((slot, 0, B, gt, rec, None, 0)):
-                        return
-                    continue
-                # gather into pinned staging with the library's memcpy threads (ctypes releases the GIL: the
-                # main thread keeps launching kernels meanwhile)
-                nth = max(1, min(4, (os.cpu_count() or 4) // max(1, self.world_size)))  # ranks share the host cores
-                check(lib.var_host_gather_rows(self.images_host.data_ptr(), 3 * 96 * 96, h_items.data_ptr(), b,
+                    return put((slot, 0, B, gt, rec, None, 0))
+                check(lib.var_host_gather_rows(self.images_host.data_ptr(), 3 * 96 * 96, slot.h_items.data_ptr(), b,
                                                slot.h_img.data_ptr(), nth), "var_host_gather_rows")
                 new_off = torch.empty(2 * b, dtype=torch.int64)
                 cur = int(lib.var_host_gather_clips(wav_host.data_ptr(), slot.h_meta[0].data_ptr(), slot.h_meta[1].data_ptr(),
                                                     2 * b, slot.h_wav.data_ptr(), new_off.data_ptr(), nth))
                 check(cur, "var_host_gather_clips")
                 slot.h_meta[0, :2 * b] = new_off
+                t3 = _t.perf_counter(); st_["gather"] += t3 - t2
                 with torch.cuda.stream(self._ls):
                     slot.d_img[:b].copy_(slot.h_img[:b], non_blocking=True)
                     slot.d_wav[:cur].copy_(slot.h_wav[:cur], non_blocking=True)
                     slot.d_meta[:, :2 * b].copy_(slot.h_meta[:, :2 * b], non_blocking=True)
+                    # the MFCC of this batch also runs here, ahead of the consumer (into the slot's own buffer: no
+                    # allocation on the loader stream)
+                    if slot.d_snd is None or slot.d_snd.shape[1] != F:
+                        slot.d_snd = torch.empty(2 * self.batch_size, F, 40, dtype=torch.float32, device=self.device)
+                    slot.d_len32[:2 * b].copy_(slot.d_meta[1, :2 * b])
+                    mfcc_device(slot.d_wav, slot.d_meta[0, :2 * b], slot.d_len32[:2 * b], self.audio.fs, n_fft, win, hop, F,
+                                flavour=self.flavour, out=slot.d_snd[:2 * b])
                     ev = torch.cuda.Event()
                     ev.record(self._ls)
-                if not put((slot, b, B, gt, rec, ev, b * 3 * 96 * 96 + cur * 2 + 2 * 2 * b * 8)):
+                t4 = _t.perf_counter(); st_["upload"] += t4 - t3
+                ok = put((slot, b, B, gt, rec, ev, b * 3 * 96 * 96 + cur * 2 + 2 * 2 * b * 8))
+                st_["put"] += _t.perf_counter() - t4; st_["batches"] += 1
+                return ok
+
+            pending = None
+            for k, s in enumerate(starts):
+                nxt = launch_draw(k, s)
+                if nxt is None:
                     return
+                if pending is not None and not finish(pending):
+                    return
+                pending = nxt
+            if pending is not None and not finish(pending):
+                return
             put(None)
         except BaseException as e:  # noqa: BLE001 -- re-raised in the consumer
             put(e)
@@ -429,7 +474,8 @@ class DeviceTripletLoader:
             sl.free.set()
         perm = self._epoch_perm()
         q, stop = queue.Queue(maxsize=2), threading.Event()
-        th = threading.Thread(target=self._producer, args=(q, stop, perm, self._batch_starts(), max_clip), daemon=True)
+        th = threading.Thread(target=self._producer, args=(q, stop, perm, self._batch_starts(), max_clip, (n_fft, win, hop, F)),
+                              daemon=True)
         th.start()
         try:
             while True:
@@ -444,10 +490,8 @@ class DeviceTripletLoader:
                     slot.free.set()
                     continue
                 cs.wait_event(ev)
-                sounds = mfcc_device(slot.d_wav, slot.d_meta[0, :2 * b], slot.d_meta[1, :2 * b].int(), self.audio.fs,
-                                     n_fft, win, hop, F, flavour=self.flavour)
                 self.h2d_bytes += nbytes
-                yield slot.d_img[:b], sounds, gt, B, rec
+                yield slot.d_img[:b], slot.d_snd[:2 * b], gt, B, rec
                 # the consumer has launched its step on cs: mark the slot reusable once that work is done
                 slot.consumed = torch.cuda.Event()
                 slot.consumed.record(cs)
