@@ -223,6 +223,15 @@ int var_conv2d_dgrad_h16(const void* d_dy_f16, const void* d_w_f16_packed, void*
 int var_conv2d_wgrad_h16(const void* d_x_f16, const void* d_dy_f16, float* d_dw_packed, float* d_db,
                          const float* d_inv_scale, int N, int H, int W, int Cin, int Cout, int R, int S, int sh,
                          int sw, int ph, int pw, void* stream);
+/* Plain GEMMs of the 16-bit region (GRU input projection, replaces nn.GRU's x W_ih^T of models/pretext/
+ * ai2thor_pretext_model.py:33 and its backward): out[M, N] (fp32, pitch ldo) = A[M, K] (f16, pitch lda) x W[N, K]^T (f16)
+ * (+ bias) (* *d_out_scale) (* (mask > 0)); and d_dw[N][kpad] += *d_inv_scale * dY^T X over the M rows
+ * (X f16 [M, K] pitch ldx, dY f16 [M, N] pitch ldy).  K % 64 == 0. */
+int var_linear_h16(const void* d_a_f16, int64_t lda, const void* d_w_f16, const float* d_bias, float* d_out, int64_t ldo,
+                   const void* d_mask, int mask_kind, int64_t ldm, const float* d_out_scale, int M, int K, int N,
+                   int round_out, void* stream);
+int var_linear_wgrad_h16(const void* d_x_f16, int64_t ldx, const void* d_dy_f16, int64_t ldy, float* d_dw, int kpad,
+                         const float* d_inv_scale, int M, int K, int N, void* stream);
 int var_maxpool2x2_fwd(const float* d_x, float* d_y, int N, int H, int W, int C, void* stream);
 int var_maxpool2x2_bwd(const float* d_x, const float* d_dy, float* d_dx, int N, int H, int W, int C,
                        void* stream);

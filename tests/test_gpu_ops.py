@@ -301,3 +301,49 @@ def test_conv_h16_fwd_dgrad_wgrad_vs_torch(vb, case):
     assert lib.var_unpack_weight(dw.data_ptr(), dw_ref.data_ptr(), Cout, Cin, R, S, kpad, None) == 0
     assert rel_to_max(dw_ref.cpu().numpy(), w.grad.numpy()) < 2e-5
     assert rel_to_max(db.cpu().numpy(), dy_exact.sum(dim=(0, 1, 2)).numpy()) < 2e-5
+
+
+LIN16_CASES = [  # M, K, N
+    (146, 448, 3072),    # GRU input projection of two sounds: ragged last M tile, 12 column tiles, TMA-store epilogue
+    (1000, 3072, 448),   # its dX GEMM: K = 3072 (48 k-blocks), two column tiles of 224, scale + ReLU mask in the epilogue
+    (300, 512, 1536),    # W_hh-shaped
+]
+
+
+@pytest.mark.parametrize("case", LIN16_CASES)
+def test_linear_h16_fwd_and_wgrad_vs_torch(vb, case):
+    """Plain f16 GEMMs of the GRU input projection (forward with bias, backward-data with 1/S and a ReLU mask, weight
+    gradient over slabs of 256 output channels).  Operands pre-rounded to f16: only the summation order differs."""
+    lib = vb._lib.lib
+    M, K, N = case
+    g = torch.Generator().manual_seed(M + K + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).half()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, generator=g)
+    a_d, w_d, b_d = a.to(DEV), w.to(DEV), bias.to(DEV)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    rc = lib.var_linear_h16(a_d.data_ptr(), K, w_d.data_ptr(), b_d.data_ptr(), out.data_ptr(), N, None, 0, 0, None, M, K, N,
+                            0, None)
+    assert rc == 0, vb._lib.last_error()
+    ref = a.double() @ w.double().t() + bias.double()
+    assert rel_to_max(out.cpu().numpy(), ref.float().numpy()) < 1e-5
+    # scaled + masked variant (what the dX GEMM uses)
+    scale = torch.tensor([0.125], device=DEV)
+    mask = (torch.rand(M, N, generator=g) > 0.4).float().to(DEV) * 0.7
+    out2 = torch.full((M, N), float("nan"), device=DEV)
+    rc = lib.var_linear_h16(a_d.data_ptr(), K, w_d.data_ptr(), None, out2.data_ptr(), N, mask.data_ptr(), 0, N,
+                            scale.data_ptr(), M, K, N, 0, None)
+    assert rc == 0, vb._lib.last_error()
+    ref2 = (a.double() @ w.double().t()) * 0.125 * (mask.cpu().double() > 0)
+    assert rel_to_max(out2.cpu().numpy(), ref2.float().numpy()) < 1e-5
+    # weight gradient: dw[N][K] += inv * dY^T A with dY = a second f16 matrix [M, N] read at a row pitch of 2 N
+    # (output channels in slabs of 256: N must be <= 256 or a multiple of 256)
+    if N > 256 and N % 256:
+        return
+    dy_wide = (torch.randn(M, 2 * N, generator=g) * 0.25).half().to(DEV)
+    dw = torch.zeros(N, K, device=DEV)
+    rc = lib.var_linear_wgrad_h16(a_d.data_ptr(), K, dy_wide[:, N:].data_ptr(), 2 * N, dw.data_ptr(), K, scale.data_ptr(), M,
+                                  K, N, None)
+    assert rc == 0, vb._lib.last_error()
+    dw_ref = 0.125 * (dy_wide[:, N:].cpu().double().t() @ a.double())
+    assert rel_to_max(dw.cpu().numpy(), dw_ref.float().numpy()) < 1e-5

@@ -74,6 +74,8 @@ PROTOTYPES = {
     "var_conv2d_fwd_h16": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p]),
     "var_conv2d_dgrad_h16": (_i, [_p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "var_conv2d_wgrad_h16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "var_linear_h16": (_i, [_p, _i64, _p, _p, _p, _i64, _p, _i, _i64, _p, _i, _i, _i, _i, _p]),
+    "var_linear_wgrad_h16": (_i, [_p, _i64, _p, _i64, _p, _i, _p, _i, _i, _i, _p]),
     "var_maxpool2x2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "var_maxpool2x2_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "var_launch_count": (C.c_longlong, []),

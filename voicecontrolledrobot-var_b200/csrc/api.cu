@@ -208,6 +208,14 @@ int var_conv2d_wgrad_h16(const void* x, const void* dy, float* dw, float* db, co
   const ConvShape cs = make_shape(N, H, W, Cin, Cout, R, S, sh, sw, ph, pw);
   return conv_wgrad_h16(cs, x, dy, dw, db, inv_scale, nullptr, ST(stream));
 }
+int var_linear_h16(const void* a, int64_t lda, const void* w, const float* bias, float* out, int64_t ldo, const void* mask,
+                   int mask_kind, int64_t ldm, const float* out_scale, int M, int K, int N, int round_out, void* stream) {
+  return linear_h16(M, K, N, a, lda, w, bias, out, ldo, mask, mask_kind, ldm, out_scale, round_out, 0, ST(stream));
+}
+int var_linear_wgrad_h16(const void* x, int64_t ldx, const void* dy, int64_t ldy, float* dw, int kpad,
+                         const float* inv_scale, int M, int K, int N, void* stream) {
+  return linear_wgrad_h16(M, K, N, x, ldx, dy, ldy, dw, kpad, inv_scale, ST(stream));
+}
 int var_maxpool2x2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   return maxpool_fwd(x, y, N, H, W, C, ST(stream));
 }
