@@ -8,6 +8,7 @@
 #include "gru_persist.cuh"
 #include "gru_ksplit.cuh"
 #include "h16_engine.cuh"
+#include "halo_conv.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -1281,12 +1282,176 @@ bool conv_h16_ok(const ConvShape& cs) {
          cs.R >= cs.sh && cs.S >= cs.sw && !is_linear(cs);
 }
 
+// ---- im2col-free forward for the strided 64 -> 64 f16 convs (halo_conv.cuh) ----
+static int get_tmap_nhwc_strided(const void* x, int N, int H, int W, int C, int box_w, int box_h, int sw, int sh,
+                                 CUtensorMap* out) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    var_set_last_error("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || C * 2 != 128) return VAR_ERR_ARG;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // boxDim counts tensor elements spanned: ceil(boxDim / elementStride) elements land in shared memory
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(box_w * sw), (cuuint32_t)(box_h * sh), 1u};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)sw, (cuuint32_t)sh, 1u};
+  if (box[1] > 256 || box[2] > 256) return VAR_ERR_UNSUPPORTED;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (strided NHWC) failed: %d (N=%d H=%d W=%d box=%dx%d)", (int)r, N, H, W,
+             box_w, box_h);
+    var_set_last_error(buf, __FILE__, __LINE__);
+    return VAR_ERR_CUDA;
+  }
+  return VAR_OK;
+}
+
+static bool conv_halo_ok(const ConvShape& cs) {
+  static int on = -1;
+  if (on < 0) on = env_int("VAR_HALO", 1);
+  return on && cs.Cin == 64 && cs.Cout == 64 && cs.sh == 2 && cs.sw == 2 && cs.R * cs.S <= kMaxTaps && cs.R >= 2 && cs.S >= 2;
+}
+
+static int conv_fwd_halo_h16(const ConvShape& cs, const void* x, const void* w, const float* bias, void* y, int out_kind,
+                             int relu, int round_out, cudaStream_t st) {
+  auto fdiv2 = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };  // floor(v / 2)
+  int rjmin = 1 << 30, rjmax = -(1 << 30), sjmin = 1 << 30, sjmax = -(1 << 30);
+  for (int r = 0; r < cs.R; ++r) { const int j = fdiv2(r - cs.ph); rjmin = j < rjmin ? j : rjmin; rjmax = j > rjmax ? j : rjmax; }
+  for (int s_ = 0; s_ < cs.S; ++s_) { const int j = fdiv2(s_ - cs.pw); sjmin = j < sjmin ? j : sjmin; sjmax = j > sjmax ? j : sjmax; }
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.WP = cs.Q + (sjmax - sjmin);
+  if (p.WP > 128) return VAR_ERR_UNSUPPORTED;
+  p.TP = 128 / p.WP;
+  if (p.TP > cs.P) p.TP = cs.P;
+  p.TPI = (cs.P + p.TP - 1) / p.TP;
+  p.box_rows = p.TP + (rjmax - rjmin); p.box_cols = p.WP;
+  p.plane_stride = (uint32_t)(((size_t)p.box_rows * p.box_cols * 128 + 1023) / 1024 * 1024);
+  p.h_start = 2 * rjmin; p.w_start = 2 * sjmin;
+  p.N = cs.N; p.P = cs.P; p.Q = cs.Q;
+  p.bias = bias; p.out = y; p.out_kind = out_kind; p.relu = relu; p.round_out = round_out;
+  p.ntaps = cs.R * cs.S;
+  int t = 0;
+  for (int pl = 0; pl < 4; ++pl) {  // plane = rp * 2 + sp
+    p.plane_begin[pl] = t;
+    for (int r = 0; r < cs.R; ++r)
+      for (int s_ = 0; s_ < cs.S; ++s_) {
+        const int rj = fdiv2(r - cs.ph), sj = fdiv2(s_ - cs.pw);
+        const int rp = (r - cs.ph) - 2 * rj, sp = (s_ - cs.pw) - 2 * sj;
+        if (rp * 2 + sp != pl) continue;
+        p.tap_shift[t] = (uint16_t)((rj - rjmin) * p.WP + (sj - sjmin));
+        p.tap_wcol[t] = (uint16_t)(r * cs.S + s_);
+        ++t;
+      }
+  }
+  p.plane_begin[4] = t;
+  p.stages = env_int("VAR_HALO_STAGES", 4);
+  size_t smem = halo_smem_bytes(p.plane_stride, p.stages);
+  // two CTAs per SM: one MMA issuer sustains only ~1 MMA (128 x 64 x 16) per 127 clk, two independent streams overlap
+  while (smem * 2 + 4096 > 227 * 1024 && p.stages > 2) { --p.stages; smem = halo_smem_bytes(p.plane_stride, p.stages); }
+  if (smem * 2 + 4096 > 227 * 1024) return VAR_ERR_UNSUPPORTED;
+  const int kpad = round_up32(cs.R * cs.S * cs.Cin);
+  CUtensorMap tx, tw;
+  const int exp_ = env_int("VAR_HALO_EXP", 0);  // timing experiments only (wrong results): 1 = unstrided planes, 2 = 8-row aligned shifts
+  if (exp_ == 2) for (int i = 0; i < p.ntaps; ++i) p.tap_shift[i] &= ~7;
+  int rc = get_tmap_nhwc_strided(x, cs.N, cs.H, cs.W, cs.Cin, p.box_cols, p.box_rows, exp_ == 1 ? 1 : 2, exp_ == 1 ? 1 : 2, &tx);
+  if (rc) return rc;
+  rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
+  if (rc) return rc;
+  VAR_ENSURE_SMEM(halo_conv_fwd_kernel, smem);
+  const int total = cs.N * p.TPI;
+  const int grid = total < 2 * kNumSMs ? total : 2 * kNumSMs;
+  {
+    LaunchScope sc(T_GEMM_FWD16, 2.0 * cs.N * cs.P * cs.Q * 64.0 * (double)(cs.R * cs.S * 64), st);
+    halo_conv_fwd_kernel<<<grid, 224, smem, st>>>(tx, tw, p);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// im2col-free data gradient (halo_conv_dgrad_kernel): one launch for the four stride-parity classes
+static int conv_dgrad_halo_h16(const ConvShape& cs, const void* dy, const void* w, void* dx, int out_kind, const void* mask,
+                               int mask_kind, const float* out_scale, int round_out, cudaStream_t st) {
+  int drmin = 1 << 30, drmax = -(1 << 30), dsmin = 1 << 30, dsmax = -(1 << 30);
+  for (int a = 0; a < 2; ++a)
+    for (int r = 0; r < cs.R; ++r) {
+      if ((a + cs.ph - r) & 1) continue;
+      const int d = (a + cs.ph - r) / 2;  // exact
+      drmin = d < drmin ? d : drmin; drmax = d > drmax ? d : drmax;
+    }
+  for (int b = 0; b < 2; ++b)
+    for (int s_ = 0; s_ < cs.S; ++s_) {
+      if ((b + cs.pw - s_) & 1) continue;
+      const int d = (b + cs.pw - s_) / 2;
+      dsmin = d < dsmin ? d : dsmin; dsmax = d > dsmax ? d : dsmax;
+    }
+  HaloDgradParams p;
+  memset(&p, 0, sizeof(p));
+  const int H2 = (cs.H + 1) / 2, W2 = (cs.W + 1) / 2;
+  p.WP = W2 + (dsmax - dsmin);
+  if (p.WP > 128) return VAR_ERR_UNSUPPORTED;
+  p.TP = 128 / p.WP;
+  if (p.TP > H2) p.TP = H2;
+  p.TPI = (H2 + p.TP - 1) / p.TP;
+  p.box_rows = p.TP + (drmax - drmin); p.box_cols = p.WP;
+  p.plane_stride = (uint32_t)(((size_t)p.box_rows * p.box_cols * 128 + 1023) / 1024 * 1024);
+  p.h_start = drmin; p.w_start = dsmin;
+  p.N = cs.N; p.H = cs.H; p.W = cs.W;
+  p.out = dx; p.mask = mask; p.out_scale = out_scale; p.out_kind = out_kind; p.mask_kind = mask_kind; p.round_out = round_out;
+  int t = 0;
+  for (int cls = 0; cls < 4; ++cls) {  // class = a * 2 + b
+    const int a = cls >> 1, b = cls & 1;
+    p.class_begin[cls] = t;
+    for (int r = 0; r < cs.R; ++r)
+      for (int s_ = 0; s_ < cs.S; ++s_) {
+        if (((a + cs.ph - r) & 1) || ((b + cs.pw - s_) & 1)) continue;
+        const int dr = (a + cs.ph - r) / 2, ds = (b + cs.pw - s_) / 2;
+        p.tap_shift[t] = (uint16_t)((dr - drmin) * p.WP + (ds - dsmin));
+        p.tap_wcol[t] = (uint16_t)(r * cs.S + s_);
+        ++t;
+      }
+    if (t == p.class_begin[cls]) return VAR_ERR_UNSUPPORTED;  // every class needs a tap (its accumulator is overwritten by the first)
+  }
+  p.class_begin[4] = t;
+  p.stages = env_int("VAR_HALO_STAGES", 4);
+  size_t smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages);
+  while (smem * 2 + 4096 > 227 * 1024 && p.stages > 2) { --p.stages; smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages); }
+  if (smem * 2 + 4096 > 227 * 1024) return VAR_ERR_UNSUPPORTED;
+  const int kpad = round_up32(cs.R * cs.S * cs.Cin);
+  CUtensorMap ty, tw;
+  int rc = get_tmap_nhwc_strided(dy, cs.N, cs.P, cs.Q, cs.Cout, p.box_cols, p.box_rows, 1, 1, &ty);
+  if (rc) return rc;
+  rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
+  if (rc) return rc;
+  VAR_ENSURE_SMEM(halo_conv_dgrad_kernel, smem);
+  const int total = cs.N * p.TPI;
+  const int grid = total < 2 * kNumSMs ? total : 2 * kNumSMs;
+  {
+    double flops = 0.0;  // same convention as the per-class im2col launches: input pixels of the class x its taps
+    for (int cls = 0; cls < 4; ++cls)
+      flops += 2.0 * cs.N * (double)((cs.H - (cls >> 1) + 1) / 2) * (double)((cs.W - (cls & 1) + 1) / 2) * 64.0 *
+               (double)((p.class_begin[cls + 1] - p.class_begin[cls]) * 64);
+    LaunchScope sc(T_GEMM_DGRAD16, flops, st);
+    halo_conv_dgrad_kernel<<<grid, 224, smem, st>>>(ty, tw, p);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
 // y = act(conv(x, w) + b): x f16 NHWC, w f16 packed [Cout][kpad] (same indexing as the tf32 copy, K % 64 == 0),
 // y stored as fp32 (out_kind 0, optionally tf32-rounded) or f16 (out_kind 1).
 int conv_fwd_h16(const ConvShape& cs, const void* x, const void* w, const float* bias, void* y, int out_kind, int relu,
                  int round_out, cudaStream_t st) {
   prof_note("fwd16 N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
   if (!conv_h16_ok(cs)) return VAR_ERR_UNSUPPORTED;
+  if (conv_halo_ok(cs)) {
+    const int rc = conv_fwd_halo_h16(cs, x, w, bias, y, out_kind, relu, round_out, st);
+    if (rc != VAR_ERR_UNSUPPORTED) return rc;
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   GatherGeom& g = p.g[0];
@@ -1317,6 +1482,10 @@ int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx,
                    int mask_kind, const float* out_scale, int round_out, cudaStream_t st) {
   prof_note("dgrad16 N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
   if (!conv_h16_ok(cs)) return VAR_ERR_UNSUPPORTED;
+  if (conv_halo_ok(cs) && env_int("VAR_HALO_DGRAD", 1)) {
+    const int rc = conv_dgrad_halo_h16(cs, dy, w, dx, out_kind, mask, mask_kind, out_scale, round_out, st);
+    if (rc != VAR_ERR_UNSUPPORTED) return rc;
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int kfwd = cs.R * cs.S * cs.Cin, kpad = round_up32(kfwd);
