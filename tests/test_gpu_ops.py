@@ -233,10 +233,24 @@ H16_CASES = [  # N, H, W, Cin, Cout, R, S, sh, sw, ph, pw   (Cin, Cout multiples
 ]
 
 
+# launch variants of the stride-2 64 -> 64 convs (csrc/halo_conv.cuh): the defaults (im2col-free forward / data gradient, im2col
+# weight gradient), the im2col kernels alone, and the im2col-free weight gradient with other launch shapes
+H16_VARIANTS = {
+    "default": {},
+    "im2col": {"VAR_HALO": "0"},
+    "halo_alt": {"VAR_HALO_WGRAD": "1", "VAR_HALO_CPS": "2", "VAR_HALO_DG_CPS": "2"},
+}
+
+
+@pytest.mark.parametrize("variant", list(H16_VARIANTS))
 @pytest.mark.parametrize("case", H16_CASES)
-def test_conv_h16_fwd_dgrad_wgrad_vs_torch(vb, case):
+def test_conv_h16_fwd_dgrad_wgrad_vs_torch(vb, case, variant, monkeypatch):
     """The 16-bit operand region: f16 activations / weights / scaled f16 gradients through kind::f16 MMAs.
     Operands are pre-rounded to f16 (products exact in fp32), so only the summation order differs."""
+    if variant != "default" and not (case[3] == 64 and case[4] == 64 and case[7] == 2):
+        pytest.skip("launch variants only exist for the stride-2 64 -> 64 convs")
+    for k, v in H16_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
     lib = vb._lib.lib
     N, H, W, Cin, Cout, R, S, sh, sw, ph, pw = case
     g = torch.Generator().manual_seed(hash(case) % 1000)

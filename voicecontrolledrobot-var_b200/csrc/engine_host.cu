@@ -477,6 +477,10 @@ static int gmode_of(int src_kind) {
                                   : (src_kind == SRC_STRIDED_F32 ? G_SCALAR_F32 : G_SCALAR_U8);
 }
 
+static bool conv_halo32_ok(const ConvShape& cs);
+static int conv_fwd_halo_tf32(const ConvShape& cs, const float* x, const float* w, const float* bias, float* y, int relu,
+                              int round_out, cudaStream_t st);
+
 int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* sl, const float* w,
              const float* bias, float* y, int relu, int round_out, cudaStream_t st, int out_kind) {
   prof_note("fwd N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
@@ -540,6 +544,10 @@ int conv_fwd(const ConvShape& cs, const void* x, int src_kind, const SrcLayout* 
       if (rc) return rc;
       gmode = G_TMA_TILED;
     } else if (cs.R * cs.S <= kMaxTaps) {
+      if (conv_halo32_ok(cs)) {
+        rc = conv_fwd_halo_tf32(cs, reinterpret_cast<const float*>(x), w, bias, y, relu, round_out, st);
+        if (rc != VAR_ERR_UNSUPPORTED) return rc;
+      }
       rc = get_tmap_im2col(reinterpret_cast<const float*>(x), cs.N, cs.H, cs.W, cs.Cin, -cs.pw, -cs.ph,
                            cs.pw - (cs.S - 1), cs.ph - (cs.R - 1), cs.sw, cs.sh, 128,
                            (int)CU_TENSOR_MAP_SWIZZLE_128B, &ta);
@@ -1284,20 +1292,20 @@ bool conv_h16_ok(const ConvShape& cs) {
 
 // ---- im2col-free forward for the strided 64 -> 64 f16 convs (halo_conv.cuh) ----
 static int get_tmap_nhwc_strided(const void* x, int N, int H, int W, int C, int box_w, int box_h, int sw, int sh,
-                                 CUtensorMap* out) {
+                                 CUtensorMap* out, int esize = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     var_set_last_error("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
     return VAR_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || C * 2 != 128) return VAR_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || C * esize != 128) return VAR_ERR_ARG;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * esize, (cuuint64_t)W * C * esize, (cuuint64_t)H * W * C * esize};
   // boxDim counts tensor elements spanned: ceil(boxDim / elementStride) elements land in shared memory
   cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(box_w * sw), (cuuint32_t)(box_h * sh), 1u};
   cuuint32_t estr[4] = {1u, (cuuint32_t)sw, (cuuint32_t)sh, 1u};
   if (box[1] > 256 || box[2] > 256) return VAR_ERR_UNSUPPORTED;
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+  CUresult r = fn(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1311,8 +1319,7 @@ static int get_tmap_nhwc_strided(const void* x, int N, int H, int W, int C, int 
 }
 
 static bool conv_halo_ok(const ConvShape& cs) {
-  static int on = -1;
-  if (on < 0) on = env_int("VAR_HALO", 1);
+  const int on = env_int("VAR_HALO", 1);
   return on && cs.Cin == 64 && cs.Cout == 64 && cs.sh == 2 && cs.sw == 2 && cs.R * cs.S <= kMaxTaps && cs.R >= 2 && cs.S >= 2;
 }
 
@@ -1335,6 +1342,7 @@ static int conv_fwd_halo_h16(const ConvShape& cs, const void* x, const void* w, 
   p.N = cs.N; p.P = cs.P; p.Q = cs.Q;
   p.bias = bias; p.out = y; p.out_kind = out_kind; p.relu = relu; p.round_out = round_out;
   p.ntaps = cs.R * cs.S;
+  p.nplanes = 4; p.step_h = 2; p.bn = 64; p.kelems = 64; p.w_resident = 0;
   int t = 0;
   for (int pl = 0; pl < 4; ++pl) {  // plane = rp * 2 + sp
     p.plane_begin[pl] = t;
@@ -1349,11 +1357,15 @@ static int conv_fwd_halo_h16(const ConvShape& cs, const void* x, const void* w, 
       }
   }
   p.plane_begin[4] = t;
-  p.stages = env_int("VAR_HALO_STAGES", 4);
-  size_t smem = halo_smem_bytes(p.plane_stride, p.stages);
-  // two CTAs per SM: one MMA issuer sustains only ~1 MMA (128 x 64 x 16) per 127 clk, two independent streams overlap
-  while (smem * 2 + 4096 > 227 * 1024 && p.stages > 2) { --p.stages; smem = halo_smem_bytes(p.plane_stride, p.stages); }
-  if (smem * 2 + 4096 > 227 * 1024) return VAR_ERR_UNSUPPORTED;
+  // several CTAs per SM: one MMA issuer sustains only ~1 MMA (128 x 64 x 16) per 127 clk, independent streams overlap
+  const int cps = env_int("VAR_HALO_CPS", 3);
+  p.slots = env_int("VAR_HALO_SLOTS", cps >= 3 ? 2 : 3);
+  p.stages = env_int("VAR_HALO_STAGES", cps >= 3 ? 3 : 4);
+  size_t smem = halo_smem_bytes(p.plane_stride, p.stages, p.slots);
+  const size_t per_sm = 227 * 1024 - (size_t)cps * 1024;  // 1 KB reserved per resident CTA
+  while (smem * cps > per_sm && p.stages > 2) { --p.stages; smem = halo_smem_bytes(p.plane_stride, p.stages, p.slots); }
+  while (smem * cps > per_sm && p.slots > 2) { --p.slots; smem = halo_smem_bytes(p.plane_stride, p.stages, p.slots); }
+  if (smem * cps > per_sm) return VAR_ERR_UNSUPPORTED;
   const int kpad = round_up32(cs.R * cs.S * cs.Cin);
   CUtensorMap tx, tw;
   const int exp_ = env_int("VAR_HALO_EXP", 0);  // timing experiments only (wrong results): 1 = unstrided planes, 2 = 8-row aligned shifts
@@ -1362,12 +1374,73 @@ static int conv_fwd_halo_h16(const ConvShape& cs, const void* x, const void* w, 
   if (rc) return rc;
   rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
   if (rc) return rc;
-  VAR_ENSURE_SMEM(halo_conv_fwd_kernel, smem);
+  VAR_ENSURE_SMEM(halo_conv_fwd_kernel<false>, smem);
   const int total = cs.N * p.TPI;
-  const int grid = total < 2 * kNumSMs ? total : 2 * kNumSMs;
+  const int grid = total < cps * kNumSMs ? total : cps * kNumSMs;
   {
     LaunchScope sc(T_GEMM_FWD16, 2.0 * cs.N * cs.P * cs.Q * 64.0 * (double)(cs.R * cs.S * 64), st);
-    halo_conv_fwd_kernel<<<grid, 224, smem, st>>>(tx, tw, p);
+    halo_conv_fwd_kernel<false><<<grid, 224, smem, st>>>(tx, tw, p);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
+// im2col-free forward for the stride-1 tf32 convs with 32 input channels (128-byte fp32 pixels: iTHOR imgBranch.2 / .5): ONE
+// plane per tile (rows p0 - ph ... , cols -pw ... of the image, zero-filled outside), tap (r, s) starts r * WP + s rows in;
+// the weights of all taps stay resident in shared memory when two CTAs per SM still fit, else they stream through the ring.
+static bool conv_halo32_ok(const ConvShape& cs) {
+  return env_int("VAR_HALO32", 1) && cs.Cin == 32 && (cs.Cout == 32 || cs.Cout == 64) && cs.sh == 1 && cs.sw == 1 &&
+         cs.R * cs.S <= kMaxTaps && cs.R * cs.S > 1 && cs.Q + cs.S - 1 <= 128;
+}
+
+static int conv_fwd_halo_tf32(const ConvShape& cs, const float* x, const float* w, const float* bias, float* y, int relu,
+                              int round_out, cudaStream_t st) {
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.WP = cs.Q + cs.S - 1;
+  p.TP = 128 / p.WP;
+  if (p.TP > cs.P) p.TP = cs.P;
+  p.TPI = (cs.P + p.TP - 1) / p.TP;
+  p.box_rows = p.TP + cs.R - 1; p.box_cols = p.WP;
+  p.plane_stride = (uint32_t)(((size_t)p.box_rows * p.box_cols * 128 + 1023) / 1024 * 1024);
+  p.h_start = -cs.ph; p.w_start = -cs.pw;
+  p.N = cs.N; p.P = cs.P; p.Q = cs.Q;
+  p.bias = bias; p.out = y; p.out_kind = 0; p.relu = relu; p.round_out = round_out;
+  p.ntaps = cs.R * cs.S;
+  p.nplanes = 1; p.step_h = 1; p.bn = cs.Cout; p.kelems = 32;
+  for (int r = 0; r < cs.R; ++r)
+    for (int s_ = 0; s_ < cs.S; ++s_) {
+      const int t = r * cs.S + s_;
+      p.tap_shift[t] = (uint16_t)(r * p.WP + s_);
+      p.tap_wcol[t] = (uint16_t)t;
+    }
+  p.plane_begin[0] = 0;
+  for (int pl = 1; pl <= 4; ++pl) p.plane_begin[pl] = p.ntaps;
+  const int cps = env_int("VAR_HALO32_CPS", 2);
+  p.slots = env_int("VAR_HALO32_SLOTS", 2);
+  const size_t per_sm = 227 * 1024 - (size_t)cps * 1024;
+  p.w_resident = env_int("VAR_HALO32_RESIDENT", 1);
+  p.stages = p.ntaps;
+  size_t smem = halo_smem_bytes(p.plane_stride, p.stages, p.slots, p.bn);
+  if (!p.w_resident || smem * cps > per_sm) {
+    p.w_resident = 0;
+    p.stages = env_int("VAR_HALO32_STAGES", 4);
+    smem = halo_smem_bytes(p.plane_stride, p.stages, p.slots, p.bn);
+    while (smem * cps > per_sm && p.stages > 2) { --p.stages; smem = halo_smem_bytes(p.plane_stride, p.stages, p.slots, p.bn); }
+    if (smem * cps > per_sm) return VAR_ERR_UNSUPPORTED;
+  }
+  const int kpad = round_up32(cs.R * cs.S * cs.Cin);
+  CUtensorMap tx, tw;
+  int rc = get_tmap_nhwc_strided(x, cs.N, cs.H, cs.W, cs.Cin, p.box_cols, p.box_rows, 1, 1, &tx, 4);
+  if (rc) return rc;
+  rc = get_tmap_2d(w, cs.Cout, kpad, kpad, cs.Cout, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
+  if (rc) return rc;
+  VAR_ENSURE_SMEM(halo_conv_fwd_kernel<true>, smem);
+  const int total = cs.N * p.TPI;
+  const int grid = total < cps * kNumSMs ? total : cps * kNumSMs;
+  {
+    LaunchScope sc(T_GEMM_FWD, 2.0 * cs.N * cs.P * cs.Q * (double)cs.Cout * (double)(cs.R * cs.S * cs.Cin), st);
+    halo_conv_fwd_kernel<true><<<grid, 224, smem, st>>>(tx, tw, p);
   }
   VAR_CUDA_CHECK(cudaGetLastError());
   return VAR_OK;
@@ -1417,10 +1490,14 @@ static int conv_dgrad_halo_h16(const ConvShape& cs, const void* dy, const void* 
     if (t == p.class_begin[cls]) return VAR_ERR_UNSUPPORTED;  // every class needs a tap (its accumulator is overwritten by the first)
   }
   p.class_begin[4] = t;
-  p.stages = env_int("VAR_HALO_STAGES", 4);
-  size_t smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages);
-  while (smem * 2 + 4096 > 227 * 1024 && p.stages > 2) { --p.stages; smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages); }
-  if (smem * 2 + 4096 > 227 * 1024) return VAR_ERR_UNSUPPORTED;
+  const int cps = env_int("VAR_HALO_DG_CPS", 2);  // 3 CTAs per SM: MMA side 20 % faster, but the fp32 row stores then bound the kernel (0.53 -> 0.67 ms)
+  { const int e_ = env_int("VAR_HALO_DG_EXP", 0); p.b_kmajor = e_ & 1; p.exp_nostore = (e_ >> 1) & 1; }  // timing experiments (wrong results)
+  p.slots = env_int("VAR_HALO_DG_SLOTS", 2);
+  p.stages = env_int("VAR_HALO_DG_STAGES", 4);  // trimmed below to what cps CTAs per SM leave room for (2 at cps = 3)
+  size_t smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages, p.slots);
+  const size_t per_sm = 227 * 1024 - (size_t)cps * 1024;
+  while (smem * cps > per_sm && p.stages > 2) { --p.stages; smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages, p.slots); }
+  if (smem * cps > per_sm) return VAR_ERR_UNSUPPORTED;
   const int kpad = round_up32(cs.R * cs.S * cs.Cin);
   CUtensorMap ty, tw;
   int rc = get_tmap_nhwc_strided(dy, cs.N, cs.P, cs.Q, cs.Cout, p.box_cols, p.box_rows, 1, 1, &ty);
@@ -1429,7 +1506,7 @@ static int conv_dgrad_halo_h16(const ConvShape& cs, const void* dy, const void* 
   if (rc) return rc;
   VAR_ENSURE_SMEM(halo_conv_dgrad_kernel, smem);
   const int total = cs.N * p.TPI;
-  const int grid = total < 2 * kNumSMs ? total : 2 * kNumSMs;
+  const int grid = total < cps * kNumSMs ? total : cps * kNumSMs;
   {
     double flops = 0.0;  // same convention as the per-class im2col launches: input pixels of the class x its taps
     for (int cls = 0; cls < 4; ++cls)
@@ -1538,6 +1615,104 @@ int conv_dgrad_h16(const ConvShape& cs, const void* dy, const void* w, void* dx,
   return VAR_OK;
 }
 
+// im2col-free weight gradient (halo_conv_wgrad_kernel): tap pairs of one parity plane per CTA group
+static int conv_wgrad_halo_h16(const ConvShape& cs, const void* x, const void* dy, float* dw, float* db, const float* inv_scale,
+                               cudaStream_t st) {
+  auto fdiv2 = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };
+  int rjmin = 1 << 30, rjmax = -(1 << 30), sjmin = 1 << 30, sjmax = -(1 << 30);
+  for (int r = 0; r < cs.R; ++r) { const int j = fdiv2(r - cs.ph); rjmin = j < rjmin ? j : rjmin; rjmax = j > rjmax ? j : rjmax; }
+  for (int s_ = 0; s_ < cs.S; ++s_) { const int j = fdiv2(s_ - cs.pw); sjmin = j < sjmin ? j : sjmin; sjmax = j > sjmax ? j : sjmax; }
+  HaloWgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.WP = cs.Q + (sjmax - sjmin);
+  if (p.WP > 128) return VAR_ERR_UNSUPPORTED;
+  p.TP = env_int("VAR_HALO_WG_TP", 8);
+  if (p.TP > cs.P) p.TP = cs.P;
+  p.TPI = (cs.P + p.TP - 1) / p.TP;
+  p.nk = (p.TP * p.WP + 15) / 16;
+  p.box_rows = p.TP + (rjmax - rjmin); p.box_cols = p.WP;
+  if (p.box_rows > 128 || p.TP * 2 > 256) return VAR_ERR_UNSUPPORTED;
+  const int shift_max = (rjmax - rjmin) * p.WP + (sjmax - sjmin);
+  int plane_rows = p.box_rows * p.box_cols;
+  if (plane_rows < shift_max + 16 * p.nk) plane_rows = shift_max + 16 * p.nk;
+  p.plane_bytes = (uint32_t)(p.box_rows * p.box_cols * 128);
+  p.dy_bytes = (uint32_t)(p.TP * p.WP * 128);
+  p.plane_region = (uint32_t)(((size_t)plane_rows * 128 + 1023) / 1024 * 1024);
+  p.slot_stride = p.plane_region + (uint32_t)(((size_t)p.nk * 16 * 128 + 1023) / 1024 * 1024);
+  p.h_start = 2 * rjmin; p.w_start = 2 * sjmin;
+  p.N = cs.N; p.P = cs.P; p.Q = cs.Q;
+  p.dw = dw; p.db = db; p.inv_scale = inv_scale; p.kpad = round_up32(cs.R * cs.S * cs.Cin);
+  int mp = env_int("VAR_HALO_WG_PAIRS", 4);  // pairs per CTA: 64 TMEM columns each
+  if (mp < 1) mp = 1;
+  if (mp > 8) mp = 8;
+  // pairs of each parity plane, in order of their start rows
+  int npairs = 0, ng = 0;
+  for (int pl = 0; pl < 4; ++pl) {
+    int sh[kMaxTaps], id[kMaxTaps], n = 0;
+    for (int r = 0; r < cs.R; ++r)
+      for (int s_ = 0; s_ < cs.S; ++s_) {
+        const int rj = fdiv2(r - cs.ph), sj = fdiv2(s_ - cs.pw);
+        if (((r - cs.ph) - 2 * rj) * 2 + ((s_ - cs.pw) - 2 * sj) != pl) continue;
+        sh[n] = (rj - rjmin) * p.WP + (sj - sjmin); id[n] = r * cs.S + s_; ++n;
+      }
+    for (int i = 1; i < n; ++i)  // insertion sort by start row
+      for (int j = i; j > 0 && sh[j] < sh[j - 1]; --j) { int t = sh[j]; sh[j] = sh[j - 1]; sh[j - 1] = t; t = id[j]; id[j] = id[j - 1]; id[j - 1] = t; }
+    const int np = (n + 1) / 2;
+    if (np == 0) continue;
+    if (npairs + np > 32) return VAR_ERR_UNSUPPORTED;
+    const int first = npairs;
+    for (int i = 0; i < n; i += 2, ++npairs) {
+      p.pair_shift[npairs] = (uint16_t)sh[i]; p.pair_tap0[npairs] = (uint8_t)id[i];
+      if (i + 1 < n) { p.pair_lbo[npairs] = (uint16_t)(sh[i + 1] - sh[i]); p.pair_tap1[npairs] = (uint8_t)id[i + 1]; }
+      else { p.pair_lbo[npairs] = 0; p.pair_tap1[npairs] = 255; }
+    }
+    const int ngr = (np + mp - 1) / mp;
+    if (ng + ngr > 16) return VAR_ERR_UNSUPPORTED;
+    for (int gi = 0; gi < ngr; ++gi, ++ng) {
+      p.g_plane[ng] = (uint8_t)pl;
+      p.g_pair_begin[ng] = (uint8_t)(first + (np * gi) / ngr);
+    }
+  }
+  p.g_pair_begin[ng] = (uint8_t)npairs;
+  p.ngroups = ng;
+  p.slots = env_int("VAR_HALO_WG_SLOTS", 2);
+  const size_t smem = (size_t)p.slots * p.slot_stride + 1024 + 256;
+  if (smem > 227 * 1024 - 1024) return VAR_ERR_UNSUPPORTED;
+  int maxp = 0;
+  for (int g = 0; g < ng; ++g) { const int c = p.g_pair_begin[g + 1] - p.g_pair_begin[g]; maxp = c > maxp ? c : maxp; }
+  const int tm_cols = maxp <= 1 ? 64 : (maxp <= 2 ? 128 : (maxp <= 4 ? 256 : 512));
+  int cps = (int)((227 * 1024) / (smem + 1024));
+  if (cps > 512 / tm_cols) cps = 512 / tm_cols;  // co-resident CTAs must all get their TMEM columns
+  if (cps > 4) cps = 4;
+  if (cps < 1) return VAR_ERR_UNSUPPORTED;
+  // CTAs per group in proportion to its MMA count + the fixed per-tile staging cost (~0.8 of a pair)
+  const int total_tiles = cs.N * p.TPI;
+  const int want = cps * kNumSMs;
+  double wsum = 0.0;
+  for (int g = 0; g < ng; ++g) wsum += (p.g_pair_begin[g + 1] - p.g_pair_begin[g]) + 0.8;
+  int acc = 0;
+  for (int g = 0; g < ng; ++g) {
+    p.g_cta_begin[g] = acc;
+    int c = (int)(want * ((p.g_pair_begin[g + 1] - p.g_pair_begin[g]) + 0.8) / wsum);
+    if (c < 1) c = 1;
+    if (c > total_tiles) c = total_tiles;
+    acc += c;
+  }
+  p.g_cta_begin[ng] = acc;
+  CUtensorMap tx, tdy;
+  int rc = get_tmap_nhwc_strided(x, cs.N, cs.H, cs.W, cs.Cin, p.box_cols, p.box_rows, 2, 2, &tx);
+  if (rc) return rc;
+  rc = get_tmap_nhwc_strided(dy, cs.N, cs.P, cs.Q, cs.Cout, p.WP, p.TP, 1, 1, &tdy);
+  if (rc) return rc;
+  VAR_ENSURE_SMEM(halo_conv_wgrad_kernel, smem);
+  {
+    LaunchScope sc(T_WGRAD16, 2.0 * cs.N * cs.P * cs.Q * (double)cs.Cout * (double)(cs.R * cs.S * cs.Cin), st);
+    halo_conv_wgrad_kernel<<<acc, 192, smem, st>>>(tx, tdy, p);
+  }
+  VAR_CUDA_CHECK(cudaGetLastError());
+  return VAR_OK;
+}
+
 // Fallback bias gradient for f16 dY when the weight-gradient kernel has no free row group: db += inv * colsum(dy).
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const uint16_t* __restrict__ dy, long long M, int C, float* __restrict__ db,
@@ -1558,6 +1733,13 @@ int conv_wgrad_h16(const ConvShape& cs, const void* x, const void* dy, float* dw
                    int* db_done, cudaStream_t st) {
   prof_note("wgrad16 N%d H%d Ci%d Co%d R%d", cs.N, cs.H, cs.Cin, cs.Cout, cs.R);
   if (!conv_h16_ok(cs)) return VAR_ERR_UNSUPPORTED;
+  if (conv_halo_ok(cs) && env_int("VAR_HALO_WGRAD", 0)) {
+    const int rc = conv_wgrad_halo_h16(cs, x, dy, dw, db, inv_scale, st);
+    if (rc != VAR_ERR_UNSUPPORTED) {
+      if (db_done) *db_done = db != nullptr;
+      return rc;
+    }
+  }
   WgradH16Params p;
   memset(&p, 0, sizeof(p));
   p.M = cs.N * cs.P * cs.Q;

@@ -18,8 +18,8 @@
 
 namespace var {
 
-constexpr int kHaloSlots = 3;  // ring of staged parity planes (a tile uses 4 in a row; the next tile's planes stream
-                               // in while the last planes of this tile are still being multiplied)
+// plane slots (p.slots): ring of staged parity planes (a tile uses 4 in a row; the next tile's planes stream in while the
+// last planes of this tile are still being multiplied); 3 slots + 4 weight stages = 2 CTAs/SM, 2 + 3 = 3 CTAs/SM
 
 struct HaloParams {
   const float* bias;      // [64] or nullptr
@@ -27,7 +27,11 @@ struct HaloParams {
   int out_kind, relu, round_out;
   int N, P, Q;            // output extents
   int TP, WP, TPI;        // output rows per tile, row pitch of the M numbering, tiles per image
-  int ntaps, stages;      // taps; weight ring depth
+  int ntaps, stages;      // taps; weight ring depth (w_resident: == ntaps, every tap's box is loaded once per CTA)
+  int nplanes, step_h;    // 4 parity planes / tile row step 2 (stride-2 convs) or 1 plane / step 1 (stride-1 convs)
+  int bn, kelems;         // output channels (MMA N); elements per 128-byte operand row (64 f16 / 32 tf32)
+  int w_resident;
+  int slots;              // plane ring depth
   int h_start, w_start;   // tensor coordinates of plane (0, 0) element [0][0] for tile row p0 = 0: 2 * rjmin, 2 * sjmin
   int box_rows, box_cols; // plane rows / cols staged per tile (in plane units); box_cols == WP
   uint32_t plane_stride;  // bytes of one plane slot (multiple of 1024)
@@ -37,8 +41,8 @@ struct HaloParams {
   uint16_t tap_wcol[kMaxTaps];   // 64-column block of the packed weights [64][kpad] (= r * S + s)
 };
 
-__host__ __device__ inline size_t halo_smem_bytes(uint32_t plane_stride, int stages) {
-  return (size_t)kHaloSlots * plane_stride + (size_t)stages * 8192 + 1024 /*align*/ + 512 /*barriers*/;
+__host__ __device__ inline size_t halo_smem_bytes(uint32_t plane_stride, int stages, int slots, int bn = 64) {
+  return (size_t)slots * plane_stride + (size_t)stages * (size_t)bn * 128 + 1024 /*align*/ + 512 /*barriers*/;
 }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -48,33 +52,36 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-__global__ void __launch_bounds__(224, 2)
+template <bool TF32>
+__global__ void __launch_bounds__(224, 3)
 halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int stages = p.stages;
+  const int stages = p.stages, nslots = p.slots;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sH = base;                                          // kHaloSlots plane slots
-  const uint32_t sB = base + (uint32_t)kHaloSlots * p.plane_stride;  // weight ring: stages x 8 KB
-  const uint32_t bars = sB + (uint32_t)stages * 8192u;
+  const uint32_t sH = base;                                          // nslots plane slots
+  const uint32_t wbox = (uint32_t)p.bn * 128u;                   // one tap's weight box: bn rows x 128 B
+  const uint32_t sB = base + (uint32_t)nslots * p.plane_stride;  // weight ring: stages x wbox
+  const uint32_t bars = sB + (uint32_t)stages * wbox;
   auto bfull = [&](int s) { return bars + (uint32_t)s * 8u; };
   auto bempty = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
   auto pfull = [&](int b) { return bars + (uint32_t)(2 * stages + b) * 8u; };
-  auto pempty = [&](int b) { return bars + (uint32_t)(2 * stages + kHaloSlots + b) * 8u; };
-  auto tfull = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * kHaloSlots + a) * 8u; };
-  auto tempty = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * kHaloSlots + 2 + a) * 8u; };
-  const uint32_t tslot = bars + (uint32_t)(2 * stages + 2 * kHaloSlots + 4) * 8u;
+  auto pempty = [&](int b) { return bars + (uint32_t)(2 * stages + nslots + b) * 8u; };
+  auto tfull = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * nslots + a) * 8u; };
+  auto tempty = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * nslots + 2 + a) * 8u; };
+  const uint32_t tslot = bars + (uint32_t)(2 * stages + 2 * nslots + 4) * 8u;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int b = 0; b < kHaloSlots; ++b) { mbar_init(pfull(b), 1); mbar_init(pempty(b), 1); }
+    for (int b = 0; b < nslots; ++b) { mbar_init(pfull(b), 1); mbar_init(pempty(b), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
     mbar_fence_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
   }
-  if (warp == 4) tmem_alloc(tslot, 128);  // two 64-column fp32 accumulators
+  const uint32_t tcols = p.bn <= 16 ? 32u : 2u * (uint32_t)p.bn;  // two bn-column fp32 accumulators (bn = 32, 64, 128)
+  if (warp == 4) tmem_alloc(tslot, tcols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -90,12 +97,12 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       int slot = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int n = tile / p.TPI, p0 = (tile - n * p.TPI) * p.TP;
-        for (int pl = 0; pl < 4; ++pl) {  // plane = rp * 2 + sp
+        for (int pl = 0; pl < p.nplanes; ++pl) {  // plane = rp * 2 + sp
           mbar_wait(pempty(slot), (uint32_t)(ph ^ 1));
           mbar_arrive_expect_tx(pfull(slot), plane_bytes);
           tma_load_4d(sH + (uint32_t)slot * p.plane_stride, &tmX, pfull(slot), 0, p.w_start + (pl & 1),
-                      p.h_start + 2 * p0 + (pl >> 1), n);
-          if (++slot == kHaloSlots) { slot = 0; ph ^= 1; }
+                      p.h_start + p.step_h * p0 + (pl >> 1), n);
+          if (++slot == nslots) { slot = 0; ph ^= 1; }
         }
       }
     }
@@ -103,43 +110,57 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ===================== TMA producer of the weight ring =====================
     if (lane == 0) {
       int st = 0, ph = 0;
+      if (p.w_resident) {
+        if ((int)blockIdx.x < total)
+          for (int t = 0; t < p.ntaps; ++t) {
+            mbar_arrive_expect_tx(bfull(t), wbox);
+            tma_load_2d(sB + (uint32_t)t * wbox, &tmW, bfull(t), (int)p.tap_wcol[t] * p.kelems, 0);
+          }
+      } else
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x)
         for (int t = 0; t < p.ntaps; ++t) {
           mbar_wait(bempty(st), (uint32_t)(ph ^ 1));
-          mbar_arrive_expect_tx(bfull(st), 8192u);
-          tma_load_2d(sB + (uint32_t)st * 8192u, &tmW, bfull(st), (int)p.tap_wcol[t] * 64, 0);
+          mbar_arrive_expect_tx(bfull(st), wbox);
+          tma_load_2d(sB + (uint32_t)st * wbox, &tmW, bfull(st), (int)p.tap_wcol[t] * p.kelems, 0);
           if (++st == stages) { st = 0; ph ^= 1; }
         }
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_h16(64, 0, 0, 0, 0);
+      const uint32_t idesc = TF32 ? make_idesc_tf32(p.bn, 0, 0) : make_idesc_h16(p.bn, 0, 0, 0, 0);
       const uint64_t bdesc0 = make_smem_desc(sB, 16u, 1024u);
       const uint64_t adesc0 = make_smem_desc(sH, 16u, 1024u);
+      const bool resident = p.w_resident != 0;
       int st = 0, ph = 0, slot = 0, sph = 0, i = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
         const int acc = i & 1, use = i >> 1;
         mbar_wait(tempty(acc), (uint32_t)((use & 1) ^ 1));
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)p.bn;
         int t = 0;
-        for (int pl = 0; pl < 4; ++pl) {
+        for (int pl = 0; pl < p.nplanes; ++pl) {
           mbar_wait(pfull(slot), (uint32_t)sph);
           tc_fence_after();
           const uint64_t aplane = adesc0 + (uint64_t)(((uint32_t)slot * p.plane_stride) >> 4);
           for (; t < p.plane_begin[pl + 1]; ++t) {
+            if (resident) { st = t; ph = 0; }  // phase 0 of a resident box completes once and stays complete
             mbar_wait(bfull(st), (uint32_t)ph);
             tc_fence_after();
             const uint64_t ad0 = aplane + (uint64_t)((uint32_t)p.tap_shift[t] * 8u);  // rows x 128 B >> 4
-            const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * 8192u) >> 4);
+            const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * wbox) >> 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
-            umma_commit(bempty(st));
-            if (++st == stages) { st = 0; ph ^= 1; }
+            for (int j = 0; j < 4; ++j) {  // 32 bytes of K per MMA: 16 f16 or 8 tf32
+              if constexpr (TF32) umma_tf32(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
+              else umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
+            }
+            if (!resident) {
+              umma_commit(bempty(st));
+              if (++st == stages) { st = 0; ph ^= 1; }
+            }
           }
           umma_commit(pempty(slot));  // every MMA reading this plane was issued before this commit
-          if (++slot == kHaloSlots) { slot = 0; sph ^= 1; }
+          if (++slot == nslots) { slot = 0; sph ^= 1; }
         }
         umma_commit(tfull(acc));
       }
@@ -158,9 +179,8 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const long long orow = ((long long)n * p.P + p0 + pp) * p.Q + q;
       mbar_wait(tfull(acc), (uint32_t)(use & 1));
       tc_fence_after();
-      const uint32_t trow = tmem_base + (uint32_t)acc * 64u + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
+      const uint32_t trow = tmem_base + (uint32_t)acc * (uint32_t)p.bn + ((uint32_t)(warp * 32) << 16);
+      for (int c = 0; c < p.bn; c += 32) {
         float v[32];
         tmem_ld32(trow + (uint32_t)c, v);
         tmem_ld_wait();
@@ -177,7 +197,7 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.out_kind == 0) {
-            float* o = reinterpret_cast<float*>(p.out) + orow * 64 + c;
+            float* o = reinterpret_cast<float*>(p.out) + orow * p.bn + c;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 r4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -188,7 +208,7 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               *reinterpret_cast<float4*>(o + j) = r4;
             }
           } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + orow * 64 + c);
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + orow * p.bn + c);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               uint4 w4;
@@ -207,7 +227,7 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, tcols);
   }
 }
 
@@ -220,7 +240,6 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // and runs one launch per class).  Output pixels of a class are numbered m = ii * WP + j (j >= W2 are phantoms); the A
 // operand of a tap starts (dr - drmin) * WP + (ds - dsmin) rows into the tile.  B is the packed forward weight box of the
 // tap read MN-major (n = ci contiguous, k = co rows).  Accumulator use = (tile, class), two TMEM accumulators in turn.
-constexpr int kHaloDgSlots = 2;
 
 struct HaloDgradParams {
   void* out;               // dx [N, H, W, 64] fp32 (out_kind 0) or f16 (1)
@@ -229,7 +248,9 @@ struct HaloDgradParams {
   int out_kind, mask_kind, round_out;  // mask_kind 0 fp32, 1 f16
   int N, H, W;             // dx extents
   int TP, WP, TPI;         // half-resolution rows per tile, row pitch of the M numbering, tiles per image
-  int stages;              // weight ring depth
+  int stages, slots;       // weight ring depth, dy tile ring depth
+  int b_kmajor;            // 1: w is the per-tap transposed copy [ci][tap * 64 + co] (K-major B, like the forward)
+  int exp_nostore;         // timing experiment: skip the epilogue stores
   int h_start, w_start;    // dy coordinates of tile element [0][0] for tile row i0 = 0: drmin, dsmin
   int box_rows, box_cols;
   uint32_t plane_stride;
@@ -238,31 +259,31 @@ struct HaloDgradParams {
   uint16_t tap_wcol[kMaxTaps];
 };
 
-__host__ __device__ inline size_t halo_dgrad_smem_bytes(uint32_t plane_stride, int stages) {
-  return (size_t)kHaloDgSlots * plane_stride + (size_t)stages * 8192 + 1024 /*align*/ + 512 /*barriers*/;
+__host__ __device__ inline size_t halo_dgrad_smem_bytes(uint32_t plane_stride, int stages, int slots) {
+  return (size_t)slots * plane_stride + (size_t)stages * 8192 + 1024 /*align*/ + 512 /*barriers*/;
 }
 
-__global__ void __launch_bounds__(224, 2)
+__global__ void __launch_bounds__(224, 3)
 halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ HaloDgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int stages = p.stages;
+  const int stages = p.stages, nslots = p.slots;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sH = base;
-  const uint32_t sB = base + (uint32_t)kHaloDgSlots * p.plane_stride;
+  const uint32_t sB = base + (uint32_t)nslots * p.plane_stride;
   const uint32_t bars = sB + (uint32_t)stages * 8192u;
   auto bfull = [&](int s) { return bars + (uint32_t)s * 8u; };
   auto bempty = [&](int s) { return bars + (uint32_t)(stages + s) * 8u; };
   auto pfull = [&](int b) { return bars + (uint32_t)(2 * stages + b) * 8u; };
-  auto pempty = [&](int b) { return bars + (uint32_t)(2 * stages + kHaloDgSlots + b) * 8u; };
-  auto tfull = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * kHaloDgSlots + a) * 8u; };
-  auto tempty = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * kHaloDgSlots + 2 + a) * 8u; };
-  const uint32_t tslot = bars + (uint32_t)(2 * stages + 2 * kHaloDgSlots + 4) * 8u;
+  auto pempty = [&](int b) { return bars + (uint32_t)(2 * stages + nslots + b) * 8u; };
+  auto tfull = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * nslots + a) * 8u; };
+  auto tempty = [&](int a) { return bars + (uint32_t)(2 * stages + 2 * nslots + 2 + a) * 8u; };
+  const uint32_t tslot = bars + (uint32_t)(2 * stages + 2 * nslots + 4) * 8u;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-    for (int b = 0; b < kHaloDgSlots; ++b) { mbar_init(pfull(b), 1); mbar_init(pempty(b), 1); }
+    for (int b = 0; b < nslots; ++b) { mbar_init(pfull(b), 1); mbar_init(pempty(b), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
     mbar_fence_init();
     tma_prefetch_desc(&tmDY);
@@ -287,7 +308,7 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
         mbar_wait(pempty(slot), (uint32_t)(ph ^ 1));
         mbar_arrive_expect_tx(pfull(slot), plane_bytes);
         tma_load_4d(sH + (uint32_t)slot * p.plane_stride, &tmDY, pfull(slot), 0, p.w_start, p.h_start + i0, n);
-        if (++slot == kHaloDgSlots) { slot = 0; ph ^= 1; }
+        if (++slot == nslots) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -305,8 +326,10 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_h16(64, 0, 0, 0, 1);
-      const uint64_t bdesc0 = make_smem_desc(sB, 8192u, 1024u, 2);  // MN-major: 8-k-row atoms 1024 B apart
+      const uint32_t idesc = make_idesc_h16(64, 0, 0, 0, p.b_kmajor ? 0 : 1);
+      // MN-major (packed forward weights): 8-k-row atoms 1024 B apart, 16 k rows (2048 B) per MMA; K-major: 32 B per MMA
+      const uint64_t bdesc0 = p.b_kmajor ? make_smem_desc(sB, 16u, 1024u) : make_smem_desc(sB, 8192u, 1024u, 2);
+      const int bstep = p.b_kmajor ? 2 : 128;
       const uint64_t adesc0 = make_smem_desc(sH, 16u, 1024u);
       int st = 0, ph = 0, slot = 0, sph = 0, i = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -327,14 +350,14 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * 8192u) >> 4);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 128), idesc, (uint32_t)((t != t0) | (j != 0)));
+              umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc, (uint32_t)((t != t0) | (j != 0)));
             umma_commit(bempty(st));
             if (++st == stages) { st = 0; ph ^= 1; }
           }
           umma_commit(tfull(acc));
         }
         umma_commit(pempty(slot));
-        if (++slot == kHaloDgSlots) { slot = 0; sph ^= 1; }
+        if (++slot == nslots) { slot = 0; sph ^= 1; }
       }
     }
     __syncwarp();
@@ -391,7 +414,7 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
           float v[32];
           tmem_ld32(trow + (uint32_t)c, v);
           tmem_ld_wait();
-          if (valid) {
+          if (valid && !p.exp_nostore) {
             const uint32_t bits = mbits[c >> 5];
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) v[jj] = ((bits >> jj) & 1u) ? v[jj] * osc : 0.f;
@@ -428,6 +451,188 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Im2col-free weight gradient of the same convs: dW[co][tap][ci] += sum_m X_tap[m][ci] * dY[m][co] over the pixel
+// numbering m = pp * WP + q of the forward kernel above.  Both operands are MN-major views of staged images: B = the dY
+// tile (rows = m, 128 bytes = 64 co; phantom columns q >= Q and rows past the image are zero-filled by TMA, so phantom
+// pixels contribute nothing), A = the parity plane of a tap PAIR read from a shifted start row -- the two 64-channel row
+// groups of an M = 128 instruction are the two taps of the pair, LBO = (shift1 - shift0) * 128 bytes.  K = 16 pixels per
+// MMA.  A CTA owns a group of <= 8 pairs of ONE plane (64 TMEM columns each) over a range of tiles; per tile it stages that
+// plane + the dY tile once (the im2col kernel re-fetches 24 KB per 64 pixels per tap pair) and issues, for every 16-pixel
+// step, one MMA per pair -- consecutive MMAs go to different accumulators.  fp32 partial sums are added to dw with
+// red.global at the end.  Shared memory is zeroed once: reads past a plane (start shift + rounding of the pixel count to
+// 16) must meet finite values, and the dY rows behind TP * WP must stay zero.
+struct HaloWgradParams {
+  float* dw;               // [64][kpad] fp32, accumulated
+  float* db;               // [64] bias gradient (colsum of dY), accumulated by the CTAs of group 0; nullable
+  const float* inv_scale;  // device scalar or nullptr
+  int kpad;
+  int N, P, Q;
+  int TP, WP, TPI;         // output rows per tile, pitch, tiles per image
+  int nk;                  // 16-pixel MMA steps per tile = ceil(TP * WP / 16)
+  int slots;
+  int h_start, w_start, box_rows, box_cols;
+  uint32_t plane_bytes, dy_bytes;       // TMA transaction sizes
+  uint32_t plane_region, slot_stride;   // dY tile offset inside a slot; bytes per slot (multiples of 1024)
+  int ngroups;
+  int g_cta_begin[17];     // CTAs [g_cta_begin[g], g_cta_begin[g + 1]) work on group g
+  uint8_t g_plane[16];     // parity plane (rp * 2 + sp) of the group
+  uint8_t g_pair_begin[17];
+  uint16_t pair_shift[32]; // start row of the pair's first tap
+  uint16_t pair_lbo[32];   // rows between the two taps (0: single tap, second row group ignored)
+  uint8_t pair_tap0[32], pair_tap1[32];  // packed-weight tap index r * S + s (tap1 = 255: none)
+};
+
+__global__ void __launch_bounds__(192)
+halo_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const __grid_constant__ HaloWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + (uint32_t)p.slots * p.slot_stride;
+  auto full = [&](int s) { return bars + (uint32_t)s * 8u; };
+  auto empty = [&](int s) { return bars + (uint32_t)(p.slots + s) * 8u; };
+  const uint32_t tfull = bars + (uint32_t)(2 * p.slots) * 8u;
+  const uint32_t tslot = tfull + 8u;
+
+  int g = 0;
+  while (g + 1 < p.ngroups && (int)blockIdx.x >= p.g_cta_begin[g + 1]) ++g;
+  const int ncta = p.g_cta_begin[g + 1] - p.g_cta_begin[g], cidx = (int)blockIdx.x - p.g_cta_begin[g];
+  const int total = p.N * p.TPI;
+  const int tile0 = (int)(((long long)total * cidx) / ncta), tile1 = (int)(((long long)total * (cidx + 1)) / ncta);
+  const int pr0 = p.g_pair_begin[g], npair = p.g_pair_begin[g + 1] - pr0;
+  const int plane = p.g_plane[g];
+  const bool do_db = p.db != nullptr && g == 0;  // group 0 also column-sums the dY tiles it stages
+
+  for (uint32_t i = tid; i < ((uint32_t)p.slots * p.slot_stride) / 16u; i += 192u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16u), "r"(0u) : "memory");
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < p.slots; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), do_db ? 2 : 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  const uint32_t ncols = npair <= 1 ? 64u : (npair <= 2 ? 128u : (npair <= 4 ? 256u : 512u));
+  if (warp == 4) tmem_alloc(tslot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  if (tile1 > tile0) {
+    if (warp == 5) {
+      // ===================== TMA producer: plane + dY tile per slot =====================
+      if (lane == 0) {
+        int slot = 0, ph = 0;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          const int n = tile / p.TPI, p0 = (tile - n * p.TPI) * p.TP;
+          mbar_wait(empty(slot), (uint32_t)(ph ^ 1));
+          mbar_arrive_expect_tx(full(slot), p.plane_bytes + p.dy_bytes);
+          const uint32_t dst = base + (uint32_t)slot * p.slot_stride;
+          tma_load_4d(dst, &tmX, full(slot), 0, p.w_start + (plane & 1), p.h_start + 2 * p0 + (plane >> 1), n);
+          tma_load_4d(dst + p.plane_region, &tmDY, full(slot), 0, 0, p0, n);
+          if (++slot == p.slots) { slot = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 4) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_h16(64, 0, 0, 1, 1);
+        uint64_t adesc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int pr = pr0 + (q < npair ? q : 0);
+          adesc[q] = make_smem_desc(base + (uint32_t)p.pair_shift[pr] * 128u, (uint32_t)p.pair_lbo[pr] * 128u, 1024u, 2);
+        }
+        const uint64_t bdesc0 = make_smem_desc(base + p.plane_region, 1024u, 1024u, 2);
+        int slot = 0, ph = 0;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          mbar_wait(full(slot), (uint32_t)ph);
+          tc_fence_after();
+          const uint64_t soff = (uint64_t)(((uint32_t)slot * p.slot_stride) >> 4);
+          for (int j = 0; j < p.nk; ++j) {
+            const uint64_t koff = soff + (uint64_t)(j * 128);  // 16 pixel rows = 2048 B
+            const uint32_t accum = (uint32_t)((tile != tile0) | (j != 0));
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < npair) umma_f16(tmem_base + (uint32_t)q * 64u, adesc[q] + koff, bdesc0 + koff, idesc, accum);
+          }
+          umma_commit(empty(slot));
+          if (++slot == p.slots) { slot = 0; ph ^= 1; }
+        }
+        umma_commit(tfull);
+      }
+      __syncwarp();
+      tc_fence_before();
+    } else {
+      // ===================== epilogue warps 0-3: rows = (tap of the pair, ci), columns = co =====================
+      const float inv = p.inv_scale ? __ldg(p.inv_scale) : 1.f;
+      if (do_db) {
+        // bias gradient: thread = (8-channel chunk, row phase); 128-bit reads of the swizzled dY rows while the MMAs run
+        const uint32_t chunk = (uint32_t)tid & 7u, rsub = (uint32_t)tid >> 3;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint32_t rows = (uint32_t)(p.TP * p.WP);
+        int slot = 0, ph = 0;
+        for (int tile = tile0; tile < tile1; ++tile) {
+          mbar_wait(full(slot), (uint32_t)ph);
+          const uint32_t dyb = base + (uint32_t)slot * p.slot_stride + p.plane_region;
+          for (uint32_t m = rsub; m < rows; m += 16u) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(dyb + m * 128u + ((chunk ^ (m & 7u)) << 4)));
+            const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[2 * u] += f16_bits_to_f32((uint16_t)(ww[u] & 0xFFFFu));
+              acc[2 * u + 1] += f16_bits_to_f32((uint16_t)(ww[u] >> 16));
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == 0) mbar_arrive(empty(slot));
+          if (++slot == p.slots) { slot = 0; ph ^= 1; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {  // lanes l, l + 8, l + 16, l + 24 hold the same chunk
+          float a = acc[u];
+          a += __shfl_xor_sync(0xFFFFFFFFu, a, 8);
+          a += __shfl_xor_sync(0xFFFFFFFFu, a, 16);
+          if (lane < 8) atomicAdd(p.db + chunk * 8u + (uint32_t)u, a * inv);
+        }
+      }
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int row = warp * 32 + lane;
+      for (int q = 0; q < npair; ++q) {
+        const int tap = row < 64 ? (int)p.pair_tap0[pr0 + q] : (int)p.pair_tap1[pr0 + q];
+        const uint32_t trow = tmem_base + (uint32_t)q * 64u + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          float v[32];
+          tmem_ld32(trow + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (tap != 255) {
+            float* o = p.dw + (long long)c * p.kpad + tap * 64 + (row & 63);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(o + (long long)j * p.kpad, v[j] * inv);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
   }
 }
 
