@@ -90,6 +90,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of the (converged) warp: lets the compiler keep the surrounding code on the uniform datapath -- descriptors and
+// addresses of tcgen05 / TMA instructions stay in uniform registers.  A plain `lane == 0` branch makes the region divergent:
+// every operand then goes through R2UR and every UTCHMMA is wrapped in an ELECT / BRA.U.ANY loop (~100 issue cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / cp.async ---------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

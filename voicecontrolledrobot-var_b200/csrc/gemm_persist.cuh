@@ -142,7 +142,8 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
     // start-address step per MMA (>> 4): K-major 32 B; MN-major 8 k-rows (tf32, 1024 B) / 16 k-rows (16-bit, 2048 B)
     const int bstep = p.b_mn_major ? (H16 ? 128 : 64) : 2;
     int st = 0, ph = 0, i = 0;
-    if (lane == 0)  // one thread runs the whole issue loop (no warp-wide spin / re-convergence per stage)
+    // the converged warp runs the loop and one elected lane issues: descriptor arithmetic stays on the uniform datapath (a
+    // `lane == 0` loop wraps every UTCHMMA in an ELECT / BRA.U.ANY loop and moves each operand through R2UR)
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
       const int acc = nacc == 2 ? (i & 1) : 0;
       const int use = nacc == 2 ? (i >> 1) : i;            // how often this accumulator was used
@@ -153,7 +154,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         const int nsub = min(kps, num_kb - kb0);
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        {
+        if (elect_one_sync()) {
           // descriptors differ only in their 14-bit start-address field (bytes >> 4): add offsets
           // to a base descriptor instead of rebuilding both per MMA (the issuing thread is on the
           // critical path: 4 MMAs of a 64-column k-block are only 128 tensor-pipe cycles)
@@ -173,6 +174,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
           umma_commit(empty_bar(st));
           if (kb0 + kps >= num_kb) umma_commit(tfull_bar(acc));
         }
+        __syncwarp();
         if (++st == stages) { st = 0; ph ^= 1; }
       }
     }

@@ -266,7 +266,7 @@ gru_persist_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_consta
         for (int kb0 = 0; kb0 < num_kb; kb0 += kps) {
           mbar_wait(full_bar(mst), (uint32_t)mph);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {  // one lane of the converged warp: operands stay in uniform registers
             for (int sub = 0; sub < kps; ++sub) {  // base descriptor + start-address offset (bytes >> 4)
               const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)mst * stageA + (uint32_t)sub * kTileABytes) >> 4);
               const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)mst * stageB + (uint32_t)sub * tileB_bytes) >> 4);

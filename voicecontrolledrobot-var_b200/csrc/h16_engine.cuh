@@ -148,16 +148,18 @@ tc_wgrad_h16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const uint64_t adesc0 = make_smem_desc(sA, grp, 1024u, 2), bdesc0 = make_smem_desc(sB, grp, 1024u, 2);
       const int nmma = pb >> 4;  // 16 pixels (2048 B) per MMA
       int st = 0, ph = 0;
-      if (lane == 0)
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb) {  // converged warp, one elected lane issues
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA) >> 4);
-        const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB) >> 4);
-        for (int j = 0; j < nmma; ++j)
-          umma_f16(tmem_base, ad0 + (uint64_t)(j * 128), bd0 + (uint64_t)(j * 128), idesc, (uint32_t)((kb | j) != 0));
-        umma_commit(empty_bar(st));
-        if (kb == num_kb - 1) umma_commit(tfull_bar);
+        if (elect_one_sync()) {
+          const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA) >> 4);
+          const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB) >> 4);
+          for (int j = 0; j < nmma; ++j)
+            umma_f16(tmem_base, ad0 + (uint64_t)(j * 128), bd0 + (uint64_t)(j * 128), idesc, (uint32_t)((kb | j) != 0));
+          umma_commit(empty_bar(st));
+          if (kb == num_kb - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
         if (++st == stages) { st = 0; ph ^= 1; }
       }
       __syncwarp();

@@ -126,8 +126,8 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
     }
   } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
       const uint32_t idesc = TF32 ? make_idesc_tf32(p.bn, 0, 0) : make_idesc_h16(p.bn, 0, 0, 0, 0);
       const uint64_t bdesc0 = make_smem_desc(sB, 16u, 1024u);
       const uint64_t adesc0 = make_smem_desc(sH, 16u, 1024u);
@@ -149,23 +149,25 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             tc_fence_after();
             const uint64_t ad0 = aplane + (uint64_t)((uint32_t)p.tap_shift[t] * 8u);  // rows x 128 B >> 4
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * wbox) >> 4);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // 32 bytes of K per MMA: 16 f16 or 8 tf32
-              if constexpr (TF32) umma_tf32(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
-              else umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
+              for (int j = 0; j < 4; ++j) {  // 32 bytes of K per MMA: 16 f16 or 8 tf32
+                if constexpr (TF32) umma_tf32(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
+                else umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * 2), idesc, (uint32_t)((t | j) != 0));
+              }
+              if (!resident) umma_commit(bempty(st));
             }
-            if (!resident) {
-              umma_commit(bempty(st));
-              if (++st == stages) { st = 0; ph ^= 1; }
-            }
+            __syncwarp();
+            if (!resident && ++st == stages) { st = 0; ph ^= 1; }
           }
-          umma_commit(pempty(slot));  // every MMA reading this plane was issued before this commit
+          if (elect_one_sync()) umma_commit(pempty(slot));  // every MMA reading this plane was issued before this commit
+          __syncwarp();
           if (++slot == nslots) { slot = 0; sph ^= 1; }
         }
-        umma_commit(tfull(acc));
+        if (elect_one_sync()) umma_commit(tfull(acc));
+        __syncwarp();
       }
     }
-    __syncwarp();
     tc_fence_before();
   } else {
     // ===================== epilogue warps 0-3 =====================
@@ -324,8 +326,8 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
         }
     }
   } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: converged warp, one elected lane issues =====================
+    {
       const uint32_t idesc = make_idesc_h16(64, 0, 0, 0, p.b_kmajor ? 0 : 1);
       // MN-major (packed forward weights): 8-k-row atoms 1024 B apart, 16 k rows (2048 B) per MMA; K-major: 32 B per MMA
       const uint64_t bdesc0 = p.b_kmajor ? make_smem_desc(sB, 16u, 1024u) : make_smem_desc(sB, 8192u, 1024u, 2);
@@ -348,19 +350,23 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
             tc_fence_after();
             const uint64_t ad0 = aplane + (uint64_t)((uint32_t)p.tap_shift[t] * 8u);
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * 8192u) >> 4);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc, (uint32_t)((t != t0) | (j != 0)));
-            umma_commit(bempty(st));
+              for (int j = 0; j < 4; ++j)
+                umma_f16(d_tmem, ad0 + (uint64_t)(j * 2), bd0 + (uint64_t)(j * bstep), idesc, (uint32_t)((t != t0) | (j != 0)));
+              umma_commit(bempty(st));
+            }
+            __syncwarp();
             if (++st == stages) { st = 0; ph ^= 1; }
           }
-          umma_commit(tfull(acc));
+          if (elect_one_sync()) umma_commit(tfull(acc));
+          __syncwarp();
         }
-        umma_commit(pempty(slot));
+        if (elect_one_sync()) umma_commit(pempty(slot));
+        __syncwarp();
         if (++slot == nslots) { slot = 0; sph ^= 1; }
       }
     }
-    __syncwarp();
     tc_fence_before();
   } else {
     // ===================== epilogue warps 0-3 =====================
@@ -543,8 +549,8 @@ halo_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
       }
     } else if (warp == 4) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
+      // ===================== MMA issuer: converged warp, one elected lane issues =====================
+      {
         const uint32_t idesc = make_idesc_h16(64, 0, 0, 1, 1);
         uint64_t adesc[8];
 #pragma unroll
@@ -558,19 +564,22 @@ halo_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           mbar_wait(full(slot), (uint32_t)ph);
           tc_fence_after();
           const uint64_t soff = (uint64_t)(((uint32_t)slot * p.slot_stride) >> 4);
-          for (int j = 0; j < p.nk; ++j) {
-            const uint64_t koff = soff + (uint64_t)(j * 128);  // 16 pixel rows = 2048 B
-            const uint32_t accum = (uint32_t)((tile != tile0) | (j != 0));
+          if (elect_one_sync()) {
+            for (int j = 0; j < p.nk; ++j) {
+              const uint64_t koff = soff + (uint64_t)(j * 128);  // 16 pixel rows = 2048 B
+              const uint32_t accum = (uint32_t)((tile != tile0) | (j != 0));
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q < npair) umma_f16(tmem_base + (uint32_t)q * 64u, adesc[q] + koff, bdesc0 + koff, idesc, accum);
+              for (int q = 0; q < 8; ++q)
+                if (q < npair) umma_f16(tmem_base + (uint32_t)q * 64u, adesc[q] + koff, bdesc0 + koff, idesc, accum);
+            }
+            umma_commit(empty(slot));
           }
-          umma_commit(empty(slot));
+          __syncwarp();
           if (++slot == p.slots) { slot = 0; ph ^= 1; }
         }
-        umma_commit(tfull);
+        if (elect_one_sync()) umma_commit(tfull);
+        __syncwarp();
       }
-      __syncwarp();
       tc_fence_before();
     } else {
       // ===================== epilogue warps 0-3: rows = (tap of the pair, ci), columns = co =====================
