@@ -605,7 +605,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(full_bar(st), (uint32_t)ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one_sync()) {  // one lane of the converged warp: operands stay in uniform registers
         const uint32_t a0 = sA + (uint32_t)st * kTileABytes;
         const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
 #pragma unroll
@@ -833,7 +833,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint32_t a0 = sA + (uint32_t)st * tileA_bytes;
           const uint32_t b0 = sB + (uint32_t)st * tileB_bytes;
 #pragma unroll
@@ -1014,11 +1014,10 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const uint32_t lbo = (uint32_t)p.mn_lbo, sbo = (uint32_t)p.mn_sbo, lt = (uint32_t)p.mn_type;
       const uint64_t adesc0 = make_smem_desc(sA, lbo, sbo, lt), bdesc0 = make_smem_desc(sB, lbo, sbo, lt);
       int st = 0, ph = 0;
-      if (lane == 0)  // one thread runs the whole issue loop
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb) {  // converged warp, one elected lane issues
         mbar_wait(full_bar(st), (uint32_t)ph);
         tc_fence_after();
-        {
+        if (elect_one_sync()) {
           for (int sub = 0; sub < kps; ++sub) {  // base descriptor + start-address offset (bytes >> 4)
             const uint64_t ad0 = adesc0 + (uint64_t)(((uint32_t)st * stageA + (uint32_t)sub * tileA_bytes) >> 4);
             const uint64_t bd0 = bdesc0 + (uint64_t)(((uint32_t)st * stageB + (uint32_t)sub * tileB_bytes) >> 4);
@@ -1030,9 +1029,9 @@ tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           umma_commit(empty_bar(st));
           if (kb == num_kb - 1) umma_commit(tfull_bar);
         }
+        __syncwarp();
         if (++st == stages) { st = 0; ph ^= 1; }
       }
-      __syncwarp();
       tc_fence_before();
     }
   }
