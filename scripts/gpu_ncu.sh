@@ -16,10 +16,14 @@ ncu -i gpurun_out/prof_wgrad.ncu-rep --page raw --csv > gpurun_out/prof_wgrad_ra
 ncu --set full --clock-control none --import-source on -k regex:"gru_persist|gru_bwd_ksplit|mfcc" -s 9 -c 3 -f -o gpurun_out/prof_gru $CMD > gpurun_out/ncu_full_gru.log 2>&1
 echo "== gru/mfcc capture exit $?"
 ncu -i gpurun_out/prof_gru.ncu-rep --page raw --csv > gpurun_out/prof_gru_raw.csv 2> /dev/null
-ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_persist" -s 84 -c 28 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_persist" -s 66 -c 22 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1
 echo "== gemm capture exit $?"
 ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv > gpurun_out/prof_gemm_raw.csv 2> /dev/null
-for f in prof_wgrad prof_gru prof_gemm; do
+# the im2col-free conv kernels (6 launches per step: snd.conv2/3 forward + data gradient, imgBranch.2/.5 forward)
+ncu --set full --clock-control none --import-source on -k regex:"halo_conv" -s 18 -c 6 -f -o gpurun_out/prof_halo $CMD > gpurun_out/ncu_full_halo.log 2>&1
+echo "== halo capture exit $?"
+ncu -i gpurun_out/prof_halo.ncu-rep --page raw --csv > gpurun_out/prof_halo_raw.csv 2> /dev/null
+for f in prof_wgrad prof_gru prof_gemm prof_halo; do
   sz=$(stat -c %s gpurun_out/$f.ncu-rep 2>/dev/null || echo 0)
   if [ "$sz" -gt 14000000 ]; then echo "dropping oversized report $f ($sz bytes)"; rm -f gpurun_out/$f.ncu-rep; fi
 done

@@ -48,7 +48,8 @@ FAMILY = {"wgrad": (("tc_wgrad_tma",), ("cin1_wgrad",), ("cin3_wgrad",), ("tc_wg
           "gru_step": (("gru_persist_kernel",),), "gru_bwd": (("gru_bwd_ksplit",),),
           "mfcc": (("mfcc_kernel",),),
           # the 16-bit forward and dgrad GEMMs are the same kernel template: one entry serves both tags
-          "gemm_fwd16": (("tc_gemm_persist", ", 1>"),), "gemm_dgrad16": (("tc_gemm_persist", ", 1>"),),
+          "gemm_fwd16": (("halo_conv_fwd_kernel<0>",), ("tc_gemm_persist", ", 1>")),
+          "gemm_dgrad16": (("halo_conv_dgrad_kernel",), ("tc_gemm_persist", ", 1>")),
           "gemm_fwd": (("tc_gemm_persist", ", 0>"),), "gemm_dgrad": (("tc_gemm_persist", ", 0>"),)}
 traffic = {}
 
@@ -57,7 +58,7 @@ def to_bytes(v, unit):
     return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-for part in ("wgrad", "gru", "gemm"):
+for part in ("wgrad", "gru", "gemm", "halo"):
     path = f"gpurun_out/prof_{part}_raw.csv"
     if not os.path.exists(path):
         continue
