@@ -76,8 +76,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
     // ===================== TMA producer =====================
     constexpr int KSH = H16 ? 6 : 5;  // log2(elements per 128-byte k-block row)
     const int nb_boxes = p.b_mn_major ? (bn >> KSH) : p.nbox;
-    const bool multi = nb_boxes >= 3;
-    if (lane == 0 || (multi && lane <= 3 && lane - 1 < nb_boxes)) {
+    {  // the converged warp runs the loop, one elected lane issues every box of a stage from uniform registers
       int st = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int ntile = tile % n_tiles, mtile = tile / n_tiles;
@@ -98,34 +97,34 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         for (int it0 = 0; it0 < num_kb; it0 += kps) {
           const int nsub = min(kps, num_kb - it0);
           mbar_wait(empty_bar(st), (uint32_t)(ph ^ 1));
-          if (lane == 0) mbar_arrive_expect_tx(full_bar(st), (uint32_t)nsub * ((uint32_t)kTileABytes + tileB_bytes));
+          const bool leader = elect_one_sync();
+          if (leader) mbar_arrive_expect_tx(full_bar(st), (uint32_t)nsub * ((uint32_t)kTileABytes + tileB_bytes));
           for (int sub = 0; sub < nsub; ++sub) {
             const int it = it0 + sub;
             const uint32_t dstA = sA + (uint32_t)st * stageA + (uint32_t)sub * kTileABytes;
             const uint32_t dstB = sB + (uint32_t)st * stageB + (uint32_t)sub * tileB_bytes;
             const int c0 = GMODE == G_TMA_IM2COL ? (cb << KSH) : (it << KSH);
-            if (lane == 0) {
+            if (leader) {
               if constexpr (GMODE == G_TMA_IM2COL)
                 tma_load_im2col_4d(dstA, &tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
               else
                 tma_load_2d(dstA, &tmA, full_bar(st), it << KSH, m0);
-            }
-            if (!p.b_mn_major) {
-              for (int b = 0; b < p.nbox; ++b)
-                if (lane == (multi ? 1 + (b % 3) : 0))
+              if (!p.b_mn_major) {
+                for (int b = 0; b < p.nbox; ++b)
                   tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, &tmB, full_bar(st), it << KSH,
                               p.boxbase[b] + ntile * p.box_rows);
-            } else {
-              const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
-              const int k0 = cb << KSH;
-              // one box = {128 bytes of n, one k-block of k rows}: 4 KB (tf32: 32 x 32) or 8 KB (16-bit: 64 x 64)
-              for (int gidx = 0; gidx < (bn >> KSH); ++gidx)
-                if (lane == (multi ? 1 + (gidx % 3) : 0))
+              } else {
+                const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
+                const int k0 = cb << KSH;
+                // one box = {128 bytes of n, one k-block of k rows}: 4 KB (tf32: 32 x 32) or 8 KB (16-bit: 64 x 64)
+                for (int gidx = 0; gidx < (bn >> KSH); ++gidx)
                   tma_load_2d(dstB + (uint32_t)gidx * (H16 ? 8192u : 4096u), &tmB, full_bar(st),
                               rs * p.cin_total + ntile * bn + (gidx << KSH), k0);
+              }
             }
             if (++cb == period) { cb = 0; ++tap; }
           }
+          __syncwarp();
           if (++st == stages) { st = 0; ph ^= 1; }
         }
       }

@@ -337,9 +337,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
       // thread becomes the bottleneck once a k-block needs more than two TMA instructions.
       // A warp without a box to load must stay out of the loop: an idle waiter can fall two
       // phases behind an mbarrier and then never sees its parity flip.
-      const int nb_boxes = p.b_mn_major ? (bn >> 5) : p.nbox;
-      const bool multi = nb_boxes >= 3;  // up to 3 instructions per k-block: one issuer is fastest
-      if (lane == 0 && (warp == 0 || (multi && warp - 1 < nb_boxes))) {
+      // (Round 2, end: warp 0 alone runs the loop CONVERGED and one elected lane issues every box of the k-block from
+      // uniform registers -- the per-instruction cost that made a single issuer the bottleneck was the ELECT / R2UR
+      // wrapping of divergent `lane == 0` code, not the TMA unit.)
+      if (warp == 0) {
         int st = 0, ph = 0;
         int w0 = 0, h0 = 0, n0 = 0;
         if constexpr (GMODE == G_TMA_IM2COL) {
@@ -359,26 +360,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
           const uint32_t dstA = sA + (uint32_t)st * kTileABytes;
           const uint32_t dstB = sB + (uint32_t)st * tileB_bytes;
           const int c0 = GMODE == G_TMA_IM2COL ? (cb << 5) : (it << 5);
-          if (warp == 0) {
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(full_bar(st), (uint32_t)kTileABytes + tileB_bytes);
             if constexpr (GMODE == G_TMA_IM2COL)
               tma_load_im2col_4d(dstA, tmA, full_bar(st), c0, w0, h0, n0, p.tap_w[tap], p.tap_h[tap]);
             else
               tma_load_2d(dstA, tmA, full_bar(st), it * 32, m0);
-          }
-          if (!p.b_mn_major) {
-            for (int b = 0; b < p.nbox; ++b)
-              if (warp == (multi ? 1 + (b % 3) : 0))
+            if (!p.b_mn_major) {
+              for (int b = 0; b < p.nbox; ++b)
                 tma_load_2d(dstB + (uint32_t)(b * p.box_rows) * 128u, tmB, full_bar(st), it * 32,
                             p.boxbase[b] + ntile * p.box_rows);
-          } else {
-            const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
-            const int k0 = cb << 5;
-            for (int gidx = 0; gidx < (bn >> 5); ++gidx)
-              if (warp == (multi ? 1 + (gidx % 3) : 0))
+            } else {
+              const int rs = GMODE == G_TMA_IM2COL ? (int)p.tap_id[tap] : tap;
+              const int k0 = cb << 5;
+              for (int gidx = 0; gidx < (bn >> 5); ++gidx)
                 tma_load_2d(dstB + (uint32_t)gidx * 4096u, tmB, full_bar(st),
                             rs * p.cin_total + ntile * bn + gidx * 32, k0);
+            }
           }
+          __syncwarp();
           if (++cb == period) { cb = 0; ++tap; }
           if (++st == stages) { st = 0; ph ^= 1; }
         }
