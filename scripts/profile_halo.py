@@ -25,8 +25,8 @@ def timeit(fn, iters=10):
 VARIANTS = [
     {},
     {"VAR_HALO_CPS": "2"},
+    {"VAR_HALO_DG_CPS": "3"},
     {"VAR_HALO_CPS": "1", "VAR_HALO_SLOTS": "5", "VAR_HALO_STAGES": "8"},
-    {"VAR_WGRAD16_NACC": "1"},
 ]
 for (H, W, Cin, Cout, R, S, sh, sw, ph, pw) in [(300, 20, 64, 64, 11, 5, 2, 2, 5, 5), (150, 13, 64, 64, 7, 3, 2, 2, 1, 1)]:
     P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1

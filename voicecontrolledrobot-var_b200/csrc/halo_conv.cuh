@@ -92,36 +92,43 @@ halo_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 6) {
     // ===================== TMA producer of the parity planes (its own warp: the two producers wait on barriers with
     // very different rhythms, and two spinning lanes of one warp starve each other) =====================
-    if (lane == 0) {
+    {  // converged warp, one elected lane issues (see elect_one_sync)
       const uint32_t plane_bytes = (uint32_t)p.box_rows * (uint32_t)p.box_cols * 128u;
       int slot = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int n = tile / p.TPI, p0 = (tile - n * p.TPI) * p.TP;
         for (int pl = 0; pl < p.nplanes; ++pl) {  // plane = rp * 2 + sp
           mbar_wait(pempty(slot), (uint32_t)(ph ^ 1));
-          mbar_arrive_expect_tx(pfull(slot), plane_bytes);
-          tma_load_4d(sH + (uint32_t)slot * p.plane_stride, &tmX, pfull(slot), 0, p.w_start + (pl & 1),
-                      p.h_start + p.step_h * p0 + (pl >> 1), n);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(pfull(slot), plane_bytes);
+            tma_load_4d(sH + (uint32_t)slot * p.plane_stride, &tmX, pfull(slot), 0, p.w_start + (pl & 1),
+                        p.h_start + p.step_h * p0 + (pl >> 1), n);
+          }
+          __syncwarp();
           if (++slot == nslots) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
     // ===================== TMA producer of the weight ring =====================
-    if (lane == 0) {
+    {
       int st = 0, ph = 0;
       if (p.w_resident) {
-        if ((int)blockIdx.x < total)
+        if ((int)blockIdx.x < total && elect_one_sync())
           for (int t = 0; t < p.ntaps; ++t) {
             mbar_arrive_expect_tx(bfull(t), wbox);
             tma_load_2d(sB + (uint32_t)t * wbox, &tmW, bfull(t), (int)p.tap_wcol[t] * p.kelems, 0);
           }
+        __syncwarp();
       } else
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x)
         for (int t = 0; t < p.ntaps; ++t) {
           mbar_wait(bempty(st), (uint32_t)(ph ^ 1));
-          mbar_arrive_expect_tx(bfull(st), wbox);
-          tma_load_2d(sB + (uint32_t)st * wbox, &tmW, bfull(st), (int)p.tap_wcol[t] * p.kelems, 0);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bfull(st), wbox);
+            tma_load_2d(sB + (uint32_t)st * wbox, &tmW, bfull(st), (int)p.tap_wcol[t] * p.kelems, 0);
+          }
+          __syncwarp();
           if (++st == stages) { st = 0; ph ^= 1; }
         }
     }
@@ -302,26 +309,32 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
   const int ntaps = p.class_begin[4];
   if (warp == 6) {
     // ===================== TMA producer of the dy tiles =====================
-    if (lane == 0) {
+    {
       const uint32_t plane_bytes = (uint32_t)p.box_rows * (uint32_t)p.box_cols * 128u;
       int slot = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int n = tile / p.TPI, i0 = (tile - n * p.TPI) * p.TP;
         mbar_wait(pempty(slot), (uint32_t)(ph ^ 1));
-        mbar_arrive_expect_tx(pfull(slot), plane_bytes);
-        tma_load_4d(sH + (uint32_t)slot * p.plane_stride, &tmDY, pfull(slot), 0, p.w_start, p.h_start + i0, n);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(pfull(slot), plane_bytes);
+          tma_load_4d(sH + (uint32_t)slot * p.plane_stride, &tmDY, pfull(slot), 0, p.w_start, p.h_start + i0, n);
+        }
+        __syncwarp();
         if (++slot == nslots) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
     // ===================== TMA producer of the weight ring =====================
-    if (lane == 0) {
+    {
       int st = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x)
         for (int t = 0; t < ntaps; ++t) {
           mbar_wait(bempty(st), (uint32_t)(ph ^ 1));
-          mbar_arrive_expect_tx(bfull(st), 8192u);
-          tma_load_2d(sB + (uint32_t)st * 8192u, &tmW, bfull(st), (int)p.tap_wcol[t] * 64, 0);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bfull(st), 8192u);
+            tma_load_2d(sB + (uint32_t)st * 8192u, &tmW, bfull(st), (int)p.tap_wcol[t] * 64, 0);
+          }
+          __syncwarp();
           if (++st == stages) { st = 0; ph ^= 1; }
         }
     }
