@@ -1,5 +1,5 @@
 """Sweeps the launch shape of the im2col-free (halo) f16 conv kernels on the iTHOR sound conv2 / conv3 shapes.
-usage: python scripts/profile_halo.py [N]   (VAR_HALO_EXP variants give WRONG results: timing experiments only)"""
+usage: python scripts/profile_halo.py [N]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

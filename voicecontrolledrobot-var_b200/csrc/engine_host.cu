@@ -1368,9 +1368,7 @@ static int conv_fwd_halo_h16(const ConvShape& cs, const void* x, const void* w, 
   if (smem * cps > per_sm) return VAR_ERR_UNSUPPORTED;
   const int kpad = round_up32(cs.R * cs.S * cs.Cin);
   CUtensorMap tx, tw;
-  const int exp_ = env_int("VAR_HALO_EXP", 0);  // timing experiments only (wrong results): 1 = unstrided planes, 2 = 8-row aligned shifts
-  if (exp_ == 2) for (int i = 0; i < p.ntaps; ++i) p.tap_shift[i] &= ~7;
-  int rc = get_tmap_nhwc_strided(x, cs.N, cs.H, cs.W, cs.Cin, p.box_cols, p.box_rows, exp_ == 1 ? 1 : 2, exp_ == 1 ? 1 : 2, &tx);
+  int rc = get_tmap_nhwc_strided(x, cs.N, cs.H, cs.W, cs.Cin, p.box_cols, p.box_rows, 2, 2, &tx);
   if (rc) return rc;
   rc = get_tmap_2d_e(w, 2, cs.Cout, kpad, kpad, 64, (int)CU_TENSOR_MAP_SWIZZLE_128B, &tw);
   if (rc) return rc;
@@ -1491,7 +1489,6 @@ static int conv_dgrad_halo_h16(const ConvShape& cs, const void* dy, const void* 
   }
   p.class_begin[4] = t;
   const int cps = env_int("VAR_HALO_DG_CPS", 2);  // 3 CTAs per SM: MMA side 20 % faster, but the fp32 row stores then bound the kernel (0.53 -> 0.67 ms)
-  { const int e_ = env_int("VAR_HALO_DG_EXP", 0); p.b_kmajor = e_ & 1; p.exp_nostore = (e_ >> 1) & 1; }  // timing experiments (wrong results)
   p.slots = env_int("VAR_HALO_DG_SLOTS", 2);
   p.stages = env_int("VAR_HALO_DG_STAGES", 4);  // trimmed below to what cps CTAs per SM leave room for (2 at cps = 3)
   size_t smem = halo_dgrad_smem_bytes(p.plane_stride, p.stages, p.slots);

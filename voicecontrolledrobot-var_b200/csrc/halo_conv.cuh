@@ -258,8 +258,6 @@ struct HaloDgradParams {
   int N, H, W;             // dx extents
   int TP, WP, TPI;         // half-resolution rows per tile, row pitch of the M numbering, tiles per image
   int stages, slots;       // weight ring depth, dy tile ring depth
-  int b_kmajor;            // 1: w is the per-tap transposed copy [ci][tap * 64 + co] (K-major B, like the forward)
-  int exp_nostore;         // timing experiment: skip the epilogue stores
   int h_start, w_start;    // dy coordinates of tile element [0][0] for tile row i0 = 0: drmin, dsmin
   int box_rows, box_cols;
   uint32_t plane_stride;
@@ -341,10 +339,10 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
   } else if (warp == 4) {
     // ===================== MMA issuer: converged warp, one elected lane issues =====================
     {
-      const uint32_t idesc = make_idesc_h16(64, 0, 0, 0, p.b_kmajor ? 0 : 1);
-      // MN-major (packed forward weights): 8-k-row atoms 1024 B apart, 16 k rows (2048 B) per MMA; K-major: 32 B per MMA
-      const uint64_t bdesc0 = p.b_kmajor ? make_smem_desc(sB, 16u, 1024u) : make_smem_desc(sB, 8192u, 1024u, 2);
-      const int bstep = p.b_kmajor ? 2 : 128;
+      const uint32_t idesc = make_idesc_h16(64, 0, 0, 0, 1);
+      // B = the packed forward weight box read MN-major: 8-k-row atoms 1024 B apart, 16 k rows (2048 B) per MMA
+      const uint64_t bdesc0 = make_smem_desc(sB, 8192u, 1024u, 2);
+      constexpr int bstep = 128;
       const uint64_t adesc0 = make_smem_desc(sH, 16u, 1024u);
       int st = 0, ph = 0, slot = 0, sph = 0, i = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -433,7 +431,7 @@ halo_conv_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_co
           float v[32];
           tmem_ld32(trow + (uint32_t)c, v);
           tmem_ld_wait();
-          if (valid && !p.exp_nostore) {
+          if (valid) {
             const uint32_t bits = mbits[c >> 5];
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) v[jj] = ((bits >> jj) & 1u) ? v[jj] * osc : 0.f;
