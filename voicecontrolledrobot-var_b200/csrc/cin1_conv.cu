@@ -145,16 +145,20 @@ cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int t
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp == 8) {
-    if (lane == 0) {
+    // converged warp, one elected lane issues (operands stay in uniform registers; see elect_one_sync)
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(w_full, kWBytes);
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + (uint32_t)kb * 8192u, &tmW, w_full, kb * 32, 0);
-      mbar_wait(w_full, 0);
-      const uint32_t idesc = make_idesc_tf32(kCout, 0, 0);
-      for (int i = 0; i < nt; ++i) {
-        const int g = i & 1;
-        mbar_wait(a_full(g), (uint32_t)((i >> 1) & 1));
-        tc_fence_after();
-        const uint32_t a0 = sA + (uint32_t)g * kABytes;
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    const uint32_t idesc = make_idesc_tf32(kCout, 0, 0);
+    for (int i = 0; i < nt; ++i) {
+      const int g = i & 1;
+      mbar_wait(a_full(g), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t a0 = sA + (uint32_t)g * kABytes;
+      if (elect_one_sync()) {
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -165,8 +169,8 @@ cin1_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin1Args a, int t
           }
         umma_commit(acc_full(g));
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int g = warp >> 2, r = tid & 127, wq = warp & 3;
     const int pr = r / kQ, q = r - pr * kQ;
@@ -278,7 +282,7 @@ cin1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin1Args a, in
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp == 8) {
-    if (lane == 0) {
+    {  // converged warp; issue_dy and the MMA bursts run on one elected lane
       auto issue_dy = [&](int i) {
         const TilePos tp = tile_pos(i, tpi);
         const int g = i & 1;
@@ -289,7 +293,9 @@ cin1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin1Args a, in
             tma_load_2d(sB + (uint32_t)g * kDyBytes + (uint32_t)pb * 8192u + (uint32_t)cg * 4096u, &tmDY,
                         dy_full(g), cg * 32, m0 + pb * 32);
       };
-      for (int i = 0; i < 2 && i < nt; ++i) issue_dy(i);
+      if (elect_one_sync())
+        for (int i = 0; i < 2 && i < nt; ++i) issue_dy(i);
+      __syncwarp();
       const uint32_t idesc = make_idesc_tf32(kCout, 1, 1);
       const uint32_t lbo = (uint32_t)mn_lbo, sbo = (uint32_t)mn_sbo, lt = (uint32_t)mn_type;
       for (int i = 0; i < nt; ++i) {
@@ -299,6 +305,7 @@ cin1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin1Args a, in
         mbar_wait(dy_full(g), ph);
         tc_fence_after();
         const uint32_t a0 = sA + (uint32_t)g * kABytes, b0 = sB + (uint32_t)g * kDyBytes;
+        if (elect_one_sync()) {
 #pragma unroll
         for (int pb = 0; pb < 4; ++pb)
 #pragma unroll
@@ -309,12 +316,15 @@ cin1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin1Args a, in
             umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((i | pb | j) != 0));
           }
         umma_commit(mma_done(g));
+        }
+        __syncwarp();
         if (i >= 1 && i + 1 < nt) {  // the other group's dY buffer is free once tile i-1 retired
           mbar_wait(mma_done(g ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
-          issue_dy(i + 1);
+          if (elect_one_sync()) issue_dy(i + 1);
+          __syncwarp();
         }
       }
-      umma_commit(final_bar);
+      if (elect_one_sync()) umma_commit(final_bar);
     }
     __syncwarp();
   } else {

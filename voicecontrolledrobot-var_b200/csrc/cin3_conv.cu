@@ -146,16 +146,20 @@ cin3_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin3Args a, const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp == 8) {
-    if (lane == 0) {
+    // converged warp, one elected lane issues (operands stay in uniform registers; see elect_one_sync)
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(w_full, kWBytes);
       tma_load_2d(sW, &tmW, w_full, 0, 0);
-      mbar_wait(w_full, 0);
-      const uint32_t idesc = make_idesc_tf32(kCout, 0, 0);
-      for (int i = 0; i < nt; ++i) {
-        const int g = i & 1;
-        mbar_wait(a_full(g), (uint32_t)((i >> 1) & 1));
-        tc_fence_after();
-        const uint32_t a0 = sA + (uint32_t)g * kABytes;
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    const uint32_t idesc = make_idesc_tf32(kCout, 0, 0);
+    for (int i = 0; i < nt; ++i) {
+      const int g = i & 1;
+      mbar_wait(a_full(g), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const uint32_t a0 = sA + (uint32_t)g * kABytes;
+      if (elect_one_sync()) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint64_t ad = make_smem_desc(a0 + (uint32_t)j * 32u, 16u, 1024u);
@@ -164,8 +168,8 @@ cin3_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const Cin3Args a, const
         }
         umma_commit(acc_full(g));
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int g = warp >> 2, r = tid & 127, wq = warp & 3;
     const int pr = r / a.Q, q = r - pr * a.Q;
@@ -273,7 +277,7 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin3Args a, co
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp == 8) {
-    if (lane == 0) {
+    {  // converged warp; issue_dy and the MMA bursts run on one elected lane
       auto issue_dy = [&](int i) {
         const TilePos tp = tile_pos(i, ge);
         const int g = i & 1;
@@ -282,7 +286,9 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin3Args a, co
         for (int pb = 0; pb < 4; ++pb)
           tma_load_2d(sB + (uint32_t)g * kDyBytes + (uint32_t)pb * 4096u, &tmDY, dy_full(g), 0, m0 + pb * 32);
       };
-      for (int i = 0; i < 2 && i < nt; ++i) issue_dy(i);
+      if (elect_one_sync())
+        for (int i = 0; i < 2 && i < nt; ++i) issue_dy(i);
+      __syncwarp();
       const uint32_t idesc = make_idesc_tf32(kCout, 1, 1);
       const uint32_t sbo = (uint32_t)mn_sbo, lt = (uint32_t)mn_type;
       for (int i = 0; i < nt; ++i) {
@@ -292,6 +298,7 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin3Args a, co
         mbar_wait(dy_full(g), ph);
         tc_fence_after();
         const uint32_t a0 = sA + (uint32_t)g * kABytes, b0 = sB + (uint32_t)g * kDyBytes;
+        if (elect_one_sync()) {
 #pragma unroll
         for (int pb = 0; pb < 4; ++pb)
 #pragma unroll
@@ -303,12 +310,15 @@ cin3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const Cin3Args a, co
             umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((i | pb | j) != 0));
           }
         umma_commit(mma_done(g));
+        }
+        __syncwarp();
         if (i >= 1 && i + 1 < nt) {  // the other group's dY buffer is free once tile i-1 retired
           mbar_wait(mma_done(g ^ 1), (uint32_t)(((i - 1) >> 1) & 1));
-          issue_dy(i + 1);
+          if (elect_one_sync()) issue_dy(i + 1);
+          __syncwarp();
         }
       }
-      umma_commit(final_bar);
+      if (elect_one_sync()) umma_commit(final_bar);
     }
     __syncwarp();
   } else {
