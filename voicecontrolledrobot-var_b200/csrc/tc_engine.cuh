@@ -332,14 +332,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB0, const __grid_constant__
       rc.base = (long long)rc.n * g.sN;
     }
     if constexpr (kTmaA) {
-      // lane 0 of the four epilogue warps share the TMA issue of every k-block (warp 0: the A
-      // tile and the expect_tx arm; warps 1-3: the weight boxes round-robin) -- a single issuing
-      // thread becomes the bottleneck once a k-block needs more than two TMA instructions.
-      // A warp without a box to load must stay out of the loop: an idle waiter can fall two
-      // phases behind an mbarrier and then never sees its parity flip.
-      // (Round 2, end: warp 0 alone runs the loop CONVERGED and one elected lane issues every box of the k-block from
-      // uniform registers -- the per-instruction cost that made a single issuer the bottleneck was the ELECT / R2UR
-      // wrapping of divergent `lane == 0` code, not the TMA unit.)
+      // Warp 0 runs the producer loop CONVERGED and one elected lane issues every box of the k-block from uniform
+      // registers.  (Until the end of round 2 lane 0 of all four epilogue warps shared the issue, because one `lane == 0`
+      // thread was the bottleneck beyond two TMA instructions per k-block: that cost was the ELECT / R2UR wrapping nvcc
+      // puts around tensor-map instructions in divergent code, not the TMA unit.)  The other warps stay out of the loop:
+      // an idle waiter can fall two phases behind an mbarrier and then never sees its parity flip.
       if (warp == 0) {
         int st = 0, ph = 0;
         int w0 = 0, h0 = 0, n0 = 0;
