@@ -63,6 +63,59 @@ def test_module_refuses_cpu_tensors(vb):
     assert d["image_feat"] is None and d["sound_feat_positive"] is None
 
 
+def _reference_imgcnn():
+    """The layer list of models/RL/ai2thor_RL_model.py:15-27 (plain torch, fp32, CPU)."""
+    nn = torch.nn
+    return nn.Sequential(
+        nn.Conv2d(3, 32, 3, stride=1, padding=1), nn.ReLU(), nn.Conv2d(32, 32, 3, stride=1, padding=1), nn.ReLU(),
+        nn.MaxPool2d(2, stride=2), nn.Conv2d(32, 64, 3, stride=1, padding=1), nn.ReLU(), nn.MaxPool2d(2, stride=2),
+        nn.Conv2d(64, 64, 3, stride=1, padding=1), nn.ReLU(), nn.MaxPool2d(2, stride=2),
+        nn.Conv2d(64, 128, 3, stride=1, padding=1), nn.ReLU(), nn.MaxPool2d(2, stride=2),
+        nn.Conv2d(128, 128, 3, stride=2, padding=1), nn.ReLU(), nn.Flatten())
+
+
+def test_policy_imgcnn_state_dict_layout(vb):
+    """the policy net's image CNN mirror keeps the reference's keys and shapes."""
+    mod = import_module(f"{PKG}.models.RL.ai2thor_RL_model")
+    ref = _reference_imgcnn()
+    sd = {"imgCNN." + k: v for k, v in ref.state_dict().items()}
+    sd["cnnMlp.0.weight"] = torch.zeros(512, 1152)  # other policy tensors are ignored
+    m = mod.ai2thorImgCNN.from_policy_state_dict(sd)
+    got = m.imgCNN.state_dict()
+    assert list(got) == list(ref.state_dict())
+    for k, v in ref.state_dict().items():
+        assert torch.equal(got[k], v)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 96, 96))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,dtype", [(3, torch.uint8), (40, torch.float32), (300, torch.uint8)])
+def test_policy_imgcnn_forward_vs_torch(vb, N, dtype):
+    """ai2thorNet_VAR.imgCNN (models/RL/ai2thor_RL_model.py:15-27) served by the VAR image-branch kernels: flattened
+    [N, 1152] features against plain fp32 PyTorch (tf32 MMAs: 2e-3 of the feature scale, as for image_feat_raw)."""
+    mod = import_module(f"{PKG}.models.RL.ai2thor_RL_model")
+    torch.manual_seed(7)
+    ref = _reference_imgcnn()
+    m = mod.ai2thorImgCNN.from_policy_state_dict({"imgCNN." + k: v for k, v in ref.state_dict().items()})
+    img_u8 = torch.from_numpy(synth.make_images(5, N))
+    x = img_u8.float() / 255
+    with torch.no_grad():
+        want = ref(x)
+    got = m((img_u8 if dtype == torch.uint8 else x).to(DEV))
+    assert got.shape == (N, 1152) and got.dtype == torch.float32
+    err = (got.cpu() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-3, err
+    # weights changed in place (a PPO update of the policy): the engine copy follows
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.mul_(0.5)
+        m.imgCNN.load_state_dict(ref.state_dict())
+        want2 = ref(x)
+    got2 = m(img_u8.to(DEV))
+    assert (got2.cpu() - want2).abs().max().item() / want2.abs().max().item() < 2e-3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,B", [("kuka", 6), ("ithor", 2)])
 def test_module_forward_backward_through_autograd(vb, kind, B):
