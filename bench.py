@@ -415,6 +415,8 @@ def run_b200(args):
     # branches serialised for this pass: with the two-stream overlap on, the events around a small
     # kernel also count the time it waits for SMs held by the other branch
     eng.set_overlap(False)
+    step_graph_was = getattr(eng, "use_step_graph", False)
+    eng.use_step_graph = False  # per-launch events need the individual launches, not a graph replay
     trainer.train_epoch(eng, batches, lr, 1, 0, max_steps=1)
     lib.var_prof_begin()
     prof_steps = 3
@@ -422,6 +424,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     prof = vb._lib.prof_end()
     eng.set_overlap(True)
+    eng.use_step_graph = step_graph_was
     step_kernel_ms = sum(v[0] for v in prof.values()) / prof_steps
     hbm, bf16_burst, bf16_sus, src = measured_peaks()
     tf32_peak = measure_tf32_peak(dev)

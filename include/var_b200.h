@@ -253,6 +253,9 @@ int var_triplet_fwd_bwd(const float* d_h_img, const float* d_h_pos, const float*
  * recurrent kernels use f16 operands (decides which tensor peak a family is compared with).
  * ---------------------------------------------------------------------------------- */
 long long var_launch_count(void);
+/* Kernels launched by replaying a CUDA graph that was captured from this library's launches (the host mirror's
+ * graphed training step / reward query): the capture counted them once, every replay reports them here. */
+int var_launch_count_add(long long n);
 int var_prof_begin(void);
 int var_prof_end(double* ms, double* flops, long long* count, int ntags);
 int var_prof_num_tags(void);

@@ -58,14 +58,20 @@ class VAR_Pretext(Pretext):
                     snd = torch.cat([sp[lo:hi].reshape(-1, F, 40), sn[lo:hi].reshape(-1, F, 40)]).float()
                     yield (image[lo:hi].to(self.device).contiguous(), snd.to(self.device).contiguous(), b)
             batches = host_batches()
+        # one GPU: the step's ~80 launches are replayed as one CUDA graph per batch slot (engine.triplet_step_graphed);
+        # with a process group the mid-backward bucket event of the gradient all-reduce keeps the eager launches
+        graphed = world == 1 and getattr(eng, "use_step_graph", False) and hasattr(eng, "triplet_step_graphed")
         for img, snd, global_b in batches:
-            eng.zero_grad()
             stepped = not (img is None or img.shape[0] == 0)
             if not stepped:
                 # ragged tail batch smaller than the world size: this rank has no triplet, but it must
                 # still take part in both collectives and in the (identical) Adam step
+                eng.zero_grad()
                 loss = torch.zeros((), dtype=torch.float32, device=self.device)
+            elif graphed:
+                loss = eng.triplet_step_graphed(img, snd, margin=cfg.tripletMargin, loss_denominator=global_b)
             else:
+                eng.zero_grad()
                 loss = eng.triplet_step(img, snd, margin=cfg.tripletMargin, loss_denominator=global_b)
             if world > 1:
                 if hasattr(eng, "allreduce_grads"):

@@ -79,6 +79,7 @@ PROTOTYPES = {
     "var_maxpool2x2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "var_maxpool2x2_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "var_launch_count": (C.c_longlong, []),
+    "var_launch_count_add": (C.c_int, [C.c_longlong]),
     "var_prof_begin": (_i, []),
     "var_prof_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), _i]),
     "var_prof_num_tags": (_i, []),

@@ -1871,6 +1871,13 @@ long long var_launch_count(void) {
   std::lock_guard<std::mutex> lk(p.mu);
   return p.launches;
 }
+int var_launch_count_add(long long n) {
+  if (n < 0) return VAR_ERR_ARG;
+  auto& p = var::prof();
+  std::lock_guard<std::mutex> lk(p.mu);
+  p.launches += n;
+  return VAR_OK;
+}
 int var_prof_begin(void) {
   auto& p = var::prof();
   std::lock_guard<std::mutex> lk(p.mu);

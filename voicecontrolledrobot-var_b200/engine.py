@@ -9,6 +9,7 @@ reward query (Envs/vec_env/vec_pretext_normalize.py:82-101).
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -47,6 +48,9 @@ class VarEngine:
         self._ws_need = {}
         self._reward_graphs = {}
         self._bucket = None
+        # graphed training step (triplet_step_graphed): VAR_STEP_GRAPH=0 keeps the ~80 individual launches per step
+        self.use_step_graph = os.environ.get("VAR_STEP_GRAPH", "1") != "0"
+        self._step_graphs = {}
 
     def __del__(self):
         try:
@@ -93,6 +97,7 @@ class VarEngine:
     def set_overlap(self, on):
         """Image / sound branch overlap on two streams (default on)."""
         check(lib.var_net_set_overlap(self._net, 1 if on else 0), "var_net_set_overlap")
+        self._step_graphs.clear()  # captured with the other stream layout
 
     def zero_grad(self):
         self.grads.zero_()
@@ -171,6 +176,48 @@ class VarEngine:
                                        float(margin), denom, ptr(ws), ws.numel(), ptr(loss_out), ptr(feats_out),
                                        stream_ptr()), "var_net_triplet_step")
         return loss_out
+
+    def triplet_step_graphed(self, images, sounds, margin=1.0, loss_denominator=None):
+        """zero_grad() + triplet_step() of one batch as ONE CUDA-graph replay (VAR/pretext_VAR.py:56-68: the step is
+        ~80 dependent kernel launches; when the trainer reads the loss every step the GPU otherwise idles while the
+        host issues them).  A graph belongs to the buffers it was captured on -- the loaders hand out a small ring of
+        preallocated batch slots, so a handful of graphs serve a whole run: the first step of a shape runs eagerly (sets
+        kernel attributes, sizes the workspace), every slot met after that is captured once and replayed from then on.
+        Returns a fresh device scalar with the loss.  Results are those of the eager step: the graph holds the same
+        kernels on the same streams."""
+        B = images.shape[0]
+        denom = float(B if loss_denominator is None else loss_denominator)
+        ws = self._workspace(B, 2 * B, True)
+        shape_key = (tuple(images.shape), images.dtype, tuple(sounds.shape), float(margin), denom)
+        key = (images.data_ptr(), sounds.data_ptr(), ws.data_ptr()) + shape_key
+        ent = self._step_graphs.get(key)
+        if ent is None:
+            # eager the first time a SHAPE is seen (that run sets kernel attributes and sizes the workspace, none of which
+            # may happen inside a capture); eager for good once buffers keep changing (host tuples, not loader slots)
+            warm = shape_key in self._step_graphs
+            if not warm or len(self._step_graphs) >= 24:
+                self._step_graphs.setdefault(shape_key, True)
+                self.zero_grad()
+                return self.triplet_step(images, sounds, margin, loss_denominator)
+            ent = self._step_graphs[key] = {}
+        if "graph" not in ent:
+            self._check_inputs(images, sounds)
+            loss = torch.zeros((), dtype=torch.float32, device=self.device)
+            l0 = lib.var_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self.zero_grad()
+                loss.zero_()  # the tail kernel ADDS the batch's hinge sum into it
+                self.triplet_step(images, sounds, margin, loss_denominator, loss_out=loss)
+            # the library counted the launches while they were being recorded: the first replay is their execution
+            ent.update(graph=g, loss=loss, launches=int(lib.var_launch_count() - l0), counted=True,
+                       keep=(images, sounds, ws))
+        ent["graph"].replay()
+        if ent["counted"]:
+            ent["counted"] = False
+        else:
+            check(lib.var_launch_count_add(ent["launches"]), "var_launch_count_add")
+        return ent["loss"].clone()
 
     def reward(self, images, goal_sounds=None, goal_feat_cached=None, env_reward=None, out=None):
         """-> (img_feat [N, D], goal_feat [N, D], img_sound_dot [N], reward [N]); `out` = the four
