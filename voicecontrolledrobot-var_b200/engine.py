@@ -185,6 +185,9 @@ class VarEngine:
         kernel attributes, sizes the workspace), every slot met after that is captured once and replayed from then on.
         Returns a fresh device scalar with the loss.  Results are those of the eager step: the graph holds the same
         kernels on the same streams."""
+        if not self.use_step_graph:
+            self.zero_grad()
+            return self.triplet_step(images, sounds, margin, loss_denominator)
         B = images.shape[0]
         denom = float(B if loss_denominator is None else loss_denominator)
         ws = self._workspace(B, 2 * B, True)
@@ -205,10 +208,19 @@ class VarEngine:
             loss = torch.zeros((), dtype=torch.float32, device=self.device)
             l0 = lib.var_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self.zero_grad()
+                    loss.zero_()  # the tail kernel ADDS the batch's hinge sum into it
+                    self.triplet_step(images, sounds, margin, loss_denominator, loss_out=loss)
+            except Exception as exc:  # a driver / torch build that cannot capture the step: same kernels, launched one by one
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({exc!r}); using individual launches")
+                self.use_step_graph = False
+                self._step_graphs.clear()
+                torch.cuda.synchronize(self.device)
                 self.zero_grad()
-                loss.zero_()  # the tail kernel ADDS the batch's hinge sum into it
-                self.triplet_step(images, sounds, margin, loss_denominator, loss_out=loss)
+                return self.triplet_step(images, sounds, margin, loss_denominator)
             # the library counted the launches while they were being recorded: the first replay is their execution
             ent.update(graph=g, loss=loss, launches=int(lib.var_launch_count() - l0), counted=True,
                        keep=(images, sounds, ws))
