@@ -130,3 +130,49 @@ def test_train_epoch_ragged_tail_smaller_than_world(tmp_path):
         eng.triplet_step(images[s:s + 8], None, loss_denominator=min(8, 17 - s))
         eng.adam_step(0.01)
     assert torch.allclose(eng.params, r[0]["params"], atol=1e-5)
+
+
+class GraphedFakeEngine(FakeEngine):
+    """FakeEngine + the graphed-step entry point of VarEngine (zero_grad + triplet_step in one call)."""
+
+    def __init__(self, n):
+        super().__init__(n)
+        self.use_step_graph = True
+        self.graphed_calls = 0
+        self.eager_calls = 0
+
+    def triplet_step(self, img, snd, margin=1.0, loss_denominator=None):
+        self.eager_calls += 1
+        return super().triplet_step(img, snd, margin, loss_denominator)
+
+    def triplet_step_graphed(self, img, snd, margin=1.0, loss_denominator=None):
+        self.graphed_calls += 1
+        self.zero_grad()
+        return FakeEngine.triplet_step(self, img, snd, margin, loss_denominator)
+
+
+def test_train_epoch_routes_single_gpu_steps_through_the_graphed_step():
+    """One process (world == 1): every non-empty batch goes through engine.triplet_step_graphed (which owns the
+    zero_grad), with the same weights as the individually launched steps; engines without it, a switched-off flag
+    and world > 1 keep the eager sequence."""
+    sys.path.insert(0, ROOT)
+    from importlib import import_module
+    tr = import_module("voicecontrolledrobot-var_b200.VAR.pretext_VAR")
+    t = object.__new__(tr.VAR_Pretext)
+    t.device = torch.device("cpu")
+    cfg = type("C", (), {})()
+    cfg.sound_dim = (1, 2, 40); cfg.tripletMargin = 1.0; cfg.pretextAdamL2 = 0.0
+    t.config = cfg
+    n, bs = 20, 8
+    images = (torch.arange(n * 8, dtype=torch.float32).reshape(n, 8) % 5)
+    batches = [(images[s:s + bs], torch.zeros(min(bs, n - s), 1, 2, 40), torch.zeros(min(bs, n - s), 1, 2, 40), None)
+               for s in range(0, n, bs)]
+    g, e = GraphedFakeEngine(8), FakeEngine(8)
+    lg = t.train_epoch(g, batches, 0.01)
+    le = t.train_epoch(e, batches, 0.01)
+    assert g.graphed_calls == 3 and g.eager_calls == 0 and g.steps == 3
+    assert torch.equal(g.params, e.params) and [float(a) for a in lg] == [float(b) for b in le]
+    off = GraphedFakeEngine(8)
+    off.use_step_graph = False
+    t.train_epoch(off, batches, 0.01)
+    assert off.graphed_calls == 0 and off.eager_calls == 3 and torch.equal(off.params, e.params)
