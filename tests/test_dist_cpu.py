@@ -152,9 +152,9 @@ class GraphedFakeEngine(FakeEngine):
 
 
 def test_train_epoch_routes_single_gpu_steps_through_the_graphed_step():
-    """One process (world == 1): every non-empty batch goes through engine.triplet_step_graphed (which owns the
-    zero_grad), with the same weights as the individually launched steps; engines without it, a switched-off flag
-    and world > 1 keep the eager sequence."""
+    """One process (world == 1), batches in loader slots: every non-empty batch goes through
+    engine.triplet_step_graphed (which owns the zero_grad), with the same weights as the individually launched steps;
+    engines without it, a switched-off flag and reference-style host tuples keep the eager sequence."""
     sys.path.insert(0, ROOT)
     from importlib import import_module
     tr = import_module("voicecontrolledrobot-var_b200.VAR.pretext_VAR")
@@ -167,12 +167,19 @@ def test_train_epoch_routes_single_gpu_steps_through_the_graphed_step():
     images = (torch.arange(n * 8, dtype=torch.float32).reshape(n, 8) % 5)
     batches = [(images[s:s + bs], torch.zeros(min(bs, n - s), 1, 2, 40), torch.zeros(min(bs, n - s), 1, 2, 40), None)
                for s in range(0, n, bs)]
+    def stream():  # what DeviceTripletLoader.stream() yields: (images, sounds, gt, global batch, record) in loader slots
+        for image, sp, sn, _ in batches:
+            yield image, torch.cat([sp, sn]), None, image.shape[0], None
+
     g, e = GraphedFakeEngine(8), FakeEngine(8)
-    lg = t.train_epoch(g, batches, 0.01)
+    lg = t.train_epoch(g, stream(), 0.01)
     le = t.train_epoch(e, batches, 0.01)
     assert g.graphed_calls == 3 and g.eager_calls == 0 and g.steps == 3
     assert torch.equal(g.params, e.params) and [float(a) for a in lg] == [float(b) for b in le]
     off = GraphedFakeEngine(8)
     off.use_step_graph = False
-    t.train_epoch(off, batches, 0.01)
+    t.train_epoch(off, stream(), 0.01)
     assert off.graphed_calls == 0 and off.eager_calls == 3 and torch.equal(off.params, e.params)
+    host = GraphedFakeEngine(8)  # reference-style host tuples: fresh tensors per batch, nothing to replay
+    t.train_epoch(host, batches, 0.01)
+    assert host.graphed_calls == 0 and host.eager_calls == 3 and torch.equal(host.params, e.params)

@@ -40,6 +40,7 @@ class VAR_Pretext(Pretext):
         sound_negative, gt).  `on_step(loss)` runs after each step's launches (e.g. to read the loss)."""
         cfg = self.config
         losses = []
+        slot_batches = True  # batches live in the loader's preallocated slots (stable buffers)
         if isinstance(data_generator, DeviceTripletLoader):
             data_generator.rank, data_generator.world_size = rank, world
             batches = ((img, snd, gB) for img, snd, _, gB, _ in data_generator.raw_batches())
@@ -58,9 +59,11 @@ class VAR_Pretext(Pretext):
                     snd = torch.cat([sp[lo:hi].reshape(-1, F, 40), sn[lo:hi].reshape(-1, F, 40)]).float()
                     yield (image[lo:hi].to(self.device).contiguous(), snd.to(self.device).contiguous(), b)
             batches = host_batches()
+            slot_batches = False  # fresh tensors every batch: a captured graph would be replayed once
         # one GPU: the step's ~80 launches are replayed as one CUDA graph per batch slot (engine.triplet_step_graphed);
         # with a process group the mid-backward bucket event of the gradient all-reduce keeps the eager launches
-        graphed = world == 1 and getattr(eng, "use_step_graph", False) and hasattr(eng, "triplet_step_graphed")
+        graphed = (world == 1 and slot_batches and getattr(eng, "use_step_graph", False)
+                   and hasattr(eng, "triplet_step_graphed"))
         for img, snd, global_b in batches:
             stepped = not (img is None or img.shape[0] == 0)
             if not stepped:
