@@ -11,6 +11,9 @@
 //     A_tap[m] = plane(rp, sp)[(p + rj) * WP + q + sj] = plane rows  m + shift(tap),
 // and tcgen05.mma accepts any 128-byte-aligned start inside a swizzled image (csrc/halo_probe.cu).  Fill per tile drops
 // from 1.3 MB to 92 KB of input + 440 KB of weights, at the price of (WP - Q) / WP wasted MMA rows.
+// An M = 128 operand that starts `shift` rows into a plane reads up to 128 - TP * WP + (column span) < 66 rows (8.3 KB) past the
+// plane's last row: phantom output rows only, and always inside the CTA's allocation (the next plane slot or the weight ring,
+// which is at least 16 KB).
 // CTA = 224 threads, persistent over tiles: warp 6 streams the parity planes through a ring of slots, warp 5 the weight
 // ring, warp 4 issues the MMAs (two TMEM accumulators), warps 0-3 are the epilogue (bias / ReLU / rounding, f16 or fp32 rows).
 #pragma once
