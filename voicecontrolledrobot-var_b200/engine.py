@@ -180,11 +180,12 @@ class VarEngine:
     def triplet_step_graphed(self, images, sounds, margin=1.0, loss_denominator=None):
         """zero_grad() + triplet_step() of one batch as ONE CUDA-graph replay (VAR/pretext_VAR.py:56-68: the step is
         ~80 dependent kernel launches; when the trainer reads the loss every step the GPU otherwise idles while the
-        host issues them).  A graph belongs to the buffers it was captured on -- the loaders hand out a small ring of
-        preallocated batch slots, so a handful of graphs serve a whole run: the first step of a shape runs eagerly (sets
-        kernel attributes, sizes the workspace), every slot met after that is captured once and replayed from then on.
-        Returns a fresh device scalar with the loss.  Results are those of the eager step: the graph holds the same
-        kernels on the same streams."""
+        host issues them).  A graph belongs to the buffers it was captured on -- the loaders hand out a ring of three
+        preallocated batch slots, so three graphs serve a whole run.  The first step of a shape runs eagerly (that run
+        sets kernel attributes and sizes the workspace, none of which may happen inside a capture) and its slot is
+        captured right behind it; every other slot is captured the first time it is met and replayed from then on, so
+        after three steps nothing is captured any more.  Returns a fresh device scalar with the loss.  Results are
+        those of the eager step: the graph holds the same kernels on the same streams."""
         if not self.use_step_graph:
             self.zero_grad()
             return self.triplet_step(images, sounds, margin, loss_denominator)
@@ -195,41 +196,46 @@ class VarEngine:
         key = (images.data_ptr(), sounds.data_ptr(), ws.data_ptr()) + shape_key
         ent = self._step_graphs.get(key)
         if ent is None:
-            # eager the first time a SHAPE is seen (that run sets kernel attributes and sizes the workspace, none of which
-            # may happen inside a capture); eager for good once buffers keep changing (host tuples, not loader slots)
-            warm = shape_key in self._step_graphs
-            if not warm or len(self._step_graphs) >= 24:
-                self._step_graphs.setdefault(shape_key, True)
+            if len(self._step_graphs) >= 24:  # buffers keep changing: stay eager
                 self.zero_grad()
                 return self.triplet_step(images, sounds, margin, loss_denominator)
-            ent = self._step_graphs[key] = {}
-        if "graph" not in ent:
-            self._check_inputs(images, sounds)
-            loss = torch.zeros((), dtype=torch.float32, device=self.device)
-            l0 = lib.var_launch_count()
-            g = torch.cuda.CUDAGraph()
-            try:
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self.zero_grad()
-                    loss.zero_()  # the tail kernel ADDS the batch's hinge sum into it
-                    self.triplet_step(images, sounds, margin, loss_denominator, loss_out=loss)
-            except Exception as exc:  # a driver / torch build that cannot capture the step: same kernels, launched one by one
-                import warnings
-                warnings.warn(f"CUDA-graph capture of the training step failed ({exc!r}); using individual launches")
-                self.use_step_graph = False
-                self._step_graphs.clear()
-                torch.cuda.synchronize(self.device)
+            if shape_key not in self._step_graphs:
+                self._step_graphs[shape_key] = True
+                self.zero_grad()
+                loss = self.triplet_step(images, sounds, margin, loss_denominator)
+                self._capture_step(key, images, sounds, margin, loss_denominator, ws)  # records only; runs nothing
+                return loss
+            ent = self._capture_step(key, images, sounds, margin, loss_denominator, ws)
+            if ent is None:  # capture failed: eager from now on
                 self.zero_grad()
                 return self.triplet_step(images, sounds, margin, loss_denominator)
-            # the library counted the launches while they were being recorded: the first replay is their execution
-            ent.update(graph=g, loss=loss, launches=int(lib.var_launch_count() - l0), counted=True,
-                       keep=(images, sounds, ws))
         ent["graph"].replay()
         if ent["counted"]:
-            ent["counted"] = False
+            ent["counted"] = False  # the library counted these launches while they were recorded
         else:
             check(lib.var_launch_count_add(ent["launches"]), "var_launch_count_add")
         return ent["loss"].clone()
+
+    def _capture_step(self, key, images, sounds, margin, loss_denominator, ws):
+        self._check_inputs(images, sounds)
+        loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        l0 = lib.var_launch_count()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self.zero_grad()
+                loss.zero_()  # the tail kernel ADDS the batch's hinge sum into it
+                self.triplet_step(images, sounds, margin, loss_denominator, loss_out=loss)
+        except Exception as exc:  # a driver / torch build that cannot capture the step: same kernels, launched one by one
+            import warnings
+            warnings.warn(f"CUDA-graph capture of the training step failed ({exc!r}); using individual launches")
+            self.use_step_graph = False
+            self._step_graphs.clear()
+            torch.cuda.synchronize(self.device)
+            return None
+        ent = dict(graph=g, loss=loss, launches=int(lib.var_launch_count() - l0), counted=True, keep=(images, sounds, ws))
+        self._step_graphs[key] = ent
+        return ent
 
     def reward(self, images, goal_sounds=None, goal_feat_cached=None, env_reward=None, out=None):
         """-> (img_feat [N, D], goal_feat [N, D], img_sound_dot [N], reward [N]); `out` = the four
