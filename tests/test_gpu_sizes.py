@@ -274,3 +274,29 @@ def test_two_rank_slices_on_one_device_equal_single_step(vb, net, B):
     scale = float(whole.grads.abs().max())
     # fp32 atomics accumulate in a different order in the two runs; rows are otherwise identical
     assert float((gsum - whole.grads).abs().max()) <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("net,B", [(omodel.KUKA, 24), (omodel.ITHOR, 6)])
+def test_graphed_step_equals_individual_launches(vb, net, B):
+    """VarEngine.triplet_step_graphed (the single-GPU train_epoch path: zero_grad + fused triplet step replayed as one
+    CUDA graph per batch slot) against the individually launched step on a twin engine, six steps over two alternating
+    batch slots: same loss and same gradients (up to the order of fp32 atomics) on the eager, the capturing and the
+    replayed calls."""
+    sd = omodel.init_state_dict(net, 43)
+    slots = []
+    for k in range(2):
+        images, sp, sn = synth.model_case(net, B, 7000 + B + k)
+        slots.append((torch.from_numpy(images).to(DEV),
+                      torch.cat([torch.from_numpy(sp[:, 0]), torch.from_numpy(sn[:, 0])]).contiguous().to(DEV)))
+    g, _ = _engine(vb, net, sd=sd)
+    e, _ = _engine(vb, net, sd=sd)
+    assert g.use_step_graph
+    for step in range(6):  # slot 0: eager (+ capture), replay, replay; slot 1: capture + replay, replay, replay
+        img, snd = slots[step % 2]
+        lg = float(g.triplet_step_graphed(img, snd, margin=1.0))
+        e.zero_grad()
+        le = float(e.triplet_step(img, snd, margin=1.0))
+        assert abs(lg - le) <= 1e-5 * max(1.0, abs(le)), (step, lg, le)
+        scale = float(e.grads.abs().max())
+        assert float((g.grads - e.grads).abs().max()) <= 1e-4 * scale, step
+    assert sum(1 for v in g._step_graphs.values() if isinstance(v, dict)) == 2
