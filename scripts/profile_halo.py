@@ -23,10 +23,12 @@ def timeit(fn, iters=10):
 
 
 VARIANTS = [
-    {},
+    {},                                   # shipped: im2col-free fwd (3 CTAs/SM) + dgrad (2 CTAs/SM), im2col wgrad
+    {"VAR_HALO": "0"},                    # im2col kernels for all three passes
+    {"VAR_HALO_WGRAD": "1"},              # im2col-free weight gradient (slower)
     {"VAR_HALO_CPS": "2"},
     {"VAR_HALO_DG_CPS": "3"},
-    {"VAR_HALO_CPS": "1", "VAR_HALO_SLOTS": "5", "VAR_HALO_STAGES": "8"},
+    {"VAR_HALO_CPS": "1", "VAR_HALO_SLOTS": "5", "VAR_HALO_STAGES": "8"},   # one MMA stream per SM
 ]
 for (H, W, Cin, Cout, R, S, sh, sw, ph, pw) in [(300, 20, 64, 64, 11, 5, 2, 2, 5, 5), (150, 13, 64, 64, 7, 3, 2, 2, 1, 1)]:
     P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
